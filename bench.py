@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its named config, on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|...]
+
+metric    decoded points/s (whole job, all N GPUs); output GB/s is reported beside it
+workload  N=1: BASELINE.json configs[1] -- 10,000 synthetic point clouds x 100,000 points, 14-bit quantized
+          positions, delta prediction + wrap, rANS symbols (scheme chosen by the upstream selection rule);
+          N>1: the same batch PER GPU (work shards by buffer, no collective: weak scaling)
+step      one pass of the attribute-decode hot path over the whole batch
+value     inputs (compressed bytes + stream descriptors) resident in HBM when the timed region starts
+e2e       the same metric through the public call with HOST buffers: index + H2D + kernels + D2H per step
+roofline  algorithmic bytes (compressed in + decoded out) of the dominant kernel / its CUDA-event
+          duration measured inside the timed steps, against MEASURED_PEAKS.json
+cpu_baseline  the CPU oracle (a linear-time port of the reference's algorithm; the C# itself cannot run: no .NET
+          in the image, and it cannot decode point clouds at all) on a bounded sample, all host cores
+
+--impl reference times that CPU oracle as the reference arm (the one other place oracle/ is executed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (clouds per GPU, points per cloud, generator kwargs, description)
+    "c2": (10000, 100000, dict(pos_bits=14, scheme=-1),
+           "BASELINE configs[1]: 10k point clouds x 100k points, 14-bit positions, delta+wrap, rANS (upstream scheme rule)"),
+    "c2raw": (10000, 100000, dict(pos_bits=14, scheme=1), "configs[1] with the Raw scheme forced"),
+    "c2tagged": (10000, 100000, dict(pos_bits=14, scheme=0), "configs[1] with the Tagged scheme forced"),
+    "c3": (10000, 100000, dict(pos_bits=14, scheme=-1, normal_bits=10, colors=1),
+           "BASELINE configs[2]: configs[1] + 10-bit octahedral normals + 8-bit RGB"),
+    "small": (1024, 100000, dict(pos_bits=14, scheme=-1), "CI-sized configs[1]: 1,024 clouds x 100k points"),
+    "tiny": (64, 20000, dict(pos_bits=14, scheme=-1), "smoke-sized"),
+}
+METRIC = "decoded points/sec"
+UNIT = "points/s"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_workload(name, rank, unique, arena_out=None):
+    """Synthetic batch for one rank.  `unique` distinct clouds are generated (seed 0xD5AC0000 + rank*2^20 + k) and
+    tiled to the batch size with neighbours always distinct (copy j of cloud u sits at index j*unique + u)."""
+    from draco_sharp_b200 import synth_gen as G
+    n_bufs, n_points, kw, _ = WORKLOADS[name]
+    u = n_bufs if unique <= 0 else min(unique, n_bufs)
+    spec = G.make_spec(n_points, seed=0xD5AC0000 + (rank << 20), **kw)
+    arena_u, offs_u, lens_u, sums_u, schemes_u, used_u = G.synth_batch(spec, u, n_threads=host_cores())
+    if u == n_bufs:
+        return arena_u, offs_u, lens_u, sums_u, schemes_u, used_u
+    reps = (n_bufs + u - 1) // u
+    stride = (used_u + 15) // 16 * 16
+    total = stride * reps
+    arena = arena_out(total) if arena_out else np.empty(total, dtype=np.uint8)
+    offs = np.zeros(n_bufs, dtype=np.uint64)
+    lens = np.zeros(n_bufs, dtype=np.uint64)
+    sums = np.zeros((n_bufs, 3), dtype=np.uint64)
+    schemes = np.zeros((n_bufs, 3), dtype=np.int32)
+    for j in range(reps):
+        arena[j * stride: j * stride + used_u] = arena_u[:used_u]
+        lo = j * u
+        hi = min(n_bufs, lo + u)
+        offs[lo:hi] = offs_u[: hi - lo] + np.uint64(j * stride)
+        lens[lo:hi] = lens_u[: hi - lo]
+        sums[lo:hi] = sums_u[: hi - lo]
+        schemes[lo:hi] = schemes_u[: hi - lo]
+    return arena, offs, lens, sums, schemes, total
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_oracle_rate(workload, seconds_target=15.0, threads=None):
+    """The CPU oracle on a bounded sample of the same workload, one buffer per thread.  Returns points/s etc."""
+    from oracle import pyoracle as O  # cpu_baseline / reference arm only
+    from draco_sharp_b200 import synth_gen as G
+    from draco_sharp_b200 import build as B
+    B.build_oracle()
+    O.lib()
+    n_bufs, n_points, kw, _ = WORKLOADS[workload]
+    threads = threads or host_cores()
+    # ~1e7 points/s/core for positions only: size the sample for about seconds_target core-seconds
+    per_cloud = n_points * (1 + (1 if kw.get("normal_bits") else 0) + (1 if kw.get("colors") else 0))
+    n_sample = int(max(threads, min(n_bufs, seconds_target * 0.8e7 / max(per_cloud, 1))))
+    n_sample = max(threads, (n_sample // threads) * threads)
+    spec = G.make_spec(n_points, seed=0xD5AC0000, **kw)
+    arena, offs, lens, _, _, _ = G.synth_batch(spec, n_sample, n_threads=threads)
+    chunks = [(offs[t::threads], lens[t::threads]) for t in range(threads)]
+    results = [None] * threads
+
+    def work(t):
+        results[t] = O.decode_bench(arena, chunks[t][0], chunks[t][1])
+
+    def run():
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    return n_sample, n_points, threads, run, results
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own algorithm on the host CPU (oracle port; the C# needs .NET, absent)."""
+    if rank != 0:
+        return
+    n_sample, n_points, threads, run, results = cpu_oracle_rate(args.workload, seconds_target=20.0)
+    for _ in range(max(1, min(args.warmup, 1))):
+        run()
+    times = [run() for _ in range(max(1, args.steps))]
+    dt = float(np.mean(times))
+    pts = sum(r[0] for r in results)
+    outb = sum(r[1] for r in results)
+    val = pts / dt
+    n_bufs = WORKLOADS[args.workload][0]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32->f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3],
+                   "clouds_per_gpu": n_bufs, "points_per_cloud": n_points},
+        "output_GBps": outb / dt / 1e9,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d of the workload's clouds x %d points per step, one buffer per thread; C oracle "
+                                   "-O2 (linear-time port of the C# algorithm; the C# is O(n^2) and throws on point clouds)" % (n_sample, n_points)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--unique", type=int, default=2048, help="distinct clouds generated per rank (0 = all distinct)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import draco_sharp_b200 as D
+    from draco_sharp_b200 import build as B
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "draco_sharp_b200", "libdracob200.so")):
+        B.build_all()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the decode path is CUDA only (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+
+    # ---- synthetic inputs, host side (pinned, so the e2e leg copies at full PCIe speed) ----
+    t0 = time.perf_counter()
+    pinned = {}
+
+    def pinned_arena(nbytes):
+        pinned["in"] = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        return pinned["in"].numpy()
+
+    arena, offs, lens, sums, schemes, used = make_workload(args.workload, rank, args.unique, pinned_arena)
+    if "in" not in pinned:  # all-distinct path returned a pageable arena
+        pinned["in"] = torch.empty(used, dtype=torch.uint8, pin_memory=True)
+        pinned["in"].numpy()[:] = arena[:used]
+        arena = pinned["in"].numpy()
+    gen_s = time.perf_counter() - t0
+
+    dec = D.DracoBatchDecoder([local_rank])
+    stream = torch.cuda.current_stream()
+    dec.set_stream(0, stream.cuda_stream)
+    batch = dec.index_arena(arena, offs, lens)
+    n_bufs = batch.n_bufs
+    points = batch.points
+    out_bytes = batch.out_bytes
+    in_bytes = batch.in_bytes
+    algo_bytes = batch.algo_bytes
+    dec.upload(batch)
+    d_out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+
+    def step():
+        dec.decode_resident(batch, dev_out=d_out.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    # parity gate before any number is reported: word checksums of a sample of decoded attributes
+    from draco_sharp_b200 import synth_gen as G
+    for k in list(range(0, n_bufs, max(1, n_bufs // 16)))[:16]:
+        assert batch.status(k) == 0, "buffer %d failed: %d" % (k, batch.status(k))
+        ai = batch.attr_info(k, 0)
+        got = d_out[ai.out_off: ai.out_off + ai.out_bytes].cpu().numpy()
+        assert G.word_checksum(got) == int(sums[k, 0]), "decoded positions of buffer %d do not match the generator" % k
+    bad = sum(1 for k in range(n_bufs) if batch.status(k) != 0)
+    assert bad == 0, "%d buffers failed" % bad
+
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    dom_ms = []
+    launches = 0
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        st = dec.stats()
+        dom_ms.append(st.ms_dominant)
+        launches += st.n_launches
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tp = torch.tensor([float(points), float(out_bytes), float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+        total_points, total_out, total_launches = float(tp[0]), float(tp[1]), int(tp[2])
+    else:
+        total_points, total_out, total_launches = float(points), float(out_bytes), launches
+    ms_per_step = ms / args.steps
+    value = total_points / (ms_per_step * 1e-3)
+    stats = dec.stats()
+
+    # ---- e2e: host buffers in, host buffers out, through the public call (index + H2D + kernels + D2H) ----
+    h_out = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    e2e_ms = []
+    for i in range(args.e2e_steps + 1):
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        b2 = dec.index_arena(arena, offs, lens)
+        dec.decode(b2, out_ptr=h_out.data_ptr())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        b2.free()
+        if i > 0:
+            e2e_ms.append(dt)
+    e2e_t = float(np.mean(e2e_ms))
+    if dist:
+        t = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    k = n_bufs // 2
+    ai = batch.attr_info(k, 0)
+    assert G.word_checksum(h_out.numpy()[ai.out_off: ai.out_off + ai.out_bytes]) == int(sums[k, 0])
+    e2e_value = total_points / (e2e_t * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        dom = float(np.mean(dom_ms)) if dom_ms else 0.0
+        achieved = (algo_bytes / (dom * 1e-3) / 1e9) if dom > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i32->f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3],
+                       "clouds_per_gpu": n_bufs, "points_per_cloud": WORKLOADS[args.workload][1],
+                       "unique_clouds_per_gpu": int(n_bufs if args.unique <= 0 else min(args.unique, n_bufs)),
+                       "symbol_scheme_of_positions": {0: "tagged", 1: "raw"}.get(int(schemes[0, 0]), "n/a"),
+                       "compressed_bytes_per_gpu": in_bytes, "output_bytes_per_gpu": out_bytes,
+                       "l2": "inputs+outputs (%.1f GB per step) exceed the 126 MB L2" % ((in_bytes + out_bytes) / 1e9),
+                       "generate_s": round(gen_s, 1)},
+            "output_GBps": total_out / (ms_per_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": profile_traffic(args.workload),
+                         "peak_source": peak_src, "kernel": stats.dominant_name.decode(), "kernel_ms": dom,
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "note": "serial rANS chains: %d streams x %d symbols; residency waves %d, %d lanes/warp, %d B smem/stream"
+                                 % (n_bufs, WORKLOADS[args.workload][1] * 3, stats.n_waves, stats.lanes_per_warp, stats.smem_per_stream)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": e2e_t, "steps": args.e2e_steps,
+                    "what": "dcb_index_arena + dcb_decode: host indexing, H2D from pinned memory, kernels, D2H to pinned memory"},
+            "gpu_launches": total_launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_sample, n_points, threads, run, results = cpu_oracle_rate(args.workload)
+            run()
+            dt = run()
+            line["cpu_baseline"] = {
+                "value": sum(r[0] for r in results) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "%d clouds x %d points of the same workload, one buffer per thread, C oracle -O2" % (n_sample, n_points)}
+        print(json.dumps(line))
+    batch.free()
+    dec.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1221 @@
+// draco_sharp_b200/csrc/dcb_api.cu -- C ABI of libdracob200.so (include/dracob200.h): host indexer,
+// launch planner and the decode driver.  Host code only; the kernels are in dcb_kernels.cu.
+//
+// Host-side reference semantics restated here (src/Draco/IO/...):
+//   header             DracoDecoder.cs:44-64 (magic, version, geometry type, method, flags)
+//   metadata (skipped) Metadata/MetadataDecoder.cs:5-49
+//   ATTRIBUTES         ConnectivityDecoder.cs:16-44, Mesh/MeshEdgeBreakerDecoder.cs:642-662 (DEC_ID),
+//                      Attributes/AttributesDecoder.cs:19-63 (DEC_DATA),
+//                      Attributes/SequentialAttributeDecodersController.cs:16-27 (decoder type bytes)
+//   entry counts       Attributes/LinearSequencer.cs:7-13 (num_points), MeshAttributeIndicesEncodingObserver.cs:14-21
+// The payload walk itself is dcb_walk.h.  There is NO CPU decode path in this library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+#include <tuple>
+#include <vector>
+
+#include "dcb_internal.h"
+#include "dcb_kernels.h"
+#include "dcb_walk.h"
+
+namespace {
+
+constexpr uint64_t kFrontPad = 64;     // bytes before the first buffer in the device input arena
+constexpr uint64_t kBackPad = 64;      // bytes after the last one (16-byte window loads may overrun)
+constexpr uint32_t kNumSMsDefault = 148;
+constexpr uint32_t kSmemPerSM = 227 * 1024;
+constexpr uint32_t kSmemPerCtaReserve = 1024;
+constexpr uint64_t kTabArenaBudget = 1ull << 30;
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct MeshMapsHost {
+  std::vector<uint32_t> opposite, corner_to_vertex, data_to_corner;
+  std::vector<int32_t> vertex_to_data;
+  bool set = false;
+  uint64_t dev_off[4] = {0, 0, 0, 0};
+};
+
+struct BufRec {
+  const uint8_t *src = nullptr;
+  uint64_t len = 0;
+  uint64_t arena_off = 0;  // inside the shard's device input arena
+  int shard = 0;
+  int local = 0;           // index inside the shard
+  dcb_buffer_info info{};
+  bool is_eb = false;
+  std::vector<MeshMapsHost> maps;  // per attributes decoder
+  std::vector<uint32_t> dec_entries;
+};
+
+struct Group {            // one kernel launch (or a few, for global tables)
+  int kind;               // 0 raw, 1 tag, 2 serial post, 3 para, 4 copy
+  int ncp;
+  bool wide, table_global;
+  uint32_t compact, prec_bits, entries, lut_shift, slot_bytes, lanes;
+  uint64_t total_symbols, max_bytes;
+  uint32_t max_entries;
+  std::vector<uint32_t> order;
+  uint64_t order_off;     // offset (in uint32) inside the shard's device order array
+};
+
+struct Shard {
+  int device = 0;
+  std::vector<int> bufs;
+  std::vector<StreamDesc> streams, streams0;
+  std::vector<BufWalk> walks, walks0;
+  std::vector<uint8_t> tags_launched;
+  uint64_t in_bytes = 0, out_bytes = 0, dbg_bytes = 0, aux_bytes = 0, maps_bytes = 0;
+  uint64_t out_base = 0, dbg_base = 0;  // offset of this shard inside the batch-wide host arenas
+  // device
+  uint8_t *d_in = nullptr, *d_out = nullptr, *d_dbg = nullptr, *d_aux = nullptr, *d_tab = nullptr, *d_maps = nullptr;
+  uint64_t tab_cap = 0, dbg_cap = 0;
+  StreamDesc *d_streams = nullptr;
+  BufWalk *d_walks = nullptr;
+  uint32_t *d_order = nullptr;
+  uint64_t order_cap = 0;
+  uint8_t *h_stage = nullptr;  // pinned staging for the packed input
+  bool uploaded = false, dirty = true, own_out = false;
+  uint8_t *ext_out = nullptr, *ext_dbg = nullptr;
+};
+
+}  // namespace
+
+struct dcb_ctx {
+  std::vector<int> devices;
+  std::vector<cudaStream_t> streams;
+  std::vector<bool> own_stream;
+  std::vector<int> num_sms;
+  dcb_launch_stats stats{};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct dcb_batch {
+  std::vector<BufRec> bufs;
+  std::vector<Shard> shards;
+  const uint8_t *host_arena = nullptr;  // dcb_index_arena: buffers live in one host arena
+  bool direct = false;                  // single shard + 16-byte aligned offsets: upload the arena as is
+  uint64_t direct_lo = 0, direct_hi = 0;
+  uint64_t total_out = 0, total_dbg = 0, total_in = 0, total_points = 0, algo_bytes = 0;
+  int n_devices = 1;
+};
+
+namespace {
+
+#define CUDA_TRY(x)                          \
+  do {                                       \
+    cudaError_t e_ = (x);                    \
+    if (e_ != cudaSuccess) {                 \
+      cudaGetLastError();                    \
+      return e_ == cudaErrorMemoryAllocation ? DCB_ERR_OOM : DCB_ERR_CUDA; \
+    }                                        \
+  } while (0)
+
+// ---- host reader for the container header (before the ATTRIBUTES payload) ----
+struct HRd {
+  const uint8_t *p;
+  uint64_t len, pos;
+  int err;
+  bool need(uint64_t n) {
+    if (err) return false;
+    if (pos > len || len - pos < n) { err = DCB_ERR_EOF; return false; }
+    return true;
+  }
+  uint32_t u8() { return need(1) ? p[pos++] : 0u; }
+  uint32_t u16() { if (!need(2)) return 0; uint32_t v = p[pos] | (p[pos + 1] << 8); pos += 2; return v; }
+  uint32_t u32() {
+    if (!need(4)) return 0;
+    uint32_t v = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+    pos += 4;
+    return v;
+  }
+  uint64_t varint() {
+    uint64_t result = 0;
+    unsigned shift = 0;
+    if (err) return 0;
+    for (int i = 0; i < 10; ++i) {
+      if (pos >= len) { err = DCB_ERR_EOF; return 0; }
+      uint32_t b = p[pos++];
+      result |= (uint64_t)(b & 0x7F) << shift;
+      if (!(b & 0x80)) return result;
+      shift += 7;
+    }
+    err = DCB_ERR_EOF;
+    return 0;
+  }
+};
+
+// Metadata/MetadataDecoder.cs:5-49 (skip only)
+void skip_metadata_element(HRd &r, int depth) {
+  if (depth > 64) { r.err = DCB_ERR_UNSUPPORTED; return; }
+  uint64_t n = r.varint();
+  for (uint64_t i = 0; i < n && !r.err; ++i) {
+    uint32_t ks = r.u8();
+    if (r.need(ks)) r.pos += ks;
+    uint32_t vs = r.u8();
+    if (r.need(vs)) r.pos += vs;
+  }
+  uint64_t ns = r.varint();
+  for (uint64_t i = 0; i < ns && !r.err; ++i) {
+    uint32_t ks = r.u8();
+    if (r.need(ks)) r.pos += ks;
+    skip_metadata_element(r, depth + 1);
+  }
+}
+void skip_metadata(HRd &r) {
+  uint64_t n = r.varint();
+  for (uint64_t i = 0; i < n && !r.err; ++i) {
+    (void)r.varint();
+    skip_metadata_element(r, 0);
+  }
+  skip_metadata_element(r, 0);
+}
+
+// DracoDecoder.DecodeHeader + the connectivity prefix that is host business.  Fills info; returns
+// the offset of the ATTRIBUTES section for geometry the library can walk on its own.
+void parse_header(BufRec &b) {
+  dcb_buffer_info &inf = b.info;
+  memset(&inf, 0, sizeof inf);
+  HRd r{b.src, b.len, 0, 0};
+  if (!r.need(5)) { inf.status = DCB_ERR_EOF; return; }
+  if (memcmp(b.src, "DRACO", 5) != 0) { inf.status = DCB_ERR_MAGIC; return; }
+  r.pos = 5;
+  inf.version_major = (int32_t)r.u8();
+  inf.version_minor = (int32_t)r.u8();
+  inf.geometry_type = (int32_t)r.u8();
+  inf.encoder_method = (int32_t)r.u8();
+  inf.flags = (int32_t)r.u16();
+  if (r.err) { inf.status = r.err; return; }
+  if (inf.version_major != 2 || inf.version_minor != 2) { inf.status = DCB_ERR_UNSUPPORTED; return; }
+  if (inf.flags & 0x8000) skip_metadata(r);
+  if (r.err) { inf.status = r.err; return; }
+  if (inf.geometry_type == 0) {  // point cloud (B-1: upstream sequential container)
+    if (inf.encoder_method != 0) { inf.status = DCB_ERR_UNSUPPORTED; return; }  // kd-tree: absent from the reference
+    int32_t np = (int32_t)r.u32();
+    if (r.err) { inf.status = r.err; return; }
+    if (np < 0) { inf.status = DCB_ERR_ATTR; return; }
+    inf.n_points = (uint32_t)np;
+    inf.attr_section_off = r.pos;
+  } else if (inf.geometry_type == 1) {
+    if (inf.encoder_method == 1) {
+      // Edgebreaker: connectivity is host work (DracoDecoder.cs:80-88 -> MeshEdgeBreakerDecoder); the
+      // caller reports where ATTRIBUTES starts with dcb_set_attr_section + dcb_set_mesh_maps.
+      b.is_eb = true;
+      inf.needs_connectivity = 1;
+    } else if (inf.encoder_method == 0) {
+      // sequential mesh connectivity (MeshSequentialDecoder.cs:8-118): host work as well
+      inf.needs_connectivity = 1;
+    } else {
+      inf.status = DCB_ERR_UNSUPPORTED;
+    }
+  } else {
+    inf.status = DCB_ERR_UNSUPPORTED;
+  }
+}
+
+// DEC_ID + DEC_DATA: creates the StreamDescs of one buffer (appended to sh.streams) and its BufWalk.
+void parse_attr_section(BufRec &b, Shard &sh, int buf_index) {
+  dcb_buffer_info &inf = b.info;
+  BufWalk w;
+  memset(&w, 0, sizeof w);
+  w.begin = b.arena_off;
+  w.end = b.arena_off + b.len;
+  w.stream_first = (int32_t)sh.streams.size();
+  w.blocked = -1;
+  w.phase = 2;
+  w.geom_type = (uint8_t)inf.geometry_type;
+  w.method = (uint8_t)inf.encoder_method;
+  auto finish = [&](int status) {
+    if (status && !inf.status) inf.status = status;
+    w.status = inf.status;
+    w.stream_count = (int32_t)sh.streams.size() - w.stream_first;
+    inf.n_attrs = w.stream_count;
+    sh.walks[b.local] = w;
+  };
+  if (inf.status) return finish(inf.status);
+  if (inf.needs_connectivity) return finish(0);  // attributes are indexed by dcb_index_finish
+  HRd r{b.src, b.len, inf.attr_section_off, 0};
+  const int n_dec = (int)r.u8();  // ConnectivityDecoder.cs:18
+  if (r.err) return finish(r.err);
+  inf.n_attr_decoders = n_dec;
+  if (b.is_eb) {  // DEC_ID: MeshEdgeBreakerDecoder.cs:642-662 (att_data_id, decoder type, traversal method)
+    for (int i = 0; i < n_dec; ++i) { r.u8(); r.u8(); r.u8(); }
+    if (r.err) return finish(r.err);
+  }
+  for (int d = 0; d < n_dec; ++d) {
+    uint64_t na = r.varint();
+    if (r.err) return finish(r.err);
+    if (na > (b.len - r.pos)) return finish(DCB_ERR_EOF);
+    const size_t first = sh.streams.size();
+    for (uint64_t i = 0; i < na; ++i) {
+      StreamDesc s;
+      memset(&s, 0, sizeof s);
+      s.buf_begin = w.begin;
+      s.buf_end = w.end;
+      s.buf_index = buf_index;
+      s.attr_index = (int32_t)(sh.streams.size() - (size_t)w.stream_first);
+      s.decoder_id = (uint8_t)d;
+      s.scheme = SCHEME_EMPTY;
+      s.pred_method = PRED_NONE;
+      s.transform = XF_NONE;
+      s.att_type = (uint8_t)r.u8();
+      s.data_type = (uint8_t)r.u8();
+      s.nc = (uint8_t)r.u8();
+      s.normalized = r.u8() != 0;
+      s.unique_id = (uint32_t)r.varint();
+      sh.streams.push_back(s);
+      if (r.err) return finish(r.err);
+      if (s.att_type >= 5 || s.data_type == 0 || s.data_type >= DT_COUNT || s.nc == 0) return finish(DCB_ERR_ATTR);
+    }
+    int status = 0;
+    for (uint64_t i = 0; i < na && !status; ++i) {
+      StreamDesc &s = sh.streams[first + i];
+      s.seq_type = (uint8_t)r.u8();
+      if (r.err) { status = r.err; break; }
+      if (s.seq_type > 3) { status = DCB_ERR_UNSUPPORTED; break; }
+      if (s.seq_type == SEQ_QUANTIZATION && s.data_type != DT_FLOAT32) status = DCB_ERR_ATTR;
+      if (s.seq_type == SEQ_NORMALS && (s.data_type != DT_FLOAT32 || s.nc != 3)) status = DCB_ERR_ATTR;
+      s.ncp = (s.seq_type == SEQ_NORMALS) ? 2 : s.nc;  // AttributeOctahedronTransform.cs:23-26, B-8
+      if (s.nc > 4 && s.seq_type == SEQ_QUANTIZATION) status = DCB_ERR_UNSUPPORTED;
+      // kernels are specialised for 1..4 portable components
+      if (!status && s.seq_type != SEQ_GENERIC && s.ncp > 4) status = DCB_ERR_UNSUPPORTED;
+    }
+    if (status) return finish(status);
+    // entry count of this decoder: LinearSequencer.cs:7-13 (B-2) / traversal observer for Edgebreaker
+    uint32_t n_entries = inf.n_points;
+    bool has_maps = false;
+    if (b.is_eb) {
+      if ((size_t)d >= b.maps.size() || !b.maps[d].set) return finish(DCB_ERR_MAPS);
+      n_entries = (uint32_t)b.maps[d].data_to_corner.size();
+      has_maps = true;
+    }
+    for (uint64_t i = 0; i < na; ++i) {
+      StreamDesc &s = sh.streams[first + i];
+      s.n_entries = n_entries;
+      s.has_maps = has_maps ? 1 : 0;
+      if (has_maps) {
+        s.n_corners = (uint32_t)b.maps[d].opposite.size();
+        s.n_vertices = (uint32_t)b.maps[d].vertex_to_data.size();
+      }
+      const uint64_t esz = (s.seq_type == SEQ_NORMALS) ? 12ull : (uint64_t)dcb_dtype_len(s.data_type) * s.nc;
+      s.out_bytes = esz * n_entries;
+    }
+  }
+  w.pos = b.arena_off + r.pos;
+  w.stream_count = (int32_t)sh.streams.size() - w.stream_first;
+  w.phase = w.stream_count > 0 ? 0 : 2;
+  // host part of the payload walk (stops at the first Tagged bit area)
+  if (w.stream_count > 0) walk_continue(b.src - b.arena_off, w, sh.streams.data());
+  finish(w.status);
+}
+
+void free_shard_device(Shard &sh) {
+  if (!sh.d_in && !sh.d_streams && !sh.h_stage && !sh.d_out) return;
+  cudaSetDevice(sh.device);
+  cudaFree(sh.d_in);
+  if (sh.own_out) cudaFree(sh.d_out);
+  cudaFree(sh.d_dbg);
+  cudaFree(sh.d_aux);
+  cudaFree(sh.d_tab);
+  cudaFree(sh.d_maps);
+  cudaFree(sh.d_streams);
+  cudaFree(sh.d_walks);
+  cudaFree(sh.d_order);
+  if (sh.h_stage) cudaFreeHost(sh.h_stage);
+  sh.d_in = sh.d_out = sh.d_dbg = sh.d_aux = sh.d_tab = sh.d_maps = nullptr;
+  sh.d_streams = nullptr;
+  sh.d_walks = nullptr;
+  sh.d_order = nullptr;
+  sh.h_stage = nullptr;
+  sh.uploaded = false;
+}
+
+// Lay out outputs / scratch of a shard once its streams exist.
+void layout_shard(Shard &sh) {
+  uint64_t out = 0, dbg = 0, aux = 0;
+  for (size_t bi = 0; bi < sh.walks.size(); ++bi) {
+    const BufWalk &w = sh.walks[bi];
+    bool any_unready = false;
+    for (int i = 0; i < w.stream_count; ++i) {
+      const StreamDesc &s = sh.streams[w.stream_first + i];
+      if (s.state < ST_READY || s.scheme == SCHEME_TAGGED) any_unready = true;
+    }
+    for (int i = 0; i < w.stream_count; ++i) {
+      StreamDesc &s = sh.streams[w.stream_first + i];
+      s.out_off = out;
+      out = align_up(out + s.out_bytes, 128);
+      const uint64_t nv = (uint64_t)s.n_entries * (s.ncp ? s.ncp : s.nc);
+      s.dbg_off = dbg;
+      dbg = align_up(dbg + nv * 4, 16);
+      if (w.status) continue;
+      if (s.seq_type != SEQ_GENERIC && (s.scheme == SCHEME_TAGGED || (any_unready && s.state < ST_READY))) {
+        s.tag_off = aux;
+        aux = align_up(aux + align_up(s.n_entries, 16) + 8ull * ((s.n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK + 1), 16);
+      }
+      if (s.seq_type != SEQ_GENERIC && s.has_maps && (s.recon == RECON_PARA_WRAP || s.state < ST_READY)) {
+        s.aux_off = aux;
+        aux = align_up(aux + (2ull * nv + 3ull * s.n_entries) * 4, 16);
+      }
+    }
+  }
+  sh.out_bytes = out;
+  sh.dbg_bytes = dbg;
+  sh.aux_bytes = aux;
+}
+
+int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, const uint64_t *offs,
+               const uint64_t *lens, int n_bufs, dcb_batch **out) {
+  if (!out || n_bufs < 0 || (n_bufs > 0 && !lens) || (n_bufs > 0 && !arena && !ptrs)) return DCB_ERR_ARG;
+  dcb_batch *b = new (std::nothrow) dcb_batch();
+  if (!b) return DCB_ERR_OOM;
+  b->n_devices = ctx ? (int)ctx->devices.size() : 1;
+  b->host_arena = arena;
+  b->bufs.resize((size_t)n_bufs);
+  b->shards.resize((size_t)b->n_devices);
+  for (int d = 0; d < b->n_devices; ++d) b->shards[d].device = ctx ? ctx->devices[d] : 0;
+  bool aligned = arena != nullptr;
+  for (int k = 0; k < n_bufs; ++k) {
+    BufRec &r = b->bufs[k];
+    r.src = arena ? arena + offs[k] : ptrs[k];
+    r.len = lens[k];
+    if (arena && (offs[k] & 15)) aligned = false;
+    if (!r.src && r.len) { delete b; return DCB_ERR_ARG; }
+    parse_header(r);
+  }
+  // shard by buffer: longest-processing-time-first on compressed bytes; no collective
+  std::vector<int> idx((size_t)n_bufs);
+  for (int k = 0; k < n_bufs; ++k) idx[k] = k;
+  std::vector<uint64_t> load((size_t)b->n_devices, 0);
+  if (b->n_devices > 1) {
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return b->bufs[x].len > b->bufs[y].len; });
+    for (int k : idx) {
+      int best = 0;
+      for (int d = 1; d < b->n_devices; ++d)
+        if (load[d] < load[best]) best = d;
+      b->bufs[k].shard = best;
+      load[best] += b->bufs[k].len + 64;
+    }
+  }
+  for (int k = 0; k < n_bufs; ++k) {
+    Shard &sh = b->shards[b->bufs[k].shard];
+    b->bufs[k].local = (int)sh.bufs.size();
+    b->bufs[k].info.device = b->bufs[k].shard;
+    sh.bufs.push_back(k);
+  }
+  b->direct = aligned && b->n_devices == 1 && n_bufs > 0;
+  if (b->direct) {
+    uint64_t lo = ~0ull, hi = 0;
+    for (int k = 0; k < n_bufs; ++k) {
+      lo = std::min(lo, offs[k]);
+      hi = std::max(hi, offs[k] + lens[k]);
+    }
+    b->direct_lo = lo;
+    b->direct_hi = hi;
+    for (int k = 0; k < n_bufs; ++k) b->bufs[k].arena_off = kFrontPad + (offs[k] - lo);
+    b->shards[0].in_bytes = kFrontPad + (hi - lo) + kBackPad;
+  } else {
+    for (Shard &sh : b->shards) {
+      uint64_t pos = kFrontPad;
+      for (int k : sh.bufs) {
+        b->bufs[k].arena_off = pos;
+        pos = align_up(pos + b->bufs[k].len, 16);
+      }
+      sh.in_bytes = pos + kBackPad;
+    }
+  }
+  for (Shard &sh : b->shards) sh.walks.resize(sh.bufs.size());
+  for (int k = 0; k < n_bufs; ++k) {
+    BufRec &r = b->bufs[k];
+    parse_attr_section(r, b->shards[r.shard], k);
+  }
+  *out = b;
+  return DCB_OK;
+}
+
+void finalize_layout(dcb_batch *b) {
+  uint64_t out_base = 0, dbg_base = 0;
+  b->total_in = 0;
+  b->total_points = 0;
+  b->algo_bytes = 0;
+  for (Shard &sh : b->shards) {
+    layout_shard(sh);
+    sh.out_base = out_base;
+    sh.dbg_base = dbg_base;
+    out_base += align_up(sh.out_bytes, 128);
+    dbg_base += align_up(sh.dbg_bytes, 128);
+    sh.streams0 = sh.streams;
+    sh.walks0 = sh.walks;
+    sh.dirty = true;
+  }
+  b->total_out = out_base;
+  b->total_dbg = dbg_base;
+  for (const BufRec &r : b->bufs) {
+    b->total_in += r.len;
+    if (r.info.status == DCB_OK && !r.info.needs_connectivity) {
+      b->total_points += r.info.n_points;
+      b->algo_bytes += r.len;
+      const Shard &sh = b->shards[r.shard];
+      const BufWalk &w = sh.walks[r.local];
+      for (int i = 0; i < w.stream_count; ++i) b->algo_bytes += sh.streams[w.stream_first + i].out_bytes;
+      for (const MeshMapsHost &m : r.maps)
+        if (m.set) b->algo_bytes += 4ull * (m.opposite.size() + m.corner_to_vertex.size() + m.data_to_corner.size() + m.vertex_to_data.size());
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch planning
+// ---------------------------------------------------------------------------------------------
+uint32_t ceil_log2(uint32_t v) {
+  uint32_t l = 0;
+  while ((1ull << l) < v) ++l;
+  return l;
+}
+
+struct RawKey {
+  int ncp, wide, compact, prec, size_class;
+  bool operator<(const RawKey &o) const {
+    return std::tie(ncp, wide, compact, prec, size_class) < std::tie(o.ncp, o.wide, o.compact, o.prec, o.size_class);
+  }
+};
+
+uint32_t slot_bytes_for(const Group &g, uint32_t k) {
+  const uint32_t nb = (1u << g.prec_bits) >> k;
+  const uint32_t words = nb + 1u + (g.compact ? 2u * g.entries : g.entries);
+  return (uint32_t)align_up((uint64_t)words * (g.wide ? 4u : 2u), 16);
+}
+
+// Choose LUT granularity, lanes per warp-CTA and the table home for every rANS group of a shard so
+// that as many streams as possible are resident at once: the chains are serial, so the batch time
+// is (waves) x (longest chain) and a second wave doubles it.
+void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms) {
+  const uint32_t budget = kSmemPerSM - 8 * kSmemPerCtaReserve;
+  std::vector<uint32_t> per_sm(gs.size()), kmin(gs.size()), kcap(gs.size());
+  for (size_t i = 0; i < gs.size(); ++i) {
+    Group &g = *gs[i];
+    per_sm[i] = std::min<uint32_t>(1024u, (uint32_t)((g.order.size() + num_sms - 1) / num_sms));
+    const uint32_t le = ceil_log2(std::max(2u, g.entries));
+    // finest LUT: ~4 buckets per table entry; coarsest: ~1 bucket per 4 entries (>= 16 buckets)
+    kmin[i] = g.prec_bits > le + 2 ? g.prec_bits - le - 2 : 0;
+    kcap[i] = std::max(kmin[i], std::min<uint32_t>(g.prec_bits - 4, g.prec_bits > le ? g.prec_bits - le + 2 : 2));
+    g.lut_shift = kmin[i];
+  }
+  for (;;) {
+    uint64_t total = 0;
+    for (size_t i = 0; i < gs.size(); ++i) total += (uint64_t)per_sm[i] * slot_bytes_for(*gs[i], gs[i]->lut_shift);
+    if (total <= budget) break;
+    int best = -1;
+    uint64_t best_share = 0;
+    for (size_t i = 0; i < gs.size(); ++i) {
+      Group &g = *gs[i];
+      if (g.lut_shift >= kcap[i]) continue;
+      const uint64_t share = (uint64_t)per_sm[i] * ((1u << g.prec_bits) >> g.lut_shift) * (g.wide ? 4u : 2u);
+      if (share > best_share) { best_share = share; best = (int)i; }
+    }
+    if (best < 0) break;
+    gs[best]->lut_shift++;
+  }
+  // share of the SM each group may use when not everything fits: proportional to its demand
+  uint64_t total = 0;
+  for (size_t i = 0; i < gs.size(); ++i) total += (uint64_t)per_sm[i] * slot_bytes_for(*gs[i], gs[i]->lut_shift);
+  for (size_t i = 0; i < gs.size(); ++i) {
+    Group &g = *gs[i];
+    g.slot_bytes = slot_bytes_for(g, g.lut_shift);
+    g.table_global = g.slot_bytes > 48 * 1024;
+    if (g.table_global) {
+      // tables in HBM/L2: LUT ~ 2 buckets per entry, any size
+      const uint32_t le = ceil_log2(std::max(2u, g.entries));
+      g.lut_shift = g.prec_bits > le + 1 ? g.prec_bits - le - 1 : 0;
+      g.slot_bytes = slot_bytes_for(g, g.lut_shift);
+      g.lanes = 32;
+      continue;
+    }
+    uint32_t want = per_sm[i];
+    if (total > budget) {
+      const uint64_t my = (uint64_t)budget * ((uint64_t)per_sm[i] * g.slot_bytes) / total;
+      want = std::max<uint32_t>(1u, (uint32_t)(my / g.slot_bytes));
+    }
+    const uint32_t ctas = (want + 31) / 32;
+    g.lanes = std::min<uint32_t>(32u, (want + ctas - 1) / ctas);
+    while (g.lanes > 1 && (uint64_t)g.lanes * g.slot_bytes > kSmemPerSM - kSmemPerCtaReserve) --g.lanes;
+  }
+}
+
+int ensure_order(Shard &sh, uint64_t n) {
+  if (n <= sh.order_cap) return DCB_OK;
+  cudaFree(sh.d_order);
+  sh.d_order = nullptr;
+  sh.order_cap = 0;
+  CUDA_TRY(cudaMalloc(&sh.d_order, std::max<uint64_t>(n, 1024) * 4));
+  sh.order_cap = std::max<uint64_t>(n, 1024);
+  return DCB_OK;
+}
+
+int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
+  if (sh.uploaded) return DCB_OK;
+  cudaStream_t st = ctx->streams[dev_index];
+  CUDA_TRY(cudaSetDevice(sh.device));
+  CUDA_TRY(cudaMalloc(&sh.d_in, sh.in_bytes));
+  CUDA_TRY(cudaMemsetAsync(sh.d_in, 0, kFrontPad, st));
+  CUDA_TRY(cudaMemsetAsync(sh.d_in + sh.in_bytes - kBackPad, 0, kBackPad, st));
+  if (b->direct) {
+    CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, b->host_arena + b->direct_lo, b->direct_hi - b->direct_lo,
+                             cudaMemcpyHostToDevice, st));
+  } else if (!sh.bufs.empty()) {
+    CUDA_TRY(cudaMallocHost(&sh.h_stage, sh.in_bytes));
+    for (int k : sh.bufs) memcpy(sh.h_stage + b->bufs[k].arena_off, b->bufs[k].src, b->bufs[k].len);
+    CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, sh.h_stage + kFrontPad, sh.in_bytes - kFrontPad - kBackPad,
+                             cudaMemcpyHostToDevice, st));
+  }
+  // mesh maps
+  uint64_t mbytes = 0;
+  for (int k : sh.bufs)
+    for (MeshMapsHost &m : b->bufs[k].maps)
+      if (m.set) {
+        const uint64_t sz[4] = {m.opposite.size(), m.corner_to_vertex.size(), m.data_to_corner.size(), m.vertex_to_data.size()};
+        for (int j = 0; j < 4; ++j) {
+          m.dev_off[j] = mbytes;
+          mbytes = align_up(mbytes + sz[j] * 4, 16);
+        }
+      }
+  sh.maps_bytes = mbytes;
+  if (mbytes) {
+    CUDA_TRY(cudaMalloc(&sh.d_maps, mbytes));
+    for (int k : sh.bufs)
+      for (MeshMapsHost &m : b->bufs[k].maps)
+        if (m.set) {
+          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[0], m.opposite.data(), m.opposite.size() * 4, cudaMemcpyHostToDevice, st));
+          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[1], m.corner_to_vertex.data(), m.corner_to_vertex.size() * 4, cudaMemcpyHostToDevice, st));
+          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[2], m.data_to_corner.data(), m.data_to_corner.size() * 4, cudaMemcpyHostToDevice, st));
+          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[3], m.vertex_to_data.data(), m.vertex_to_data.size() * 4, cudaMemcpyHostToDevice, st));
+        }
+    for (int k : sh.bufs) {
+      const BufRec &r = b->bufs[k];
+      const BufWalk &w = sh.walks0[r.local];
+      for (int i = 0; i < w.stream_count; ++i) {
+        for (std::vector<StreamDesc> *vs : {&sh.streams0, &sh.streams}) {
+          StreamDesc &s = (*vs)[w.stream_first + i];
+          if (s.has_maps && s.decoder_id < r.maps.size())
+            for (int j = 0; j < 4; ++j) s.map_off[j] = r.maps[s.decoder_id].dev_off[j];
+        }
+      }
+    }
+  }
+  if (!sh.streams.empty()) CUDA_TRY(cudaMalloc(&sh.d_streams, sh.streams.size() * sizeof(StreamDesc)));
+  if (!sh.walks.empty()) CUDA_TRY(cudaMalloc(&sh.d_walks, sh.walks.size() * sizeof(BufWalk)));
+  if (sh.aux_bytes) CUDA_TRY(cudaMalloc(&sh.d_aux, sh.aux_bytes));
+  sh.uploaded = true;
+  sh.dirty = true;
+  return DCB_OK;
+}
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+// Decode everything of one shard into (d_out, d_dbg).  Asynchronous on the shard's stream except
+// for the resolve round trips of Tagged streams.
+int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *d_out, uint8_t *d_dbg, uint32_t flags,
+                 bool timed) {
+  cudaStream_t st = ctx->streams[dev_index];
+  CUDA_TRY(cudaSetDevice(sh.device));
+  const uint32_t num_sms = (uint32_t)ctx->num_sms[dev_index];
+  dcb_launch_stats &stats = ctx->stats;
+  if (sh.streams.empty()) return DCB_OK;
+  // fresh descriptors: the decode must not depend on what an earlier decode left behind
+  if (sh.dirty) {
+    sh.streams = sh.streams0;
+    sh.walks = sh.walks0;
+    CUDA_TRY(cudaMemcpyAsync(sh.d_streams, sh.streams.data(), sh.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(sh.d_walks, sh.walks.data(), sh.walks.size() * sizeof(BufWalk), cudaMemcpyHostToDevice, st));
+    sh.dirty = false;
+  }
+  sh.tags_launched.assign(sh.streams.size(), 0);
+  DevArenas A{sh.d_in, d_out, d_dbg, sh.d_aux, sh.d_tab, sh.d_maps};
+  const uint32_t dump = flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS);
+  if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+
+  // ---- Tagged streams: decode tags, resume the walks behind their bit areas ----
+  for (;;) {
+    Group g{};
+    g.kind = 1; g.ncp = 1; g.wide = false; g.compact = 0; g.prec_bits = 12; g.entries = 0;
+    std::vector<uint32_t> blocked;
+    for (size_t bi = 0; bi < sh.walks.size(); ++bi) {
+      const BufWalk &w = sh.walks[bi];
+      if (w.status != DCB_OK || w.blocked < 0) continue;
+      const uint32_t si = (uint32_t)(w.stream_first + w.blocked);
+      if (sh.tags_launched[si]) continue;
+      sh.tags_launched[si] = 1;
+      g.order.push_back(si);
+      g.entries = std::max(g.entries, sh.streams[si].num_symbols);
+      g.total_symbols += sh.streams[si].n_entries;
+      blocked.push_back((uint32_t)bi);
+    }
+    if (g.order.empty()) break;
+    sh.dirty = true;
+    std::stable_sort(g.order.begin(), g.order.end(),
+                     [&](uint32_t x, uint32_t y) { return sh.streams[x].n_entries > sh.streams[y].n_entries; });
+    std::vector<Group *> gs{&g};
+    plan_rans_groups(gs, num_sms);
+    if (g.table_global) return DCB_ERR_STATE;  // cannot happen: tag alphabets are tiny (<= 2^24 guarded by table size)
+    int rc = ensure_order(sh, g.order.size() + blocked.size());
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(sh.d_order, g.order.data(), g.order.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(sh.d_order + g.order.size(), blocked.data(), blocked.size() * 4, cudaMemcpyHostToDevice, st));
+    RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.slot_bytes, g.lut_shift, dump, 0};
+    CUDA_TRY(dcb_launch_rans_tag(L, A, g.lanes * g.slot_bytes, st));
+    CUDA_TRY(dcb_launch_resolve(A, sh.d_walks, sh.d_order + g.order.size(), (uint32_t)blocked.size(), sh.d_streams, st));
+    stats.n_launches += 2;
+    stats.n_streams += (int32_t)g.order.size();
+    CUDA_TRY(cudaMemcpyAsync(sh.streams.data(), sh.d_streams, sh.streams.size() * sizeof(StreamDesc), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(sh.walks.data(), sh.d_walks, sh.walks.size() * sizeof(BufWalk), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+
+  // ---- classify ----
+  std::map<RawKey, Group> raw;
+  Group post[5], para[5], copy{};
+  for (int n = 1; n <= 4; ++n) {
+    post[n] = Group{}; post[n].kind = 2; post[n].ncp = n;
+    para[n] = Group{}; para[n].kind = 3; para[n].ncp = n;
+  }
+  copy.kind = 4;
+  bool has_para = false;
+  for (size_t bi = 0; bi < sh.walks.size(); ++bi) {
+    const BufWalk &w = sh.walks[bi];
+    if (w.status != DCB_OK) continue;
+    for (int i = 0; i < w.stream_count; ++i) {
+      const uint32_t si = (uint32_t)(w.stream_first + i);
+      const StreamDesc &s = sh.streams[si];
+      if (s.state != ST_READY) continue;
+      if (s.scheme == SCHEME_GENERIC) {
+        copy.order.push_back(si);
+        copy.max_bytes = std::max(copy.max_bytes, s.out_bytes);
+        continue;
+      }
+      if (s.n_entries == 0) continue;
+      if (s.scheme == SCHEME_RAW) {
+        RawKey key;
+        key.ncp = s.ncp;
+        key.wide = (s.prec_bits > 15 || s.num_symbols > 65535u) ? 1 : 0;
+        key.compact = (2ull * s.n_active + 1 < s.num_symbols) ? 1 : 0;
+        key.prec = s.prec_bits;
+        const uint32_t entries = key.compact ? s.n_active : s.num_symbols;
+        key.size_class = (int)ceil_log2(std::max(16u, entries));
+        Group &g = raw[key];
+        if (g.order.empty()) {
+          g.kind = 0; g.ncp = key.ncp; g.wide = key.wide != 0; g.compact = (uint32_t)key.compact; g.prec_bits = (uint32_t)key.prec;
+        }
+        g.entries = std::max(g.entries, entries);
+        g.total_symbols += (uint64_t)s.n_entries * s.ncp;
+        g.order.push_back(si);
+      } else {
+        post[s.ncp].order.push_back(si);
+      }
+      if (s.recon == RECON_PARA_WRAP) {
+        para[s.ncp].order.push_back(si);
+        para[s.ncp].max_entries = std::max(para[s.ncp].max_entries, s.n_entries);
+        has_para = true;
+      }
+    }
+  }
+  std::vector<Group *> rgs;
+  for (auto &kv : raw) rgs.push_back(&kv.second);
+  plan_rans_groups(rgs, num_sms);
+  // device order lists
+  uint64_t n_order = 0;
+  auto add = [&](Group &g) {
+    g.order_off = n_order;
+    n_order += g.order.size();
+  };
+  for (Group *g : rgs) {
+    std::stable_sort(g->order.begin(), g->order.end(),
+                     [&](uint32_t x, uint32_t y) { return sh.streams[x].n_entries > sh.streams[y].n_entries; });
+    add(*g);
+  }
+  for (int n = 1; n <= 4; ++n) { add(post[n]); add(para[n]); }
+  add(copy);
+  if (n_order == 0) {
+    if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+    return DCB_OK;
+  }
+  {
+    int rc = ensure_order(sh, n_order);
+    if (rc) return rc;
+    std::vector<uint32_t> all;
+    all.reserve(n_order);
+    for (Group *g : rgs) all.insert(all.end(), g->order.begin(), g->order.end());
+    for (int n = 1; n <= 4; ++n) {
+      all.insert(all.end(), post[n].order.begin(), post[n].order.end());
+      all.insert(all.end(), para[n].order.begin(), para[n].order.end());
+    }
+    all.insert(all.end(), copy.order.begin(), copy.order.end());
+    CUDA_TRY(cudaMemcpyAsync(sh.d_order, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // `all` is a stack vector; the copy is tiny
+  }
+  // dominant group: most symbols
+  Group *dom = nullptr;
+  for (Group *g : rgs)
+    if (!dom || g->total_symbols > dom->total_symbols) dom = g;
+  // ---- launches ----
+  for (Group *g : rgs) {
+    const uint32_t n = (uint32_t)g->order.size();
+    const bool is_dom = timed && dev_index == 0 && g == dom;
+    if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+    if (g->table_global) {
+      const uint64_t per = std::max<uint64_t>(1, kTabArenaBudget / g->slot_bytes);
+      const uint64_t chunk = std::min<uint64_t>(per, n);
+      if (sh.tab_cap < chunk * g->slot_bytes) {
+        cudaFree(sh.d_tab);
+        sh.d_tab = nullptr;
+        sh.tab_cap = 0;
+        CUDA_TRY(cudaMalloc(&sh.d_tab, chunk * g->slot_bytes));
+        sh.tab_cap = chunk * g->slot_bytes;
+        A.tab = sh.d_tab;
+      }
+      for (uint64_t o = 0; o < n; o += chunk) {
+        RansLaunch L{sh.d_streams, sh.d_order + g->order_off + o, (uint32_t)std::min<uint64_t>(chunk, n - o), 32,
+                     g->slot_bytes, g->lut_shift, dump, g->compact};
+        CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, true, A, 0, st));
+        stats.n_launches++;
+      }
+    } else {
+      RansLaunch L{sh.d_streams, sh.d_order + g->order_off, n, g->lanes, g->slot_bytes, g->lut_shift, dump, g->compact};
+      CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, g->lanes * g->slot_bytes, st));
+      stats.n_launches++;
+    }
+    if (is_dom) {
+      CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+      stats.lanes_per_warp = (int32_t)g->lanes;
+      stats.smem_per_stream = g->slot_bytes;
+      const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, (kSmemPerSM) / std::max<uint32_t>(1u, g->lanes * g->slot_bytes + kSmemPerCtaReserve))) * g->lanes;
+      stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);
+      snprintf(stats.dominant_name, sizeof stats.dominant_name, "rans_raw_fused<ncp=%d,%s,%s,k=%u>", g->ncp,
+               g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->lut_shift);
+    }
+    stats.n_streams += (int32_t)n;
+  }
+  for (int n = 1; n <= 4; ++n)
+    if (!post[n].order.empty()) {
+      CUDA_TRY(dcb_launch_serial_post(sh.d_streams, sh.d_order + post[n].order_off, (uint32_t)post[n].order.size(), n, dump, A, st));
+      stats.n_launches++;
+    }
+  if (!copy.order.empty()) {
+    CUDA_TRY(dcb_launch_copy(sh.d_streams, sh.d_order + copy.order_off, (uint32_t)copy.order.size(), copy.max_bytes, A, st));
+    stats.n_launches++;
+  }
+  for (int n = 1; n <= 4; ++n)
+    if (!para[n].order.empty()) {
+      CUDA_TRY(dcb_launch_para(sh.d_streams, sh.d_order + para[n].order_off, (uint32_t)para[n].order.size(), n,
+                               para[n].max_entries, dump, A, st));
+      stats.n_launches += 2;
+    }
+  if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+  if (has_para) {
+    // parallelogram kernels validate the caller's maps on the device: fetch their verdicts
+    CUDA_TRY(cudaMemcpyAsync(sh.streams.data(), sh.d_streams, sh.streams.size() * sizeof(StreamDesc), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    sh.dirty = true;
+  }
+  (void)b;
+  return DCB_OK;
+}
+
+// after a decode: fold walk / stream statuses into the buffer records
+void collect_status(dcb_batch *b) {
+  for (BufRec &r : b->bufs) {
+    if (r.info.status) continue;
+    const Shard &sh = b->shards[r.shard];
+    const BufWalk &w = sh.walks[r.local];
+    if (w.status) { r.info.status = w.status; continue; }
+    for (int i = 0; i < w.stream_count; ++i) {
+      const StreamDesc &s = sh.streams[w.stream_first + i];
+      if (s.status) { r.info.status = s.status; break; }
+    }
+  }
+}
+
+int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags) {
+  if (!ctx || !b) return DCB_ERR_ARG;
+  if ((int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
+  if ((dev_out || dev_dbg) && b->n_devices != 1) return DCB_ERR_ARG;
+  const uint32_t dump = flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS);
+  if (dump == (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS)) return DCB_ERR_ARG;  // one debug arena
+  for (const BufRec &r : b->bufs)
+    if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;  // dcb_index_finish not run
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  for (int d = 0; d < b->n_devices; ++d) {
+    Shard &sh = b->shards[d];
+    int rc = upload_shard(ctx, b, sh, d);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(sh.device));
+    uint8_t *o = (uint8_t *)dev_out;
+    if (!o) {
+      if (!sh.d_out && sh.out_bytes) {
+        CUDA_TRY(cudaMalloc(&sh.d_out, sh.out_bytes));
+        sh.own_out = true;
+      }
+      o = sh.d_out;
+    }
+    sh.ext_out = o;
+    uint8_t *g = (uint8_t *)dev_dbg;
+    if (dump && !g) {
+      if (sh.dbg_cap < sh.dbg_bytes) {
+        cudaFree(sh.d_dbg);
+        sh.d_dbg = nullptr;
+        sh.dbg_cap = 0;
+        CUDA_TRY(cudaMalloc(&sh.d_dbg, std::max<uint64_t>(sh.dbg_bytes, 16)));
+        sh.dbg_cap = std::max<uint64_t>(sh.dbg_bytes, 16);
+      }
+      g = sh.d_dbg;
+    }
+    sh.ext_dbg = g;
+  }
+  for (int d = 0; d < b->n_devices; ++d) {
+    Shard &sh = b->shards[d];
+    int rc = decode_shard(ctx, b, sh, d, sh.ext_out, sh.ext_dbg, flags, true);
+    if (rc) return rc;
+  }
+  return DCB_OK;
+}
+
+int sync_all(dcb_ctx *ctx) {
+  for (size_t d = 0; d < ctx->devices.size(); ++d) {
+    CUDA_TRY(cudaSetDevice(ctx->devices[d]));
+    CUDA_TRY(cudaStreamSynchronize(ctx->streams[d]));
+  }
+  return DCB_OK;
+}
+
+void finish_stats(dcb_ctx *ctx) {
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->stats.ms_total = ms;
+  else cudaGetLastError();
+  ms = 0.0f;
+  if (ctx->stats.dominant_name[0] && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_dominant = ms;
+  else cudaGetLastError();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int dcb_version(void) { return DCB_VERSION; }
+
+int dcb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+const char *dcb_error_string(int code) {
+  switch (code) {
+    case DCB_OK: return "ok";
+    case DCB_ERR_EOF: return "unexpected end of buffer";
+    case DCB_ERR_MAGIC: return "not a Draco buffer";
+    case DCB_ERR_UNSUPPORTED: return "unsupported bitstream feature";
+    case DCB_ERR_SCHEME: return "invalid symbol coding scheme";
+    case DCB_ERR_BITLEN: return "invalid symbol bit length";
+    case DCB_ERR_TABLE: return "invalid rANS probability table";
+    case DCB_ERR_RANS_INIT: return "invalid rANS stream";
+    case DCB_ERR_PRED: return "invalid prediction scheme";
+    case DCB_ERR_WRAP: return "invalid wrap transform bounds";
+    case DCB_ERR_QUANT: return "invalid quantization parameters";
+    case DCB_ERR_ATTR: return "invalid attribute descriptor";
+    case DCB_ERR_TAG: return "invalid tagged bit length";
+    case DCB_ERR_NUM_SYMBOLS: return "empty symbol alphabet";
+    case DCB_ERR_MAPS: return "missing or inconsistent mesh connectivity maps";
+    case DCB_ERR_CONNECTIVITY: return "connectivity decode failed";
+    case DCB_ERR_ARG: return "invalid argument";
+    case DCB_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+    case DCB_ERR_CUDA: return "CUDA error";
+    case DCB_ERR_OOM: return "out of memory";
+    case DCB_ERR_STATE: return "call order violated";
+    default: return "unknown error";
+  }
+}
+
+int dcb_create(const int *device_ids, int n_devices, dcb_ctx **out) {
+  if (!out || n_devices < 0) return DCB_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return DCB_ERR_NO_DEVICE;
+  }
+  dcb_ctx *c = new (std::nothrow) dcb_ctx();
+  if (!c) return DCB_ERR_OOM;
+  if (!device_ids || n_devices == 0) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { delete c; return DCB_ERR_NO_DEVICE; }
+    c->devices.push_back(cur);
+  } else {
+    for (int i = 0; i < n_devices; ++i) c->devices.push_back(device_ids[i]);
+  }
+  for (int dev : c->devices) {
+    cudaDeviceProp p;
+    if (dev < 0 || dev >= count || cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.major != 10) {
+      cudaGetLastError();
+      dcb_destroy(c);
+      return DCB_ERR_NO_DEVICE;  // kernels are sm_100a only: no fallback
+    }
+    cudaStream_t st = nullptr;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      dcb_destroy(c);
+      return DCB_ERR_CUDA;
+    }
+    c->streams.push_back(st);
+    c->own_stream.push_back(true);
+    c->num_sms.push_back(p.multiProcessorCount > 0 ? p.multiProcessorCount : (int)kNumSMsDefault);
+  }
+  cudaSetDevice(c->devices[0]);
+  for (auto &e : c->ev) cudaEventCreate(&e);
+  *out = c;
+  return DCB_OK;
+}
+
+void dcb_destroy(dcb_ctx *ctx) {
+  if (!ctx) return;
+  for (size_t i = 0; i < ctx->streams.size(); ++i)
+    if (ctx->own_stream[i]) {
+      cudaSetDevice(ctx->devices[i]);
+      cudaStreamDestroy(ctx->streams[i]);
+    }
+  for (auto &e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  delete ctx;
+}
+
+int dcb_set_stream(dcb_ctx *ctx, int dev_index, void *cuda_stream) {
+  if (!ctx || dev_index < 0 || dev_index >= (int)ctx->streams.size()) return DCB_ERR_ARG;
+  if (ctx->own_stream[dev_index]) {
+    cudaSetDevice(ctx->devices[dev_index]);
+    cudaStreamDestroy(ctx->streams[dev_index]);
+  }
+  ctx->streams[dev_index] = (cudaStream_t)cuda_stream;
+  ctx->own_stream[dev_index] = false;
+  return DCB_OK;
+}
+
+int dcb_index(dcb_ctx *ctx, const uint8_t *const *bufs, const uint64_t *lens, int n_bufs, dcb_batch **out) {
+  int rc = make_batch(ctx, nullptr, bufs, nullptr, lens, n_bufs, out);
+  if (rc == DCB_OK) finalize_layout(*out);
+  return rc;
+}
+
+int dcb_index_arena(dcb_ctx *ctx, const uint8_t *arena, const uint64_t *offs, const uint64_t *lens, int n_bufs,
+                    dcb_batch **out) {
+  if (!arena || !offs) return DCB_ERR_ARG;
+  int rc = make_batch(ctx, arena, nullptr, offs, lens, n_bufs, out);
+  if (rc == DCB_OK) finalize_layout(*out);
+  return rc;
+}
+
+int dcb_get_buffer_info(const dcb_batch *b, int buf, dcb_buffer_info *out) {
+  if (!b || !out || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+  *out = b->bufs[buf].info;
+  return DCB_OK;
+}
+
+int dcb_get_attr_info(const dcb_batch *b, int buf, int attr, dcb_attr_info *out) {
+  if (!b || !out || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+  const BufRec &r = b->bufs[buf];
+  const Shard &sh = b->shards[r.shard];
+  const BufWalk &w = sh.walks[r.local];
+  if (attr < 0 || attr >= w.stream_count) return DCB_ERR_ARG;
+  const StreamDesc &s = sh.streams[w.stream_first + attr];
+  memset(out, 0, sizeof *out);
+  out->att_type = s.att_type;
+  out->data_type = s.data_type;
+  out->num_components = s.nc;
+  out->normalized = s.normalized;
+  out->unique_id = s.unique_id;
+  out->seq_decoder_type = s.seq_type;
+  out->decoder_id = s.decoder_id;
+  out->pred_method = s.pred_method;
+  out->transform = s.transform;
+  out->scheme = (s.scheme == SCHEME_TAGGED || s.scheme == SCHEME_RAW) ? (int32_t)s.scheme : -1;
+  out->precision_bits = s.prec_bits;
+  out->n_entries = s.n_entries;
+  out->out_bytes = s.out_bytes;
+  out->out_off = sh.out_base + s.out_off;
+  out->dbg_off = sh.dbg_base + s.dbg_off;
+  out->xf_a = s.xf_a;
+  out->xf_b = s.xf_b;
+  for (int c = 0; c < 4; ++c) out->q_min[c] = s.q_min[c];
+  out->q_range = s.q_range;
+  out->q_bits = s.q_bits;
+  out->resolved = s.state == ST_READY;
+  return DCB_OK;
+}
+
+uint64_t dcb_batch_out_bytes(const dcb_batch *b) { return b ? b->total_out : 0; }
+uint64_t dcb_batch_dbg_bytes(const dcb_batch *b) { return b ? b->total_dbg : 0; }
+uint64_t dcb_batch_in_bytes(const dcb_batch *b) { return b ? b->total_in : 0; }
+uint64_t dcb_batch_points(const dcb_batch *b) { return b ? b->total_points : 0; }
+uint64_t dcb_batch_algo_bytes(const dcb_batch *b) { return b ? b->algo_bytes : 0; }
+
+int dcb_set_attr_section(dcb_batch *b, int buf, uint64_t attr_section_off, uint32_t n_points) {
+  if (!b || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+  BufRec &r = b->bufs[buf];
+  if (!r.info.needs_connectivity) return DCB_ERR_STATE;
+  if (attr_section_off > r.len) return DCB_ERR_ARG;
+  r.info.attr_section_off = attr_section_off;
+  r.info.n_points = n_points;
+  return DCB_OK;
+}
+
+int dcb_set_mesh_maps(dcb_batch *b, int buf, int attr_decoder, const uint32_t *opposite,
+                      const uint32_t *corner_to_vertex, uint64_t n_corners, const uint32_t *data_to_corner,
+                      uint64_t n_entries, const int32_t *vertex_to_data, uint64_t n_vertices) {
+  if (!b || buf < 0 || buf >= (int)b->bufs.size() || attr_decoder < 0 || attr_decoder > 255) return DCB_ERR_ARG;
+  if ((n_corners && (!opposite || !corner_to_vertex)) || (n_entries && !data_to_corner) || (n_vertices && !vertex_to_data))
+    return DCB_ERR_ARG;
+  if (n_corners > 0xFFFFFFFFull || n_entries > 0xFFFFFFFFull || n_vertices > 0xFFFFFFFFull) return DCB_ERR_ARG;
+  BufRec &r = b->bufs[buf];
+  if (!r.info.needs_connectivity) return DCB_ERR_STATE;
+  if (r.maps.size() <= (size_t)attr_decoder) r.maps.resize((size_t)attr_decoder + 1);
+  MeshMapsHost &m = r.maps[attr_decoder];
+  m.opposite.assign(opposite, opposite + n_corners);
+  m.corner_to_vertex.assign(corner_to_vertex, corner_to_vertex + n_corners);
+  m.data_to_corner.assign(data_to_corner, data_to_corner + n_entries);
+  m.vertex_to_data.assign(vertex_to_data, vertex_to_data + n_vertices);
+  m.set = true;
+  return DCB_OK;
+}
+
+int dcb_index_finish(dcb_ctx *ctx, dcb_batch *b) {
+  (void)ctx;
+  if (!b) return DCB_ERR_ARG;
+  for (Shard &sh : b->shards)
+    if (sh.uploaded) return DCB_ERR_STATE;
+  // rebuild every shard's stream list with the connectivity-dependent buffers included
+  for (Shard &sh : b->shards) {
+    sh.streams.clear();
+    std::fill(sh.walks.begin(), sh.walks.end(), BufWalk{});
+  }
+  for (size_t k = 0; k < b->bufs.size(); ++k) {
+    BufRec &r = b->bufs[k];
+    if (r.info.needs_connectivity && r.info.status == DCB_OK) {
+      if (r.info.attr_section_off == 0) r.info.status = DCB_ERR_CONNECTIVITY;
+      r.info.needs_connectivity = 0;
+    }
+    parse_attr_section(r, b->shards[r.shard], (int)k);
+  }
+  finalize_layout(b);
+  return DCB_OK;
+}
+
+int dcb_upload(dcb_ctx *ctx, dcb_batch *b) {
+  if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
+  for (const BufRec &r : b->bufs)
+    if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;
+  for (int d = 0; d < b->n_devices; ++d) {
+    int rc = upload_shard(ctx, b, b->shards[d], d);
+    if (rc) return rc;
+  }
+  return sync_all(ctx);
+}
+
+int dcb_decode_resident(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags) {
+  int rc = decode_all(ctx, b, dev_out, dev_dbg, flags);
+  if (rc) return rc;
+  rc = sync_all(ctx);
+  if (rc) return rc;
+  finish_stats(ctx);
+  collect_status(b);
+  return DCB_OK;
+}
+
+int dcb_download(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg) {
+  if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
+  for (int d = 0; d < b->n_devices; ++d) {
+    Shard &sh = b->shards[d];
+    CUDA_TRY(cudaSetDevice(sh.device));
+    if (host_out && sh.ext_out && sh.out_bytes)
+      CUDA_TRY(cudaMemcpyAsync(host_out + sh.out_base, sh.ext_out, sh.out_bytes, cudaMemcpyDeviceToHost, ctx->streams[d]));
+    if (host_dbg && sh.ext_dbg && sh.dbg_bytes)
+      CUDA_TRY(cudaMemcpyAsync(host_dbg + sh.dbg_base, sh.ext_dbg, sh.dbg_bytes, cudaMemcpyDeviceToHost, ctx->streams[d]));
+  }
+  return sync_all(ctx);
+}
+
+int dcb_decode(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg, uint32_t flags) {
+  if (!host_out && b && b->total_out) return DCB_ERR_ARG;
+  if ((flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS)) && !host_dbg) return DCB_ERR_ARG;
+  int rc = decode_all(ctx, b, nullptr, nullptr, flags);
+  if (rc) return rc;
+  rc = dcb_download(ctx, b, host_out, host_dbg);
+  if (rc) return rc;
+  finish_stats(ctx);
+  collect_status(b);
+  return DCB_OK;
+}
+
+int dcb_decode_scatter(dcb_ctx *ctx, dcb_batch *b, uint8_t *const *outs, int n_outs, uint32_t flags) {
+  if (!outs && n_outs) return DCB_ERR_ARG;
+  int rc = decode_all(ctx, b, nullptr, nullptr, flags & ~(DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS));
+  if (rc) return rc;
+  int k = 0;
+  for (const BufRec &r : b->bufs) {
+    const Shard &sh = b->shards[r.shard];
+    const BufWalk &w = sh.walks[r.local];
+    CUDA_TRY(cudaSetDevice(sh.device));
+    for (int i = 0; i < w.stream_count; ++i, ++k) {
+      if (k >= n_outs) break;
+      const StreamDesc &s = sh.streams[w.stream_first + i];
+      if (outs[k] && s.out_bytes && r.info.status == DCB_OK && w.status == DCB_OK)
+        CUDA_TRY(cudaMemcpyAsync(outs[k], sh.ext_out + s.out_off, s.out_bytes, cudaMemcpyDeviceToHost, ctx->streams[r.shard]));
+    }
+  }
+  rc = sync_all(ctx);
+  if (rc) return rc;
+  finish_stats(ctx);
+  collect_status(b);
+  return DCB_OK;
+}
+
+void *dcb_device_out(const dcb_batch *b, int dev_index) {
+  if (!b || dev_index < 0 || dev_index >= (int)b->shards.size()) return nullptr;
+  return b->shards[dev_index].ext_out;
+}
+
+int dcb_sync(dcb_ctx *ctx) { return ctx ? sync_all(ctx) : DCB_ERR_ARG; }
+
+int dcb_status(const dcb_batch *b, int buf) {
+  if (!b || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+  return b->bufs[buf].info.status;
+}
+
+void dcb_batch_free(dcb_batch *b) {
+  if (!b) return;
+  for (Shard &sh : b->shards) free_shard_device(sh);
+  delete b;
+}
+
+int dcb_last_stats(const dcb_ctx *ctx, dcb_launch_stats *out) {
+  if (!ctx || !out) return DCB_ERR_ARG;
+  *out = ctx->stats;
+  return DCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// draco_sharp_b200/csrc/dcb_internal.h -- structures shared by the host indexer, the C-ABI layer
+// and the sm_100a kernels of libdracob200.so.  Product code: nothing here touches oracle/.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/dracob200.h"
+
+#if defined(__CUDACC__)
+#define DCB_HD __host__ __device__ __forceinline__
+#else
+#define DCB_HD inline
+#endif
+
+// wire enums (numeric values are part of the bitstream; src/Draco/IO/Enums/*.cs)
+enum : int32_t {
+  DT_INT8 = 1, DT_UINT8 = 2, DT_INT16 = 3, DT_UINT16 = 4, DT_INT32 = 5, DT_UINT32 = 6,
+  DT_INT64 = 7, DT_UINT64 = 8, DT_FLOAT32 = 9, DT_FLOAT64 = 10, DT_BOOL = 11, DT_COUNT = 12
+};
+enum : int32_t { SEQ_GENERIC = 0, SEQ_INTEGER = 1, SEQ_QUANTIZATION = 2, SEQ_NORMALS = 3 };
+enum : int32_t { PRED_NONE = -2, PRED_DIFFERENCE = 0, PRED_PARALLELOGRAM = 1, PRED_COUNT = 7 };
+enum : int32_t { XF_NONE = -1, XF_DELTA = 0, XF_WRAP = 1, XF_OCT = 2, XF_OCT_CANON = 3, XF_COUNT = 4 };
+// symbol source of a stream
+enum : uint8_t {
+  SCHEME_TAGGED = 0,      // SymbolDecoding.cs:30-50
+  SCHEME_RAW = 1,         // SymbolDecoding.cs:52-67
+  SCHEME_EMPTY = 253,     // zero values: nothing is read (SymbolDecoding.cs:9-13)
+  SCHEME_GENERIC = 254,   // PORTABLE(generic): n x byte_stride raw bytes (SequentialAttributeDecoder.cs:75-86)
+  SCHEME_UNCOMPRESSED = 255  // compressed == 0: num_bytes per value (SequentialIntegerAttributeDecoder.cs:68-84)
+};
+
+// how the portable integers of a stream are reconstructed from corrections
+enum : uint8_t {
+  RECON_NONE = 0,          // no prediction scheme object: values = zig-zag(symbols)
+  RECON_DELTA_WRAP = 1,    // PredictionSchemeDeltaDecoder + wrap transform
+  RECON_DELTA_OCT = 2,     // PredictionSchemeDeltaDecoder + octahedron transform (non canonical)
+  RECON_DELTA_OCT_CANON = 3,
+  RECON_PARA_WRAP = 4      // MeshPredictionSchemeParallelogramDecoder + wrap transform
+};
+// how portable integers become attribute bytes
+enum : uint8_t {
+  STORE_DEQUANT = 0,  // AttributeQuantizationTransform.InverseTransformAttribute -> float32 x nc
+  STORE_OCT_UNIT = 1, // AttributeOctahedronTransform.InverseTransformAttribute  -> float32 x 3
+  STORE_NARROW = 2,   // StoreTypedValues<T>: low sizeof(T) bytes of each int32
+  STORE_COPY = 3      // generic attribute: raw bytes
+};
+// walk progress of one attribute
+enum : uint8_t {
+  ST_UNPARSED = 0,
+  ST_TAGS_PENDING = 1,  // Tagged: table + payload located, bit area length unknown until the tags are decoded
+  ST_PORTABLE = 2,      // PORTABLE fully located (incl. PRED_DATA)
+  ST_READY = 3          // XFORM_PARAMS read too: the stream can be decoded end to end
+};
+
+// One attribute of one buffer.  Offsets are absolute byte offsets into the device input arena of
+// the shard that owns the buffer.
+struct StreamDesc {
+  uint64_t buf_begin, buf_end;   // the owning .drc buffer inside the arena
+  uint64_t table_off;            // first byte of RANS_TABLE (the num_symbols varint)
+  uint64_t payload_off;          // first byte of the rANS payload
+  uint64_t payload_len;
+  uint64_t bits_off;             // Tagged: first byte of the LSB-first bit area
+  uint64_t raw_off;              // uncompressed ints / generic: first value byte
+  uint64_t out_off;              // output arena offset of the attribute
+  uint64_t out_bytes;
+  uint64_t dbg_off;              // debug arena offset (int32 per portable value)
+  uint64_t aux_off;              // scratch arena offset (corrections int32[nv]), 16-byte aligned
+  uint64_t tag_off;              // scratch arena offset (tags u8[n] then u32 chunk sums), 16-byte aligned
+  uint64_t map_off[4];           // parallelogram: opposite, corner_to_vertex, data_to_corner, vertex_to_data
+  uint64_t bits_total;           // device-written: bits consumed in the Tagged bit area
+  uint32_t n_corners, n_vertices;
+  uint32_t n_entries;
+  uint32_t num_symbols;          // table alphabet size
+  uint32_t n_active;             // symbols with non-zero probability
+  uint32_t unique_id;
+  int32_t xf_a, xf_b;            // wrap min,max | oct max_quantized_value, center
+  float q_min[4];
+  float q_range;
+  int32_t q_bits;
+  int32_t buf_index, attr_index; // position in the batch (attr_index is relative to the buffer)
+  int32_t status;                // device-written DCB_ERR_* (0 = ok)
+  int32_t irregular;             // device-written: delta+wrap stream that needs the serial recurrence
+  int8_t pred_method, transform;
+  uint8_t nc, ncp;               // attribute components / portable components
+  uint8_t scheme;                // SCHEME_*
+  uint8_t prec_bits, max_bit_length;
+  uint8_t recon, store;
+  uint8_t data_type;             // output DataType
+  uint8_t att_type, normalized, seq_type, decoder_id;
+  uint8_t zigzag;
+  uint8_t raw_num_bytes;         // uncompressed: bytes per value
+  uint8_t state;                 // ST_*
+  uint8_t compressed;
+  uint8_t has_maps;              // host supplied connectivity maps for this attribute's decoder
+  uint8_t pad_[5];
+};
+
+// Resumable container walk of one buffer (runs on the host; continues on the device behind Tagged
+// bit areas, whose length is only known once the tags are decoded).
+struct BufWalk {
+  uint64_t begin, end;      // arena offsets of this buffer
+  uint64_t pos;             // where the walk continues
+  int32_t status;
+  int32_t stream_first, stream_count;
+  int32_t cur;              // relative index of the stream being parsed
+  int32_t dec_start;        // relative index of the first stream of the current attributes decoder
+  int32_t phase;            // 0 PORTABLE pass, 1 XFORM_PARAMS pass, 2 done
+  int32_t blocked;          // relative stream index whose Tagged bit area blocks the walk, or -1
+  uint8_t geom_type, method, pad_[2];
+};
+
+DCB_HD int dcb_dtype_len(int dt) {
+  switch (dt) {
+    case DT_INT8: case DT_UINT8: case DT_BOOL: return 1;
+    case DT_INT16: case DT_UINT16: return 2;
+    case DT_INT32: case DT_UINT32: case DT_FLOAT32: return 4;
+    case DT_INT64: case DT_UINT64: case DT_FLOAT64: return 8;
+    default: return -1;
+  }
+}
+// RAnsSymbolCoding.cs:10-26
+DCB_HD int dcb_rans_precision(int max_bit_length) {
+  int p = 3 * max_bit_length / 2;
+  return p < 12 ? 12 : (p > 20 ? 20 : p);
+}
+
+// ---- launch plan for the lane-per-stream rANS kernels ----
+struct RansLaunch {
+  StreamDesc *d_streams;          // device array of all streams of the shard
+  const uint32_t *d_order;        // stream indices handled by this launch (sorted by length, desc)
+  uint32_t n_streams;
+  uint32_t lanes_per_warp;        // active lanes per warp-CTA
+  uint32_t slot_bytes;            // shared (or global scratch) memory per lane
+  uint32_t lut_shift;             // log2(slots per LUT bucket)
+  uint32_t dump;                  // DCB_DUMP_* flags
+  uint32_t compact;               // 1: tables indexed by active-symbol rank (+ id map), 0: by symbol id
+};

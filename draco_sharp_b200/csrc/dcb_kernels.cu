@@ -1,0 +1,578 @@
+// draco_sharp_b200/csrc/dcb_kernels.cu -- sm_100a kernels of the Draco attribute-decode hot path.
+//
+// No tensor cores: nothing here is a dense contraction.  The work is serial rANS state chains
+// (one chain per compressed attribute stream), integer prediction recurrences and a float
+// epilogue.  Parallelism comes from the batch: every lane of a warp owns ONE stream and runs its
+// chain; the per-stream probability tables live in that lane's slice of shared memory; the
+// compressed bytes are pulled through a register window fed by 16-byte read-only loads issued one
+// chunk ahead, so the only latency on the critical path is  smem LUT -> smem cum window -> IMAD ->
+// renormalisation.  Everything after the symbol (zig-zag, delta + wrap / octahedron transform,
+// dequantisation, store) hangs off the chain and runs in its shadow.
+//
+// Kernels:
+//   rans_raw_fused_kernel   SymbolDecoding.DecodeRawSymbols (Entropy/SymbolDecoding.cs:52-67) + RAnsDecoder.Read
+//                           (Entropy/RAnsDecoder.cs:56-99) + zig-zag + PredictionSchemeDeltaDecoder + transform +
+//                           dequantise / oct->unit / narrow, in one pass; parallelogram streams emit corrections
+//   rans_tag_kernel         the tag half of SymbolDecoding.DecodeTaggedSymbols (SymbolDecoding.cs:30-50)
+//   resolve_kernel          continues the container walk behind Tagged bit areas (dcb_walk.h)
+//   serial_post_kernel      Tagged bit fields / uncompressed ints / stored corrections -> prediction -> store
+//   para_deps_kernel        MeshPredictionSchemeParallelogramDecoder.GetParallelogramEntries (:56-59) for all p
+//   para_chain_kernel       MeshPredictionSchemeParallelogramDecoder.ComputeOriginalValues (:29-54)
+//   copy_kernel             SequentialAttributeDecoder.DecodeValues (generic attributes, :75-86)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dcb_device.cuh"
+#include "dcb_internal.h"
+#include "dcb_kernels.h"
+#include "dcb_walk.h"
+
+using namespace dcb;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// rans_raw_fused: one warp per CTA, `lanes` active lanes, one Raw stream per lane.
+// TABLE_GLOBAL: the lane tables live in a global scratch arena instead of shared memory (alphabets
+// too large for smem: precision 16..20).
+// ---------------------------------------------------------------------------------------------
+template <int NCP, typename T, bool DUMP, bool TABLE_GLOBAL>
+__global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+                                                            const uint32_t *__restrict__ order, uint32_t n_streams,
+                                                            uint32_t lanes, uint32_t slot_bytes, uint32_t lut_shift,
+                                                            uint32_t compact, uint8_t *__restrict__ out,
+                                                            uint8_t *__restrict__ dbg, uint8_t *__restrict__ aux,
+                                                            uint8_t *__restrict__ tab_arena, uint32_t dump) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t lane = threadIdx.x;
+  const uint32_t slot = blockIdx.x * lanes + lane;
+  const bool have = lane < lanes && slot < n_streams;
+  StreamDesc *dp = have ? &streams[order[slot]] : nullptr;
+
+  LaneTable<T> tab;
+  RansState rs;
+  ByteWin bw;
+  uint32_t n_entries = 0;
+  int status = DCB_OK;
+  if (have) {
+    const StreamDesc &d = *dp;
+    n_entries = d.n_entries;
+    uint8_t *base = TABLE_GLOBAL ? tab_arena + (size_t)slot * slot_bytes : smem + (size_t)lane * slot_bytes;
+    uint32_t cap_entries;
+    carve_table<T>(base, slot_bytes, d.prec_bits, lut_shift, compact != 0, tab, cap_entries);
+    if (n_entries > 0) {
+      status = build_table<T>(arena, d, tab, lut_shift, compact != 0, cap_entries);
+      if (status == DCB_OK) status = rans_init(arena, d, rs);
+      if (status == DCB_OK) bw.init(arena, d.payload_off + rs.off);
+    }
+    if (status != DCB_OK) {
+      dp->status = status;
+      n_entries = 0;
+    }
+  }
+  // warp-uniform trip count
+  uint32_t n_max = n_entries;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+  if (n_max == 0) return;
+
+  PostParams pp;
+  uint8_t *optr = nullptr;
+  int32_t *dptr = nullptr;
+  if (have) {
+    const StreamDesc &d = *dp;
+    pp.load(d);
+    optr = out + d.out_off;
+    if (DUMP) dptr = reinterpret_cast<int32_t *>(dbg + d.dbg_off);
+    if (pp.recon == RECON_PARA_WRAP) {
+      // corrections only: the parallelogram recurrence runs in its own kernel
+      optr = aux + d.aux_off;
+      pp.store = STORE_NARROW;
+      pp.dsize = 4;
+    }
+  } else {
+    pp.recon = RECON_NONE; pp.store = STORE_NARROW; pp.dsize = 4; pp.zig = true;
+    pp.mn = pp.mx = pp.max_diff = 0;
+  }
+  int32_t prev[NCP];
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) prev[c] = 0;
+
+  const uint32_t n_groups = (n_max + 3u) >> 2;
+  for (uint32_t g = 0; g < n_groups; ++g) {
+    const uint32_t e0 = g << 2;
+    if (e0 < n_entries) {
+      const uint32_t cnt = min(4u, n_entries - e0);
+      int32_t v[4][NCP];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((uint32_t)j < cnt) {
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) {
+            const uint32_t idx = rans_step<T>(rs, bw, tab, lut_shift);
+            const uint32_t sym = compact ? (uint32_t)tab.sym[idx] : idx;
+            if (DUMP && (dump & DCB_DUMP_SYMBOLS)) dptr[(size_t)(e0 + j) * NCP + c] = (int32_t)sym;
+            v[j][c] = pp.zig ? zigzag_dec(sym) : (int32_t)sym;
+          }
+          if (pp.recon == RECON_DELTA_WRAP) {
+#pragma unroll
+            for (int c = 0; c < NCP; ++c) {
+              prev[c] = wrap_original(prev[c], v[j][c], pp.mn, pp.mx, pp.max_diff);
+              v[j][c] = prev[c];
+            }
+          } else if (pp.recon == RECON_DELTA_OCT || pp.recon == RECON_DELTA_OCT_CANON) {
+            if (NCP == 2) {
+              oct_original(pp.box, pp.recon == RECON_DELTA_OCT_CANON, prev[0], prev[NCP - 1], v[j][0], v[j][NCP - 1]);
+              v[j][0] = prev[0];
+              v[j][NCP - 1] = prev[NCP - 1];
+            }
+          }
+          if (DUMP && (dump & DCB_DUMP_QINTS)) {
+#pragma unroll
+            for (int c = 0; c < NCP; ++c) dptr[(size_t)(e0 + j) * NCP + c] = v[j][c];
+          }
+        }
+      }
+      if (cnt == 4) {
+        store_group4<NCP>(pp, optr, e0, v);
+      } else {
+        for (uint32_t j = 0; j < cnt; ++j) {
+          int32_t t[NCP];
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) t[c] = j == 0 ? v[0][c] : (j == 1 ? v[1][c] : v[2][c]);
+          store_entry<NCP>(pp, optr, e0 + j, t);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rans_tag_kernel: the tag stream of a Tagged attribute (32-symbol alphabet, 12-bit precision).
+// One stream per lane.  Writes one byte per point (the bit length), the running bit offset at every
+// TAG_CHUNK points (for the parallel bit-field extraction) and bits_total; fails the stream on
+// tag > 32 (DecoderBuffer.cs:141) or when the bit area would run past the buffer.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+                                                      const uint32_t *__restrict__ order, uint32_t n_streams,
+                                                      uint32_t lanes, uint32_t slot_bytes, uint32_t lut_shift,
+                                                      uint8_t *__restrict__ aux) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  typedef uint16_t T;
+  const uint32_t lane = threadIdx.x;
+  const uint32_t slot = blockIdx.x * lanes + lane;
+  const bool have = lane < lanes && slot < n_streams;
+  StreamDesc *dp = have ? &streams[order[slot]] : nullptr;
+  LaneTable<T> tab;
+  RansState rs;
+  ByteWin bw;
+  uint32_t n_entries = 0;
+  int status = DCB_OK;
+  uint32_t ncp = 1;
+  uint64_t avail_bits = 0;
+  uint8_t *tags = nullptr;
+  uint64_t *chunk_bits = nullptr;
+  if (have) {
+    const StreamDesc &d = *dp;
+    n_entries = d.n_entries;
+    ncp = d.ncp;
+    avail_bits = (d.buf_end - d.bits_off) * 8ull;
+    tags = aux + d.tag_off;
+    chunk_bits = reinterpret_cast<uint64_t *>(aux + d.tag_off + (((uint64_t)n_entries + 15ull) & ~15ull));
+    uint32_t cap_entries;
+    carve_table<T>(smem + (size_t)lane * slot_bytes, slot_bytes, d.prec_bits, lut_shift, false, tab, cap_entries);
+    status = build_table<T>(arena, d, tab, lut_shift, false, cap_entries);
+    if (status == DCB_OK) status = rans_init(arena, d, rs);
+    if (status == DCB_OK) bw.init(arena, d.payload_off + rs.off);
+    if (status != DCB_OK) {
+      dp->status = status;
+      n_entries = 0;
+    }
+  }
+  uint32_t n_max = n_entries;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+  uint64_t bits = 0;
+  uint32_t packed = 0;
+  for (uint32_t e = 0; e < n_max; ++e) {
+    if (e < n_entries) {
+      if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
+      const uint32_t tag = rans_step<T>(rs, bw, tab, lut_shift) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+      if (tag > 32u) {
+        status = DCB_ERR_TAG;
+        n_entries = 0;
+      } else {
+        bits += (uint64_t)tag * ncp;
+        if (bits > avail_bits) {
+          status = DCB_ERR_EOF;
+          n_entries = 0;
+        }
+      }
+      packed |= tag << (8u * (e & 3u));
+      if ((e & 3u) == 3u) {
+        *reinterpret_cast<uint32_t *>(tags + (e & ~3u)) = packed;
+        packed = 0;
+      } else if (e + 1 >= n_entries) {
+        for (uint32_t k = 0; k <= (e & 3u); ++k) tags[(e & ~3u) + k] = (uint8_t)(packed >> (8u * k));
+      }
+    }
+  }
+  if (have) {
+    dp->bits_total = bits;
+    if (status != DCB_OK) dp->status = status;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// resolve_kernel: one thread per buffer whose walk stopped at a Tagged bit area.
+// ---------------------------------------------------------------------------------------------
+__global__ void resolve_kernel(const uint8_t *__restrict__ arena, BufWalk *walks, const uint32_t *__restrict__ list,
+                               uint32_t n, StreamDesc *streams) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  BufWalk w = walks[list[i]];
+  walk_continue(arena, w, streams);
+  walks[list[i]] = w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// serial_post_kernel: one stream per lane; sources that need no rANS chain.
+//   Tagged        tags (u8 per point, from rans_tag_kernel) + LSB-first bit fields (DecoderBuffer.cs:138-154, B-4)
+//   Uncompressed  raw_num_bytes little-endian bytes per value (SequentialIntegerAttributeDecoder.cs:68-84, B-6)
+//   Empty         n_entries * ncp == 0
+// followed by zig-zag, the serial prediction recurrence and the store.  This is the path for
+// octahedron transforms and irregular wrap streams behind a Tagged source, and the general fallback.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t read_bits_lsb(const uint8_t *p, uint64_t bitpos, uint32_t count) {
+  if (count == 0) return 0;
+  const uint64_t byte = bitpos >> 3;
+  const uint32_t sh = (uint32_t)(bitpos & 7u);
+  uint64_t w = 0;
+  const uint32_t need = (sh + count + 7u) >> 3;  // <= 5
+  for (uint32_t k = 0; k < need; ++k) w |= (uint64_t)p[byte + k] << (8u * k);
+  w >>= sh;
+  return count == 32 ? (uint32_t)w : ((uint32_t)w & ((1u << count) - 1u));
+}
+
+template <int NCP, bool DUMP>
+__global__ void __launch_bounds__(32) serial_post_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+                                                         const uint32_t *__restrict__ order, uint32_t n_streams,
+                                                         uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
+                                                         uint8_t *__restrict__ aux, uint32_t dump) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_streams) return;
+  StreamDesc &d = streams[order[slot]];
+  if (d.status != DCB_OK) return;
+  const uint32_t n_entries = d.n_entries;
+  PostParams pp;
+  pp.load(d);
+  uint8_t *optr = out + d.out_off;
+  int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
+  if (pp.recon == RECON_PARA_WRAP) {
+    optr = aux + d.aux_off;
+    pp.store = STORE_NARROW;
+    pp.dsize = 4;
+  }
+  const uint8_t scheme = d.scheme;
+  const uint8_t *tags = aux + d.tag_off;
+  const uint8_t *bits = arena + d.bits_off;
+  const uint8_t *raw = arena + d.raw_off;
+  const uint32_t nb = d.raw_num_bytes;
+  uint64_t bitpos = 0;
+  int32_t prev[NCP];
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) prev[c] = 0;
+  for (uint32_t e = 0; e < n_entries; ++e) {
+    int32_t v[NCP];
+    uint32_t tag = 0;
+    if (scheme == SCHEME_TAGGED) tag = tags[e];
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) {
+      uint32_t sym = 0;
+      if (scheme == SCHEME_TAGGED) {
+        sym = read_bits_lsb(bits, bitpos, tag);
+        bitpos += tag;
+      } else {
+        const uint8_t *q = raw + ((uint64_t)e * NCP + c) * nb;
+        for (uint32_t k = 0; k < nb; ++k) sym |= (uint32_t)q[k] << (8u * k);
+      }
+      if (DUMP && (dump & DCB_DUMP_SYMBOLS)) dptr[(size_t)e * NCP + c] = (int32_t)sym;
+      v[c] = pp.zig ? zigzag_dec(sym) : (int32_t)sym;
+    }
+    if (pp.recon == RECON_DELTA_WRAP) {
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) {
+        prev[c] = wrap_original(prev[c], v[c], pp.mn, pp.mx, pp.max_diff);
+        v[c] = prev[c];
+      }
+    } else if (pp.recon == RECON_DELTA_OCT || pp.recon == RECON_DELTA_OCT_CANON) {
+      if (NCP == 2) {
+        oct_original(pp.box, pp.recon == RECON_DELTA_OCT_CANON, prev[0], prev[NCP - 1], v[0], v[NCP - 1]);
+        v[0] = prev[0];
+        v[NCP - 1] = prev[NCP - 1];
+      }
+    }
+    if (DUMP && (dump & DCB_DUMP_QINTS) && pp.recon != RECON_PARA_WRAP) {
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) dptr[(size_t)e * NCP + c] = v[c];
+    }
+    store_entry<NCP>(pp, optr, e, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// parallelogram prediction
+// ---------------------------------------------------------------------------------------------
+// deps[p] = (opp, next, prev) entry ids of the parallelogram of entry p, or (-1,*,*) when the
+// predictor falls back to entry p-1.  Depends on the connectivity maps only: fully parallel.
+__global__ void para_deps_kernel(StreamDesc *streams, const uint32_t *__restrict__ order, uint32_t n_streams,
+                                 const uint8_t *__restrict__ maps, uint8_t *__restrict__ aux) {
+  for (uint32_t si = blockIdx.y; si < n_streams; si += gridDim.y) {
+  StreamDesc &d = streams[order[si]];
+  if (d.status != DCB_OK) continue;
+  const uint32_t n = d.n_entries;
+  const uint32_t *opp = reinterpret_cast<const uint32_t *>(maps + d.map_off[0]);
+  const uint32_t *c2v = reinterpret_cast<const uint32_t *>(maps + d.map_off[1]);
+  const uint32_t *d2c = reinterpret_cast<const uint32_t *>(maps + d.map_off[2]);
+  const int32_t *v2d = reinterpret_cast<const int32_t *>(maps + d.map_off[3]);
+  const uint32_t n_corners = d.n_corners, n_vertices = d.n_vertices;
+  // deps live behind the corrections in the stream's scratch: int32[n * ncp] | qints int32[n * ncp] | int32[3 n]
+  int32_t *deps = reinterpret_cast<int32_t *>(aux + d.aux_off) + 2ull * n * d.ncp;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    int32_t e_o = -1, e_n = -1, e_p = -1;
+    if (p > 0) {
+      const uint32_t corner = d2c[p];
+      if (corner != 0xFFFFFFFFu && corner < n_corners) {
+        const uint32_t oc = opp[corner];  // MeshPredictionSchemeParallelogramDecoder.cs:66
+        if (oc != 0xFFFFFFFFu) {
+          if (oc >= n_corners) {
+            d.status = DCB_ERR_MAPS;
+          } else {
+            const uint32_t nx = (oc % 3u == 2u) ? oc - 2u : oc + 1u;  // CornerTable.Next
+            const uint32_t pv = (oc % 3u == 0u) ? oc + 2u : oc - 1u;  // CornerTable.Previous
+            const uint32_t v_o = c2v[oc], v_n = c2v[nx], v_p = c2v[pv];
+            if (v_o >= n_vertices || v_n >= n_vertices || v_p >= n_vertices) {
+              d.status = DCB_ERR_MAPS;
+            } else {
+              const int32_t a = v2d[v_o], b = v2d[v_n], c = v2d[v_p];
+              if (a < (int32_t)p && b < (int32_t)p && c < (int32_t)p) {  // :75
+                if (a < 0 || b < 0 || c < 0) d.status = DCB_ERR_MAPS;
+                else { e_o = a; e_n = b; e_p = c; }
+              }
+            }
+          }
+        }
+      }
+    }
+    deps[3ull * p] = e_o;
+    deps[3ull * p + 1] = e_n;
+    deps[3ull * p + 2] = e_p;
+  }
+  }
+}
+
+// The recurrence itself: serial per stream, one stream per lane.  The last DCB_PARA_RING entries
+// live in the lane's shared-memory ring (98.6 % of the dependencies of a depth-first traversal fall
+// inside 32 entries); older ones are re-read from the quantized-int scratch in HBM/L2.
+template <int NCP, bool DUMP>
+__global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
+                                                        uint32_t n_streams, uint8_t *__restrict__ out,
+                                                        uint8_t *__restrict__ dbg, uint8_t *__restrict__ aux,
+                                                        uint32_t dump) {
+  __shared__ int32_t ring[32][DCB_PARA_RING][NCP];
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_streams) return;
+  StreamDesc &d = streams[order[slot]];
+  if (d.status != DCB_OK) return;
+  const uint32_t n = d.n_entries;
+  PostParams pp;
+  pp.load(d);
+  uint8_t *optr = out + d.out_off;
+  int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
+  const int32_t *corr = reinterpret_cast<const int32_t *>(aux + d.aux_off);
+  int32_t *qints = reinterpret_cast<int32_t *>(aux + d.aux_off) + (uint64_t)n * NCP;
+  const int32_t *deps = qints + (uint64_t)n * NCP;
+  int32_t(*my)[NCP] = ring[threadIdx.x];
+  int32_t prev[NCP];
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) prev[c] = 0;
+  int32_t dn_o = -1, dn_n = -1, dn_p = -1;
+  for (uint32_t p = 0; p < n; ++p) {
+    const int32_t e_o = dn_o, e_n = dn_n, e_p = dn_p;
+    if (p + 1 < n) {  // prefetch the next entry's dependencies
+      dn_o = deps[3ull * (p + 1)];
+      dn_n = deps[3ull * (p + 1) + 1];
+      dn_p = deps[3ull * (p + 1) + 2];
+    }
+    int32_t v[NCP];
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) v[c] = corr[(uint64_t)p * NCP + c];
+    int32_t pred[NCP];
+    if (e_o >= 0) {
+      int32_t a[NCP], b[NCP], o[NCP];
+      auto fetch = [&](int32_t e, int32_t *dst) {
+        if (p - (uint32_t)e <= DCB_PARA_RING) {
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) dst[c] = my[(uint32_t)e % DCB_PARA_RING][c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) dst[c] = qints[(uint64_t)e * NCP + c];
+        }
+      };
+      fetch(e_n, a);
+      fetch(e_p, b);
+      fetch(e_o, o);
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) pred[c] = (int32_t)((uint32_t)a[c] + (uint32_t)b[c] - (uint32_t)o[c]);  // :84
+    } else {
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) pred[c] = prev[c];  // :36 (p == 0: zeros) and :49-50 (entry p-1)
+    }
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) {
+      prev[c] = wrap_original(pred[c], v[c], pp.mn, pp.mx, pp.max_diff);
+      my[p % DCB_PARA_RING][c] = prev[c];
+      qints[(uint64_t)p * NCP + c] = prev[c];
+    }
+    if (DUMP && (dump & DCB_DUMP_QINTS)) {
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) dptr[(size_t)p * NCP + c] = prev[c];
+    }
+    store_entry<NCP>(pp, optr, p, prev);
+  }
+}
+
+// generic attributes: n * byte_stride raw bytes
+__global__ void copy_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams, const uint32_t *__restrict__ order,
+                            uint32_t n_streams, uint8_t *__restrict__ out) {
+  for (uint32_t si = blockIdx.y; si < n_streams; si += gridDim.y) {
+    const StreamDesc &d = streams[order[si]];
+    if (d.status != DCB_OK) continue;
+    const uint8_t *src = arena + d.raw_off;
+    uint8_t *dst = out + d.out_off;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.out_bytes; i += (uint64_t)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+template <int NCP, typename T, bool DUMP, bool TG>
+static cudaError_t launch_raw_t(const RansLaunch &p, const DevArenas &a, uint32_t smem_bytes, cudaStream_t st) {
+  auto k = rans_raw_fused_kernel<NCP, T, DUMP, TG>;
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+  }
+  const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
+  k<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, p.slot_bytes,
+                                  p.lut_shift, p.compact, a.out, a.dbg, a.aux, a.tab, p.dump);
+  return cudaGetLastError();
+}
+
+template <int NCP, typename T>
+static cudaError_t launch_raw_n(const RansLaunch &p, bool table_global, const DevArenas &a, uint32_t smem_bytes,
+                                cudaStream_t st) {
+  const bool dump = p.dump != 0;
+  if (table_global)
+    return dump ? launch_raw_t<NCP, T, true, true>(p, a, 0, st) : launch_raw_t<NCP, T, false, true>(p, a, 0, st);
+  return dump ? launch_raw_t<NCP, T, true, false>(p, a, smem_bytes, st) : launch_raw_t<NCP, T, false, false>(p, a, smem_bytes, st);
+}
+
+cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool table_global, const DevArenas &a,
+                                uint32_t smem_bytes, cudaStream_t st) {
+#define DCB_CASE(N)                                                                  \
+  case N:                                                                            \
+    return wide ? launch_raw_n<N, uint32_t>(p, table_global, a, smem_bytes, st)      \
+                : launch_raw_n<N, uint16_t>(p, table_global, a, smem_bytes, st);
+  switch (ncp) {
+    DCB_CASE(1)
+    DCB_CASE(2)
+    DCB_CASE(3)
+    DCB_CASE(4)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef DCB_CASE
+}
+
+cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, uint32_t smem_bytes, cudaStream_t st) {
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rans_tag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+  }
+  const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
+  rans_tag_kernel<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp,
+                                                p.slot_bytes, p.lut_shift, a.aux);
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_resolve(const DevArenas &a, BufWalk *d_walks, const uint32_t *d_list, uint32_t n,
+                               StreamDesc *d_streams, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  resolve_kernel<<<(n + 63) / 64, 64, 0, st>>>(a.in, d_walks, d_list, n, d_streams);
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t dump,
+                                   const DevArenas &a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const uint32_t grid = (n + 31) / 32;
+#define DCB_CASE(N)                                                                                              \
+  case N:                                                                                                        \
+    if (dump)                                                                                                    \
+      serial_post_kernel<N, true><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump);  \
+    else                                                                                                         \
+      serial_post_kernel<N, false><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump); \
+    break;
+  switch (ncp) {
+    DCB_CASE(1)
+    DCB_CASE(2)
+    DCB_CASE(3)
+    DCB_CASE(4)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef DCB_CASE
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
+                            uint32_t dump, const DevArenas &a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  uint32_t gx = (max_entries + 255) / 256;
+  gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+  para_deps_kernel<<<dim3(gx, n > 65535u ? 65535u : n), 256, 0, st>>>(d_streams, d_order, n, a.maps, a.aux);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const uint32_t grid = (n + 31) / 32;
+#define DCB_CASE(N)                                                                                     \
+  case N:                                                                                               \
+    if (dump)                                                                                           \
+      para_chain_kernel<N, true><<<grid, 32, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump);  \
+    else                                                                                                \
+      para_chain_kernel<N, false><<<grid, 32, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump); \
+    break;
+  switch (ncp) {
+    DCB_CASE(1)
+    DCB_CASE(2)
+    DCB_CASE(3)
+    DCB_CASE(4)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef DCB_CASE
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_copy(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint64_t max_bytes,
+                            const DevArenas &a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  uint64_t gx = (max_bytes + 255) / 256;
+  gx = gx < 1 ? 1 : (gx > 2048 ? 2048 : gx);
+  copy_kernel<<<dim3((uint32_t)gx, n > 65535u ? 65535u : n), 256, 0, st>>>(a.in, d_streams, d_order, n, a.out);
+  return cudaGetLastError();
+}

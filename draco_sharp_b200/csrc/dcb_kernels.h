@@ -1,0 +1,33 @@
+// draco_sharp_b200/csrc/dcb_kernels.h -- host-callable launchers of the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dcb_internal.h"
+
+#define DCB_TAG_CHUNK 1024u  // points per bit-offset checkpoint of a Tagged stream
+#define DCB_PARA_RING 64u    // entries of the per-stream shared-memory ring of the parallelogram chain
+
+// device arenas of one shard
+struct DevArenas {
+  const uint8_t *in;  // compressed buffers, each on a 16-byte boundary
+  uint8_t *out;       // attribute outputs, each on a 128-byte boundary
+  uint8_t *dbg;       // DCB_DUMP_*: int32 per portable value
+  uint8_t *aux;       // scratch: corrections / tags / parallelogram dependencies
+  uint8_t *tab;       // scratch: probability tables that do not fit shared memory
+  const uint8_t *maps;  // mesh connectivity maps
+};
+
+// Raw-scheme rANS decode fused with inverse prediction + transform + store; one stream per lane.
+cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool table_global, const DevArenas &a,
+                                uint32_t smem_bytes, cudaStream_t st);
+// tag stream of Tagged attributes; one stream per lane
+cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, uint32_t smem_bytes, cudaStream_t st);
+cudaError_t dcb_launch_resolve(const DevArenas &a, BufWalk *d_walks, const uint32_t *d_list, uint32_t n,
+                               StreamDesc *d_streams, cudaStream_t st);
+cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t dump,
+                                   const DevArenas &a, cudaStream_t st);
+cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
+                            uint32_t dump, const DevArenas &a, cudaStream_t st);
+cudaError_t dcb_launch_copy(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint64_t max_bytes,
+                            const DevArenas &a, cudaStream_t st);

@@ -1,0 +1,932 @@
+/*
+ * oracle/draco_oracle.c -- CPU ORACLE. TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * Linear-time plain-C restatement of the attribute-decode hot path of
+ * B3zaleel/draco-sharp (a C# port of Google Draco, bitstream v2.2).  Every
+ * function cites the reference file:line it follows ("D/" = src/Draco/).
+ * The product path (draco_sharp_b200/csrc, libdracob200.so) never links or
+ * calls this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs do, as the checker / CPU baseline.
+ *
+ * PARITY PINNING.  The reference cannot run here (no .NET in the image) and its
+ * own tests hold no golden vector for symbol decode, prediction or
+ * dequantisation.  What IS pinned (tests/test_oracle_*.py):
+ *   - the reference's own KATs: varint 98 / 1739 and the 9-bit LSB-first value
+ *     0b001100010 (tests/Draco.UnitTests/IO/EncoderBufferTests.cs:7-46), the
+ *     int -3 <-> uint 4294967293 reinterpret (IO/ConstantsTests.cs:7-21), IntSqrt
+ *     0/4/48722615824 (IO/Core/MathUtilitiesTests.cs:7-20);
+ *   - the only upstream-produced artefact in the repo,
+ *     src/Draco.Examples/Samples/house_04.obj.drc: all nine Raw rANS streams
+ *     self-check (0 bytes left, final state == 4*2^precision), the position
+ *     attribute's symbols / corrections / quantized ints / floats match the
+ *     SHA-256 goldens of SURVEY.md Appendix C, and every dequantised position
+ *     lies within half a quantisation step of a `v` line of house_04.obj.
+ * The Tagged symbol scheme is anchored by no upstream artefact (it crashes in the
+ * C#, Appendix B-3): for it and for the octahedral transforms parity is
+ * "unpinned by reference artefacts" and rests on the mirrored encoder/decoder
+ * code plus generator<->oracle round trips.
+ *
+ * Where the C# throws or corrupts this file follows the
+ * Draco bitstream semantics the C# is porting; each such place is marked "B-n".
+ *
+ * Build: gcc -O2 -fPIC -shared -ffp-contract=off (no -ffast-math: float results
+ * must be two separately rounded binary32 operations, as RyuJIT produces).
+ */
+#include "draco_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* byte reader: BinaryReader semantics (D/IO/DecoderBuffer.cs:51-109)         */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  const uint8_t *p;
+  uint64_t len, pos;
+  int err;
+} rd_t;
+
+static int rd_need(rd_t *r, uint64_t n) {
+  if (r->err) return 0;
+  if (r->pos > r->len || r->len - r->pos < n) {
+    r->err = ORC_ERR_EOF;
+    return 0;
+  }
+  return 1;
+}
+static uint8_t rd_u8(rd_t *r) { return rd_need(r, 1) ? r->p[r->pos++] : 0; }
+static int8_t rd_i8(rd_t *r) { return (int8_t)rd_u8(r); }
+static uint16_t rd_u16(rd_t *r) {
+  if (!rd_need(r, 2)) return 0;
+  uint16_t v = (uint16_t)(r->p[r->pos] | (r->p[r->pos + 1] << 8));
+  r->pos += 2;
+  return v;
+}
+static uint32_t rd_u32(rd_t *r) {
+  if (!rd_need(r, 4)) return 0;
+  const uint8_t *q = r->p + r->pos;
+  r->pos += 4;
+  return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+}
+static int32_t rd_i32(rd_t *r) { return (int32_t)rd_u32(r); }
+static float rd_f32(rd_t *r) {
+  uint32_t u = rd_u32(r);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+/* LEB128 unsigned: D/IO/DecoderBuffer.cs:26-42.  (More than 10 bytes is rejected; the C#
+ * would keep shifting with a wrapped byte counter.) */
+int orc_varint(const uint8_t *p, uint64_t len, uint64_t *pos, uint64_t *out) {
+  uint64_t result = 0;
+  unsigned shift = 0;
+  for (int i = 0; i < 10; ++i) {
+    if (*pos >= len) return ORC_ERR_EOF;
+    uint8_t b = p[(*pos)++];
+    result |= (uint64_t)(b & 0x7F) << shift;
+    if ((b & 0x80) == 0) {
+      *out = result;
+      return ORC_OK;
+    }
+    shift += 7;
+  }
+  return ORC_ERR_EOF;
+}
+static uint64_t rd_varint(rd_t *r) {
+  uint64_t v = 0;
+  if (r->err) return 0;
+  int e = orc_varint(r->p, r->len, &r->pos, &v);
+  if (e) r->err = e;
+  return v;
+}
+
+/* LSB-first bit reader: D/IO/DecoderBuffer.cs:138-154,177-184 with B-4 applied
+ * (full 32-bit assembly; no eager byte).  bitpos counts bits from p[0] bit 0. */
+uint32_t orc_read_bits_lsb(const uint8_t *p, uint64_t len, uint64_t *bitpos, int count, int *err) {
+  uint32_t value = 0;
+  for (int i = 0; i < count; ++i) {
+    uint64_t byte = *bitpos >> 3;
+    if (byte >= len) {
+      if (err) *err = ORC_ERR_EOF;
+      return value;
+    }
+    value |= (uint32_t)((p[byte] >> (*bitpos & 7)) & 1u) << i;
+    ++*bitpos;
+  }
+  return value;
+}
+
+/* D/IO/BitUtilities.cs:72-81 */
+int32_t orc_zigzag(uint32_t v) {
+  int positive = (v & 1u) == 0;
+  v >>= 1;
+  return positive ? (int32_t)v : (int32_t)(0u - v - 1u);
+}
+/* D/IO/Constants.cs:183-225 (int -> uint reinterpret used by the wrap transform) */
+uint32_t orc_reinterpret_i2u(int32_t v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  return u;
+}
+/* D/IO/Core/MathUtilities.cs:5-25 */
+uint64_t orc_int_sqrt(uint64_t number) {
+  if (number == 0) return 0;
+  uint64_t act = number, root = 1;
+  while (act >= 2) {
+    root *= 2;
+    act /= 4;
+  }
+  do {
+    root = (root + number / root) / 2;
+  } while (root * root > number);
+  return root;
+}
+/* D/IO/Entropy/RAnsSymbolCoding.cs:10-26 */
+int orc_rans_precision(int mbl) {
+  int p = (3 * mbl) / 2;
+  return p < 12 ? 12 : (p > 20 ? 20 : p);
+}
+
+/* ------------------------------------------------------------------------- */
+/* rANS symbol decoder                                                        */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int prec_bits;
+  uint32_t prec, l_base;
+  uint32_t num_symbols;
+  uint32_t *prob, *cum, *lut;
+  const uint8_t *buf;
+  int64_t off;
+  uint32_t state;
+} rans_t;
+
+static void rans_free(rans_t *a) {
+  free(a->prob);
+  free(a->cum);
+  free(a->lut);
+  memset(a, 0, sizeof *a);
+}
+
+/* Table parse: D/IO/Entropy/RAnsSymbolDecoder.cs:12-51; LUT: D/IO/Entropy/RAnsDecoder.cs:69-88 */
+static int rans_create(rans_t *a, rd_t *r, int max_bit_length) {
+  memset(a, 0, sizeof *a);
+  a->prec_bits = orc_rans_precision(max_bit_length);
+  a->prec = 1u << a->prec_bits;
+  a->l_base = a->prec * 4u;
+  uint64_t ns = rd_varint(r);
+  if (r->err) return r->err;
+  /* every table byte describes at most 64 symbols; anything larger cannot be backed by data */
+  if (ns > (r->len - r->pos) * 64u || ns > (1u << 24)) return ORC_ERR_EOF;
+  a->num_symbols = (uint32_t)ns;
+  if (ns == 0) return ORC_OK;
+  a->prob = (uint32_t *)calloc(ns, 4);
+  a->cum = (uint32_t *)calloc(ns, 4);
+  a->lut = (uint32_t *)calloc(a->prec, 4);
+  for (uint32_t i = 0; i < a->num_symbols; ++i) {
+    uint8_t pd = rd_u8(r);
+    if (r->err) return r->err;
+    uint32_t token = pd & 3u;
+    if (token == 3) {
+      uint32_t offset = (uint32_t)pd >> 2;
+      if (i + offset >= a->num_symbols) return ORC_ERR_TABLE; /* :31 */
+      for (uint32_t j = 0; j < offset + 1; ++j) a->prob[i + j] = 0;
+      i += offset;
+    } else {
+      uint32_t prob = (uint32_t)pd >> 2;
+      for (uint32_t b = 0; b < token; ++b) {
+        uint32_t eb = rd_u8(r);
+        prob |= eb << (8 * (b + 1) - 2);
+      }
+      if (r->err) return r->err;
+      a->prob[i] = prob;
+    }
+  }
+  uint32_t cum = 0, act = 0;
+  for (uint32_t i = 0; i < a->num_symbols; ++i) {
+    a->cum[i] = cum;
+    /* 64-bit guard: the C# adds in uint and compares, a 2^32 wrap needs prob >= 2^22 which the
+     * table encoding cannot express (max 22 bits) but four of them could wrap: reject via 64-bit */
+    uint64_t c64 = (uint64_t)cum + a->prob[i];
+    if (c64 > a->prec) return ORC_ERR_TABLE; /* RAnsDecoder.cs:80 */
+    cum = (uint32_t)c64;
+    for (uint32_t j = act; j < cum; ++j) a->lut[j] = i;
+    act = cum;
+  }
+  if (cum != a->prec) return ORC_ERR_TABLE; /* :87 */
+  return ORC_OK;
+}
+
+/* D/IO/Entropy/RAnsSymbolDecoder.cs:53-59 + D/IO/Entropy/RAnsDecoder.cs:20-54 */
+static int rans_start(rans_t *a, rd_t *r, uint64_t *payload_off, uint64_t *payload_len) {
+  uint64_t n = rd_varint(r);
+  if (r->err) return r->err;
+  if (!rd_need(r, n)) return r->err; /* short ReadBytes -> IndexOutOfRange in ReadInit */
+  const uint8_t *buf = r->p + r->pos;
+  if (payload_off) *payload_off = r->pos;
+  if (payload_len) *payload_len = n;
+  r->pos += n;
+  int64_t offset = (int64_t)n;
+  if (offset < 1) return ORC_ERR_RANS_INIT;
+  a->buf = buf;
+  uint32_t x = (uint32_t)buf[offset - 1] >> 6;
+  if (x == 0) {
+    a->off = offset - 1;
+    a->state = buf[offset - 1] & 0x3Fu;
+  } else if (x == 1) {
+    if (offset < 2) return ORC_ERR_RANS_INIT;
+    a->off = offset - 2;
+    a->state = ((uint32_t)buf[offset - 2] | ((uint32_t)buf[offset - 1] << 8)) & 0x3FFFu;
+  } else if (x == 2) {
+    if (offset < 3) return ORC_ERR_RANS_INIT;
+    a->off = offset - 3;
+    a->state = ((uint32_t)buf[offset - 3] | ((uint32_t)buf[offset - 2] << 8) | ((uint32_t)buf[offset - 1] << 16)) &
+               0x3FFFFFu;
+  } else {
+    if (offset < 4) return ORC_ERR_RANS_INIT; /* C#: IndexOutOfRangeException */
+    a->off = offset - 4;
+    a->state = ((uint32_t)buf[offset - 4] | ((uint32_t)buf[offset - 3] << 8) | ((uint32_t)buf[offset - 2] << 16) |
+                ((uint32_t)buf[offset - 1] << 24)) &
+               0x3FFFFFFFu;
+  }
+  a->state += a->l_base;
+  if (a->state >= a->l_base * 256u) return ORC_ERR_RANS_INIT; /* :53 */
+  return ORC_OK;
+}
+
+/* D/IO/Entropy/RAnsDecoder.cs:56-67,90-99 */
+static inline uint32_t rans_read(rans_t *a) {
+  while (a->state < a->l_base && a->off > 0) a->state = a->state * 256u + a->buf[--a->off];
+  uint32_t quo = a->state >> a->prec_bits;
+  uint32_t rem = a->state & (a->prec - 1u);
+  uint32_t s = a->lut[rem];
+  a->state = quo * a->prob[s] + rem - a->cum[s];
+  return s;
+}
+
+/* D/IO/Entropy/SymbolDecoding.cs:7-67 (Tagged with B-3 / B-4 applied) */
+int orc_decode_symbols(const uint8_t *p, uint64_t len, uint64_t *pos, uint32_t num_values, uint32_t nc,
+                       uint32_t *out, orc_attr *diag) {
+  if (num_values == 0) return ORC_OK; /* :9-13 reads nothing */
+  rd_t r = {p, len, *pos, 0};
+  rans_t a;
+  int st = ORC_OK;
+  uint8_t scheme = rd_u8(&r);
+  if (r.err) return r.err;
+  if (diag) diag->scheme = scheme;
+  if (scheme == 0) { /* Tagged :30-50 */
+    if (diag) {
+      diag->max_bit_length = 5;
+      diag->table_off = r.pos;
+    }
+    st = rans_create(&a, &r, 5);
+    if (diag) {
+      diag->precision = a.prec_bits;
+      diag->table_symbols = a.num_symbols;
+    }
+    if (!st && a.num_symbols == 0) st = ORC_ERR_NUM_SYMBOLS; /* :36 (ReadInit would also fail on null tables) */
+    if (!st) st = rans_start(&a, &r, diag ? &diag->payload_off : NULL, diag ? &diag->payload_len : NULL);
+    if (st) {
+      rans_free(&a);
+      return st;
+    }
+    const uint8_t *bits = p + r.pos;
+    uint64_t bits_len = len - r.pos, bitpos = 0;
+    uint32_t vid = 0;
+    for (uint32_t i = 0; i < num_values; i += nc) {
+      uint32_t bit_length = rans_read(&a) & 0xFFu; /* (byte) cast :41 */
+      if (bit_length > 32) {
+        st = ORC_ERR_TAG;
+        break;
+      }
+      for (uint32_t j = 0; j < nc && vid < num_values; ++j) {
+        int e = 0;
+        out[vid++] = orc_read_bits_lsb(bits, bits_len, &bitpos, (int)bit_length, &e);
+        if (e) st = e;
+      }
+      if (st) break;
+    }
+    if (diag) {
+      diag->final_state = a.state;
+      diag->leftover = (uint64_t)a.off;
+      diag->bits_off = r.pos;
+      diag->bits_len = (bitpos + 7) / 8;
+    }
+    r.pos += (bitpos + 7) / 8; /* EndBitDecoding: ceil(bits/8) bytes (B-4) */
+    rans_free(&a);
+    if (st) return st;
+  } else if (scheme == 1) { /* Raw :52-67 */
+    uint8_t mbl = rd_u8(&r);
+    if (r.err) return r.err;
+    if (mbl < 1 || mbl > 18) return ORC_ERR_BITLEN;
+    if (diag) {
+      diag->max_bit_length = mbl;
+      diag->table_off = r.pos;
+    }
+    st = rans_create(&a, &r, mbl);
+    if (diag) {
+      diag->precision = a.prec_bits;
+      diag->table_symbols = a.num_symbols;
+    }
+    if (!st && a.num_symbols == 0) st = ORC_ERR_NUM_SYMBOLS; /* :59 */
+    if (!st) st = rans_start(&a, &r, diag ? &diag->payload_off : NULL, diag ? &diag->payload_len : NULL);
+    if (st) {
+      rans_free(&a);
+      return st;
+    }
+    for (uint32_t i = 0; i < num_values; ++i) out[i] = rans_read(&a);
+    if (diag) {
+      diag->final_state = a.state;
+      diag->leftover = (uint64_t)a.off;
+    }
+    rans_free(&a);
+  } else {
+    return ORC_ERR_SCHEME; /* :26 */
+  }
+  *pos = r.pos;
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* prediction schemes + transforms                                            */
+/* ------------------------------------------------------------------------- */
+
+/* D/IO/Attributes/PredictionSchemes/PredictionSchemeWrapTransform.cs:67-86 (clamp) and
+ * PredictionSchemeWrapDecodingTransform.cs:46-67 (mod-2^32 add, one +-max_diff) */
+static inline int32_t wrap_original(int32_t pred, int32_t corr, int32_t mn, int32_t mx, int32_t max_diff) {
+  if (pred > mx)
+    pred = mx;
+  else if (pred < mn)
+    pred = mn;
+  int32_t o = (int32_t)((uint32_t)pred + (uint32_t)corr);
+  if (o > mx)
+    o = (int32_t)((uint32_t)o - (uint32_t)max_diff);
+  else if (o < mn)
+    o = (int32_t)((uint32_t)o + (uint32_t)max_diff);
+  return o;
+}
+
+/* D/IO/Attributes/PredictionSchemes/PredictionSchemeDeltaDecoder.cs:23-37 with the wrap transform */
+void orc_delta_wrap(const int32_t *corr, uint32_t n, int nc, int32_t mn, int32_t mx, int32_t *out) {
+  int32_t max_diff = (int32_t)(1u + (uint32_t)mx - (uint32_t)mn); /* WrapTransform.cs:88-92 */
+  for (int c = 0; c < nc && n > 0; ++c) out[c] = wrap_original(0, corr[c], mn, mx, max_diff); /* :30 */
+  for (uint64_t i = (uint64_t)nc; i < (uint64_t)n * nc; ++i)
+    out[i] = wrap_original(out[i - nc], corr[i], mn, mx, max_diff); /* :32-35 */
+}
+
+/* D/IO/Attributes/PredictionSchemes/MeshPredictionSchemeParallelogramDecoder.cs:29-89 */
+int orc_parallelogram_wrap(const int32_t *corr, uint32_t n, int nc, int32_t mn, int32_t mx,
+                           const orc_mesh_maps *m, int32_t *out) {
+  int32_t max_diff = (int32_t)(1u + (uint32_t)mx - (uint32_t)mn);
+  if (n == 0) return ORC_OK;
+  if (!m || m->n_entries < n) return ORC_ERR_MAPS;
+  for (int c = 0; c < nc; ++c) out[c] = wrap_original(0, corr[c], mn, mx, max_diff); /* :36 */
+  for (uint32_t p = 1; p < n; ++p) {                                                 /* :38 */
+    uint32_t corner = m->data_to_corner[p];
+    uint64_t dst = (uint64_t)p * nc;
+    int used = 0;
+    if (corner != 0xFFFFFFFFu && corner < m->n_corners) {
+      uint32_t oc = m->opposite[corner]; /* :66 */
+      if (oc != 0xFFFFFFFFu) {
+        if (oc >= m->n_corners) return ORC_ERR_MAPS;
+        uint32_t nx = (oc % 3u == 2u) ? oc - 2u : oc + 1u; /* CornerTable.Next :64-67 */
+        uint32_t pv = (oc % 3u == 0u) ? oc + 2u : oc - 1u; /* CornerTable.Previous :69-72 */
+        uint32_t v_o = m->corner_to_vertex[oc], v_n = m->corner_to_vertex[nx], v_p = m->corner_to_vertex[pv];
+        if (v_o >= m->n_vertices || v_n >= m->n_vertices || v_p >= m->n_vertices) return ORC_ERR_MAPS;
+        int32_t e_o = m->vertex_to_data[v_o], e_n = m->vertex_to_data[v_n], e_p = m->vertex_to_data[v_p]; /* :56-59 */
+        if (e_o < (int32_t)p && e_n < (int32_t)p && e_p < (int32_t)p) {                                   /* :75 */
+          if (e_o < 0 || e_n < 0 || e_p < 0) return ORC_ERR_MAPS; /* C#: IndexOutOfRangeException */
+          for (int c = 0; c < nc; ++c) {
+            int32_t pred = (int32_t)((uint32_t)out[(uint64_t)e_n * nc + c] + (uint32_t)out[(uint64_t)e_p * nc + c] -
+                                     (uint32_t)out[(uint64_t)e_o * nc + c]); /* :84 */
+            out[dst + c] = wrap_original(pred, corr[dst + c], mn, mx, max_diff);
+          }
+          used = 1;
+        }
+      }
+    }
+    if (!used) {
+      uint64_t src = (uint64_t)(p - 1) * nc; /* :49-50 */
+      for (int c = 0; c < nc; ++c) out[dst + c] = wrap_original(out[src + c], corr[dst + c], mn, mx, max_diff);
+    }
+  }
+  return ORC_OK;
+}
+
+/* Octahedron tool box: D/IO/Attributes/OctahedronToolBox.cs:13-21,144-212 */
+typedef struct {
+  int32_t bits, max_q, max_value, center;
+} octbox_t;
+static void octbox_set(octbox_t *t, int bits) {
+  t->bits = bits;
+  t->max_q = (int32_t)((1u << bits) - 1u);
+  t->max_value = t->max_q - 1;
+  t->center = t->max_value / 2;
+}
+static inline int32_t iabs32(int32_t v) { return v < 0 ? (int32_t)(0u - (uint32_t)v) : v; }
+static inline int oct_in_diamond(const octbox_t *t, int32_t s, int32_t tt) { /* :144-150 (asserts dropped, B-9) */
+  uint32_t st = (uint32_t)iabs32(s) + (uint32_t)iabs32(tt);
+  return st <= (uint32_t)t->center;
+}
+static inline void oct_invert_diamond(const octbox_t *t, int32_t *s, int32_t *tt) { /* :152-194 */
+  int32_t sign_s, sign_t;
+  if (*s >= 0 && *tt >= 0) {
+    sign_s = 1;
+    sign_t = 1;
+  } else if (*s <= 0 && *tt <= 0) {
+    sign_s = -1;
+    sign_t = -1;
+  } else {
+    sign_s = (*s > 0) ? 1 : -1;
+    sign_t = (*tt > 0) ? 1 : -1;
+  }
+  int32_t corner_s = sign_s * t->center, corner_t = sign_t * t->center;
+  /* all arithmetic mod 2^32 (C# int, unchecked) */
+  int32_t us = (int32_t)((uint32_t)*s + (uint32_t)*s - (uint32_t)corner_s);
+  int32_t ut = (int32_t)((uint32_t)*tt + (uint32_t)*tt - (uint32_t)corner_t);
+  int32_t temp = us;
+  if (sign_s * sign_t >= 0) {
+    us = (int32_t)(0u - (uint32_t)ut);
+    ut = (int32_t)(0u - (uint32_t)temp);
+  } else {
+    us = ut;
+    ut = temp;
+  }
+  us = (int32_t)((uint32_t)us + (uint32_t)corner_s);
+  ut = (int32_t)((uint32_t)ut + (uint32_t)corner_t);
+  *s = us / 2; /* truncating division, as C# */
+  *tt = ut / 2;
+}
+static inline int32_t oct_mod_max(const octbox_t *t, int32_t x) { /* :205-212 */
+  if (x > t->center) return (int32_t)((uint32_t)x - (uint32_t)t->max_q);
+  return x < -t->center ? (int32_t)((uint32_t)x + (uint32_t)t->max_q) : x;
+}
+/* ...CanonicalizedTransform.cs:43-89 */
+static inline int oct_rotation_count(int32_t sx, int32_t sy) {
+  if (sx == 0) return sy == 0 ? 0 : (sy > 0 ? 3 : 1);
+  if (sx > 0) return sy >= 0 ? 2 : 1;
+  return sy <= 0 ? 0 : 3;
+}
+static inline void oct_rotate(int32_t *p0, int32_t *p1, int rot) {
+  int32_t a = *p0, b = *p1;
+  switch (rot) {
+    case 1: *p0 = b; *p1 = (int32_t)(0u - (uint32_t)a); break;
+    case 2: *p0 = (int32_t)(0u - (uint32_t)a); *p1 = (int32_t)(0u - (uint32_t)b); break;
+    case 3: *p0 = (int32_t)(0u - (uint32_t)b); *p1 = a; break;
+    default: break;
+  }
+}
+/* PredictionSchemeNormalOctahedronCanonicalizedDecodingTransform.cs:48-78 (canonical=1) and
+ * PredictionSchemeNormalOctahedronDecodingTransform.cs:47-67 (canonical=0); asserts dropped and
+ * AddAsUnsigned = plain mod-2^32 add (B-9). */
+static inline void oct_original(const octbox_t *t, int canonical, const int32_t *pred_in, const int32_t *corr,
+                                int32_t *out) {
+  int32_t p0 = (int32_t)((uint32_t)pred_in[0] - (uint32_t)t->center);
+  int32_t p1 = (int32_t)((uint32_t)pred_in[1] - (uint32_t)t->center);
+  int in_diamond = oct_in_diamond(t, p0, p1);
+  if (!in_diamond) oct_invert_diamond(t, &p0, &p1);
+  int bottom_left = 1, rot = 0;
+  if (canonical) {
+    bottom_left = (p0 == 0 && p1 == 0) ? 1 : (p0 < 0 && p1 <= 0);
+    rot = oct_rotation_count(p0, p1);
+    if (!bottom_left) oct_rotate(&p0, &p1, rot);
+  }
+  int32_t o0 = oct_mod_max(t, (int32_t)((uint32_t)p0 + (uint32_t)corr[0]));
+  int32_t o1 = oct_mod_max(t, (int32_t)((uint32_t)p1 + (uint32_t)corr[1]));
+  if (canonical && !bottom_left) oct_rotate(&o0, &o1, (4 - rot) % 4);
+  if (!in_diamond) oct_invert_diamond(t, &o0, &o1);
+  out[0] = (int32_t)((uint32_t)o0 + (uint32_t)t->center);
+  out[1] = (int32_t)((uint32_t)o1 + (uint32_t)t->center);
+}
+/* Delta decoder (PredictionSchemeDeltaDecoder.cs:23-37) with an octahedron transform; nc = 2.
+ * max_q -> tool box per PredictionSchemeNormalOctahedronTransform.cs:44-53. */
+void orc_delta_oct(const int32_t *corr, uint32_t n, int32_t max_q, int canonical, int32_t *out) {
+  octbox_t t;
+  int msb = -1;
+  for (uint32_t v = (uint32_t)max_q; v; v >>= 1) ++msb;
+  octbox_set(&t, msb + 1);
+  int32_t zero[2] = {0, 0};
+  if (n == 0) return;
+  oct_original(&t, canonical, zero, corr, out);
+  for (uint32_t i = 1; i < n; ++i) oct_original(&t, canonical, out + 2 * (uint64_t)(i - 1), corr + 2 * (uint64_t)i, out + 2 * (uint64_t)i);
+}
+
+/* D/IO/Attributes/AttributeQuantizationTransform.cs:179-199 + D/IO/Core/Dequantizer.cs:14-23.
+ * delta = range / (float)max_q : one rounded binary32 division;
+ * out = (float)q * delta + min : two separately rounded binary32 operations. */
+void orc_dequantize(const int32_t *q, uint32_t n, int nc, const float *mn, float range, int bits, float *out) {
+  int32_t max_q = (int32_t)((1u << bits) - 1u);
+  volatile float delta = range / (float)max_q;
+  for (uint64_t i = 0; i < (uint64_t)n; ++i)
+    for (int c = 0; c < nc; ++c) {
+      volatile float prod = (float)q[i * nc + c] * delta;
+      out[i * nc + c] = prod + mn[c];
+    }
+}
+
+/* D/IO/Attributes/AttributeOctahedronTransform.cs:82-102 + OctahedronToolBox.cs:139-142,220-239
+ * with B-10 / B-11 applied: Float32 target, norm = x^2+y^2+z^2.  Arithmetic types follow the C#:
+ * x,y,z and the squared norm are binary32; 1/sqrt and the final products are binary64, then
+ * rounded to binary32. */
+void orc_oct_to_unit(const int32_t *st, uint32_t n, int bits, float *out) {
+  octbox_t t;
+  octbox_set(&t, bits);
+  volatile float scale = 2.0f / (float)t.max_value; /* :19 */
+  for (uint64_t i = 0; i < (uint64_t)n; ++i) {
+    volatile float ys = (float)st[2 * i] * scale;
+    volatile float zs = (float)st[2 * i + 1] * scale;
+    float y = ys - 1.0f, z = zs - 1.0f; /* :141 */
+    volatile float x1 = 1.0f - fabsf(y);
+    float x = x1 - fabsf(z); /* :224 */
+    float x_offset = (-x < 0) ? 0.0f : -x;
+    y += (y < 0) ? x_offset : -x_offset;
+    z += (z < 0) ? x_offset : -x_offset;
+    volatile float xx = x * x, yy = y * y, zz = z * z;
+    volatile float s1 = xx + yy;
+    float norm_squared = s1 + zz; /* B-11 */
+    if ((double)norm_squared < 1E-6) {
+      out[3 * i] = 0;
+      out[3 * i + 1] = 0;
+      out[3 * i + 2] = 0;
+    } else {
+      double d = 1.0 / sqrt((double)norm_squared); /* 1.0f / Math.Sqrt(double) */
+      out[3 * i] = (float)((double)x * d);
+      out[3 * i + 1] = (float)((double)y * d);
+      out[3 * i + 2] = (float)((double)z * d);
+    }
+  }
+}
+
+static int dtype_len(int dt) { /* D/IO/Constants.cs:133-143 */
+  switch (dt) {
+    case 1: case 2: case 11: return 1;
+    case 3: case 4: return 2;
+    case 5: case 6: case 9: return 4;
+    case 7: case 8: case 10: return 8;
+    default: return -1;
+  }
+}
+
+/* D/IO/Attributes/SequentialIntegerAttributeDecoder.cs:103-160 with B-12 applied (tight stride):
+ * keep the low sizeof(T) bytes of every int32. */
+void orc_narrow(const int32_t *q, uint64_t count, int data_type, uint8_t *out) {
+  int sz = dtype_len(data_type);
+  for (uint64_t i = 0; i < count; ++i) {
+    uint32_t u = (uint32_t)q[i];
+    for (int b = 0; b < sz; ++b) out[i * sz + b] = (uint8_t)(u >> (8 * b));
+  }
+}
+
+uint64_t orc_fnv1a(const uint8_t *p, uint64_t n, uint64_t h) {
+  if (h == 0) h = 1469598103934665603ull;
+  for (uint64_t i = 0; i < n; ++i) {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+/* ------------------------------------------------------------------------- */
+/* container walk                                                             */
+/* ------------------------------------------------------------------------- */
+
+/* D/IO/Metadata/MetadataDecoder.cs:5-49 (skip only; the sub-metadata crash at :45 is not mirrored) */
+static void skip_metadata_element(rd_t *r, int depth) {
+  if (depth > 64) {
+    r->err = ORC_ERR_UNSUPPORTED;
+    return;
+  }
+  uint64_t n = rd_varint(r);
+  for (uint64_t i = 0; i < n && !r->err; ++i) {
+    uint8_t ks = rd_u8(r);
+    if (rd_need(r, ks)) r->pos += ks;
+    uint8_t vs = rd_u8(r);
+    if (rd_need(r, vs)) r->pos += vs;
+  }
+  uint64_t ns = rd_varint(r);
+  for (uint64_t i = 0; i < ns && !r->err; ++i) {
+    uint8_t ks = rd_u8(r);
+    if (rd_need(r, ks)) r->pos += ks;
+    skip_metadata_element(r, depth + 1);
+  }
+}
+static void skip_metadata(rd_t *r) {
+  uint64_t n = rd_varint(r);
+  for (uint64_t i = 0; i < n && !r->err; ++i) {
+    (void)rd_varint(r);
+    skip_metadata_element(r, 0);
+  }
+  skip_metadata_element(r, 0);
+}
+
+/* implemented in orc_eb.c: Edgebreaker connectivity + per-decoder traversal maps.  Returns
+ * ORC_ERR_UNSUPPORTED when that file is not linked in. */
+int orc_eb_decode_connectivity(const uint8_t *buf, uint64_t len, uint64_t *pos, int traversal_type, orc_result *res);
+int orc_eb_build_maps(orc_result *res, const uint8_t *dec_ids, int n_dec);
+int orc_seq_mesh_connectivity(const uint8_t *buf, uint64_t len, uint64_t *pos, orc_result *res);
+
+/* PORTABLE(int-like): D/IO/Attributes/SequentialIntegerAttributeDecoder.cs:23-101 */
+static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh_maps *maps, int n_maps) {
+  uint32_t n = a->n_entries;
+  if (a->seq_type == 0) { /* generic: SequentialAttributeDecoder.cs:75-86 */
+    uint64_t stride = (uint64_t)dtype_len(a->data_type) * a->nc;
+    a->out_bytes = stride * n;
+    if (!rd_need(r, a->out_bytes)) return r->err;
+    a->out = (uint8_t *)malloc(a->out_bytes ? a->out_bytes : 1);
+    memcpy(a->out, r->p + r->pos, a->out_bytes);
+    r->pos += a->out_bytes;
+    return ORC_OK;
+  }
+  a->pred_method = rd_i8(r); /* :25 */
+  if (r->err) return r->err;
+  if (a->pred_method < -2 || a->pred_method >= 7) return ORC_ERR_PRED; /* :26 */
+  a->transform = -1;
+  if (a->pred_method != -2) {
+    a->transform = rd_i8(r); /* :30 */
+    if (r->err) return r->err;
+    if (a->transform < -1 || a->transform >= 4) return ORC_ERR_PRED; /* :31 */
+  }
+  /* which scheme objects exist: :46-51 (Wrap only) / SequentialNormalAttributeDecoder.cs:19-27 (B-8) */
+  int has_scheme = 0;
+  if (a->pred_method != -2) {
+    if (a->seq_type == 3)
+      has_scheme = (a->transform == 2 || a->transform == 3);
+    else
+      has_scheme = (a->transform == 1);
+  }
+  int is_mesh = res->geom_type == 1;
+  int mesh_scheme = 0; /* PredictionSchemeDecoderFactory.cs:9-75 */
+  if (has_scheme && is_mesh && res->method == 1) {
+    /* Edgebreaker meshes have corner table + encoding data: mesh schemes apply */
+    if (a->pred_method == 1)
+      mesh_scheme = 1;
+    else if (a->pred_method != 0)
+      return ORC_ERR_UNSUPPORTED; /* multi-/constrained-/texcoords/geometric-normal: SURVEY 8f-3 */
+  }
+  int ncp = a->nc_portable;
+  uint64_t nv = (uint64_t)n * ncp;
+  a->compressed = rd_u8(r); /* :61 */
+  if (r->err) return r->err;
+  a->symbols = (uint32_t *)calloc(nv ? nv : 1, 4);
+  a->corr = (int32_t *)calloc(nv ? nv : 1, 4);
+  a->qints = (int32_t *)calloc(nv ? nv : 1, 4);
+  a->scheme = -1;
+  if (a->compressed > 0) {
+    int st = orc_decode_symbols(r->p, r->len, &r->pos, (uint32_t)nv, (uint32_t)ncp, a->symbols, a); /* :65 */
+    if (st) return st;
+  } else { /* :68-84 with B-6 applied */
+    uint8_t nb = rd_u8(r);
+    if (r->err) return r->err;
+    if (nb > 4) return ORC_ERR_UNSUPPORTED;
+    if (!rd_need(r, (uint64_t)nb * nv)) return r->err;
+    for (uint64_t i = 0; i < nv; ++i) {
+      uint32_t v = 0;
+      for (int b = 0; b < nb; ++b) v |= (uint32_t)r->p[r->pos++] << (8 * b);
+      a->symbols[i] = v;
+    }
+  }
+  /* zig-zag iff no scheme or the transform's corrections may be negative: :86-90 with B-5 */
+  int zigzag = (!has_scheme) || (a->transform == 1);
+  for (uint64_t i = 0; i < nv; ++i) a->corr[i] = zigzag ? orc_zigzag(a->symbols[i]) : (int32_t)a->symbols[i];
+  if (!has_scheme) {
+    memcpy(a->qints, a->corr, nv * 4);
+    return ORC_OK;
+  }
+  /* PRED_DATA :93 */
+  if (a->transform == 1) { /* PredictionSchemeWrapDecodingTransform.cs:69-75 */
+    a->xf_a = rd_i32(r);
+    a->xf_b = rd_i32(r);
+    if (r->err) return r->err;
+    if (a->xf_a > a->xf_b) return ORC_ERR_WRAP;
+    int64_t diff = (int64_t)a->xf_b - (int64_t)a->xf_a; /* WrapTransform.cs:90-91 (int overflow -> negative) */
+    if ((int32_t)diff < 0 || diff >= 2147483647ll) return ORC_ERR_WRAP;
+    if (nv > 0) {
+      if (mesh_scheme) {
+        if (!maps || a->decoder_id >= n_maps) return ORC_ERR_MAPS;
+        int st = orc_parallelogram_wrap(a->corr, n, ncp, a->xf_a, a->xf_b, &maps[a->decoder_id], a->qints);
+        if (st) return st;
+      } else {
+        orc_delta_wrap(a->corr, n, ncp, a->xf_a, a->xf_b, a->qints);
+      }
+    }
+  } else { /* octahedron transforms */
+    a->xf_a = rd_i32(r); /* max_quantized_value */
+    if (a->transform == 3) a->xf_b = rd_i32(r); /* center_value (ignored) ...CanonicalizedDecodingTransform.cs:80-84 */
+    if (r->err) return r->err;
+    if (a->xf_a % 2 == 0) return ORC_ERR_QUANT; /* ...OctahedronTransform.cs:50 */
+    int msb = -1;
+    for (uint32_t v = (uint32_t)a->xf_a; v; v >>= 1) ++msb;
+    if (msb + 1 < 2 || msb + 1 > 30) return ORC_ERR_QUANT; /* OctahedronToolBox.cs:15 */
+    if (mesh_scheme) return ORC_ERR_UNSUPPORTED;           /* parallelogram on normals: not a Draco combination */
+    if (nv > 0) orc_delta_oct(a->corr, n, a->xf_a, a->transform == 3, a->qints);
+  }
+  return ORC_OK;
+}
+
+/* XFORM_PARAMS + store: SequentialQuantizationAttributeDecoder.cs:26-47,
+ * SequentialNormalAttributeDecoder.cs:38-50 (B-7), SequentialIntegerAttributeDecoder.cs:14-21,103-160 */
+static int decode_xform_params(rd_t *r, orc_attr *a) {
+  if (a->seq_type == 2) { /* AttributeQuantizationTransform.cs:110-121 */
+    for (int c = 0; c < a->nc; ++c) {
+      float f = rd_f32(r);
+      if (c < 4) a->qmin[c] = f;
+    }
+    a->qrange = rd_f32(r);
+    a->qbits = rd_u8(r);
+    if (r->err) return r->err;
+    if (a->qbits < 1 || a->qbits > 30) return ORC_ERR_QUANT;
+  } else if (a->seq_type == 3) { /* AttributeOctahedronTransform.cs:39-42 */
+    a->qbits = rd_u8(r);
+    if (r->err) return r->err;
+    if (a->qbits < 2 || a->qbits > 30) return ORC_ERR_QUANT;
+  }
+  return ORC_OK;
+}
+static int store_values(orc_attr *a) {
+  uint32_t n = a->n_entries;
+  if (a->seq_type == 0) return ORC_OK;
+  if (a->seq_type == 2) {
+    a->out_bytes = (uint64_t)n * a->nc * 4;
+    a->out = (uint8_t *)malloc(a->out_bytes ? a->out_bytes : 1);
+    orc_dequantize(a->qints, n, a->nc, a->qmin, a->qrange, a->qbits, (float *)a->out);
+  } else if (a->seq_type == 3) {
+    a->out_bytes = (uint64_t)n * 12;
+    a->out = (uint8_t *)malloc(a->out_bytes ? a->out_bytes : 1);
+    orc_oct_to_unit(a->qints, n, a->qbits, (float *)a->out);
+  } else {
+    if (a->data_type < 1 || a->data_type > 6) return ORC_ERR_UNSUPPORTED; /* :137-138 */
+    int sz = dtype_len(a->data_type);
+    a->out_bytes = (uint64_t)n * a->nc * sz;
+    a->out = (uint8_t *)malloc(a->out_bytes ? a->out_bytes : 1);
+    orc_narrow(a->qints, (uint64_t)n * a->nc, a->data_type, a->out);
+  }
+  return ORC_OK;
+}
+
+static int decode_impl(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps_in, int n_maps_in, orc_result *res) {
+  rd_t r = {buf, len, 0, 0};
+  /* header: D/IO/DracoDecoder.cs:44-64 */
+  if (!rd_need(&r, 5)) return ORC_ERR_EOF;
+  if (memcmp(buf, "DRACO", 5) != 0) return ORC_ERR_MAGIC;
+  r.pos = 5;
+  res->ver_major = rd_u8(&r);
+  res->ver_minor = rd_u8(&r);
+  res->geom_type = rd_u8(&r);
+  res->method = rd_u8(&r);
+  res->flags = rd_u16(&r);
+  if (r.err) return r.err;
+  if (res->ver_major != 2 || res->ver_minor != 2) return ORC_ERR_UNSUPPORTED; /* build targets v2.2 (Appendix A) */
+  if (res->flags & 0x8000) skip_metadata(&r);                                  /* :26-29 */
+  if (r.err) return r.err;
+  const orc_mesh_maps *maps = maps_in;
+  int n_maps = n_maps_in;
+  int eb = 0;
+  if (res->geom_type == 0) { /* point cloud: B-1, upstream sequential container */
+    if (res->method != 0) return ORC_ERR_UNSUPPORTED; /* kd-tree coding: absent from the reference */
+    int32_t np = rd_i32(&r);
+    if (r.err) return r.err;
+    if (np < 0) return ORC_ERR_ATTR;
+    res->n_points = (uint32_t)np;
+  } else if (res->geom_type == 1) {
+    if (res->method == 0) {
+      int st = orc_seq_mesh_connectivity(buf, len, &r.pos, res);
+      if (st) return st;
+    } else if (res->method == 1) {
+      uint8_t tt = rd_u8(&r); /* DracoDecoder.cs:80 */
+      if (r.err) return r.err;
+      int st = orc_eb_decode_connectivity(buf, len, &r.pos, tt, res);
+      if (st) return st;
+      eb = 1;
+    } else
+      return ORC_ERR_UNSUPPORTED;
+  } else
+    return ORC_ERR_UNSUPPORTED;
+
+  /* ATTRIBUTES: D/IO/ConnectivityDecoder.cs:16-44 */
+  res->attr_section_off = r.pos;
+  int n_dec = rd_u8(&r);
+  if (r.err) return r.err;
+  res->n_decoders = n_dec;
+  uint8_t *ids = (uint8_t *)calloc((size_t)(n_dec ? n_dec : 1), 3);
+  int status = ORC_OK;
+  if (eb) { /* DEC_ID: MeshEdgeBreakerDecoder.cs:642-662 */
+    for (int i = 0; i < n_dec; ++i) {
+      ids[3 * i] = rd_u8(&r);
+      ids[3 * i + 1] = rd_u8(&r);
+      ids[3 * i + 2] = rd_u8(&r);
+    }
+    if (r.err) status = r.err;
+    if (!status && !maps) {
+      status = orc_eb_build_maps(res, ids, n_dec);
+      maps = res->maps;
+      n_maps = res->n_maps;
+    }
+  }
+  /* DEC_DATA: AttributesDecoder.cs:19-63 + SequentialAttributeDecodersController.cs:16-27 */
+  int cap = 0;
+  int *dec_first = (int *)calloc((size_t)(n_dec ? n_dec : 1), sizeof(int));
+  int *dec_count = (int *)calloc((size_t)(n_dec ? n_dec : 1), sizeof(int));
+  for (int d = 0; d < n_dec && !status; ++d) {
+    uint64_t na = rd_varint(&r);
+    if (r.err) { status = r.err; break; }
+    if (na > (len - r.pos)) { status = ORC_ERR_EOF; break; }
+    dec_first[d] = res->n_attrs;
+    dec_count[d] = (int)na;
+    if (res->n_attrs + (int)na > cap) {
+      cap = (res->n_attrs + (int)na) * 2;
+      res->attrs = (orc_attr *)realloc(res->attrs, (size_t)cap * sizeof(orc_attr));
+    }
+    for (uint64_t i = 0; i < na; ++i) {
+      orc_attr *a = &res->attrs[res->n_attrs];
+      memset(a, 0, sizeof *a);
+      a->decoder_id = d;
+      a->scheme = -1;
+      a->pred_method = -2;
+      a->transform = -1;
+      a->att_type = rd_u8(&r);
+      a->data_type = rd_u8(&r);
+      a->nc = rd_u8(&r);
+      a->normalized = rd_u8(&r) != 0;
+      a->unique_id = (uint32_t)rd_varint(&r);
+      res->n_attrs++;
+      if (r.err) { status = r.err; break; }
+      if (a->att_type >= 5 || a->data_type == 0 || a->data_type >= 12 || a->nc == 0) { status = ORC_ERR_ATTR; break; }
+    }
+    for (int i = 0; i < (int)na && !status; ++i) {
+      orc_attr *a = &res->attrs[dec_first[d] + i];
+      a->seq_type = rd_u8(&r);
+      if (r.err) { status = r.err; break; }
+      if (a->seq_type > 3) { status = ORC_ERR_UNSUPPORTED; break; } /* controller :78 */
+      if (a->seq_type == 2 && a->data_type != 9) status = ORC_ERR_ATTR; /* SequentialQuantizationAttributeDecoder.cs:13 */
+      if (a->seq_type == 3 && (a->data_type != 9 || a->nc != 3)) status = ORC_ERR_ATTR; /* Normal :14-15 */
+      a->nc_portable = (a->seq_type == 3) ? 2 : a->nc; /* AttributeOctahedronTransform.cs:23-26, B-8 */
+      if (a->nc > 4 && a->seq_type == 2) status = ORC_ERR_UNSUPPORTED; /* q-min array is float[4] here */
+    }
+  }
+  /* DEC_PAYLOAD: AttributesDecoder.cs:65-70 -- all PORTABLE of a decoder, then all XFORM_PARAMS */
+  for (int d = 0; d < n_dec && !status; ++d) {
+    uint32_t n_entries = res->n_points; /* LinearSequencer.cs:7-13 (B-2) */
+    if (eb) {
+      if (!maps || d >= n_maps) { status = ORC_ERR_MAPS; break; }
+      n_entries = (uint32_t)maps[d].n_entries; /* MeshAttributeIndicesEncodingObserver.cs:14-21 */
+    }
+    for (int i = 0; i < dec_count[d] && !status; ++i) {
+      orc_attr *a = &res->attrs[dec_first[d] + i];
+      a->n_entries = n_entries;
+      status = decode_portable(&r, res, a, maps, n_maps);
+    }
+    for (int i = 0; i < dec_count[d] && !status; ++i) status = decode_xform_params(&r, &res->attrs[dec_first[d] + i]);
+    for (int i = 0; i < dec_count[d] && !status; ++i) status = store_values(&res->attrs[dec_first[d] + i]);
+  }
+  res->end_off = r.pos;
+  free(ids);
+  free(dec_first);
+  free(dec_count);
+  return status;
+}
+
+int orc_decode(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps, int n_maps, orc_result **out) {
+  orc_result *res = (orc_result *)calloc(1, sizeof *res);
+  res->status = decode_impl(buf, len, maps, n_maps, res);
+  *out = res;
+  return res->status;
+}
+
+void orc_free(orc_result *r) {
+  if (!r) return;
+  for (int i = 0; i < r->n_attrs; ++i) {
+    free(r->attrs[i].symbols);
+    free(r->attrs[i].corr);
+    free(r->attrs[i].qints);
+    free(r->attrs[i].out);
+  }
+  for (int i = 0; i < r->n_maps; ++i) {
+    free((void *)r->maps[i].opposite);
+    free((void *)r->maps[i].corner_to_vertex);
+    free((void *)r->maps[i].data_to_corner);
+    free((void *)r->maps[i].vertex_to_data);
+  }
+  free(r->maps);
+  free(r->attrs);
+  free(r->faces);
+  free(r);
+}
+
+int orc_decode_bench(const uint8_t *buf, uint64_t len, uint64_t *points, uint64_t *out_bytes, uint64_t *checksum) {
+  orc_result *res = NULL;
+  int st = orc_decode(buf, len, NULL, 0, &res);
+  if (!st) {
+    if (points) *points += res->n_points;
+    for (int i = 0; i < res->n_attrs; ++i) {
+      if (out_bytes) *out_bytes += res->attrs[i].out_bytes;
+      if (checksum && res->attrs[i].out_bytes) {
+        /* cheap touch of the output so the work cannot be elided */
+        const uint8_t *o = res->attrs[i].out;
+        *checksum += o[0] + o[res->attrs[i].out_bytes - 1] + o[res->attrs[i].out_bytes / 2];
+      }
+    }
+  }
+  orc_free(res);
+  return st;
+}

@@ -1,0 +1,115 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from draco_sharp_b200 import _native as N
+from draco_sharp_b200 import synth_gen as G
+
+from common import cloud, compare_with_oracle, gpu_decode_all
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("scheme", [1, 0, -1])
+def test_positions_small_sizes(gpu_decoder, scheme):
+    bufs = [cloud(n, seed=10 + n, scheme=scheme) for n in (0, 1, 2, 3, 4, 5, 7, 8, 33, 100, 1000, 4099)]
+    gpu = gpu_decode_all(gpu_decoder, bufs)
+    assert compare_with_oracle(gpu, bufs) == len(bufs)
+
+
+@pytest.mark.parametrize("scheme", [1, 0, -1])
+def test_positions_normals_colors(gpu_decoder, scheme):
+    bufs = [cloud(n, seed=77 + n, scheme=scheme, normal_bits=10, colors=1) for n in (1, 6, 257, 5000)]
+    bufs += [cloud(3000, seed=5, scheme=scheme, pos_bits=0, normal_bits=7, colors=0),
+             cloud(3000, seed=6, scheme=scheme, pos_bits=0, normal_bits=0, colors=1),
+             cloud(2000, seed=7, scheme=scheme, pos_bits=22, normal_bits=12, colors=1),
+             cloud(2000, seed=8, scheme=scheme, pos_bits=1, normal_bits=2, colors=1)]
+    gpu = gpu_decode_all(gpu_decoder, bufs)
+    assert compare_with_oracle(gpu, bufs) == len(bufs)
+
+
+def test_config2_shape_batch(gpu_decoder):
+    """BASELINE config 2 shape at a size the oracle finishes in seconds: 48 clouds x 100k points, 14-bit."""
+    bufs = [cloud(100000, seed=0xD5AC0000 + k, scheme=1) for k in range(48)]
+    gpu = gpu_decode_all(gpu_decoder, bufs, want=("out", "qints"))
+    assert compare_with_oracle(gpu, bufs) == len(bufs)
+
+
+def test_ragged_batch_mixed_schemes(gpu_decoder):
+    rng = np.random.default_rng(3)
+    bufs = []
+    for k in range(40):
+        n = int(rng.integers(0, 20000))
+        bufs.append(cloud(n, seed=1000 + k, scheme=int(rng.integers(-1, 2)), normal_bits=int(rng.choice([0, 8, 10])),
+                          colors=int(rng.integers(0, 2)), pos_bits=int(rng.choice([0, 8, 11, 14, 16, 20]))))
+    gpu = gpu_decode_all(gpu_decoder, bufs)
+    assert compare_with_oracle(gpu, bufs) == len(bufs)
+
+
+def test_wide_alphabets(gpu_decoder):
+    """Precisions 15..20 (u32 tables, global-memory tables): large deltas over wide quantisation."""
+    bufs = [cloud(60000, seed=40 + i, scheme=1, pos_bits=pb, rho=rho)
+            for i, (pb, rho) in enumerate([(16, (999, 1000)), (20, (9999, 10000)), (18, (9999, 10000)), (14, (199, 200))])]
+    gpu = gpu_decode_all(gpu_decoder, bufs)
+    assert compare_with_oracle(gpu, bufs) == len(bufs)
+
+
+def test_malformed_buffers_status_parity(gpu_decoder):
+    """Truncated and bit-flipped buffers: per-buffer status codes (the reference's exception sites) must agree
+    with the oracle, and one bad buffer must not poison its neighbours."""
+    rng = np.random.default_rng(11)
+    good = [cloud(3000, seed=90, scheme=1, normal_bits=10, colors=1), cloud(3000, seed=91, scheme=0, colors=1)]
+    bufs = []
+    for g in good:
+        bufs.append(g)
+        for cut in (0, 3, 5, 9, 11, 16, 30, 40, 60, 100, len(g) // 2, len(g) - 9, len(g) - 1):
+            bufs.append(g[:cut].copy())
+        for _ in range(60):
+            b = g.copy()
+            pos = int(rng.integers(0, min(len(b), 1400)))
+            b[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            bufs.append(b)
+    gpu = gpu_decode_all(gpu_decoder, bufs, want=("out",))
+    n_ok = compare_with_oracle(gpu, bufs)
+    assert n_ok >= 2
+
+
+def test_full_size_checksums(gpu_decoder):
+    """Size-independent property at a large batch: the word checksum of every decoded attribute equals the
+    checksum of the generator's source values pushed through the reference dequantisation formula."""
+    sp = G.make_spec(100000, seed=0xD5AC0000, scheme=1, colors=1)
+    arena, offs, lens, sums, schemes, used = G.synth_batch(sp, 256)
+    batch = gpu_decoder.index_arena(arena, offs, lens)
+    out, _ = gpu_decoder.decode(batch)
+    assert batch.points == 256 * 100000
+    for k in range(256):
+        assert batch.status(k) == 0
+        a0 = batch.attr_info(k, 0)
+        a1 = batch.attr_info(k, 1)
+        assert G.word_checksum(out[a0.out_off: a0.out_off + a0.out_bytes]) == int(sums[k, 0])
+        assert G.word_checksum(out[a1.out_off: a1.out_off + a1.out_bytes]) == int(sums[k, 2])
+    st = gpu_decoder.stats()
+    assert st.n_launches >= 1
+    batch.free()
+
+
+def test_resident_decode_into_torch_tensor(gpu_decoder):
+    """Split form: upload once, decode into caller-owned device memory (a torch tensor), twice, same bytes."""
+    import torch
+    sp = G.make_spec(20000, seed=5, scheme=-1, normal_bits=10, colors=1)
+    arena, offs, lens, sums, schemes, used = G.synth_batch(sp, 32)
+    batch = gpu_decoder.index_arena(arena, offs, lens)
+    gpu_decoder.upload(batch)
+    out = torch.zeros(batch.out_bytes, dtype=torch.uint8, device="cuda")
+    gpu_decoder.decode_resident(batch, dev_out=out.data_ptr())
+    first = out.cpu().numpy().copy()
+    out.zero_()
+    gpu_decoder.decode_resident(batch, dev_out=out.data_ptr())
+    assert np.array_equal(first, out.cpu().numpy())
+    bufs = [arena[int(o): int(o + l)] for o, l in zip(offs, lens)]
+    host, _ = gpu_decoder.decode(gpu_decoder.index(bufs))
+    for k in range(32):
+        for a in range(3):
+            ai = batch.attr_info(k, a)
+            assert np.array_equal(first[ai.out_off: ai.out_off + ai.out_bytes], host[ai.out_off: ai.out_off + ai.out_bytes])
+    batch.free()
