@@ -27,7 +27,7 @@
 
 namespace {
 
-constexpr uint64_t kFrontPad = 64;     // bytes before the first buffer in the device input arena
+constexpr uint64_t kFrontPad = 256;    // bytes before the first buffer in the device input arena
 constexpr uint64_t kBackPad = 64;      // bytes after the last one (16-byte window loads may overrun)
 constexpr uint32_t kNumSMsDefault = 148;
 constexpr uint32_t kSmemPerSM = 227 * 1024;
@@ -59,7 +59,7 @@ struct Group {            // one kernel launch (or a few, for global tables)
   int kind;               // 0 raw, 1 tag, 2 serial post, 3 para, 4 copy
   int ncp;
   bool wide, table_global;
-  uint32_t compact, prec_bits, entries, lut_shift, slot_bytes, lanes;
+  uint32_t compact, prec_bits, entries, lut_shift, lut_bytes, ent_bytes, lanes, zig, mode;
   uint64_t total_symbols, max_bytes;
   uint32_t max_entries;
   std::vector<uint32_t> order;
@@ -480,71 +480,85 @@ uint32_t ceil_log2(uint32_t v) {
 }
 
 struct RawKey {
-  int ncp, wide, compact, prec, size_class;
+  int ncp, wide, compact, prec, size_class, zig, mode;
   bool operator<(const RawKey &o) const {
-    return std::tie(ncp, wide, compact, prec, size_class) < std::tie(o.ncp, o.wide, o.compact, o.prec, o.size_class);
+    return std::tie(ncp, wide, compact, prec, size_class, zig, mode) <
+           std::tie(o.ncp, o.wide, o.compact, o.prec, o.size_class, o.zig, o.mode);
   }
 };
 
-uint32_t slot_bytes_for(const Group &g, uint32_t k) {
-  const uint32_t nb = (1u << g.prec_bits) >> k;
-  const uint32_t words = nb + 1u + (g.compact ? 2u * g.entries : g.entries);
-  return (uint32_t)align_up((uint64_t)words * (g.wide ? 4u : 2u), 16);
+uint32_t ent_bytes_for(const Group &g) {
+  const uint32_t sz = g.wide ? 4u : 2u;
+  return (uint32_t)align_up((uint64_t)(g.entries + 2u) * sz + (g.compact ? (uint64_t)g.entries * sz : 0ull), 16);
 }
+uint32_t lut_bytes_for(const Group &g, uint32_t k) { return ((1u << g.prec_bits) >> k) * (g.wide ? 4u : 2u); }
+uint32_t lane_bytes_for(const Group &g, uint32_t k) { return lut_bytes_for(g, k) + ent_bytes_for(g) + DCB_RING_BYTES; }
 
 // Choose LUT granularity, lanes per warp-CTA and the table home for every rANS group of a shard so
 // that as many streams as possible are resident at once: the chains are serial, so the batch time
 // is (waves) x (longest chain) and a second wave doubles it.
 void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms) {
-  const uint32_t budget = kSmemPerSM - 8 * kSmemPerCtaReserve;
-  std::vector<uint32_t> per_sm(gs.size()), kmin(gs.size()), kcap(gs.size());
+  const uint32_t budget = kSmemPerSM - 10 * kSmemPerCtaReserve;
+  std::vector<uint32_t> per_sm(gs.size()), kcap(gs.size());
   for (size_t i = 0; i < gs.size(); ++i) {
     Group &g = *gs[i];
     per_sm[i] = std::min<uint32_t>(1024u, (uint32_t)((g.order.size() + num_sms - 1) / num_sms));
     const uint32_t le = ceil_log2(std::max(2u, g.entries));
+    const uint32_t kfloor = g.wide ? 2u : 1u;
     // finest LUT: ~4 buckets per table entry; coarsest: ~1 bucket per 4 entries (>= 16 buckets)
-    kmin[i] = g.prec_bits > le + 2 ? g.prec_bits - le - 2 : 0;
-    kcap[i] = std::max(kmin[i], std::min<uint32_t>(g.prec_bits - 4, g.prec_bits > le ? g.prec_bits - le + 2 : 2));
-    g.lut_shift = kmin[i];
+    uint32_t kmin = g.prec_bits > le + 2 ? g.prec_bits - le - 2 : 0;
+    kmin = std::max(kmin, kfloor);
+    kcap[i] = std::max(kmin, std::min<uint32_t>(g.prec_bits - 4, g.prec_bits > le ? g.prec_bits - le + 2 : 2));
+    g.lut_shift = kmin;
   }
-  for (;;) {
+  auto total_for = [&]() {
     uint64_t total = 0;
-    for (size_t i = 0; i < gs.size(); ++i) total += (uint64_t)per_sm[i] * slot_bytes_for(*gs[i], gs[i]->lut_shift);
-    if (total <= budget) break;
+    for (size_t i = 0; i < gs.size(); ++i) total += (uint64_t)per_sm[i] * lane_bytes_for(*gs[i], gs[i]->lut_shift);
+    return total;
+  };
+  for (;;) {
+    if (total_for() <= budget) break;
     int best = -1;
     uint64_t best_share = 0;
     for (size_t i = 0; i < gs.size(); ++i) {
       Group &g = *gs[i];
       if (g.lut_shift >= kcap[i]) continue;
-      const uint64_t share = (uint64_t)per_sm[i] * ((1u << g.prec_bits) >> g.lut_shift) * (g.wide ? 4u : 2u);
+      const uint64_t share = (uint64_t)per_sm[i] * lut_bytes_for(g, g.lut_shift);
       if (share > best_share) { best_share = share; best = (int)i; }
     }
     if (best < 0) break;
     gs[best]->lut_shift++;
   }
   // share of the SM each group may use when not everything fits: proportional to its demand
-  uint64_t total = 0;
-  for (size_t i = 0; i < gs.size(); ++i) total += (uint64_t)per_sm[i] * slot_bytes_for(*gs[i], gs[i]->lut_shift);
+  const uint64_t total = total_for();
   for (size_t i = 0; i < gs.size(); ++i) {
     Group &g = *gs[i];
-    g.slot_bytes = slot_bytes_for(g, g.lut_shift);
-    g.table_global = g.slot_bytes > 48 * 1024;
+    g.ent_bytes = ent_bytes_for(g);
+    g.lut_bytes = lut_bytes_for(g, g.lut_shift);
+    const uint32_t lane_bytes = lane_bytes_for(g, g.lut_shift);
+    g.table_global = lane_bytes > 40 * 1024;
     if (g.table_global) {
-      // tables in HBM/L2: LUT ~ 2 buckets per entry, any size
+      // tables in HBM/L2 (u32 entries): LUT ~ 2 buckets per entry, any size
+      g.wide = true;
       const uint32_t le = ceil_log2(std::max(2u, g.entries));
-      g.lut_shift = g.prec_bits > le + 1 ? g.prec_bits - le - 1 : 0;
-      g.slot_bytes = slot_bytes_for(g, g.lut_shift);
+      g.lut_shift = std::max<uint32_t>(2u, g.prec_bits > le + 1 ? g.prec_bits - le - 1 : 0);
+      g.ent_bytes = ent_bytes_for(g);
+      g.lut_bytes = lut_bytes_for(g, g.lut_shift);
       g.lanes = 32;
       continue;
     }
     uint32_t want = per_sm[i];
     if (total > budget) {
-      const uint64_t my = (uint64_t)budget * ((uint64_t)per_sm[i] * g.slot_bytes) / total;
-      want = std::max<uint32_t>(1u, (uint32_t)(my / g.slot_bytes));
+      const uint64_t my = (uint64_t)budget * ((uint64_t)per_sm[i] * lane_bytes) / total;
+      want = std::max<uint32_t>(1u, (uint32_t)(my / lane_bytes));
     }
-    const uint32_t ctas = (want + 31) / 32;
-    g.lanes = std::min<uint32_t>(32u, (want + ctas - 1) / ctas);
-    while (g.lanes > 1 && (uint64_t)g.lanes * g.slot_bytes > kSmemPerSM - kSmemPerCtaReserve) --g.lanes;
+    uint32_t ctas = (want + 31) / 32;
+    if (const char *e = getenv("DCB_CTAS_PER_SM")) ctas = std::max<uint32_t>(ctas, (uint32_t)atoi(e));  // experiments
+    g.lanes = std::max<uint32_t>(1u, std::min<uint32_t>(32u, (want + ctas - 1) / ctas));
+    // a CTA must fit an SM (with its alignment slack) and, for u16 tables, address its entries with 16 bits
+    while (g.lanes > 1 && ((uint64_t)g.lanes * lane_bytes + g.lut_bytes + 256 > kSmemPerSM - kSmemPerCtaReserve ||
+                           (!g.wide && (uint64_t)g.lanes * g.ent_bytes > 65535)))
+      --g.lanes;
   }
 }
 
@@ -645,7 +659,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   // ---- Tagged streams: decode tags, resume the walks behind their bit areas ----
   for (;;) {
     Group g{};
-    g.kind = 1; g.ncp = 1; g.wide = false; g.compact = 0; g.prec_bits = 12; g.entries = 0;
+    g.kind = 1; g.ncp = 1; g.wide = false; g.compact = 0; g.prec_bits = 12; g.entries = 0; g.zig = 0; g.mode = 0;
     std::vector<uint32_t> blocked;
     for (size_t bi = 0; bi < sh.walks.size(); ++bi) {
       const BufWalk &w = sh.walks[bi];
@@ -669,8 +683,9 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(sh.d_order, g.order.data(), g.order.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(sh.d_order + g.order.size(), blocked.data(), blocked.size() * 4, cudaMemcpyHostToDevice, st));
-    RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.slot_bytes, g.lut_shift, dump, 0};
-    CUDA_TRY(dcb_launch_rans_tag(L, A, g.lanes * g.slot_bytes, st));
+    RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.lut_bytes, g.ent_bytes, g.entries,
+                 g.lut_shift, dump, 0, 0, 0};
+    CUDA_TRY(dcb_launch_rans_tag(L, A, st));
     CUDA_TRY(dcb_launch_resolve(A, sh.d_walks, sh.d_order + g.order.size(), (uint32_t)blocked.size(), sh.d_streams, st));
     stats.n_launches += 2;
     stats.n_streams += (int32_t)g.order.size();
@@ -704,14 +719,20 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       if (s.scheme == SCHEME_RAW) {
         RawKey key;
         key.ncp = s.ncp;
-        key.wide = (s.prec_bits > 15 || s.num_symbols > 65535u) ? 1 : 0;
         key.compact = (2ull * s.n_active + 1 < s.num_symbols) ? 1 : 0;
         key.prec = s.prec_bits;
         const uint32_t entries = key.compact ? s.n_active : s.num_symbols;
+        key.wide = (s.prec_bits > 15 || s.num_symbols > 65535u || (uint64_t)entries * (key.compact ? 4 : 2) + 4 > 60000u) ? 1 : 0;
         key.size_class = (int)ceil_log2(std::max(16u, entries));
+        key.zig = s.zigzag ? 1 : 0;
+        key.mode = 0;
+        if (s.recon == RECON_DELTA_WRAP && s.store == STORE_DEQUANT) key.mode = 1;
+        else if (s.recon == RECON_DELTA_WRAP && s.store == STORE_NARROW && dcb_dtype_len(s.data_type) == 1) key.mode = 2;
+        else if (s.recon == RECON_DELTA_OCT_CANON && s.store == STORE_OCT_UNIT) key.mode = 3;
         Group &g = raw[key];
         if (g.order.empty()) {
           g.kind = 0; g.ncp = key.ncp; g.wide = key.wide != 0; g.compact = (uint32_t)key.compact; g.prec_bits = (uint32_t)key.prec;
+          g.zig = (uint32_t)key.zig; g.mode = (uint32_t)key.mode;
         }
         g.entries = std::max(g.entries, entries);
         g.total_symbols += (uint64_t)s.n_entries * s.ncp;
@@ -770,35 +791,41 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     const bool is_dom = timed && dev_index == 0 && g == dom;
     if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (g->table_global) {
-      const uint64_t per = std::max<uint64_t>(1, kTabArenaBudget / g->slot_bytes);
-      const uint64_t chunk = std::min<uint64_t>(per, n);
-      if (sh.tab_cap < chunk * g->slot_bytes) {
+      const uint64_t slot_bytes = (uint64_t)g->lut_bytes + g->ent_bytes;
+      // chunk: a multiple of 32 slots whose tables fit the scratch budget and 32-bit entry offsets
+      uint64_t per = std::max<uint64_t>(32, std::min<uint64_t>(kTabArenaBudget / slot_bytes, 0xF0000000ull / slot_bytes) / 32 * 32);
+      const uint64_t chunk = std::min<uint64_t>(per, align_up(n, 32));
+      if (sh.tab_cap < chunk * slot_bytes) {
         cudaFree(sh.d_tab);
         sh.d_tab = nullptr;
         sh.tab_cap = 0;
-        CUDA_TRY(cudaMalloc(&sh.d_tab, chunk * g->slot_bytes));
-        sh.tab_cap = chunk * g->slot_bytes;
-        A.tab = sh.d_tab;
+        CUDA_TRY(cudaMalloc(&sh.d_tab, chunk * slot_bytes));
+        sh.tab_cap = chunk * slot_bytes;
       }
+      A.tab = sh.d_tab;
       for (uint64_t o = 0; o < n; o += chunk) {
         RansLaunch L{sh.d_streams, sh.d_order + g->order_off + o, (uint32_t)std::min<uint64_t>(chunk, n - o), 32,
-                     g->slot_bytes, g->lut_shift, dump, g->compact};
-        CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, true, A, 0, st));
+                     g->lut_bytes, g->ent_bytes, g->entries, g->lut_shift, dump, g->compact, g->zig, 0};
+        CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, true, A, st));
         stats.n_launches++;
       }
     } else {
-      RansLaunch L{sh.d_streams, sh.d_order + g->order_off, n, g->lanes, g->slot_bytes, g->lut_shift, dump, g->compact};
-      CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, g->lanes * g->slot_bytes, st));
+      RansLaunch L{sh.d_streams, sh.d_order + g->order_off, n, g->lanes, g->lut_bytes, g->ent_bytes, g->entries,
+                   g->lut_shift, dump, g->compact, g->zig, g->mode};
+      CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
       stats.n_launches++;
     }
     if (is_dom) {
       CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
       stats.lanes_per_warp = (int32_t)g->lanes;
-      stats.smem_per_stream = g->slot_bytes;
-      const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, (kSmemPerSM) / std::max<uint32_t>(1u, g->lanes * g->slot_bytes + kSmemPerCtaReserve))) * g->lanes;
+      stats.smem_per_stream = (uint64_t)g->lut_bytes + g->ent_bytes + DCB_RING_BYTES;
+      RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->ent_bytes, g->entries, g->lut_shift, 0, g->compact, g->zig, g->mode};
+      const uint32_t cta_smem = dcb_rans_smem_bytes(Ls, g->table_global) + kSmemPerCtaReserve;
+      const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, kSmemPerSM / cta_smem)) * g->lanes;
       stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);
-      snprintf(stats.dominant_name, sizeof stats.dominant_name, "rans_raw_fused<ncp=%d,%s,%s,k=%u>", g->ncp,
-               g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->lut_shift);
+      snprintf(stats.dominant_name, sizeof stats.dominant_name, "rans_raw_fused<ncp=%d,%s,%s,mode=%u,k=%u,%s>", g->ncp,
+               g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->mode, g->lut_shift,
+               g->compact ? "compact" : "dense");
     }
     stats.n_streams += (int32_t)n;
   }

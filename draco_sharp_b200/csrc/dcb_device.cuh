@@ -158,12 +158,13 @@ struct PostParams {
 
 // Store ONE entry (NCP portable ints in v) at entry index e of the attribute output.
 template <int NCP>
-__device__ __forceinline__ void store_entry(const PostParams &pp, uint8_t *optr, uint64_t e, const int32_t *v) {
-  if (pp.store == STORE_DEQUANT) {
+__device__ __forceinline__ void store_entry(const PostParams &pp, int store, int dsize, uint8_t *optr, uint64_t e,
+                                            const int32_t *v) {
+  if (store == STORE_DEQUANT) {
     float *o = reinterpret_cast<float *>(optr) + e * NCP;
 #pragma unroll
     for (int c = 0; c < NCP; ++c) o[c] = pp.dequant(v[c], c);
-  } else if (pp.store == STORE_OCT_UNIT) {
+  } else if (store == STORE_OCT_UNIT) {
     if (NCP == 2) {
       float ox, oy, oz;
       oct_to_unit(v[0], v[NCP - 1], pp.oct_scale, ox, oy, oz);
@@ -171,11 +172,11 @@ __device__ __forceinline__ void store_entry(const PostParams &pp, uint8_t *optr,
       o[0] = ox; o[1] = oy; o[2] = oz;
     }
   } else {
-    if (pp.dsize == 1) {
+    if (dsize == 1) {
       uint8_t *o = optr + e * NCP;
 #pragma unroll
       for (int c = 0; c < NCP; ++c) o[c] = (uint8_t)v[c];
-    } else if (pp.dsize == 2) {
+    } else if (dsize == 2) {
       uint16_t *o = reinterpret_cast<uint16_t *>(optr) + e * NCP;
 #pragma unroll
       for (int c = 0; c < NCP; ++c) o[c] = (uint16_t)v[c];
@@ -191,8 +192,9 @@ __device__ __forceinline__ void store_entry(const PostParams &pp, uint8_t *optr,
 // occupies 4 * bytes_per_entry bytes starting on a 16-byte boundary whenever that size is a multiple
 // of 16 (attribute outputs start on 128-byte boundaries), so it is written as 128-bit stores.
 template <int NCP>
-__device__ __forceinline__ void store_group4(const PostParams &pp, uint8_t *optr, uint64_t e4, const int32_t (*v)[NCP]) {
-  if (pp.store == STORE_DEQUANT) {
+__device__ __forceinline__ void store_group4(const PostParams &pp, int store, int dsize, uint8_t *optr, uint64_t e4,
+                                             const int32_t (*v)[NCP]) {
+  if (store == STORE_DEQUANT) {
     float f[4 * NCP];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -201,7 +203,7 @@ __device__ __forceinline__ void store_group4(const PostParams &pp, uint8_t *optr
     float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(optr) + e4 * NCP);
 #pragma unroll
     for (int k = 0; k < NCP; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-  } else if (pp.store == STORE_OCT_UNIT) {
+  } else if (store == STORE_OCT_UNIT) {
     if (NCP == 2) {
       float f[12];
 #pragma unroll
@@ -210,12 +212,12 @@ __device__ __forceinline__ void store_group4(const PostParams &pp, uint8_t *optr
 #pragma unroll
       for (int k = 0; k < 3; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
     }
-  } else if (pp.dsize == 4) {
+  } else if (dsize == 4) {
     int4 *o = reinterpret_cast<int4 *>(reinterpret_cast<int32_t *>(optr) + e4 * NCP);
     const int32_t *f = &v[0][0];
 #pragma unroll
     for (int k = 0; k < NCP; ++k) o[k] = make_int4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-  } else if (pp.dsize == 1) {
+  } else if (dsize == 1) {
     // 4 entries x NCP bytes = NCP 32-bit words
     uint32_t *o = reinterpret_cast<uint32_t *>(optr + e4 * NCP);
     const int32_t *f = &v[0][0];
@@ -233,200 +235,270 @@ __device__ __forceinline__ void store_group4(const PostParams &pp, uint8_t *optr
 }
 
 // ---------------------------------------------------------------------------------------------
-// compressed-byte window: bytes are consumed from the END of the payload towards its start
-// (RAnsDecoder.cs:60 `Buffer[--BufferOffset]`).  `win` holds the next bytes MSB-first; it is
-// refilled from a 16-byte chunk held in registers while the following chunk is already in flight.
+// rANS lane: everything one lane needs to run one stream's chain.
+//
+// Shared-memory layout of a warp-CTA (all regions sized for `lanes` lanes, uniform per launch):
+//   LUT region     lane l at  lut0 + l * lut_bytes        lut_bytes = nb * sizeof(T), power of two, region
+//                                                          aligned to lut_bytes  ->  address = base | index
+//   ring region    lane l at  ring0 + l * 128             128-byte aligned       ->  address = base | offset
+//   entry region   lane l at  ent0 + l * ent_bytes        cum[ne + 2] then val[ne] (T each)
+// LUT entries hold the byte offset (from ent0) of cum[i] for the first table entry i that owns part
+// of the bucket, so the second-level loads need no index arithmetic.  T = uint16_t needs 2^prec and
+// lanes * ent_bytes below 65536, else uint32_t.
+//
+// compressed bytes: rANS consumes the payload from its END towards its start (RAnsDecoder.cs:60
+// `Buffer[--BufferOffset]`).  Every lane owns a 128-byte ring, direct-mapped by arena address (byte g
+// lives at ring[g % 128]); 16-byte chunks are pulled ahead of the read position with per-lane
+// cp.async (LDGSTS), so the per-symbol byte fetch is two aligned LDS + one funnel shift.
 // ---------------------------------------------------------------------------------------------
-struct ByteWin {
-  uint64_t win;
-  int nwin;
-  uint32_t c0, c1, c2, c3;  // current chunk; c3 = highest addresses = consumed first
-  int ncur;
-  uint4 nxt;
-  const uint8_t *arena;
-  int64_t next_addr;
+#ifndef DCB_RING_BYTES
+#define DCB_RING_BYTES 128u
+#endif
 
-  __device__ __forceinline__ uint4 load16(int64_t a) const {
-    a = a < 0 ? 0 : a;
-    return __ldg(reinterpret_cast<const uint4 *>(arena + a));
-  }
-  __device__ __forceinline__ void refill() {
-    if (nwin <= 4) {
-      const uint32_t w = c3;
-      c3 = c2; c2 = c1; c1 = c0;
-      --ncur;
-      win |= (uint64_t)w << (32 - 8 * nwin);
-      nwin += 4;
-      if (ncur == 0) {
-        c0 = nxt.x; c1 = nxt.y; c2 = nxt.z; c3 = nxt.w;
-        ncur = 4;
-        nxt = load16(next_addr);
-        next_addr -= 16;
-      }
-    }
-  }
-  // end = arena offset one past the last unread byte
-  __device__ __forceinline__ void init(const uint8_t *arena_, uint64_t end) {
-    arena = arena_;
-    const int64_t a0 = end == 0 ? 0 : (int64_t)((end - 1) & ~15ull);
-    const uint4 c = load16(a0);
-    c0 = c.x; c1 = c.y; c2 = c.z; c3 = c.w;
-    ncur = 4;
-    nxt = load16(a0 - 16);
-    next_addr = a0 - 32;
-    win = 0;
-    nwin = 0;
-    int drop = (int)(a0 + 16 - (int64_t)end);
-    while (drop >= 4) {
-      c3 = c2; c2 = c1; c1 = c0;
-      --ncur;
-      drop -= 4;
-    }
-    refill();
-    if (drop) { win <<= 8 * drop; nwin -= drop; }
-    refill();
-  }
-};
-
-// ---------------------------------------------------------------------------------------------
-// per-lane probability table:
-//   lut[0..nb)   index of the symbol owning slot (b << lut_shift)
-//   cum[0..ne]   cumulative probability of table entry i (cum[ne] = 2^prec)
-//   sym[0..ne)   symbol id of entry i (compact tables only; dense tables index by symbol id)
-// T = uint16_t when 2^prec and the ids fit, else uint32_t.
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-struct LaneTable {
-  T *lut, *cum, *sym;
-};
-
-template <typename T>
-__device__ __forceinline__ void carve_table(uint8_t *base, uint32_t slot_bytes, uint32_t prec_bits, uint32_t lut_shift,
-                                            bool compact, LaneTable<T> &t, uint32_t &cap_entries) {
-  const uint32_t nb = (1u << prec_bits) >> lut_shift;
-  const uint32_t words = slot_bytes / sizeof(T);
-  cap_entries = words > nb + 1u ? (compact ? (words - nb - 1u) / 2u : (words - nb - 1u)) : 0u;
-  t.lut = reinterpret_cast<T *>(base);
-  t.cum = t.lut + nb;
-  t.sym = t.cum + cap_entries + 1u;
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
+  return v;
 }
 
-// Parse RANS_TABLE at d.table_off into the lane's table (RAnsSymbolDecoder.cs:12-51, RAnsDecoder.cs:69-88).
-template <typename T>
-__device__ int build_table(const uint8_t *arena, const StreamDesc &d, LaneTable<T> t, uint32_t lut_shift, bool compact,
-                           uint32_t cap_entries) {
-  uint64_t pos = d.table_off;
-  const uint64_t end = d.buf_end;
-  for (int i = 0; i < 10; ++i) {  // skip the num_symbols varint (value parsed by the indexer)
-    if (pos >= end) return DCB_ERR_EOF;
-    if (!(arena[pos++] & 0x80)) break;
-  }
-  const uint32_t ns = d.num_symbols;
-  const uint32_t prec = 1u << d.prec_bits;
-  if (!compact && ns > cap_entries) return DCB_ERR_TABLE;
-  uint64_t c = 0;
-  uint32_t ne = 0;
-  bool overflow = false;
-  for (uint32_t i = 0; i < ns; ++i) {
-    if (pos >= end) return DCB_ERR_EOF;
-    const uint32_t pd = arena[pos++];
-    const uint32_t token = pd & 3u;
-    if (token == 3u) {
-      const uint32_t off = pd >> 2;
-      if (i + off >= ns) return DCB_ERR_TABLE;
-      if (!compact)
-        for (uint32_t j = 0; j <= off; ++j) t.cum[i + j] = (T)(c > prec ? prec : c);
-      i += off;
-    } else {
-      uint32_t prob = pd >> 2;
-      for (uint32_t b = 0; b < token; ++b) {
-        if (pos >= end) return DCB_ERR_EOF;
-        prob |= (uint32_t)arena[pos++] << (8 * (b + 1) - 2);
-      }
-      if (compact) {
-        if (prob) {
-          if (c + prob > prec || ne >= cap_entries) overflow = true;
-          if (!overflow) {
-            t.cum[ne] = (T)c;
-            t.sym[ne] = (T)i;
-            ++ne;
-          }
-        }
-      } else {
-        if (c + prob > prec) overflow = true;
-        t.cum[i] = (T)(c > prec ? prec : c);
-      }
-      c += prob;
-    }
-  }
-  if (overflow || c != prec) return DCB_ERR_TABLE;
-  if (!compact) ne = ns;
-  t.cum[ne] = (T)prec;
-  const uint32_t nb = prec >> lut_shift;
-  uint32_t i = 0;
-  for (uint32_t b = 0; b < nb; ++b) {
-    const uint32_t slot = b << lut_shift;
-    while ((uint32_t)t.cum[i + 1] <= slot) ++i;
-    t.lut[b] = (T)i;
-  }
-  return DCB_OK;
-}
+// geometry of the tables of one launch (uniform over the grid)
+struct TableGeom {
+  uint32_t lut_bytes;   // per lane, power of two
+  uint32_t ent_bytes;   // per lane
+  uint32_t cap_entries; // table entries a lane can hold
+  uint32_t lut_shift;   // log2(slots per LUT bucket)
+  uint32_t compact;     // 1: entries = symbols with prob > 0 (+ value map), 0: entries = symbol ids
+  uint32_t zig;         // value map holds zig-zag decoded values (compact) / apply zig-zag (dense)
+};
 
-// rANS state of one lane
-struct RansState {
-  uint32_t x;     // state
-  uint32_t off;   // unread payload bytes (BufferOffset)
+template <typename T, bool GLOBAL>
+struct RansLane {
+  // state chain
+  uint32_t x;
+  uint32_t p1;          // low 32 bits of (arena offset of the next unread byte) = ptr - 1
+  // constants
   uint32_t L, L8, L16, mask, prec_bits;
-};
+  uint32_t lut_base;    // smem address (GLOBAL: byte offset) of the lane's LUT
+  uint32_t lut_mask, lut_sh;
+  uint32_t ring;        // smem address of the lane's ring
+  uint32_t ent_off;     // byte offset of the lane's cum[0] from ent0
+  uint32_t val_delta;   // byte distance cum[i] -> val[i]
+  const uint8_t *ent0;  // entry region (generic pointer: shared or global)
+  const uint8_t *lut0;  // GLOBAL only
+  // byte supply
+  const uint8_t *arena;
+  int64_t end;          // arena offset one past the first unread byte at init
+  uint32_t p1_init;
+  uint32_t off_init;    // unread payload bytes at init (BufferOffset)
+  int64_t loaded_lo;
 
-// RAnsDecoder.ReadInit (RAnsDecoder.cs:20-54)
-__device__ __forceinline__ int rans_init(const uint8_t *arena, const StreamDesc &d, RansState &s) {
-  const uint64_t n = d.payload_len;
-  if (n < 1) return DCB_ERR_RANS_INIT;
-  const uint8_t *p = arena + d.payload_off;
-  const uint32_t tag = (uint32_t)p[n - 1] >> 6;
-  if (n < tag + 1) return DCB_ERR_RANS_INIT;
-  uint32_t v = 0;
-  for (uint32_t i = 0; i <= tag; ++i) v |= (uint32_t)p[n - 1 - tag + i] << (8 * i);
-  v &= (tag == 0) ? 0x3Fu : (tag == 1) ? 0x3FFFu : (tag == 2) ? 0x3FFFFFu : 0x3FFFFFFFu;
-  s.prec_bits = d.prec_bits;
-  s.L = 4u << d.prec_bits;
-  s.L8 = s.L >> 8;
-  s.L16 = s.L >> 16;
-  s.mask = (1u << d.prec_bits) - 1u;
-  s.x = v + s.L;
-  s.off = (uint32_t)(n - (tag + 1));
-  if (s.x >= s.L * 256u) return DCB_ERR_RANS_INIT;
-  return DCB_OK;
-}
+  __device__ __forceinline__ uint32_t consumed() const { return p1_init - p1; }
+  __device__ __forceinline__ uint32_t bytes_left() const { return off_init - consumed(); }
 
-// One RAnsDecoder.Read() (RAnsDecoder.cs:56-67,90-99): renormalise, then decode.  Returns the table
-// entry index.
-template <typename T>
-__device__ __forceinline__ uint32_t rans_step(RansState &s, ByteWin &w, const LaneTable<T> &t, uint32_t lut_shift) {
-  uint32_t x = s.x;
-  // while (state < L && off > 0) state = state * 256 + buf[--off];   L is a multiple of 256, so the
-  // number of iterations depends on x alone: one per threshold L, L/256, L/65536 that x is below.
-  uint32_t n = (x < s.L ? 1u : 0u) + (x < s.L8 ? 1u : 0u) + (x < s.L16 ? 1u : 0u);
-  n = min(n, s.off);
-  const uint32_t sh = 8u * n;
-  x = __funnelshift_l((uint32_t)(w.win >> 32), x, sh);
-  w.win <<= sh;
-  w.nwin -= (int)n;
-  s.off -= n;
-  w.refill();
-  const uint32_t r = x & s.mask;
-  const uint32_t q = x >> s.prec_bits;
-  uint32_t i = t.lut[r >> lut_shift];
-  uint32_t ca = t.cum[i];
-  uint32_t cb = t.cum[i + 1];
-  while (r >= cb) {
-    ++i;
-    ca = cb;
-    cb = t.cum[i + 1];
+  template <int MAX_CHUNKS>
+  __device__ __forceinline__ void top_up() {
+    const int64_t ptr = end - (int64_t)consumed();
+    const int64_t floor_lo = ((ptr + 15) & ~15ll) - (int64_t)DCB_RING_BYTES;
+#pragma unroll
+    for (int k = 0; k < MAX_CHUNKS; ++k) {
+      if (loaded_lo - 16 >= floor_lo) {
+        loaded_lo -= 16;
+        cp_async16(ring | ((uint32_t)loaded_lo & (DCB_RING_BYTES - 1u)), arena + loaded_lo);
+      }
+    }
+    cp_async_commit();
   }
-  s.x = q * (cb - ca) + (r - ca);
-  return i;
-}
+
+  // the 4 bytes [ptr-4, ptr) with byte ptr-1 in the most significant position: the two ring words are
+  // requested as soon as the read position is known (prefetch), combined when the next step needs them
+  uint32_t pk_hi, pk_lo, pk_sh;
+  __device__ __forceinline__ void prefetch() {
+    pk_hi = lds_u32(ring | (p1 & (DCB_RING_BYTES - 4u)));
+    pk_lo = lds_u32(ring | ((p1 + DCB_RING_BYTES - 4u) & (DCB_RING_BYTES - 4u)));
+    pk_sh = (p1 & 3u) * 8u + 8u;
+  }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_rc(pk_lo, pk_hi, pk_sh); }
+
+  __device__ __forceinline__ uint32_t lut_load(uint32_t xx) const {
+    const uint32_t a = lut_base | ((xx >> lut_sh) & lut_mask);
+    if (GLOBAL) return *reinterpret_cast<const T *>(lut0 + a);
+    uint32_t v;
+    if (sizeof(T) == 2) asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(v) : "r"(a));
+    else asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
+    return v;
+  }
+
+  // One RAnsDecoder.Read() (RAnsDecoder.cs:56-67,90-99): renormalise, then decode.
+  //   while (state < L && off > 0) state = state * 256 + buf[--off];
+  // L is a multiple of 256, so the iteration count depends on x alone: one per threshold L, L/256,
+  // L/65536 that x is below, capped by the bytes left.  CAREFUL = false assumes the caller has
+  // checked that enough bytes are left for the cap not to bind.
+  // Returns the byte offset (from ent0) of cum[entry].
+  template <bool CAREFUL>
+  __device__ __forceinline__ uint32_t step() {
+    const uint32_t v = peek();
+    uint32_t sh;  // 8 * bytes to shift in
+    if (sizeof(T) == 2 && !GLOBAL) {
+      // precision <= 15: x >= 4 > L/65536, at most two bytes
+      const uint32_t sh2 = x < L8 ? 16u : 8u;
+      sh = x < L ? sh2 : 0u;
+    } else {
+      const uint32_t sh3 = x < L16 ? 24u : 16u;
+      const uint32_t sh2 = x < L8 ? sh3 : 8u;
+      sh = x < L ? sh2 : 0u;
+    }
+    if (CAREFUL) sh = min(sh, 8u * bytes_left());
+    const uint32_t xr = __funnelshift_l(v, x, sh);
+    p1 -= sh >> 3;
+    prefetch();
+    const uint32_t r = xr & mask;
+    const uint32_t q = xr >> prec_bits;
+    uint32_t o = lut_load(xr);
+    // two candidates per probe; the LUT granularity makes a third one rare
+    const T *cp = reinterpret_cast<const T *>(ent0 + o);
+    uint32_t c0 = cp[0], c1 = cp[1], c2 = cp[2];
+    if (__builtin_expect(r >= c2, 0)) {
+      do {
+        o += (uint32_t)sizeof(T);
+        c0 = c1;
+        c1 = c2;
+        c2 = *reinterpret_cast<const T *>(ent0 + o + 2u * (uint32_t)sizeof(T));
+      } while (r >= c2);
+    }
+    const bool second = r >= c1;
+    const uint32_t xa = q * (c1 - c0) + (r - c0);
+    const uint32_t xb = q * (c2 - c1) + (r - c1);
+    x = second ? xb : xa;
+    return o + (second ? (uint32_t)sizeof(T) : 0u);
+  }
+
+  // table entry -> symbol value.  compact: val[] holds the value (zig-zag decoded when geom.zig);
+  // dense: the entry index is the symbol id.
+  __device__ __forceinline__ int32_t value(uint32_t o, bool compact, bool zig) const {
+    if (compact) {
+      if (sizeof(T) == 2) {
+        return zig ? (int32_t) * reinterpret_cast<const int16_t *>(ent0 + o + val_delta)
+                   : (int32_t) * reinterpret_cast<const uint16_t *>(ent0 + o + val_delta);
+      }
+      return *reinterpret_cast<const int32_t *>(ent0 + o + val_delta);
+    }
+    const uint32_t sym = (o - ent_off) / (uint32_t)sizeof(T);
+    return zig ? zigzag_dec(sym) : (int32_t)sym;
+  }
+  // the symbol id itself (debug dumps)
+  __device__ __forceinline__ uint32_t symbol(uint32_t o, const TableGeom &g) const {
+    const int32_t v = value(o, g.compact != 0, g.zig != 0);
+    if (!g.zig) return (uint32_t)v;
+    return v >= 0 ? ((uint32_t)v << 1) : ((((uint32_t)(-(v + 1))) << 1) | 1u);
+  }
+
+  // RAnsDecoder.ReadInit (RAnsDecoder.cs:20-54)
+  __device__ int init_state(const uint8_t *arena_, const StreamDesc &d) {
+    const uint64_t n = d.payload_len;
+    if (n < 1) return DCB_ERR_RANS_INIT;
+    const uint8_t *p = arena_ + d.payload_off;
+    const uint32_t tag = (uint32_t)p[n - 1] >> 6;
+    if (n < tag + 1) return DCB_ERR_RANS_INIT;
+    uint32_t v = 0;
+    for (uint32_t i = 0; i <= tag; ++i) v |= (uint32_t)p[n - 1 - tag + i] << (8 * i);
+    v &= (tag == 0) ? 0x3Fu : (tag == 1) ? 0x3FFFu : (tag == 2) ? 0x3FFFFFu : 0x3FFFFFFFu;
+    prec_bits = d.prec_bits;
+    L = 4u << d.prec_bits;
+    L8 = L >> 8;
+    L16 = L >> 16;
+    mask = (1u << d.prec_bits) - 1u;
+    x = v + L;
+    if (x >= L * 256u) return DCB_ERR_RANS_INIT;
+    off_init = (uint32_t)(n - (tag + 1));
+    arena = arena_;
+    end = (int64_t)(d.payload_off + off_init);
+    p1_init = (uint32_t)end - 1u;
+    p1 = p1_init;
+    loaded_lo = (end + 15) & ~15ll;
+    return DCB_OK;
+  }
+  __device__ __forceinline__ void init_ring(uint32_t ring_addr) {
+    ring = ring_addr;
+    top_up<DCB_RING_BYTES / 16>();
+    cp_async_wait<0>();
+    prefetch();
+  }
+
+  // Parse RANS_TABLE at d.table_off into the lane's table (RAnsSymbolDecoder.cs:12-51, RAnsDecoder.cs:69-88).
+  // lut/ent point at the lane's LUT and entry slices (generic pointers).
+  __device__ int build(const uint8_t *arena_, const StreamDesc &d, const TableGeom &g, T *lut, T *ent,
+                       uint32_t ent_off_) {
+    ent_off = ent_off_;
+    val_delta = (g.cap_entries + 2u) * (uint32_t)sizeof(T);
+    lut_sh = g.lut_shift - (sizeof(T) == 2 ? 1u : 2u);
+    lut_mask = g.lut_bytes - (uint32_t)sizeof(T);
+    T *cum = ent;
+    T *val = ent + g.cap_entries + 2u;
+    uint64_t pos = d.table_off;
+    const uint64_t bend = d.buf_end;
+    for (int i = 0; i < 10; ++i) {  // skip the num_symbols varint (value parsed by the indexer)
+      if (pos >= bend) return DCB_ERR_EOF;
+      if (!(arena_[pos++] & 0x80)) break;
+    }
+    const uint32_t ns = d.num_symbols;
+    const uint32_t prec = 1u << d.prec_bits;
+    if (!g.compact && ns > g.cap_entries) return DCB_ERR_TABLE;
+    uint64_t c = 0;
+    uint32_t ne = 0;
+    bool overflow = false;
+    for (uint32_t i = 0; i < ns; ++i) {
+      if (pos >= bend) return DCB_ERR_EOF;
+      const uint32_t pd = arena_[pos++];
+      const uint32_t token = pd & 3u;
+      if (token == 3u) {
+        const uint32_t off = pd >> 2;
+        if (i + off >= ns) return DCB_ERR_TABLE;
+        if (!g.compact)
+          for (uint32_t j = 0; j <= off; ++j) cum[i + j] = (T)(c > prec ? prec : c);
+        i += off;
+      } else {
+        uint32_t prob = pd >> 2;
+        for (uint32_t b = 0; b < token; ++b) {
+          if (pos >= bend) return DCB_ERR_EOF;
+          prob |= (uint32_t)arena_[pos++] << (8 * (b + 1) - 2);
+        }
+        if (g.compact) {
+          if (prob) {
+            if (c + prob > prec || ne >= g.cap_entries) overflow = true;
+            if (!overflow) {
+              cum[ne] = (T)c;
+              val[ne] = (T)(g.zig ? (uint32_t)zigzag_dec(i) : i);
+              ++ne;
+            }
+          }
+        } else {
+          if (c + prob > prec) overflow = true;
+          cum[i] = (T)(c > prec ? prec : c);
+        }
+        c += prob;
+      }
+    }
+    if (overflow || c != prec) return DCB_ERR_TABLE;
+    if (!g.compact) ne = ns;
+    cum[ne] = (T)prec;
+    cum[ne + 1] = (T)prec;  // pad: the two-candidate probe reads cum[i + 2]
+    const uint32_t nb = prec >> g.lut_shift;
+    uint32_t i = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+      const uint32_t slot = b << g.lut_shift;
+      while ((uint32_t)cum[i + 1] <= slot) ++i;
+      lut[b] = (T)(ent_off + i * (uint32_t)sizeof(T));
+    }
+    return DCB_OK;
+  }
+};
 
 }  // namespace dcb

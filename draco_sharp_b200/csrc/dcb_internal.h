@@ -129,8 +129,12 @@ struct RansLaunch {
   const uint32_t *d_order;        // stream indices handled by this launch (sorted by length, desc)
   uint32_t n_streams;
   uint32_t lanes_per_warp;        // active lanes per warp-CTA
-  uint32_t slot_bytes;            // shared (or global scratch) memory per lane
+  uint32_t lut_bytes;             // per lane: LUT size (power of two)
+  uint32_t ent_bytes;             // per lane: cum[cap + 2] (+ val[cap] for compact tables)
+  uint32_t cap_entries;           // table entries a lane can hold
   uint32_t lut_shift;             // log2(slots per LUT bucket)
   uint32_t dump;                  // DCB_DUMP_* flags
-  uint32_t compact;               // 1: tables indexed by active-symbol rank (+ id map), 0: by symbol id
+  uint32_t compact;               // 1: tables indexed by active-symbol rank (+ value map), 0: by symbol id
+  uint32_t zig;                   // symbols are zig-zag coded corrections
+  uint32_t mode;                  // 0 generic post-processing, 1..3 specialised (dcb_kernels.cu)
 };

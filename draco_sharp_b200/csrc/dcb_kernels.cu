@@ -36,11 +36,82 @@ namespace {
 // TABLE_GLOBAL: the lane tables live in a global scratch arena instead of shared memory (alphabets
 // too large for smem: precision 16..20).
 // ---------------------------------------------------------------------------------------------
-template <int NCP, typename T, bool DUMP, bool TABLE_GLOBAL>
+// post-processing mode of a launch: 0 = per-stream (runtime) recon/store kinds; the others pin them at
+// compile time for the hot shapes
+//   1  delta + wrap  -> dequantise to float      (quantized positions / tex coords)
+//   2  delta + wrap  -> narrow to uint8          (colours)
+//   3  delta + canonicalized octahedron -> unit vector (normals)
+template <int MODE>
+__device__ __forceinline__ int recon_of(const PostParams &pp) {
+  return (MODE == 1 || MODE == 2) ? (int)RECON_DELTA_WRAP : (MODE == 3 ? (int)RECON_DELTA_OCT_CANON : pp.recon);
+}
+template <int MODE>
+__device__ __forceinline__ int store_of(const PostParams &pp) {
+  return MODE == 1 ? (int)STORE_DEQUANT : (MODE == 2 ? (int)STORE_NARROW : (MODE == 3 ? (int)STORE_OCT_UNIT : pp.store));
+}
+template <int MODE>
+__device__ __forceinline__ int dsize_of(const PostParams &pp) {
+  return MODE == 2 ? 1 : pp.dsize;
+}
+
+// shared-memory carve-up of a warp-CTA (see RansLane)
+struct SmemLayout {
+  uint32_t lut0, ring0, ent0;  // byte offsets from the dynamic shared-memory base
+};
+__device__ __forceinline__ SmemLayout smem_layout(uint32_t base_addr, uint32_t lanes, const TableGeom &g, bool table_global) {
+  SmemLayout l;
+  uint32_t a = base_addr;
+  if (!table_global) {
+    a = (a + g.lut_bytes - 1u) & ~(g.lut_bytes - 1u);
+    l.lut0 = a - base_addr;
+    a += lanes * g.lut_bytes;
+  } else {
+    l.lut0 = 0;
+  }
+  a = (a + DCB_RING_BYTES - 1u) & ~(DCB_RING_BYTES - 1u);
+  l.ring0 = a - base_addr;
+  a += lanes * DCB_RING_BYTES;
+  l.ent0 = a - base_addr;
+  return l;
+}
+
+// decode one entry: NCP symbols -> corrections -> prediction; leaves the portable ints in v and prev
+// TAB: 0 = table kind (dense / compact) read from the launch geometry, 1 = dense, 2 = compact
+template <int NCP, typename T, bool TG, bool DUMP, int MODE, int TAB, bool CAREFUL>
+__device__ __forceinline__ void decode_entry(RansLane<T, TG> &rl, const TableGeom &g, const PostParams &pp, int32_t *prev,
+                                             int32_t *v, int32_t *dptr, uint32_t dump, uint64_t e) {
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) {
+    const uint32_t o = rl.template step<CAREFUL>();
+    const bool compact = TAB == 0 ? g.compact != 0 : TAB == 2;
+    const bool zig = MODE == 0 ? g.zig != 0 : MODE != 3;
+    v[c] = rl.value(o, compact, zig);
+    if (DUMP && (dump & DCB_DUMP_SYMBOLS)) dptr[e * NCP + c] = (int32_t)rl.symbol(o, g);
+  }
+  const int recon = recon_of<MODE>(pp);
+  if (recon == RECON_DELTA_WRAP) {
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) {
+      prev[c] = wrap_original(prev[c], v[c], pp.mn, pp.mx, pp.max_diff);
+      v[c] = prev[c];
+    }
+  } else if (recon == RECON_DELTA_OCT || recon == RECON_DELTA_OCT_CANON) {
+    if (NCP == 2) {
+      oct_original(pp.box, recon == RECON_DELTA_OCT_CANON, prev[0], prev[NCP - 1], v[0], v[NCP - 1]);
+      v[0] = prev[0];
+      v[NCP - 1] = prev[NCP - 1];
+    }
+  }
+  if (DUMP && (dump & DCB_DUMP_QINTS)) {
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) dptr[e * NCP + c] = v[c];
+  }
+}
+
+template <int NCP, typename T, bool DUMP, bool TABLE_GLOBAL, int MODE, int TAB>
 __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                             const uint32_t *__restrict__ order, uint32_t n_streams,
-                                                            uint32_t lanes, uint32_t slot_bytes, uint32_t lut_shift,
-                                                            uint32_t compact, uint8_t *__restrict__ out,
+                                                            uint32_t lanes, TableGeom geom, uint8_t *__restrict__ out,
                                                             uint8_t *__restrict__ dbg, uint8_t *__restrict__ aux,
                                                             uint8_t *__restrict__ tab_arena, uint32_t dump) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -48,102 +119,85 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   const uint32_t slot = blockIdx.x * lanes + lane;
   const bool have = lane < lanes && slot < n_streams;
   StreamDesc *dp = have ? &streams[order[slot]] : nullptr;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const SmemLayout lay = smem_layout(smem_base, lanes, geom, TABLE_GLOBAL);
 
-  LaneTable<T> tab;
-  RansState rs;
-  ByteWin bw;
+  RansLane<T, TABLE_GLOBAL> rl;
   uint32_t n_entries = 0;
-  int status = DCB_OK;
   if (have) {
     const StreamDesc &d = *dp;
     n_entries = d.n_entries;
-    uint8_t *base = TABLE_GLOBAL ? tab_arena + (size_t)slot * slot_bytes : smem + (size_t)lane * slot_bytes;
-    uint32_t cap_entries;
-    carve_table<T>(base, slot_bytes, d.prec_bits, lut_shift, compact != 0, tab, cap_entries);
+    int status = DCB_OK;
     if (n_entries > 0) {
-      status = build_table<T>(arena, d, tab, lut_shift, compact != 0, cap_entries);
-      if (status == DCB_OK) status = rans_init(arena, d, rs);
-      if (status == DCB_OK) bw.init(arena, d.payload_off + rs.off);
+      T *lut, *ent;
+      uint32_t ent_off;
+      if (TABLE_GLOBAL) {
+        // per launch slot: [LUT region | entry region] in the global scratch arena
+        const uint32_t n_slots = gridDim.x * lanes;
+        rl.lut0 = tab_arena;
+        rl.ent0 = tab_arena + (size_t)n_slots * geom.lut_bytes;
+        rl.lut_base = slot * geom.lut_bytes;
+        ent_off = slot * geom.ent_bytes;
+        lut = reinterpret_cast<T *>(tab_arena + (size_t)slot * geom.lut_bytes);
+        ent = reinterpret_cast<T *>(const_cast<uint8_t *>(rl.ent0) + (size_t)slot * geom.ent_bytes);
+      } else {
+        rl.lut0 = nullptr;
+        rl.ent0 = smem + lay.ent0;
+        rl.lut_base = smem_base + lay.lut0 + lane * geom.lut_bytes;
+        ent_off = lane * geom.ent_bytes;
+        lut = reinterpret_cast<T *>(smem + lay.lut0 + (size_t)lane * geom.lut_bytes);
+        ent = reinterpret_cast<T *>(smem + lay.ent0 + (size_t)lane * geom.ent_bytes);
+      }
+      status = rl.build(arena, d, geom, lut, ent, ent_off);
+      if (status == DCB_OK) status = rl.init_state(arena, d);
+      if (status == DCB_OK) rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
     }
     if (status != DCB_OK) {
       dp->status = status;
       n_entries = 0;
     }
   }
-  // warp-uniform trip count
-  uint32_t n_max = n_entries;
+  // groups of 4 entries every active lane of the warp can run without per-lane bounds checks
+  uint32_t g_min = n_entries ? (n_entries >> 2) : 0xFFFFFFFFu;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
-  if (n_max == 0) return;
+  for (int o = 16; o > 0; o >>= 1) g_min = min(g_min, __shfl_xor_sync(0xffffffffu, g_min, o));
+  if (n_entries == 0) return;  // idle lane, empty or failed stream (no warp-level operation below)
 
   PostParams pp;
-  uint8_t *optr = nullptr;
-  int32_t *dptr = nullptr;
-  if (have) {
-    const StreamDesc &d = *dp;
-    pp.load(d);
-    optr = out + d.out_off;
-    if (DUMP) dptr = reinterpret_cast<int32_t *>(dbg + d.dbg_off);
-    if (pp.recon == RECON_PARA_WRAP) {
-      // corrections only: the parallelogram recurrence runs in its own kernel
-      optr = aux + d.aux_off;
-      pp.store = STORE_NARROW;
-      pp.dsize = 4;
-    }
-  } else {
-    pp.recon = RECON_NONE; pp.store = STORE_NARROW; pp.dsize = 4; pp.zig = true;
-    pp.mn = pp.mx = pp.max_diff = 0;
+  pp.load(*dp);
+  uint8_t *optr = out + dp->out_off;
+  int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + dp->dbg_off) : nullptr;
+  if (MODE == 0 && pp.recon == RECON_PARA_WRAP) {
+    // corrections only: the parallelogram recurrence runs in its own kernel
+    optr = aux + dp->aux_off;
+    pp.store = STORE_NARROW;
+    pp.dsize = 4;
   }
+  const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp);
   int32_t prev[NCP];
 #pragma unroll
   for (int c = 0; c < NCP; ++c) prev[c] = 0;
 
-  const uint32_t n_groups = (n_max + 3u) >> 2;
-  for (uint32_t g = 0; g < n_groups; ++g) {
-    const uint32_t e0 = g << 2;
-    if (e0 < n_entries) {
-      const uint32_t cnt = min(4u, n_entries - e0);
-      int32_t v[4][NCP];
+  // ---- main loop: 4 entries (4 * NCP symbols) per iteration, renormalisation bounds checked once per group ----
+  constexpr uint32_t kGroupBytes = 4u * NCP * 3u;
+  uint32_t g = 0;
+  for (; g < g_min; ++g) {
+    if (rl.bytes_left() < kGroupBytes) break;  // per lane: the rest of this stream runs the careful loop
+    int32_t v[4][NCP];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if ((uint32_t)j < cnt) {
-#pragma unroll
-          for (int c = 0; c < NCP; ++c) {
-            const uint32_t idx = rans_step<T>(rs, bw, tab, lut_shift);
-            const uint32_t sym = compact ? (uint32_t)tab.sym[idx] : idx;
-            if (DUMP && (dump & DCB_DUMP_SYMBOLS)) dptr[(size_t)(e0 + j) * NCP + c] = (int32_t)sym;
-            v[j][c] = pp.zig ? zigzag_dec(sym) : (int32_t)sym;
-          }
-          if (pp.recon == RECON_DELTA_WRAP) {
-#pragma unroll
-            for (int c = 0; c < NCP; ++c) {
-              prev[c] = wrap_original(prev[c], v[j][c], pp.mn, pp.mx, pp.max_diff);
-              v[j][c] = prev[c];
-            }
-          } else if (pp.recon == RECON_DELTA_OCT || pp.recon == RECON_DELTA_OCT_CANON) {
-            if (NCP == 2) {
-              oct_original(pp.box, pp.recon == RECON_DELTA_OCT_CANON, prev[0], prev[NCP - 1], v[j][0], v[j][NCP - 1]);
-              v[j][0] = prev[0];
-              v[j][NCP - 1] = prev[NCP - 1];
-            }
-          }
-          if (DUMP && (dump & DCB_DUMP_QINTS)) {
-#pragma unroll
-            for (int c = 0; c < NCP; ++c) dptr[(size_t)(e0 + j) * NCP + c] = v[j][c];
-          }
-        }
-      }
-      if (cnt == 4) {
-        store_group4<NCP>(pp, optr, e0, v);
-      } else {
-        for (uint32_t j = 0; j < cnt; ++j) {
-          int32_t t[NCP];
-#pragma unroll
-          for (int c = 0; c < NCP; ++c) t[c] = j == 0 ? v[0][c] : (j == 1 ? v[1][c] : v[2][c]);
-          store_entry<NCP>(pp, optr, e0 + j, t);
-        }
-      }
-    }
+    for (int j = 0; j < 4; ++j)
+      decode_entry<NCP, T, TABLE_GLOBAL, DUMP, MODE, TAB, false>(rl, geom, pp, prev, v[j], dptr, dump, (uint64_t)g * 4 + j);
+    store_group4<NCP>(pp, store, dsize, optr, (uint64_t)g * 4, v);
+    rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
+    cp_async_wait<1>();
+  }
+  // ---- per-lane tail: exact `off > 0` handling ----
+  for (uint32_t e = g * 4u; e < n_entries; ++e) {
+    int32_t v[NCP];
+    decode_entry<NCP, T, TABLE_GLOBAL, DUMP, MODE, TAB, true>(rl, geom, pp, prev, v, dptr, dump, e);
+    store_entry<NCP>(pp, store, dsize, optr, e, v);
+    rl.template top_up<(3 * NCP + 15) / 16 + 1>();
+    cp_async_wait<0>();
   }
 }
 
@@ -155,72 +209,61 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                       const uint32_t *__restrict__ order, uint32_t n_streams,
-                                                      uint32_t lanes, uint32_t slot_bytes, uint32_t lut_shift,
-                                                      uint8_t *__restrict__ aux) {
+                                                      uint32_t lanes, TableGeom geom, uint8_t *__restrict__ aux) {
   extern __shared__ __align__(16) uint8_t smem[];
   typedef uint16_t T;
   const uint32_t lane = threadIdx.x;
   const uint32_t slot = blockIdx.x * lanes + lane;
-  const bool have = lane < lanes && slot < n_streams;
-  StreamDesc *dp = have ? &streams[order[slot]] : nullptr;
-  LaneTable<T> tab;
-  RansState rs;
-  ByteWin bw;
-  uint32_t n_entries = 0;
-  int status = DCB_OK;
-  uint32_t ncp = 1;
-  uint64_t avail_bits = 0;
-  uint8_t *tags = nullptr;
-  uint64_t *chunk_bits = nullptr;
-  if (have) {
-    const StreamDesc &d = *dp;
-    n_entries = d.n_entries;
-    ncp = d.ncp;
-    avail_bits = (d.buf_end - d.bits_off) * 8ull;
-    tags = aux + d.tag_off;
-    chunk_bits = reinterpret_cast<uint64_t *>(aux + d.tag_off + (((uint64_t)n_entries + 15ull) & ~15ull));
-    uint32_t cap_entries;
-    carve_table<T>(smem + (size_t)lane * slot_bytes, slot_bytes, d.prec_bits, lut_shift, false, tab, cap_entries);
-    status = build_table<T>(arena, d, tab, lut_shift, false, cap_entries);
-    if (status == DCB_OK) status = rans_init(arena, d, rs);
-    if (status == DCB_OK) bw.init(arena, d.payload_off + rs.off);
-    if (status != DCB_OK) {
-      dp->status = status;
-      n_entries = 0;
-    }
+  if (lane >= lanes || slot >= n_streams) return;
+  StreamDesc *dp = &streams[order[slot]];
+  const StreamDesc &d = *dp;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const SmemLayout lay = smem_layout(smem_base, lanes, geom, false);
+  RansLane<T, false> rl;
+  const uint32_t n_entries = d.n_entries;
+  const uint32_t ncp = d.ncp;
+  const uint64_t avail_bits = (d.buf_end - d.bits_off) * 8ull;
+  uint8_t *tags = aux + d.tag_off;
+  uint64_t *chunk_bits = reinterpret_cast<uint64_t *>(aux + d.tag_off + (((uint64_t)n_entries + 15ull) & ~15ull));
+  rl.lut0 = nullptr;
+  rl.ent0 = smem + lay.ent0;
+  rl.lut_base = smem_base + lay.lut0 + lane * geom.lut_bytes;
+  int status = rl.build(arena, d, geom, reinterpret_cast<T *>(smem + lay.lut0 + (size_t)lane * geom.lut_bytes),
+                        reinterpret_cast<T *>(smem + lay.ent0 + (size_t)lane * geom.ent_bytes), lane * geom.ent_bytes);
+  if (status == DCB_OK) status = rl.init_state(arena, d);
+  if (status != DCB_OK) {
+    dp->status = status;
+    dp->bits_total = 0;
+    return;
   }
-  uint32_t n_max = n_entries;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+  rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
   uint64_t bits = 0;
   uint32_t packed = 0;
-  for (uint32_t e = 0; e < n_max; ++e) {
-    if (e < n_entries) {
-      if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-      const uint32_t tag = rans_step<T>(rs, bw, tab, lut_shift) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
-      if (tag > 32u) {
-        status = DCB_ERR_TAG;
-        n_entries = 0;
-      } else {
-        bits += (uint64_t)tag * ncp;
-        if (bits > avail_bits) {
-          status = DCB_ERR_EOF;
-          n_entries = 0;
-        }
-      }
-      packed |= tag << (8u * (e & 3u));
-      if ((e & 3u) == 3u) {
-        *reinterpret_cast<uint32_t *>(tags + (e & ~3u)) = packed;
-        packed = 0;
-      } else if (e + 1 >= n_entries) {
-        for (uint32_t k = 0; k <= (e & 3u); ++k) tags[(e & ~3u) + k] = (uint8_t)(packed >> (8u * k));
-      }
+  for (uint32_t e = 0; e < n_entries; ++e) {
+    if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
+    const uint32_t o = rl.step<true>();
+    const uint32_t tag = ((o - rl.ent_off) >> 1) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+    if (tag > 32u) {
+      status = DCB_ERR_TAG;
+      break;
+    }
+    bits += (uint64_t)tag * ncp;
+    if (bits > avail_bits) {
+      status = DCB_ERR_EOF;
+      break;
+    }
+    packed |= tag << (8u * (e & 3u));
+    if ((e & 3u) == 3u) {
+      *reinterpret_cast<uint32_t *>(tags + (e & ~3u)) = packed;
+      packed = 0;
+      rl.top_up<2>();
+      cp_async_wait<1>();
+    } else if (e + 1 == n_entries) {
+      for (uint32_t k = 0; k <= (e & 3u); ++k) tags[(e & ~3u) + k] = (uint8_t)(packed >> (8u * k));
     }
   }
-  if (have) {
-    dp->bits_total = bits;
-    if (status != DCB_OK) dp->status = status;
-  }
+  dp->bits_total = bits;
+  if (status != DCB_OK) dp->status = status;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -316,7 +359,7 @@ __global__ void __launch_bounds__(32) serial_post_kernel(const uint8_t *__restri
 #pragma unroll
       for (int c = 0; c < NCP; ++c) dptr[(size_t)e * NCP + c] = v[c];
     }
-    store_entry<NCP>(pp, optr, e, v);
+    store_entry<NCP>(pp, pp.store, pp.dsize, optr, e, v);
   }
 }
 
@@ -438,7 +481,7 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
 #pragma unroll
       for (int c = 0; c < NCP; ++c) dptr[(size_t)p * NCP + c] = prev[c];
     }
-    store_entry<NCP>(pp, optr, p, prev);
+    store_entry<NCP>(pp, pp.store, pp.dsize, optr, p, prev);
   }
 }
 
@@ -460,34 +503,65 @@ __global__ void copy_kernel(const uint8_t *__restrict__ arena, StreamDesc *strea
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-template <int NCP, typename T, bool DUMP, bool TG>
-static cudaError_t launch_raw_t(const RansLaunch &p, const DevArenas &a, uint32_t smem_bytes, cudaStream_t st) {
-  auto k = rans_raw_fused_kernel<NCP, T, DUMP, TG>;
+static TableGeom geom_of(const RansLaunch &p) {
+  TableGeom g;
+  g.lut_bytes = p.lut_bytes;
+  g.ent_bytes = p.ent_bytes;
+  g.cap_entries = p.cap_entries;
+  g.lut_shift = p.lut_shift;
+  g.compact = p.compact;
+  g.zig = p.zig;
+  return g;
+}
+
+uint32_t dcb_rans_smem_bytes(const RansLaunch &p, bool table_global) {
+  // worst-case alignment slack + LUTs + rings + entries (see smem_layout)
+  uint32_t b = DCB_RING_BYTES + p.lanes_per_warp * DCB_RING_BYTES;
+  if (!table_global) b += p.lut_bytes + p.lanes_per_warp * (p.lut_bytes + p.ent_bytes);
+  return b;
+}
+
+template <int NCP, typename T, bool DUMP, bool TG, int MODE, int TAB = 0>
+static cudaError_t launch_raw_t(const RansLaunch &p, const DevArenas &a, cudaStream_t st) {
+  auto k = rans_raw_fused_kernel<NCP, T, DUMP, TG, MODE, TAB>;
+  const uint32_t smem_bytes = dcb_rans_smem_bytes(p, TG);
   if (smem_bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
   }
   const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
-  k<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, p.slot_bytes,
-                                  p.lut_shift, p.compact, a.out, a.dbg, a.aux, a.tab, p.dump);
+  k<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, geom_of(p), a.out, a.dbg,
+                                  a.aux, a.tab, p.dump);
   return cudaGetLastError();
 }
 
 template <int NCP, typename T>
-static cudaError_t launch_raw_n(const RansLaunch &p, bool table_global, const DevArenas &a, uint32_t smem_bytes,
-                                cudaStream_t st) {
+static cudaError_t launch_raw_n(const RansLaunch &p, bool table_global, const DevArenas &a, cudaStream_t st) {
   const bool dump = p.dump != 0;
   if (table_global)
-    return dump ? launch_raw_t<NCP, T, true, true>(p, a, 0, st) : launch_raw_t<NCP, T, false, true>(p, a, 0, st);
-  return dump ? launch_raw_t<NCP, T, true, false>(p, a, smem_bytes, st) : launch_raw_t<NCP, T, false, false>(p, a, smem_bytes, st);
+    return dump ? launch_raw_t<NCP, T, true, true, 0>(p, a, st) : launch_raw_t<NCP, T, false, true, 0>(p, a, st);
+  return dump ? launch_raw_t<NCP, T, true, false, 0>(p, a, st) : launch_raw_t<NCP, T, false, false, 0>(p, a, st);
 }
 
 cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool table_global, const DevArenas &a,
-                                uint32_t smem_bytes, cudaStream_t st) {
-#define DCB_CASE(N)                                                                  \
-  case N:                                                                            \
-    return wide ? launch_raw_n<N, uint32_t>(p, table_global, a, smem_bytes, st)      \
-                : launch_raw_n<N, uint16_t>(p, table_global, a, smem_bytes, st);
+                                cudaStream_t st) {
+  // specialised hot shapes (u16 tables in shared memory, no debug dump)
+  if (!wide && !table_global && !p.dump) {
+#define DCB_SPEC(M, N)                                                                           \
+  if (p.mode == M && ncp == N)                                                                   \
+    return p.compact ? launch_raw_t<N, uint16_t, false, false, M, 2>(p, a, st)                   \
+                     : launch_raw_t<N, uint16_t, false, false, M, 1>(p, a, st);
+    DCB_SPEC(1, 3)
+    DCB_SPEC(1, 2)
+    DCB_SPEC(2, 3)
+    DCB_SPEC(2, 4)
+    DCB_SPEC(3, 2)
+#undef DCB_SPEC
+  }
+#define DCB_CASE(N)                                                       \
+  case N:                                                                 \
+    return wide ? launch_raw_n<N, uint32_t>(p, table_global, a, st)       \
+                : launch_raw_n<N, uint16_t>(p, table_global, a, st);
   switch (ncp) {
     DCB_CASE(1)
     DCB_CASE(2)
@@ -499,14 +573,15 @@ cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool ta
 #undef DCB_CASE
 }
 
-cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, uint32_t smem_bytes, cudaStream_t st) {
+cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, cudaStream_t st) {
+  const uint32_t smem_bytes = dcb_rans_smem_bytes(p, false);
   if (smem_bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(rans_tag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
   }
   const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
-  rans_tag_kernel<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp,
-                                                p.slot_bytes, p.lut_shift, a.aux);
+  rans_tag_kernel<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, geom_of(p),
+                                                a.aux);
   return cudaGetLastError();
 }
 

@@ -6,7 +6,8 @@
 #include "dcb_internal.h"
 
 #define DCB_TAG_CHUNK 1024u  // points per bit-offset checkpoint of a Tagged stream
-#define DCB_PARA_RING 64u    // entries of the per-stream shared-memory ring of the parallelogram chain
+#define DCB_PARA_RING 64u
+#define DCB_RING_BYTES 128u   // per-lane shared-memory ring of compressed bytes (rANS kernels)    // entries of the per-stream shared-memory ring of the parallelogram chain
 
 // device arenas of one shard
 struct DevArenas {
@@ -18,11 +19,12 @@ struct DevArenas {
   const uint8_t *maps;  // mesh connectivity maps
 };
 
+uint32_t dcb_rans_smem_bytes(const RansLaunch &p, bool table_global);
 // Raw-scheme rANS decode fused with inverse prediction + transform + store; one stream per lane.
 cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool table_global, const DevArenas &a,
-                                uint32_t smem_bytes, cudaStream_t st);
+                                cudaStream_t st);
 // tag stream of Tagged attributes; one stream per lane
-cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, uint32_t smem_bytes, cudaStream_t st);
+cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_resolve(const DevArenas &a, BufWalk *d_walks, const uint32_t *d_list, uint32_t n,
                                StreamDesc *d_streams, cudaStream_t st);
 cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t dump,
