@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdracob200.so")
+LIB_PATH = os.environ.get("DCB_LIB") or os.path.join(HERE, "libdracob200.so")
 SYNTH_PATH = os.path.join(HERE, "synth", "libdrcsynth.so")
 
 DCB_DUMP_SYMBOLS = 1
