@@ -356,7 +356,8 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         dom = float(np.mean(dom_ms)) if dom_ms else 0.0
-        achieved = (algo_bytes / (dom * 1e-3) / 1e9) if dom > 0 else 0.0
+        dom_bytes = int(stats.algo_bytes_dominant) or algo_bytes
+        achieved = (dom_bytes / (dom * 1e-3) / 1e9) if dom > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -372,7 +373,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": profile_traffic(args.workload),
                          "peak_source": peak_src, "kernel": stats.dominant_name.decode(), "kernel_ms": dom,
-                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_bytes_per_step": algo_bytes,
+                         "stage_ms": {"raw_fused": stats.ms_raw, "tag_rans": stats.ms_tag, "par_post": stats.ms_par,
+                                      "all_kernels": stats.ms_total},
                          "note": "serial rANS chains: %d streams x %d symbols; residency waves %d, %d lanes/warp, %d B smem/stream"
                                  % (n_bufs, WORKLOADS[args.workload][1] * 3, stats.n_waves, stats.lanes_per_warp, stats.smem_per_stream)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,

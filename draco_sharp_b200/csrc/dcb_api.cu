@@ -94,7 +94,10 @@ struct dcb_ctx {
   std::vector<bool> own_stream;
   std::vector<int> num_sms;
   dcb_launch_stats stats{};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_raw = false, ev_tag = false, ev_par = false;
+  uint64_t algo_raw = 0, algo_tag = 0, algo_par = 0;
+  char raw_name[96] = {0};
 };
 
 struct dcb_batch {
@@ -355,13 +358,19 @@ void layout_shard(Shard &sh) {
       s.dbg_off = dbg;
       dbg = align_up(dbg + nv * 4, 16);
       if (w.status) continue;
-      if (s.seq_type != SEQ_GENERIC && (s.scheme == SCHEME_TAGGED || (any_unready && s.state < ST_READY))) {
+      if (s.seq_type != SEQ_GENERIC &&
+          (s.scheme == SCHEME_TAGGED || s.scheme == SCHEME_UNCOMPRESSED || (any_unready && s.state < ST_READY))) {
+        // tags u8[n] | bit offset per chunk u64[nch + 1] | correction sums per chunk u32[nch][4]
+        const uint64_t nch = (s.n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
         s.tag_off = aux;
-        aux = align_up(aux + align_up(s.n_entries, 16) + 8ull * ((s.n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK + 1), 16);
+        aux = align_up(aux + align_up(s.n_entries, 16) + 8ull * (nch + 1) + 16ull * nch, 16);
       }
       if (s.seq_type != SEQ_GENERIC && s.has_maps && (s.recon == RECON_PARA_WRAP || s.state < ST_READY)) {
         s.aux_off = aux;
         aux = align_up(aux + (2ull * nv + 3ull * s.n_entries) * 4, 16);
+      } else if (s.seq_type == SEQ_NORMALS) {
+        s.aux_off = aux;  // quantized octahedral (s, t) pairs between the serial kernels and oct_unit_kernel
+        aux = align_up(aux + 8ull * s.n_entries, 16);
       }
     }
   }
@@ -685,7 +694,16 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     CUDA_TRY(cudaMemcpyAsync(sh.d_order + g.order.size(), blocked.data(), blocked.size() * 4, cudaMemcpyHostToDevice, st));
     RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.lut_bytes, g.ent_bytes, g.entries,
                  g.lut_shift, dump, 0, 0, 0};
+    const bool time_tag = timed && dev_index == 0 && !ctx->ev_tag;
+    if (time_tag) {
+      CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+      for (uint32_t si : g.order) ctx->algo_tag += sh.streams[si].payload_len + sh.streams[si].n_entries;
+    }
     CUDA_TRY(dcb_launch_rans_tag(L, A, st));
+    if (time_tag) {
+      CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
+      ctx->ev_tag = true;
+    }
     CUDA_TRY(dcb_launch_resolve(A, sh.d_walks, sh.d_order + g.order.size(), (uint32_t)blocked.size(), sh.d_streams, st));
     stats.n_launches += 2;
     stats.n_streams += (int32_t)g.order.size();
@@ -696,10 +714,13 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
 
   // ---- classify ----
   std::map<RawKey, Group> raw;
-  Group post[5], para[5], copy{};
+  Group post[5], para[5], par[5], copy{}, octs{};
+  octs.kind = 6;
+  bool par_delta[5] = {false, false, false, false, false};
   for (int n = 1; n <= 4; ++n) {
     post[n] = Group{}; post[n].kind = 2; post[n].ncp = n;
     para[n] = Group{}; para[n].kind = 3; para[n].ncp = n;
+    par[n] = Group{}; par[n].kind = 5; par[n].ncp = n;
   }
   copy.kind = 4;
   bool has_para = false;
@@ -716,6 +737,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         continue;
       }
       if (s.n_entries == 0) continue;
+      if (s.store == STORE_OCT_UNIT) {
+        octs.order.push_back(si);
+        octs.max_entries = std::max(octs.max_entries, s.n_entries);
+      }
       if (s.scheme == SCHEME_RAW) {
         RawKey key;
         key.ncp = s.ncp;
@@ -737,6 +762,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         g.entries = std::max(g.entries, entries);
         g.total_symbols += (uint64_t)s.n_entries * s.ncp;
         g.order.push_back(si);
+      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP) && !getenv("DCB_NO_PAR_POST")) {
+        // Tagged / uncompressed source, scan-able reconstruction: point-parallel kernels
+        par[s.ncp].max_entries = std::max(par[s.ncp].max_entries, s.n_entries);
+        par[s.ncp].order.push_back(si);
+        if (s.recon == RECON_DELTA_WRAP) par_delta[s.ncp] = true;
       } else {
         post[s.ncp].order.push_back(si);
       }
@@ -749,7 +779,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   }
   std::vector<Group *> rgs;
   for (auto &kv : raw) rgs.push_back(&kv.second);
-  plan_rans_groups(rgs, num_sms);
+  // the groups run one after another on the shard's stream: each one may use the whole SM
+  for (Group *g : rgs) {
+    std::vector<Group *> one{g};
+    plan_rans_groups(one, num_sms);
+  }
   // device order lists
   uint64_t n_order = 0;
   auto add = [&](Group &g) {
@@ -761,8 +795,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
                      [&](uint32_t x, uint32_t y) { return sh.streams[x].n_entries > sh.streams[y].n_entries; });
     add(*g);
   }
-  for (int n = 1; n <= 4; ++n) { add(post[n]); add(para[n]); }
+  for (int n = 1; n <= 4; ++n) { add(post[n]); add(para[n]); add(par[n]); }
   add(copy);
+  add(octs);
+
   if (n_order == 0) {
     if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
     return DCB_OK;
@@ -776,8 +812,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     for (int n = 1; n <= 4; ++n) {
       all.insert(all.end(), post[n].order.begin(), post[n].order.end());
       all.insert(all.end(), para[n].order.begin(), para[n].order.end());
+      all.insert(all.end(), par[n].order.begin(), par[n].order.end());
     }
     all.insert(all.end(), copy.order.begin(), copy.order.end());
+    all.insert(all.end(), octs.order.begin(), octs.order.end());
+
     CUDA_TRY(cudaMemcpyAsync(sh.d_order, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));  // `all` is a stack vector; the copy is tiny
   }
@@ -789,6 +828,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   for (Group *g : rgs) {
     const uint32_t n = (uint32_t)g->order.size();
     const bool is_dom = timed && dev_index == 0 && g == dom;
+    if (getenv("DCB_DEBUG_PLAN"))
+      fprintf(stderr, "[dcb plan] raw group ncp=%d wide=%d compact=%u prec=%u entries=%u mode=%u zig=%u: %u streams, %llu symbols, "
+                      "k=%u lut=%uB ent=%uB lanes=%u global=%d\n",
+              g->ncp, (int)g->wide, g->compact, g->prec_bits, g->entries, g->mode, g->zig, n,
+              (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->ent_bytes, g->lanes, (int)g->table_global);
     if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (g->table_global) {
       const uint64_t slot_bytes = (uint64_t)g->lut_bytes + g->ent_bytes;
@@ -817,23 +861,57 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     if (is_dom) {
       CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+      ctx->ev_raw = true;
+      for (uint32_t si : g->order) {
+        const StreamDesc &sd = sh.streams[si];
+        ctx->algo_raw += (sd.payload_off + sd.payload_len - sd.table_off) + sd.out_bytes;
+      }
       stats.lanes_per_warp = (int32_t)g->lanes;
       stats.smem_per_stream = (uint64_t)g->lut_bytes + g->ent_bytes + DCB_RING_BYTES;
       RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->ent_bytes, g->entries, g->lut_shift, 0, g->compact, g->zig, g->mode};
       const uint32_t cta_smem = dcb_rans_smem_bytes(Ls, g->table_global) + kSmemPerCtaReserve;
       const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, kSmemPerSM / cta_smem)) * g->lanes;
       stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);
-      snprintf(stats.dominant_name, sizeof stats.dominant_name, "rans_raw_fused<ncp=%d,%s,%s,mode=%u,k=%u,%s>", g->ncp,
+      snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_fused<ncp=%d,%s,%s,mode=%u,k=%u,%s>", g->ncp,
                g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->mode, g->lut_shift,
                g->compact ? "compact" : "dense");
     }
     stats.n_streams += (int32_t)n;
   }
-  for (int n = 1; n <= 4; ++n)
+  for (int n = 1; n <= 4; ++n) {
     if (!post[n].order.empty()) {
-      CUDA_TRY(dcb_launch_serial_post(sh.d_streams, sh.d_order + post[n].order_off, (uint32_t)post[n].order.size(), n, dump, A, st));
+      CUDA_TRY(dcb_launch_serial_post(sh.d_streams, sh.d_order + post[n].order_off, (uint32_t)post[n].order.size(), n, dump, 0, A, st));
       stats.n_launches++;
     }
+    if (!par[n].order.empty()) {
+      const uint32_t np = (uint32_t)par[n].order.size();
+      const bool time_par = timed && dev_index == 0 && !ctx->ev_par;
+      if (time_par) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[6], st));
+        for (uint32_t si : par[n].order) {
+          const StreamDesc &sd = sh.streams[si];
+          ctx->algo_par += sd.out_bytes + (sd.scheme == SCHEME_TAGGED ? sd.n_entries + (sd.bits_total + 7) / 8
+                                                                       : (uint64_t)sd.n_entries * sd.ncp * sd.raw_num_bytes);
+        }
+      }
+      CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, np,
+                                   (par[n].max_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK, n, par_delta[n], dump, A, st));
+      stats.n_launches += par_delta[n] ? 3 : 1;
+      if (par_delta[n]) {
+        // streams whose corrections break the modular-sum condition fall back to the exact serial recurrence
+        CUDA_TRY(dcb_launch_serial_post(sh.d_streams, sh.d_order + par[n].order_off, np, n, dump, 1, A, st));
+        stats.n_launches++;
+      }
+      if (time_par) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[7], st));
+        ctx->ev_par = true;
+      }
+    }
+  }
+  if (!octs.order.empty()) {
+    CUDA_TRY(dcb_launch_oct_unit(sh.d_streams, sh.d_order + octs.order_off, (uint32_t)octs.order.size(), octs.max_entries, A, st));
+    stats.n_launches++;
+  }
   if (!copy.order.empty()) {
     CUDA_TRY(dcb_launch_copy(sh.d_streams, sh.d_order + copy.order_off, (uint32_t)copy.order.size(), copy.max_bytes, A, st));
     stats.n_launches++;
@@ -878,6 +956,9 @@ int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_
   for (const BufRec &r : b->bufs)
     if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;  // dcb_index_finish not run
   memset(&ctx->stats, 0, sizeof ctx->stats);
+  ctx->ev_raw = ctx->ev_tag = ctx->ev_par = false;
+  ctx->algo_raw = ctx->algo_tag = ctx->algo_par = 0;
+  ctx->raw_name[0] = 0;
   for (int d = 0; d < b->n_devices; ++d) {
     Shard &sh = b->shards[d];
     int rc = upload_shard(ctx, b, sh, d);
@@ -922,12 +1003,27 @@ int sync_all(dcb_ctx *ctx) {
 }
 
 void finish_stats(dcb_ctx *ctx) {
+  dcb_launch_stats &st = ctx->stats;
   float ms = 0.0f;
-  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->stats.ms_total = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) st.ms_total = ms;
   else cudaGetLastError();
-  ms = 0.0f;
-  if (ctx->stats.dominant_name[0] && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_dominant = ms;
-  else cudaGetLastError();
+  if (ctx->ev_raw && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) st.ms_raw = ms;
+  if (ctx->ev_tag && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) st.ms_tag = ms;
+  if (ctx->ev_par && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) st.ms_par = ms;
+  cudaGetLastError();
+  if (st.ms_raw >= st.ms_tag && st.ms_raw >= st.ms_par && ctx->ev_raw) {
+    st.ms_dominant = st.ms_raw;
+    st.algo_bytes_dominant = ctx->algo_raw;
+    snprintf(st.dominant_name, sizeof st.dominant_name, "%s", ctx->raw_name);
+  } else if (st.ms_tag >= st.ms_par && ctx->ev_tag) {
+    st.ms_dominant = st.ms_tag;
+    st.algo_bytes_dominant = ctx->algo_tag;
+    snprintf(st.dominant_name, sizeof st.dominant_name, "rans_tag_kernel (tag stream of the Tagged scheme)");
+  } else if (ctx->ev_par) {
+    st.ms_dominant = st.ms_par;
+    st.algo_bytes_dominant = ctx->algo_par;
+    snprintf(st.dominant_name, sizeof st.dominant_name, "par_post_kernel passes (bit extract + scan + store)");
+  }
 }
 
 }  // namespace

@@ -47,11 +47,13 @@ __device__ __forceinline__ int recon_of(const PostParams &pp) {
 }
 template <int MODE>
 __device__ __forceinline__ int store_of(const PostParams &pp) {
-  return MODE == 1 ? (int)STORE_DEQUANT : (MODE == 2 ? (int)STORE_NARROW : (MODE == 3 ? (int)STORE_OCT_UNIT : pp.store));
+  // normals leave the serial kernels as quantized (s, t) pairs: the unit-vector conversion (double precision
+  // 1/sqrt, as the C#) runs in oct_unit_kernel, point-parallel, instead of stretching the serial chain
+  return MODE == 1 ? (int)STORE_DEQUANT : ((MODE == 2 || MODE == 3) ? (int)STORE_NARROW : pp.store);
 }
 template <int MODE>
 __device__ __forceinline__ int dsize_of(const PostParams &pp) {
-  return MODE == 2 ? 1 : pp.dsize;
+  return MODE == 2 ? 1 : (MODE == 3 ? 4 : pp.dsize);
 }
 
 // shared-memory carve-up of a warp-CTA (see RansLane)
@@ -167,8 +169,8 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   pp.load(*dp);
   uint8_t *optr = out + dp->out_off;
   int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + dp->dbg_off) : nullptr;
-  if (MODE == 0 && pp.recon == RECON_PARA_WRAP) {
-    // corrections only: the parallelogram recurrence runs in its own kernel
+  if (MODE == 3 || (MODE == 0 && (pp.recon == RECON_PARA_WRAP || pp.store == STORE_OCT_UNIT))) {
+    // int32 scratch: corrections for the parallelogram kernel / quantized (s, t) for oct_unit_kernel
     optr = aux + dp->aux_off;
     pp.store = STORE_NARROW;
     pp.dsize = 4;
@@ -238,11 +240,36 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
   }
   rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
   uint64_t bits = 0;
-  uint32_t packed = 0;
-  for (uint32_t e = 0; e < n_entries; ++e) {
+  uint32_t e = 0;
+  // ---- groups of 4 tags, no per-symbol branches; errors are sorted out when the group is left ----
+  for (; e + 4 <= n_entries; e += 4) {
+    if (rl.bytes_left() < 12u) break;  // renormalisation may run out of bytes: careful loop below
     if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-    const uint32_t o = rl.step<true>();
-    const uint32_t tag = ((o - rl.ent_off) >> 1) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+    uint32_t t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = ((rl.step<false>() - rl.ent_off) >> 1) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+    const uint32_t tmax = max(max(t[0], t[1]), max(t[2], t[3]));
+    const uint64_t nbits = bits + (uint64_t)(t[0] + t[1] + t[2] + t[3]) * ncp;
+    if (tmax > 32u || nbits > avail_bits) {
+      // first failing point decides the status, as in the sequential reference loop
+      for (int j = 0; j < 4 && status == DCB_OK; ++j) {
+        if (t[j] > 32u) status = DCB_ERR_TAG;
+        else {
+          bits += (uint64_t)t[j] * ncp;
+          if (bits > avail_bits) status = DCB_ERR_EOF;
+        }
+      }
+      break;
+    }
+    *reinterpret_cast<uint32_t *>(tags + e) = t[0] | (t[1] << 8) | (t[2] << 16) | (t[3] << 24);
+    bits = nbits;
+    rl.top_up<1>();
+    cp_async_wait<1>();
+  }
+  // ---- careful tail (exact `off > 0` handling, per-point checks) ----
+  for (; status == DCB_OK && e < n_entries; ++e) {
+    if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
+    const uint32_t tag = ((rl.step<true>() - rl.ent_off) >> 1) & 0xFFu;
     if (tag > 32u) {
       status = DCB_ERR_TAG;
       break;
@@ -252,15 +279,9 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
       status = DCB_ERR_EOF;
       break;
     }
-    packed |= tag << (8u * (e & 3u));
-    if ((e & 3u) == 3u) {
-      *reinterpret_cast<uint32_t *>(tags + (e & ~3u)) = packed;
-      packed = 0;
-      rl.top_up<2>();
-      cp_async_wait<1>();
-    } else if (e + 1 == n_entries) {
-      for (uint32_t k = 0; k <= (e & 3u); ++k) tags[(e & ~3u) + k] = (uint8_t)(packed >> (8u * k));
-    }
+    tags[e] = (uint8_t)tag;
+    rl.top_up<1>();
+    cp_async_wait<0>();
   }
   dp->bits_total = bits;
   if (status != DCB_OK) dp->status = status;
@@ -301,17 +322,19 @@ template <int NCP, bool DUMP>
 __global__ void __launch_bounds__(32) serial_post_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                          const uint32_t *__restrict__ order, uint32_t n_streams,
                                                          uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
-                                                         uint8_t *__restrict__ aux, uint32_t dump) {
+                                                         uint8_t *__restrict__ aux, uint32_t dump,
+                                                         uint32_t only_irregular) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_streams) return;
   StreamDesc &d = streams[order[slot]];
   if (d.status != DCB_OK) return;
+  if (only_irregular && !d.irregular) return;  // the point-parallel kernels decoded it
   const uint32_t n_entries = d.n_entries;
   PostParams pp;
   pp.load(d);
   uint8_t *optr = out + d.out_off;
   int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
-  if (pp.recon == RECON_PARA_WRAP) {
+  if (pp.recon == RECON_PARA_WRAP || pp.store == STORE_OCT_UNIT) {
     optr = aux + d.aux_off;
     pp.store = STORE_NARROW;
     pp.dsize = 4;
@@ -360,6 +383,224 @@ __global__ void __launch_bounds__(32) serial_post_kernel(const uint8_t *__restri
       for (int c = 0; c < NCP; ++c) dptr[(size_t)e * NCP + c] = v[c];
     }
     store_entry<NCP>(pp, pp.store, pp.dsize, optr, e, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// par_post_kernel: the point-parallel path behind a Tagged (or uncompressed) source.
+//
+// Once the tags are known the bit fields are position independent (SymbolDecoding.cs:37-49,
+// DecoderBuffer.cs:138-154): one CTA handles DCB_TAG_CHUNK points -- tags -> exclusive scan of
+// tag * ncp (bit offsets) -> LSB-first extraction -> zig-zag.  Delta + wrap is a prefix sum modulo
+// max_diff when every |correction| < max_diff <= 2^30 (PredictionSchemeWrapDecodingTransform.cs:46-67
+// then reduces to  out = min + (prev - min + corr) mod max_diff); streams that break the condition
+// are flagged `irregular` and re-run by the serial kernel, bit-exact with the reference recurrence.
+//   PASS 0  per-chunk sums of the corrections (one int64 per component) + irregular detection
+//   PASS 1  one thread per stream: exclusive scan of its chunk sums (tiny)
+//   PASS 2  re-extract, block scan, add the chunk prefix, reduce, dequantise / narrow, coalesced store
+// RECON_NONE streams only need PASS 2.
+// ---------------------------------------------------------------------------------------------
+struct ParChunk {
+  const uint8_t *tags;       // nullptr for uncompressed sources
+  const uint64_t *chunk_bits;
+  uint32_t *chunk_sums;      // [n_chunks][4] correction sums modulo max_diff
+  uint32_t n_chunks;
+};
+__device__ __forceinline__ ParChunk par_chunk_of(const StreamDesc &d, uint8_t *aux) {
+  ParChunk c;
+  const uint64_t n = d.n_entries;
+  c.n_chunks = (uint32_t)((n + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK);
+  uint8_t *base = aux + d.tag_off;
+  c.tags = d.scheme == SCHEME_TAGGED ? base : nullptr;
+  c.chunk_bits = reinterpret_cast<const uint64_t *>(base + ((n + 15ull) & ~15ull));
+  c.chunk_sums = reinterpret_cast<uint32_t *>(base + ((n + 15ull) & ~15ull) + 8ull * (c.n_chunks + 1));
+  return c;
+}
+
+__device__ __forceinline__ uint32_t mod_add(uint32_t a, uint32_t b, uint32_t md) {  // a, b in [0, md), md <= 2^30
+  const uint32_t s = a + b;
+  return s >= md ? s - md : s;
+}
+
+template <int NCP, int PASS, bool DUMP>
+__global__ void __launch_bounds__(256) par_post_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+                                                       const uint32_t *__restrict__ order, uint32_t n_streams,
+                                                       uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
+                                                       uint8_t *__restrict__ aux, uint32_t dump) {
+  extern __shared__ __align__(16) uint32_t sm_bits[];  // the chunk's bit fields, word aligned
+  __shared__ uint32_t warp_sums[8][NCP];
+  __shared__ uint32_t warp_bits[8];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  for (uint32_t slot = blockIdx.y; slot < n_streams; slot += gridDim.y) {
+    StreamDesc &d = streams[order[slot]];
+    if (d.status != DCB_OK) continue;
+    const uint32_t n = d.n_entries;
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t e0 = chunk * DCB_TAG_CHUNK;
+    if (e0 >= n) continue;
+    const ParChunk pc = par_chunk_of(d, aux);
+    const uint32_t cnt = min(DCB_TAG_CHUNK, n - e0);
+    const int recon = d.recon;
+    if (PASS == 0 && recon != RECON_DELTA_WRAP) continue;
+    if (PASS == 2 && recon == RECON_DELTA_WRAP && d.irregular) continue;  // the serial kernel owns it
+    __syncthreads();  // shared buffers are reused across the slot loop
+
+    // ---- bit lengths of this thread's 4 points ----
+    const uint32_t p0 = tid * 4u;
+    uint32_t tg[4];
+    const uint32_t fixed_bits = 8u * d.raw_num_bytes;
+    if (pc.tags) {
+      const uint32_t w = p0 < cnt ? *reinterpret_cast<const uint32_t *>(pc.tags + e0 + p0) : 0u;  // tags padded to 16 bytes
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tg[j] = (p0 + j < cnt) ? ((w >> (8 * j)) & 0xFFu) : 0u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tg[j] = (p0 + j < cnt) ? fixed_bits : 0u;
+    }
+    // exclusive scan of tag * NCP over the CTA (bits, < 2^18)
+    const uint32_t mine = (tg[0] + tg[1] + tg[2] + tg[3]) * NCP;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) warp_bits[warp] = incl;
+    const uint64_t bit_begin = pc.tags ? pc.chunk_bits[chunk] : (uint64_t)e0 * NCP * fixed_bits;
+    const uint64_t byte_begin = (pc.tags ? d.bits_off : d.raw_off) + (bit_begin >> 3);
+    const uint64_t word_begin = byte_begin & ~3ull;
+    __syncthreads();
+    uint32_t warp_off = 0, total_bits = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if ((uint32_t)w < warp) warp_off += warp_bits[w];
+      total_bits += warp_bits[w];
+    }
+    // chunk bit range -> shared memory (coalesced 32-bit loads from the 4-byte aligned floor)
+    const uint32_t lead = (uint32_t)((byte_begin - word_begin) * 8u + (bit_begin & 7u));  // bits before the first field
+    const uint32_t n_words = (lead + total_bits + 31u) / 32u + 1u;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(arena + word_begin);
+    for (uint32_t i = tid; i < n_words; i += 256u) sm_bits[i] = __ldg(src + i);  // arena is padded: over-read is safe
+    __syncthreads();
+
+    // ---- extract + zig-zag ----
+    uint32_t bpos = lead + warp_off + (incl - mine);
+    int32_t v[4][NCP];
+    const bool zig = d.zigzag != 0;
+    int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) {
+        const uint32_t t = tg[j];
+        const uint32_t w = bpos >> 5, sft = bpos & 31u;
+        const uint32_t raw = __funnelshift_r(sm_bits[w], sm_bits[w + 1], sft);
+        const uint32_t sym = t == 0 ? 0u : (t >= 32u ? raw : (raw & ((1u << t) - 1u)));
+        bpos += t;
+        if (DUMP && PASS == 2 && (dump & DCB_DUMP_SYMBOLS) && p0 + j < cnt) dptr[(size_t)(e0 + p0 + j) * NCP + c] = (int32_t)sym;
+        v[j][c] = zig ? zigzag_dec(sym) : (int32_t)sym;
+      }
+    }
+    PostParams pp;
+    pp.load(d);
+    if (recon == RECON_DELTA_WRAP) {
+      // ---- corrections as residues modulo max_diff (valid while |corr| < max_diff <= 2^30), block scan ----
+      const uint32_t md = (uint32_t)pp.max_diff;
+      const bool md_ok = md >= 1u && md <= (1u << 30);
+      bool bad = !md_ok;
+      uint32_t tsum[NCP];
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) {
+        tsum[c] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p0 + j < cnt) {
+            const int32_t x = v[j][c];
+            const uint32_t ax = x < 0 ? 0u - (uint32_t)x : (uint32_t)x;
+            if (ax >= md) bad = true;
+            const uint32_t res = x < 0 ? (uint32_t)x + md : (uint32_t)x;  // residue in [0, md) when not bad
+            v[j][c] = (int32_t)res;
+            tsum[c] = md_ok && !bad ? mod_add(tsum[c], res, md) : 0u;
+          }
+        }
+      }
+      if (PASS == 0) {
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(reinterpret_cast<unsigned int *>(&d.irregular), 1u);
+      }
+      uint32_t inc[NCP];
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) {
+        inc[c] = tsum[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc[c], o);
+          if (lane >= (uint32_t)o) inc[c] = mod_add(inc[c], t, md);
+        }
+        if (lane == 31) warp_sums[warp][c] = inc[c];
+      }
+      __syncthreads();
+      if (PASS == 0) {
+        if (tid < NCP) {
+          uint32_t sacc = 0;
+          for (int w = 0; w < 8; ++w) sacc = mod_add(sacc, warp_sums[w][tid], md);
+          pc.chunk_sums[(size_t)chunk * 4 + tid] = sacc;
+        }
+        continue;
+      }
+      // PASS 2: value before this thread's first point = chunk prefix + warps before + lanes before
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) {
+        // exclusive prefix inside the warp: inclusive minus own sum (mod md)
+        uint32_t before = mod_add(inc[c], md - tsum[c] == md ? 0u : md - tsum[c], md);
+        before = mod_add(before, pc.chunk_sums[(size_t)chunk * 4 + c], md);
+        for (uint32_t w = 0; w < warp; ++w) before = mod_add(before, warp_sums[w][c], md);
+        // first element: prediction = clamp(0) (PredictionSchemeDeltaDecoder.cs:30 + ClampPredictedValue)
+        const int32_t p0v = 0 > pp.mx ? pp.mx : (0 < pp.mn ? pp.mn : 0);
+        uint32_t acc = mod_add(before, (uint32_t)(p0v - pp.mn), md);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc = mod_add(acc, (uint32_t)v[j][c], md);
+          v[j][c] = (int32_t)((uint32_t)pp.mn + acc);
+        }
+      }
+    } else if (PASS != 2) {
+      continue;
+    }
+    // ---- store ----
+    if (DUMP && (dump & DCB_DUMP_QINTS)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p0 + j < cnt)
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) dptr[(size_t)(e0 + p0 + j) * NCP + c] = v[j][c];
+    }
+    uint8_t *optr = out + d.out_off;
+    if (p0 + 4 <= cnt) {
+      store_group4<NCP>(pp, pp.store, pp.dsize, optr, (uint64_t)e0 + p0, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p0 + j < cnt) store_entry<NCP>(pp, pp.store, pp.dsize, optr, (uint64_t)e0 + p0 + j, v[j]);
+    }
+  }
+}
+
+// PASS 1: exclusive scan of the chunk sums of every stream (one thread per stream and component)
+__global__ void par_scan_kernel(StreamDesc *streams, const uint32_t *__restrict__ order, uint32_t n_streams,
+                                uint8_t *__restrict__ aux) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_streams * 4u) return;
+  StreamDesc &d = streams[order[i >> 2]];
+  if (d.status != DCB_OK || d.recon != RECON_DELTA_WRAP || d.irregular) return;
+  const uint32_t c = i & 3u;
+  if (c >= d.ncp) return;
+  const ParChunk pc = par_chunk_of(d, aux);
+  const uint32_t md = 1u + (uint32_t)d.xf_b - (uint32_t)d.xf_a;
+  uint32_t run = 0;
+  for (uint32_t k = 0; k < pc.n_chunks; ++k) {
+    const uint32_t sv = pc.chunk_sums[(size_t)k * 4 + c];
+    pc.chunk_sums[(size_t)k * 4 + c] = run;
+    run = mod_add(run, sv, md);
   }
 }
 
@@ -485,6 +726,28 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
   }
 }
 
+// AttributeOctahedronTransform.InverseTransformAttribute (:82-102): quantized octahedral (s, t) -> unit vector,
+// one thread per entry, reading the int32 pairs the serial kernels left in scratch
+__global__ void oct_unit_kernel(StreamDesc *streams, const uint32_t *__restrict__ order, uint32_t n_streams,
+                                uint8_t *__restrict__ out, const uint8_t *__restrict__ aux) {
+  for (uint32_t si = blockIdx.y; si < n_streams; si += gridDim.y) {
+    const StreamDesc &d = streams[order[si]];
+    if (d.status != DCB_OK) continue;
+    const int32_t max_value = (int32_t)((1u << d.q_bits) - 2u);
+    const float scale = __fdiv_rn(2.0f, __int2float_rn(max_value));  // OctahedronToolBox.cs:19
+    const int2 *st = reinterpret_cast<const int2 *>(aux + d.aux_off);
+    float *o = reinterpret_cast<float *>(out + d.out_off);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < d.n_entries; e += gridDim.x * blockDim.x) {
+      const int2 q = st[e];
+      float x, y, z;
+      oct_to_unit(q.x, q.y, scale, x, y, z);
+      o[3ull * e] = x;
+      o[3ull * e + 1] = y;
+      o[3ull * e + 2] = z;
+    }
+  }
+}
+
 // generic attributes: n * byte_stride raw bytes
 __global__ void copy_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams, const uint32_t *__restrict__ order,
                             uint32_t n_streams, uint8_t *__restrict__ out) {
@@ -593,15 +856,15 @@ cudaError_t dcb_launch_resolve(const DevArenas &a, BufWalk *d_walks, const uint3
 }
 
 cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t dump,
-                                   const DevArenas &a, cudaStream_t st) {
+                                   uint32_t only_irregular, const DevArenas &a, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const uint32_t grid = (n + 31) / 32;
 #define DCB_CASE(N)                                                                                              \
   case N:                                                                                                        \
     if (dump)                                                                                                    \
-      serial_post_kernel<N, true><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump);  \
+      serial_post_kernel<N, true><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump, only_irregular);  \
     else                                                                                                         \
-      serial_post_kernel<N, false><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump); \
+      serial_post_kernel<N, false><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump, only_irregular); \
     break;
   switch (ncp) {
     DCB_CASE(1)
@@ -613,6 +876,35 @@ cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_orde
   }
 #undef DCB_CASE
   return cudaGetLastError();
+}
+
+// point-parallel post-processing of Tagged / uncompressed streams: `n_chunks` CTAs per pass
+template <int NCP>
+static cudaError_t launch_par_post_n(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_chunks,
+                                     bool any_delta, uint32_t dump, const DevArenas &a, cudaStream_t st) {
+  const uint32_t smem = (DCB_TAG_CHUNK * NCP * 32u) / 8u + 64u;  // worst case: 32-bit fields
+  const dim3 grid(max_chunks, n > 65535u ? 65535u : n);
+  if (any_delta) {
+    par_post_kernel<NCP, 0, false><<<grid, 256, smem, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump);
+    par_scan_kernel<<<(n * 4 + 127) / 128, 128, 0, st>>>(d_streams, d_order, n, a.aux);
+  }
+  if (dump)
+    par_post_kernel<NCP, 2, true><<<grid, 256, smem, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump);
+  else
+    par_post_kernel<NCP, 2, false><<<grid, 256, smem, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump);
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_chunks, int ncp,
+                                bool any_delta, uint32_t dump, const DevArenas &a, cudaStream_t st) {
+  if (n == 0 || max_chunks == 0) return cudaSuccess;
+  switch (ncp) {
+    case 1: return launch_par_post_n<1>(d_streams, d_order, n, max_chunks, any_delta, dump, a, st);
+    case 2: return launch_par_post_n<2>(d_streams, d_order, n, max_chunks, any_delta, dump, a, st);
+    case 3: return launch_par_post_n<3>(d_streams, d_order, n, max_chunks, any_delta, dump, a, st);
+    case 4: return launch_par_post_n<4>(d_streams, d_order, n, max_chunks, any_delta, dump, a, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
@@ -640,6 +932,15 @@ cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint
       return cudaErrorInvalidValue;
   }
 #undef DCB_CASE
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_oct_unit(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries,
+                                const DevArenas &a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  uint32_t gx = (max_entries + 255) / 256;
+  gx = gx < 1 ? 1 : (gx > 4096 ? 4096 : gx);
+  oct_unit_kernel<<<dim3(gx, n > 65535u ? 65535u : n), 256, 0, st>>>(d_streams, d_order, n, a.out, a.aux);
   return cudaGetLastError();
 }
 

@@ -180,8 +180,13 @@ typedef struct dcb_launch_stats {
   int32_t lanes_per_warp;
   uint64_t smem_per_stream;  /* bytes of shared memory per resident stream (dominant kernel) */
   float ms_total;            /* CUDA-event time of all kernels of the last decode (device 0) */
-  float ms_dominant;         /* CUDA-event time of the dominant rANS kernel(s) */
-  char dominant_name[64];
+  float ms_dominant;         /* CUDA-event time of the dominant kernel (largest share of ms_total) */
+  float ms_raw;              /* largest Raw rANS fused kernel */
+  float ms_tag;              /* tag rANS kernels + walk resolve (Tagged streams) */
+  float ms_par;              /* point-parallel bit extraction / scan / store passes (Tagged, uncompressed) */
+  float reserved;
+  uint64_t algo_bytes_dominant; /* algorithmic bytes of the dominant kernel (compulsory reads + writes) */
+  char dominant_name[96];
 } dcb_launch_stats;
 int dcb_last_stats(const dcb_ctx *ctx, dcb_launch_stats *out);
 

@@ -1,0 +1,197 @@
+"""Minimal pure-Python Draco v2.2 bitstream writer for tests (point clouds, sequential attribute encoding).
+
+Independent of the C++ generator (draco_sharp_b200/synth): it lets a test choose the *corrections* directly,
+so it can build streams no real encoder would (irregular wrap corrections, uncompressed integers, generic
+attributes, degenerate alphabets, every max_bit_length) and corrupt ones.  Layout per SURVEY.md Appendix A.
+"""
+import struct
+
+import numpy as np
+
+
+def varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def rans_precision(mbl):
+    return min(20, max(12, (3 * mbl) // 2))
+
+
+def zigzag(v):
+    v = int(v)
+    return (v << 1) if v >= 0 else (((-(v + 1)) << 1) | 1)
+
+
+def normalize_probs(freq, prec_bits):
+    """Integer probabilities summing to 2^prec_bits, >= 1 for every symbol that occurs."""
+    P = 1 << prec_bits
+    freq = np.asarray(freq, dtype=np.int64)
+    total = int(freq.sum())
+    prob = np.zeros(len(freq), dtype=np.int64)
+    nz = freq > 0
+    prob[nz] = np.maximum(1, (freq[nz] * P) // total)
+    diff = P - int(prob.sum())
+    order = np.argsort(-prob)
+    i = 0
+    while diff != 0:
+        j = order[i % len(order)]
+        if diff > 0:
+            prob[j] += diff
+            diff = 0
+        elif prob[j] > 1:
+            take = min(prob[j] - 1, -diff)
+            prob[j] -= take
+            diff += take
+        i += 1
+    assert prob.sum() == P and (prob[nz] >= 1).all()
+    return prob
+
+
+def table_bytes(prob):
+    out = bytearray(varint(len(prob)))
+    i = 0
+    n = len(prob)
+    while i < n:
+        p = int(prob[i])
+        if p == 0:
+            off = 0
+            while off < 63 and i + off + 1 < n and prob[i + off + 1] == 0:
+                off += 1
+            out.append((off << 2) | 3)
+            i += off + 1
+        else:
+            extra = 0 if p < (1 << 6) else (1 if p < (1 << 14) else 2)
+            out.append(((p << 2) & 0xFC) | extra)
+            for b in range(extra):
+                out.append((p >> (8 * (b + 1) - 2)) & 0xFF)
+            i += 1
+    return bytes(out)
+
+
+def rans_payload(symbols, prob, prec_bits):
+    P = 1 << prec_bits
+    l_base = 4 * P
+    cum = np.concatenate([[0], np.cumsum(prob)])
+    state = l_base
+    buf = bytearray()
+    for s in reversed([int(x) for x in symbols]):
+        p = int(prob[s])
+        lim = (l_base // P) * 256 * p
+        while state >= lim:
+            buf.append(state & 0xFF)
+            state >>= 8
+        state = (state // p) * P + state % p + int(cum[s])
+    s = state - l_base
+    if s < (1 << 6):
+        buf.append(s)
+    elif s < (1 << 14):
+        v = (1 << 14) + s
+        buf += bytes([v & 0xFF, v >> 8])
+    elif s < (1 << 22):
+        v = (2 << 22) + s
+        buf += bytes([v & 0xFF, (v >> 8) & 0xFF, v >> 16])
+    else:
+        v = (3 << 30) + s
+        buf += bytes([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF, v >> 24])
+    return bytes(buf)
+
+
+def symbols_raw(symbols, mbl=None):
+    """SYMBOLS field, Raw scheme (scheme byte 1)."""
+    symbols = [int(s) for s in symbols]
+    if not symbols:
+        return b""
+    freq = np.bincount(np.asarray(symbols, dtype=np.int64))
+    if mbl is None:
+        nu = int((freq > 0).sum())
+        mbl = min(18, max(1, nu.bit_length()))
+    pb = rans_precision(mbl)
+    prob = normalize_probs(freq, pb)
+    pay = rans_payload(symbols, prob, pb)
+    return bytes([1, mbl]) + table_bytes(prob) + varint(len(pay)) + pay
+
+
+def symbols_tagged(symbols, nc):
+    """SYMBOLS field, Tagged scheme (scheme byte 0): one bit-length tag per point, LSB-first bit fields."""
+    symbols = [int(s) for s in symbols]
+    if not symbols:
+        return b""
+    n = len(symbols) // nc
+    tags = []
+    for i in range(n):
+        m = max(symbols[i * nc:(i + 1) * nc])
+        tags.append(max(1, m.bit_length()))
+    freq = np.bincount(np.asarray(tags, dtype=np.int64), minlength=1)
+    prob = normalize_probs(freq, 12)
+    pay = rans_payload(tags, prob, 12)
+    acc = 0
+    nacc = 0
+    bits = bytearray()
+    for i in range(n):
+        for c in range(nc):
+            acc |= (symbols[i * nc + c] & ((1 << tags[i]) - 1)) << nacc
+            nacc += tags[i]
+            while nacc >= 8:
+                bits.append(acc & 0xFF)
+                acc >>= 8
+                nacc -= 8
+    if nacc:
+        bits.append(acc & 0xFF)
+    return bytes([0]) + table_bytes(prob) + varint(len(pay)) + pay + bytes(bits)
+
+
+def portable_int(corr, nc, pred_method=0, transform=1, scheme="raw", pred_data=b"", zig=True, num_bytes=None, mbl=None):
+    """PORTABLE(int-like): corrections (flat, entry-major) -> bytes."""
+    out = bytearray(struct.pack("<b", pred_method))
+    if pred_method != -2:
+        out += struct.pack("<b", transform)
+    syms = [zigzag(c) if zig else int(c) for c in corr]
+    if scheme == "uncompressed":
+        out.append(0)
+        out.append(num_bytes)
+        for s in syms:
+            out += int(s & ((1 << (8 * num_bytes)) - 1)).to_bytes(num_bytes, "little") if num_bytes else b""
+    else:
+        out.append(1)
+        out += symbols_raw(syms, mbl) if scheme == "raw" else symbols_tagged(syms, nc)
+    out += pred_data
+    return bytes(out)
+
+
+def wrap_data(mn, mx):
+    return struct.pack("<ii", mn, mx)
+
+
+def quant_params(mins, rng, bits):
+    return b"".join(struct.pack("<f", m) for m in mins) + struct.pack("<f", rng) + bytes([bits])
+
+
+def point_cloud(n_points, attrs, version=(2, 2), geom_type=0, method=0, flags=0, decoders=None):
+    """attrs: list of dicts {att_type, data_type, nc, normalized, unique_id, seq_type, portable, xform}.
+    decoders: list of lists of attribute indices (default: one decoder with all attributes)."""
+    out = bytearray(b"DRACO" + bytes([version[0], version[1], geom_type, method]) + struct.pack("<H", flags))
+    out += struct.pack("<i", n_points)
+    if decoders is None:
+        decoders = [list(range(len(attrs)))]
+    out.append(len(decoders))
+    for dec in decoders:
+        out += varint(len(dec))
+        for i in dec:
+            a = attrs[i]
+            out += bytes([a["att_type"], a["data_type"], a["nc"], a.get("normalized", 0)]) + varint(a.get("unique_id", i))
+        for i in dec:
+            out.append(attrs[i]["seq_type"])
+    for dec in decoders:
+        for i in dec:
+            out += attrs[i]["portable"]
+        for i in dec:
+            out += attrs[i].get("xform", b"")
+    return bytes(out)
