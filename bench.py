@@ -59,7 +59,7 @@ def make_workload(name, rank, unique, arena_out=None):
     from draco_sharp_b200 import synth_gen as G
     n_bufs, n_points, kw, _ = WORKLOADS[name]
     u = n_bufs if unique <= 0 else min(unique, n_bufs)
-    spec = G.make_spec(n_points, seed=0xD5AC0000 + (rank << 20), **kw)
+    spec = G.make_spec(n_points, seed=rank_seed(rank), **kw)
     arena_u, offs_u, lens_u, sums_u, schemes_u, used_u = G.synth_batch(spec, u, n_threads=host_cores())
     if u == n_bufs:
         return arena_u, offs_u, lens_u, sums_u, schemes_u, used_u
@@ -80,6 +80,24 @@ def make_workload(name, rank, unique, arena_out=None):
         sums[lo:hi] = sums_u[: hi - lo]
         schemes[lo:hi] = schemes_u[: hi - lo]
     return arena, offs, lens, sums, schemes, total
+
+
+def reduce_over_ranks(dist, device, ms, sums):
+    """Multi-GPU bookkeeping: the step time is the MAX over ranks, the work counters are SUMMED (whole-job value).
+    `dist` is torch.distributed (or None for one process); `sums` is a list of per-rank counters."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return ms, list(sums)
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    v = torch.tensor([float(x) for x in sums], dtype=torch.float64, device=device)
+    dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    return float(t.item()), [float(x) for x in v.tolist()]
+
+
+def rank_seed(rank):
+    """Every rank decodes its own, distinct batch (work shards by buffer: weak scaling, no collective on the data path)."""
+    return 0xD5AC0000 + (rank << 20)
 
 
 class ClockSampler:
@@ -314,16 +332,9 @@ def main():
     if dist:
         dist.barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    if dist:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        tp = torch.tensor([float(points), float(out_bytes), float(launches)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
-        total_points, total_out, total_launches = float(tp[0]), float(tp[1]), int(tp[2])
-    else:
-        total_points, total_out, total_launches = float(points), float(out_bytes), launches
+    ms, (total_points, total_out, total_launches) = reduce_over_ranks(dist, "cuda", ev0.elapsed_time(ev1),
+                                                                      [points, out_bytes, launches])
+    total_launches = int(total_launches)
     ms_per_step = ms / args.steps
     value = total_points / (ms_per_step * 1e-3)
     stats = dec.stats()
@@ -343,11 +354,8 @@ def main():
         b2.free()
         if i > 0:
             e2e_ms.append(dt)
-    e2e_t = float(np.mean(e2e_ms))
-    if dist:
-        t = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_t = float(t.item())
+    e2e_t = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
+    e2e_t, _ = reduce_over_ranks(dist, "cuda", e2e_t, [0.0])
     k = n_bufs // 2
     ai = batch.attr_info(k, 0)
     assert nocheck or G.word_checksum(h_out.numpy()[ai.out_off: ai.out_off + ai.out_bytes]) == int(sums[k, 0])

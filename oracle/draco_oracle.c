@@ -764,7 +764,8 @@ static int store_values(orc_attr *a) {
   return ORC_OK;
 }
 
-static int decode_impl(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps_in, int n_maps_in, orc_result *res) {
+static int decode_impl(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps_in, int n_maps_in,
+                       uint64_t attr_off_in, uint32_t n_points_in, orc_result *res) {
   rd_t r = {buf, len, 0, 0};
   /* header: D/IO/DracoDecoder.cs:44-64 */
   if (!rd_need(&r, 5)) return ORC_ERR_EOF;
@@ -793,10 +794,16 @@ static int decode_impl(const uint8_t *buf, uint64_t len, const orc_mesh_maps *ma
       int st = orc_seq_mesh_connectivity(buf, len, &r.pos, res);
       if (st) return st;
     } else if (res->method == 1) {
-      uint8_t tt = rd_u8(&r); /* DracoDecoder.cs:80 */
-      if (r.err) return r.err;
-      int st = orc_eb_decode_connectivity(buf, len, &r.pos, tt, res);
-      if (st) return st;
+      if (attr_off_in) { /* the caller decoded connectivity (as the C# host does for the GPU path) */
+        if (attr_off_in > len || !maps_in) return ORC_ERR_MAPS;
+        r.pos = attr_off_in;
+        res->n_points = n_points_in;
+      } else {
+        uint8_t tt = rd_u8(&r); /* DracoDecoder.cs:80 */
+        if (r.err) return r.err;
+        int st = orc_eb_decode_connectivity(buf, len, &r.pos, tt, res);
+        if (st) return st;
+      }
       eb = 1;
     } else
       return ORC_ERR_UNSUPPORTED;
@@ -817,7 +824,7 @@ static int decode_impl(const uint8_t *buf, uint64_t len, const orc_mesh_maps *ma
       ids[3 * i + 2] = rd_u8(&r);
     }
     if (r.err) status = r.err;
-    if (!status && !maps) {
+    if (!status && !attr_off_in) {
       status = orc_eb_build_maps(res, ids, n_dec);
       maps = res->maps;
       n_maps = res->n_maps;
@@ -887,8 +894,15 @@ static int decode_impl(const uint8_t *buf, uint64_t len, const orc_mesh_maps *ma
 }
 
 int orc_decode(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps, int n_maps, orc_result **out) {
+  return orc_decode_ex(buf, len, maps, n_maps, 0, 0, out);
+}
+
+/* attr_section_off != 0: mesh connectivity was decoded by the caller, who passes the per-decoder maps,
+ * the offset of ATTRIBUTES and the point count (mirrors dcb_set_attr_section / dcb_set_mesh_maps). */
+int orc_decode_ex(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps, int n_maps, uint64_t attr_section_off,
+                  uint32_t n_points, orc_result **out) {
   orc_result *res = (orc_result *)calloc(1, sizeof *res);
-  res->status = decode_impl(buf, len, maps, n_maps, res);
+  res->status = decode_impl(buf, len, maps, n_maps, attr_section_off, n_points, res);
   *out = res;
   return res->status;
 }

@@ -111,6 +111,8 @@ void orc_narrow(const int32_t *q, uint64_t count, int data_type, uint8_t *out);
 /* ---- whole-buffer decode. maps may be NULL (point clouds; Edgebreaker meshes use the
  * oracle's own host connectivity when built in, see orc_eb.c). */
 int orc_decode(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps, int n_maps, orc_result **out);
+int orc_decode_ex(const uint8_t *buf, uint64_t len, const orc_mesh_maps *maps, int n_maps, uint64_t attr_section_off,
+                  uint32_t n_points, orc_result **out);
 void orc_free(orc_result *r);
 
 /* decode + discard, for timing the CPU baseline; returns status, accumulates a checksum of outputs */

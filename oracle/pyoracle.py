@@ -62,6 +62,9 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.orc_decode.restype = C.c_int
         l.orc_decode.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcMaps), C.c_int, C.POINTER(C.POINTER(OrcResult))]
+        l.orc_decode_ex.restype = C.c_int
+        l.orc_decode_ex.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcMaps), C.c_int, C.c_uint64, C.c_uint32,
+                                    C.POINTER(C.POINTER(OrcResult))]
         l.orc_free.restype = None
         l.orc_free.argtypes = [C.POINTER(OrcResult)]
         l.orc_decode_bench.restype = C.c_int
@@ -122,7 +125,7 @@ class Result:
             })
 
 
-def decode(buf, maps=None) -> Result:
+def decode(buf, maps=None, attr_section_off=0, n_points=0) -> Result:
     """Decode one .drc buffer on the CPU.  maps: optional list of dicts (see Result.maps)."""
     a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else np.ascontiguousarray(buf, dtype=np.uint8)
     res = C.POINTER(OrcResult)()
@@ -145,7 +148,7 @@ def decode(buf, maps=None) -> Result:
             cm[i].n_entries = d.size
             cm[i].vertex_to_data = v.ctypes.data_as(C.POINTER(C.c_int32))
             cm[i].n_vertices = v.size
-    lib().orc_decode(a.ctypes.data if a.size else None, a.size, cm, n_maps, C.byref(res))
+    lib().orc_decode_ex(a.ctypes.data if a.size else None, a.size, cm, n_maps, attr_section_off, n_points, C.byref(res))
     out = Result(res.contents)
     lib().orc_free(res)
     return out

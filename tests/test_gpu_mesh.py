@@ -1,0 +1,114 @@
+"""-m gpu: the parallelogram path (Edgebreaker meshes; connectivity on the host, prediction on the GPU).
+
+Connectivity comes from the oracle's host Edgebreaker restatement, exactly as the C# host would hand its
+CornerTable / traversal maps to dcb_set_mesh_maps."""
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import drc_writer as W
+from draco_sharp_b200 import _native as N
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _mesh_buffer(attr_section):
+    """DRACO v2.2 Edgebreaker mesh header + an opaque connectivity blob + the given ATTRIBUTES section."""
+    head = b"DRACO" + bytes([2, 2, 1, 1]) + struct.pack("<H", 0) + bytes([2]) + b"\xAA" * 37  # connectivity: host business
+    return head + attr_section, len(head)
+
+
+def _decode_mesh(dec, buf, attr_off, n_points, maps, flags=0):
+    batch = dec.index([buf])
+    assert batch.buffer_info(0).needs_connectivity == 1
+    batch.set_attr_section(0, attr_off, n_points)
+    for d, m in enumerate(maps):
+        batch.set_mesh_maps(0, d, m["opposite"], m["corner_to_vertex"], m["data_to_corner"], m["vertex_to_data"])
+    batch.finish()
+    out, dbg = dec.decode(batch, flags=flags)
+    return batch, out, dbg
+
+
+def test_house_positions_on_gpu_match_goldens(gpu_decoder):
+    """The position attribute of the reference's sample asset, bytes verbatim, through the CUDA parallelogram
+    path: SHA-256 goldens of SURVEY.md Appendix C (quantized ints and floats), and the oracle."""
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    a = o.attrs[0]
+    start = a.table_off - 5                      # pred, transform, compressed, scheme, max_bit_length
+    end = a.payload_off + a.payload_len + 8      # + wrap bounds
+    portable = bytes(b[start:end])
+    xform = bytes(b[end:end + 17])               # decoder 0 holds one attribute: its XFORM_PARAMS follow directly
+    section = bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2]) + portable + xform
+    buf, attr_off = _mesh_buffer(section)
+    maps = [o.maps[0]]
+    ref = O.decode(np.frombuffer(buf, dtype=np.uint8), maps, attr_off, o.n_points)
+    assert ref.status == 0 and np.array_equal(ref.attrs[0].out, a.out)
+    for flags, key in ((N.DCB_DUMP_QINTS, "qints"), (N.DCB_DUMP_SYMBOLS, "symbols")):
+        batch, out, dbg = _decode_mesh(gpu_decoder, buf, attr_off, o.n_points, maps, flags)
+        assert batch.status(0) == 0
+        ai = batch.attr_info(0, 0)
+        assert ai.n_entries == 1775 and ai.pred_method == 1
+        got = out[ai.out_off: ai.out_off + ai.out_bytes]
+        assert sha(got) == "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
+        ints = dbg[ai.dbg_off: ai.dbg_off + 4 * 5325].view(np.int32)
+        if key == "qints":
+            assert sha(ints) == "15d5eeb7c1c24707f0bcc20b6ed5e89b6faaa5d46da4fd5f15b5872352e02be6"
+        else:
+            assert sha(ints) == "00823b9eb65a088cb18987b7016f3756f94fbccb5911d1e86912911af2fcb07b"
+        batch.free()
+
+
+@pytest.mark.parametrize("scheme", ["raw", "tagged", "uncompressed"])
+def test_parallelogram_random_corrections(gpu_decoder, scheme):
+    """Random corrections over the sample's real connectivity, several attributes per decoder, all sources."""
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    rng = np.random.default_rng(5)
+    n0, n1 = o.maps[0]["data_to_corner"].size, o.maps[1]["data_to_corner"].size
+    c_pos = rng.integers(-30, 31, size=n0 * 3)
+    c_gen = rng.integers(-3, 4, size=n0 * 1)
+    c_uv = rng.integers(-9, 10, size=n1 * 2)
+    c_pos[rng.integers(0, n0 * 3, 20)] = rng.integers(-5000, 5000, 20)  # clamp + wrap corner cases
+    sec = bytearray([2, 0xFF, 0, 0, 0, 1, 0])
+    sec += W.varint(2) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([4, 2, 1, 0]) + W.varint(1) + bytes([2, 1])
+    sec += W.varint(1) + bytes([3, 9, 2, 0]) + W.varint(2) + bytes([2])
+    sec += W.portable_int(c_pos, 3, 1, 1, scheme, W.wrap_data(0, 4095), num_bytes=2)
+    sec += W.portable_int(c_gen, 1, 1, 1, scheme, W.wrap_data(0, 255), num_bytes=1)
+    sec += W.quant_params([1.0, 2.0, 3.0], 10.0, 12)
+    sec += W.portable_int(c_uv, 2, 1, 1, scheme, W.wrap_data(0, 1023), num_bytes=2)
+    sec += W.quant_params([0.0, 0.0], 1.0, 10)
+    buf, attr_off = _mesh_buffer(bytes(sec))
+    maps = [o.maps[0], o.maps[1]]
+    ref = O.decode(np.frombuffer(buf, dtype=np.uint8), maps, attr_off, o.n_points)
+    assert ref.status == 0
+    batch, out, dbg = _decode_mesh(gpu_decoder, buf, attr_off, o.n_points, maps, N.DCB_DUMP_QINTS)
+    assert batch.status(0) == 0
+    for k, ra in enumerate(ref.attrs):
+        ai = batch.attr_info(0, k)
+        assert ai.n_entries == ra.n_entries
+        assert np.array_equal(dbg[ai.dbg_off: ai.dbg_off + 4 * ra.qints.size].view(np.int32), ra.qints), k
+        assert np.array_equal(out[ai.out_off: ai.out_off + ai.out_bytes], ra.out), k
+    batch.free()
+
+
+def test_mesh_without_maps_fails_cleanly(gpu_decoder):
+    sec = bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
+    sec += W.portable_int(np.zeros(30, dtype=np.int64), 3, 1, 1, "raw", W.wrap_data(0, 7)) + W.quant_params([0, 0, 0], 1.0, 3)
+    buf, attr_off = _mesh_buffer(sec)
+    batch = gpu_decoder.index([buf])
+    with pytest.raises(Exception):
+        gpu_decoder.decode(batch)          # dcb_index_finish was never run: DCB_ERR_STATE
+    batch.set_attr_section(0, attr_off, 10)
+    batch.finish()
+    assert batch.status(0) == -14          # DCB_ERR_MAPS
+    batch.free()
