@@ -39,6 +39,7 @@ WORKLOADS = {
     "c2tagged": (10000, 100000, dict(pos_bits=14, scheme=0), "configs[1] with the Tagged scheme forced"),
     "c3": (10000, 100000, dict(pos_bits=14, scheme=-1, normal_bits=10, colors=1),
            "BASELINE configs[2]: configs[1] + 10-bit octahedral normals + 8-bit RGB"),
+    "c2s": (7000, 100000, dict(pos_bits=14, scheme=-1), "configs[1] shape with 7,000 clouds (experiment)"),
     "small": (1024, 100000, dict(pos_bits=14, scheme=-1), "CI-sized configs[1]: 1,024 clouds x 100k points"),
     "tiny": (64, 20000, dict(pos_bits=14, scheme=-1), "smoke-sized"),
 }

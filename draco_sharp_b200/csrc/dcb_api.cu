@@ -59,7 +59,7 @@ struct Group {            // one kernel launch (or a few, for global tables)
   int kind;               // 0 raw, 1 tag, 2 serial post, 3 para, 4 copy
   int ncp;
   bool wide, table_global;
-  uint32_t compact, prec_bits, entries, lut_shift, lut_bytes, ent_bytes, lanes, zig, mode;
+  uint32_t compact, prec_bits, entries, exc, lut_shift, lut_bytes, lutb_bytes, ent_bytes, lanes, zig, mode;
   uint64_t total_symbols, max_bytes;
   uint32_t max_entries;
   std::vector<uint32_t> order;
@@ -498,7 +498,7 @@ struct RawKey {
 
 uint32_t ent_bytes_for(const Group &g) {
   const uint32_t sz = g.wide ? 4u : 2u;
-  return (uint32_t)align_up((uint64_t)(g.entries + 2u) * sz + (g.compact ? (uint64_t)g.entries * sz : 0ull), 16);
+  return (uint32_t)align_up((uint64_t)(g.entries + 2u) * sz + (g.compact ? (uint64_t)g.exc * sz : 0ull), 16);
 }
 uint32_t lut_bytes_for(const Group &g, uint32_t k) { return ((1u << g.prec_bits) >> k) * (g.wide ? 4u : 2u); }
 uint32_t lane_bytes_for(const Group &g, uint32_t k) { return lut_bytes_for(g, k) + ent_bytes_for(g) + DCB_RING_BYTES; }
@@ -568,6 +568,19 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms) {
     while (g.lanes > 1 && ((uint64_t)g.lanes * lane_bytes + g.lut_bytes + 256 > kSmemPerSM - kSmemPerCtaReserve ||
                            (!g.wide && (uint64_t)g.lanes * g.ent_bytes > 65535)))
       --g.lanes;
+    // two-region LUT (compact u16 tables): give its narrow region whatever shared memory is left per lane, up
+    // to one byte per two slots
+    g.lutb_bytes = 0;
+    if (!g.wide && g.compact) {
+      const uint32_t ctas_per_sm = std::max<uint32_t>(1u, (want + g.lanes - 1) / g.lanes);
+      const uint32_t blk = std::max(16u, ((1u << g.prec_bits) >> 7) << 2);
+      const uint64_t cta_budget = (kSmemPerSM + 1024) / ctas_per_sm - kSmemPerCtaReserve - g.lut_bytes - blk - 256;
+      const uint64_t used = (uint64_t)g.lanes * (lane_bytes + blk);
+      if (cta_budget > used) {
+        const uint64_t spare = (cta_budget - used) / g.lanes;
+        g.lutb_bytes = (uint32_t)std::min<uint64_t>((1u << g.prec_bits) >> 1, spare / 16 * 16);
+      }
+    }
   }
 }
 
@@ -692,8 +705,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(sh.d_order, g.order.data(), g.order.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(sh.d_order + g.order.size(), blocked.data(), blocked.size() * 4, cudaMemcpyHostToDevice, st));
-    RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.lut_bytes, g.ent_bytes, g.entries,
-                 g.lut_shift, dump, 0, 0, 0};
+    RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.lut_bytes, 0, g.ent_bytes, g.entries, 0,
+                 g.lut_shift, g.prec_bits, dump, 0, 0, 0};
     const bool time_tag = timed && dev_index == 0 && !ctx->ev_tag;
     if (time_tag) {
       CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
@@ -760,6 +773,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
           g.zig = (uint32_t)key.zig; g.mode = (uint32_t)key.mode;
         }
         g.entries = std::max(g.entries, entries);
+        if (key.compact) g.exc = std::max(g.exc, s.n_active - std::min(s.n_active, s.dense_prefix));
         g.total_symbols += (uint64_t)s.n_entries * s.ncp;
         g.order.push_back(si);
       } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP) && !getenv("DCB_NO_PAR_POST")) {
@@ -830,9 +844,9 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     const bool is_dom = timed && dev_index == 0 && g == dom;
     if (getenv("DCB_DEBUG_PLAN"))
       fprintf(stderr, "[dcb plan] raw group ncp=%d wide=%d compact=%u prec=%u entries=%u mode=%u zig=%u: %u streams, %llu symbols, "
-                      "k=%u lut=%uB ent=%uB lanes=%u global=%d\n",
+                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u global=%d\n",
               g->ncp, (int)g->wide, g->compact, g->prec_bits, g->entries, g->mode, g->zig, n,
-              (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->ent_bytes, g->lanes, (int)g->table_global);
+              (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->lanes, (int)g->table_global);
     if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (g->table_global) {
       const uint64_t slot_bytes = (uint64_t)g->lut_bytes + g->ent_bytes;
@@ -849,13 +863,13 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       A.tab = sh.d_tab;
       for (uint64_t o = 0; o < n; o += chunk) {
         RansLaunch L{sh.d_streams, sh.d_order + g->order_off + o, (uint32_t)std::min<uint64_t>(chunk, n - o), 32,
-                     g->lut_bytes, g->ent_bytes, g->entries, g->lut_shift, dump, g->compact, g->zig, 0};
+                     g->lut_bytes, 0, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, dump, g->compact, g->zig, 0};
         CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, true, A, st));
         stats.n_launches++;
       }
     } else {
-      RansLaunch L{sh.d_streams, sh.d_order + g->order_off, n, g->lanes, g->lut_bytes, g->ent_bytes, g->entries,
-                   g->lut_shift, dump, g->compact, g->zig, g->mode};
+      RansLaunch L{sh.d_streams, sh.d_order + g->order_off, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes,
+                   g->entries, g->exc, g->lut_shift, g->prec_bits, dump, g->compact, g->zig, g->mode};
       CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
       stats.n_launches++;
     }
@@ -867,8 +881,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         ctx->algo_raw += (sd.payload_off + sd.payload_len - sd.table_off) + sd.out_bytes;
       }
       stats.lanes_per_warp = (int32_t)g->lanes;
-      stats.smem_per_stream = (uint64_t)g->lut_bytes + g->ent_bytes + DCB_RING_BYTES;
-      RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->ent_bytes, g->entries, g->lut_shift, 0, g->compact, g->zig, g->mode};
+      stats.smem_per_stream = (uint64_t)g->lut_bytes + g->lutb_bytes + g->ent_bytes + DCB_RING_BYTES;
+      RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, 0, g->compact, g->zig, g->mode};
       const uint32_t cta_smem = dcb_rans_smem_bytes(Ls, g->table_global) + kSmemPerCtaReserve;
       const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, kSmemPerSM / cta_smem)) * g->lanes;
       stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);

@@ -271,9 +271,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 
 // geometry of the tables of one launch (uniform over the grid)
 struct TableGeom {
-  uint32_t lut_bytes;   // per lane, power of two
+  uint32_t lut_bytes;   // per lane, power of two (uniform LUT / wide region of the two-region LUT)
+  uint32_t lutb_bytes;  // per lane: narrow region of the two-region LUT (one byte per 2 slots), 0 = none
+  uint32_t blk_bytes;   // per lane: block bases of the narrow region (one u32 per 128 slots), power of two
   uint32_t ent_bytes;   // per lane
   uint32_t cap_entries; // table entries a lane can hold
+  uint32_t cap_exc;     // compact tables: value slots for entries beyond the dense symbol prefix
   uint32_t lut_shift;   // log2(slots per LUT bucket)
   uint32_t compact;     // 1: entries = symbols with prob > 0 (+ value map), 0: entries = symbol ids
   uint32_t zig;         // value map holds zig-zag decoded values (compact) / apply zig-zag (dense)
@@ -290,7 +293,20 @@ struct RansLane {
   uint32_t lut_mask, lut_sh;
   uint32_t ring;        // smem address of the lane's ring
   uint32_t ent_off;     // byte offset of the lane's cum[0] from ent0
-  uint32_t val_delta;   // byte distance cum[i] -> val[i]
+  uint32_t val_delta;   // byte distance cum[i] -> its value slot (entries beyond the dense prefix)
+  uint32_t dprefix;     // compact tables: entries 0..dprefix-1 are the symbols 0..dprefix-1
+  // two-region LUT (u16 tables in shared memory): slots below t_split are bucketed by 2^kA, where every table
+  // entry is at least 2^kA slots wide; slots from t_split on are bucketed by 2.  Either way a bucket meets at
+  // most two entries, so the probe needs no search loop.
+  // Region A holds u16 entry ranks.  Region B holds, per 2-slot bucket, a u8 rank relative to the first entry
+  // of its 128-slot block, and per block the shared-memory address of that entry's cum value.
+  uint32_t t_split, a_sh, a_mask, b_base, base_b;
+  uint32_t lutb_addr;   // smem address of the lane's region B deltas
+  uint32_t blk_addr;    // smem address of the lane's block bases (aligned to blk_bytes)
+  uint32_t blk_mask;
+  uint32_t cum_addr;    // smem address of the lane's cum[0]
+  uint32_t n_entries_tab;  // entries built (ne)
+  bool split_ok;        // the two-region LUT fits this lane's LUT capacity
   const uint8_t *ent0;  // entry region (generic pointer: shared or global)
   const uint8_t *lut0;  // GLOBAL only
   // byte supply
@@ -342,7 +358,7 @@ struct RansLane {
   // L/65536 that x is below, capped by the bytes left.  CAREFUL = false assumes the caller has
   // checked that enough bytes are left for the cap not to bind.
   // Returns the byte offset (from ent0) of cum[entry].
-  template <bool CAREFUL>
+  template <bool CAREFUL, bool SPLIT>
   __device__ __forceinline__ uint32_t step() {
     const uint32_t v = peek();
     uint32_t sh;  // 8 * bytes to shift in
@@ -361,17 +377,38 @@ struct RansLane {
     prefetch();
     const uint32_t r = xr & mask;
     const uint32_t q = xr >> prec_bits;
-    uint32_t o = lut_load(xr);
-    // two candidates per probe; the LUT granularity makes a third one rare
-    const T *cp = reinterpret_cast<const T *>(ent0 + o);
-    uint32_t c0 = cp[0], c1 = cp[1], c2 = cp[2];
-    if (__builtin_expect(r >= c2, 0)) {
-      do {
-        o += (uint32_t)sizeof(T);
-        c0 = c1;
-        c1 = c2;
-        c2 = *reinterpret_cast<const T *>(ent0 + o + 2u * (uint32_t)sizeof(T));
-      } while (r >= c2);
+    uint32_t o, c0, c1, c2;
+    if (SPLIT) {
+      // both regions hold u8 ranks relative to the first entry of their 128-slot block; blk[] holds the
+      // shared-memory address of that entry's cum value: one byte load + one word load, issued together
+      const uint32_t a_a = ((xr >> a_sh) & a_mask) | lut_base;
+      const uint32_t a_b = (r >> 1) + b_base;
+      const uint32_t a = r >= t_split ? a_b : a_a;
+      const uint32_t a_k = ((xr >> 5) & blk_mask) | blk_addr;
+      uint32_t dl, bb;
+      asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(dl) : "r"(a));
+      asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(bb) : "r"(a_k));
+      const uint32_t ca = dl * 2u + bb;
+      asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(c0) : "r"(ca));
+      asm volatile("ld.shared.u16 %0, [%1+2];\n" : "=r"(c1) : "r"(ca));
+      asm volatile("ld.shared.u16 %0, [%1+4];\n" : "=r"(c2) : "r"(ca));
+      const uint32_t rank = (ca - cum_addr) >> 1;
+      o = ent_off + 2u * rank;
+    } else {
+      o = lut_load(xr);
+      const T *cp = reinterpret_cast<const T *>(ent0 + o);
+      c0 = cp[0];
+      c1 = cp[1];
+      c2 = cp[2];
+      // uniform LUT: a bucket may meet three or more entries (rare by construction of the granularity)
+      if (__builtin_expect(r >= c2, 0)) {
+        do {
+          o += (uint32_t)sizeof(T);
+          c0 = c1;
+          c1 = c2;
+          c2 = *reinterpret_cast<const T *>(ent0 + o + 2u * (uint32_t)sizeof(T));
+        } while (r >= c2);
+      }
     }
     const bool second = r >= c1;
     const uint32_t xa = q * (c1 - c0) + (r - c0);
@@ -380,18 +417,18 @@ struct RansLane {
     return o + (second ? (uint32_t)sizeof(T) : 0u);
   }
 
-  // table entry -> symbol value.  compact: val[] holds the value (zig-zag decoded when geom.zig);
-  // dense: the entry index is the symbol id.
+  // table entry -> symbol value.  dense: the entry index is the symbol id.  compact: entries below the dense
+  // prefix are their own symbol ids, the others carry a value slot (zig-zag decoded when zig).
   __device__ __forceinline__ int32_t value(uint32_t o, bool compact, bool zig) const {
-    if (compact) {
+    const uint32_t rank = (o - ent_off) / (uint32_t)sizeof(T);
+    if (compact && rank >= dprefix) {
       if (sizeof(T) == 2) {
         return zig ? (int32_t) * reinterpret_cast<const int16_t *>(ent0 + o + val_delta)
                    : (int32_t) * reinterpret_cast<const uint16_t *>(ent0 + o + val_delta);
       }
       return *reinterpret_cast<const int32_t *>(ent0 + o + val_delta);
     }
-    const uint32_t sym = (o - ent_off) / (uint32_t)sizeof(T);
-    return zig ? zigzag_dec(sym) : (int32_t)sym;
+    return zig ? zigzag_dec(rank) : (int32_t)rank;
   }
   // the symbol id itself (debug dumps)
   __device__ __forceinline__ uint32_t symbol(uint32_t o, const TableGeom &g) const {
@@ -432,16 +469,15 @@ struct RansLane {
     prefetch();
   }
 
-  // Parse RANS_TABLE at d.table_off into the lane's table (RAnsSymbolDecoder.cs:12-51, RAnsDecoder.cs:69-88).
-  // lut/ent point at the lane's LUT and entry slices (generic pointers).
-  __device__ int build(const uint8_t *arena_, const StreamDesc &d, const TableGeom &g, T *lut, T *ent,
-                       uint32_t ent_off_) {
+  // Parse RANS_TABLE at d.table_off into the lane's cum / value arrays (RAnsSymbolDecoder.cs:12-51,
+  // RAnsDecoder.cs:69-88) and decide whether the two-region LUT fits.  The LUT itself is written by fill_lut.
+  __device__ int build(const uint8_t *arena_, const StreamDesc &d, const TableGeom &g, T *ent, uint32_t ent_off_) {
     ent_off = ent_off_;
-    val_delta = (g.cap_entries + 2u) * (uint32_t)sizeof(T);
     lut_sh = g.lut_shift - (sizeof(T) == 2 ? 1u : 2u);
     lut_mask = g.lut_bytes - (uint32_t)sizeof(T);
+    split_ok = false;
     T *cum = ent;
-    T *val = ent + g.cap_entries + 2u;
+    T *val = ent + g.cap_entries + 2u;   // value slot of entry (dprefix + j) is val[j]
     uint64_t pos = d.table_off;
     const uint64_t bend = d.buf_end;
     for (int i = 0; i < 10; ++i) {  // skip the num_symbols varint (value parsed by the indexer)
@@ -451,6 +487,7 @@ struct RansLane {
     const uint32_t ns = d.num_symbols;
     const uint32_t prec = 1u << d.prec_bits;
     if (!g.compact && ns > g.cap_entries) return DCB_ERR_TABLE;
+    dprefix = g.compact ? 0xFFFFFFFFu : 0u;  // compact: set at the first entry whose symbol id != its rank
     uint64_t c = 0;
     uint32_t ne = 0;
     bool overflow = false;
@@ -474,9 +511,15 @@ struct RansLane {
           if (prob) {
             if (c + prob > prec || ne >= g.cap_entries) overflow = true;
             if (!overflow) {
-              cum[ne] = (T)c;
-              val[ne] = (T)(g.zig ? (uint32_t)zigzag_dec(i) : i);
-              ++ne;
+              if (dprefix == 0xFFFFFFFFu && i != ne) dprefix = ne;
+              if (dprefix != 0xFFFFFFFFu) {
+                if (ne - dprefix >= g.cap_exc) overflow = true;
+                else val[ne - dprefix] = (T)(g.zig ? (uint32_t)zigzag_dec(i) : i);
+              }
+              if (!overflow) {
+                cum[ne] = (T)c;
+                ++ne;
+              }
             }
           }
         } else {
@@ -488,16 +531,84 @@ struct RansLane {
     }
     if (overflow || c != prec) return DCB_ERR_TABLE;
     if (!g.compact) ne = ns;
+    if (g.compact && dprefix == 0xFFFFFFFFu) dprefix = ne;
     cum[ne] = (T)prec;
     cum[ne + 1] = (T)prec;  // pad: the two-candidate probe reads cum[i + 2]
-    const uint32_t nb = prec >> g.lut_shift;
-    uint32_t i = 0;
-    for (uint32_t b = 0; b < nb; ++b) {
-      const uint32_t slot = b << g.lut_shift;
-      while ((uint32_t)cum[i + 1] <= slot) ++i;
-      lut[b] = (T)(ent_off + i * (uint32_t)sizeof(T));
+    n_entries_tab = ne;
+    val_delta = (g.cap_entries + 2u - (g.compact ? dprefix : 0u)) * (uint32_t)sizeof(T);
+    // ---- two-region LUT: pick the bucket size 2^kA of the wide region that needs the fewest LUT bytes ----
+    // Dense tables may hold zero-width entries between two owners of one bucket (the two-candidate probe would
+    // stop at the empty one), so the split LUT is only built for compact tables.
+    if (sizeof(T) == 2 && !GLOBAL && g.compact && g.lutb_bytes > 0) {
+      uint32_t first_narrow[8];  // first slot owned by an entry narrower than 2^kA (kA = 1..7)
+#pragma unroll
+      for (int k = 1; k <= 7; ++k) first_narrow[k] = prec;
+      for (uint32_t i = 0; i < ne; ++i) {
+        const uint32_t w = (uint32_t)cum[i + 1] - (uint32_t)cum[i];
+#pragma unroll
+        for (int k = 1; k <= 7; ++k)
+          if (w < (1u << k) && first_narrow[k] == prec) first_narrow[k] = (uint32_t)cum[i];
+      }
+      uint32_t best = 0xFFFFFFFFu, best_k = 0, best_t = 0;
+#pragma unroll
+      for (int k = 1; k <= 7; ++k) {
+        if ((uint32_t)k + 7u > d.prec_bits) continue;
+        const uint32_t t = first_narrow[k] & ~127u;   // whole 128-slot blocks on either side
+        const uint32_t na = t >> k, nbk = (prec - t) >> 1;
+        if (na > g.lut_bytes || nbk > g.lutb_bytes) continue;
+        const uint32_t need = na + nbk;
+        if (need < best) { best = need; best_k = (uint32_t)k; best_t = t; }
+      }
+      if (best_k > 0 && g.blk_bytes >= ((prec >> 7) << 2)) {
+        split_ok = true;
+        t_split = best_t;
+        a_sh = best_k;
+        a_mask = (1u << (d.prec_bits - best_k)) - 1u;
+        b_base = lutb_addr - (best_t >> 1);
+        blk_mask = ((prec >> 7) - 1u) << 2;
+      }
     }
     return DCB_OK;
+  }
+
+  // LUT entries: byte offset (from ent0) of cum[i] for the first table entry i owning part of the bucket
+  __device__ void fill_lut(const TableGeom &g, T *lut, uint8_t *lutb, uint32_t *blk, const T *cum, bool split) const {
+    const uint32_t prec = 1u << prec_bits;
+    uint32_t i = 0;
+    if (!split) {
+      const uint32_t nb = prec >> g.lut_shift;
+      for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t slot = b << g.lut_shift;
+        while ((uint32_t)cum[i + 1] <= slot) ++i;
+        lut[b] = (T)(ent_off + i * (uint32_t)sizeof(T));
+      }
+      return;
+    }
+    const uint32_t ka = a_sh;
+    const uint32_t na = t_split >> ka;
+    uint8_t *luta = reinterpret_cast<uint8_t *>(lut);
+    uint32_t cur_blk = 0xFFFFFFFFu, base_rank = 0;
+    for (uint32_t b = 0; b < na; ++b) {
+      const uint32_t slot = b << ka;
+      while ((uint32_t)cum[i + 1] <= slot) ++i;
+      if ((slot >> 7) != cur_blk) {  // first bucket of a 128-slot block: its owner is the block's base entry
+        cur_blk = slot >> 7;
+        base_rank = i;
+        blk[cur_blk] = cum_addr + 2u * i;
+      }
+      luta[b] = (uint8_t)(i - base_rank);
+    }
+    const uint32_t nbk = (prec - t_split) >> 1;
+    for (uint32_t b = 0; b < nbk; ++b) {
+      const uint32_t slot = t_split + 2u * b;
+      while ((uint32_t)cum[i + 1] <= slot) ++i;
+      if ((slot >> 7) != cur_blk) {
+        cur_blk = slot >> 7;
+        base_rank = i;
+        blk[cur_blk] = cum_addr + 2u * i;
+      }
+      lutb[b] = (uint8_t)(i - base_rank);
+    }
   }
 };
 

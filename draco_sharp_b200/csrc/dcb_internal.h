@@ -71,6 +71,7 @@ struct StreamDesc {
   uint32_t n_entries;
   uint32_t num_symbols;          // table alphabet size
   uint32_t n_active;             // symbols with non-zero probability
+  uint32_t dense_prefix;         // leading symbols 0..dense_prefix-1 all have non-zero probability
   uint32_t unique_id;
   int32_t xf_a, xf_b;            // wrap min,max | oct max_quantized_value, center
   float q_min[4];
@@ -91,7 +92,7 @@ struct StreamDesc {
   uint8_t state;                 // ST_*
   uint8_t compressed;
   uint8_t has_maps;              // host supplied connectivity maps for this attribute's decoder
-  uint8_t pad_[5];
+  uint8_t pad_[1];
 };
 
 // Resumable container walk of one buffer (runs on the host; continues on the device behind Tagged
@@ -130,9 +131,12 @@ struct RansLaunch {
   uint32_t n_streams;
   uint32_t lanes_per_warp;        // active lanes per warp-CTA
   uint32_t lut_bytes;             // per lane: LUT size (power of two)
-  uint32_t ent_bytes;             // per lane: cum[cap + 2] (+ val[cap] for compact tables)
+  uint32_t lutb_bytes;            // per lane: narrow region of the two-region LUT (0 = uniform LUT only)
+  uint32_t ent_bytes;             // per lane: cum[cap + 2] (+ val[cap_exc] for compact tables)
   uint32_t cap_entries;           // table entries a lane can hold
+  uint32_t cap_exc;               // compact tables: entries beyond the dense prefix that need a value slot
   uint32_t lut_shift;             // log2(slots per LUT bucket)
+  uint32_t prec_bits;             // rANS precision of the group
   uint32_t dump;                  // DCB_DUMP_* flags
   uint32_t compact;               // 1: tables indexed by active-symbol rank (+ value map), 0: by symbol id
   uint32_t zig;                   // symbols are zig-zag coded corrections

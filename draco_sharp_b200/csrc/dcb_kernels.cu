@@ -21,6 +21,9 @@
 //   copy_kernel             SequentialAttributeDecoder.DecodeValues (generic attributes, :75-86)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "dcb_device.cuh"
 #include "dcb_internal.h"
@@ -58,7 +61,7 @@ __device__ __forceinline__ int dsize_of(const PostParams &pp) {
 
 // shared-memory carve-up of a warp-CTA (see RansLane)
 struct SmemLayout {
-  uint32_t lut0, ring0, ent0;  // byte offsets from the dynamic shared-memory base
+  uint32_t lut0, ring0, blk0, lutb0, ent0;  // byte offsets from the dynamic shared-memory base
 };
 __device__ __forceinline__ SmemLayout smem_layout(uint32_t base_addr, uint32_t lanes, const TableGeom &g, bool table_global) {
   SmemLayout l;
@@ -73,18 +76,26 @@ __device__ __forceinline__ SmemLayout smem_layout(uint32_t base_addr, uint32_t l
   a = (a + DCB_RING_BYTES - 1u) & ~(DCB_RING_BYTES - 1u);
   l.ring0 = a - base_addr;
   a += lanes * DCB_RING_BYTES;
+  l.blk0 = l.lutb0 = a - base_addr;
+  if (!table_global && g.lutb_bytes) {
+    a = (a + g.blk_bytes - 1u) & ~(g.blk_bytes - 1u);
+    l.blk0 = a - base_addr;
+    a += lanes * g.blk_bytes;
+    l.lutb0 = a - base_addr;
+    a += (lanes * g.lutb_bytes + 15u) & ~15u;
+  }
   l.ent0 = a - base_addr;
   return l;
 }
 
 // decode one entry: NCP symbols -> corrections -> prediction; leaves the portable ints in v and prev
 // TAB: 0 = table kind (dense / compact) read from the launch geometry, 1 = dense, 2 = compact
-template <int NCP, typename T, bool TG, bool DUMP, int MODE, int TAB, bool CAREFUL>
+template <int NCP, typename T, bool TG, bool DUMP, int MODE, int TAB, bool CAREFUL, bool SPLIT>
 __device__ __forceinline__ void decode_entry(RansLane<T, TG> &rl, const TableGeom &g, const PostParams &pp, int32_t *prev,
                                              int32_t *v, int32_t *dptr, uint32_t dump, uint64_t e) {
 #pragma unroll
   for (int c = 0; c < NCP; ++c) {
-    const uint32_t o = rl.template step<CAREFUL>();
+    const uint32_t o = rl.template step<CAREFUL, SPLIT>();
     const bool compact = TAB == 0 ? g.compact != 0 : TAB == 2;
     const bool zig = MODE == 0 ? g.zig != 0 : MODE != 3;
     v[c] = rl.value(o, compact, zig);
@@ -110,6 +121,37 @@ __device__ __forceinline__ void decode_entry(RansLane<T, TG> &rl, const TableGeo
   }
 }
 
+// One stream, start to end: main loop over groups of 4 entries, then the careful per-entry tail.
+template <int NCP, typename T, bool DUMP, bool TG, int MODE, int TAB, bool SPLIT>
+__device__ __forceinline__ void run_stream(RansLane<T, TG> &rl, const TableGeom &geom, const PostParams &pp, uint8_t *optr,
+                                           int32_t *dptr, uint32_t dump, uint32_t n_entries, uint32_t g_min) {
+  const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp);
+  int32_t prev[NCP];
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) prev[c] = 0;
+  // ---- main loop: 4 entries (4 * NCP symbols) per iteration, renormalisation bounds checked once per group ----
+  constexpr uint32_t kGroupBytes = 4u * NCP * 3u;
+  uint32_t g = 0;
+  for (; g < g_min; ++g) {
+    if (rl.bytes_left() < kGroupBytes) break;  // per lane: the rest of this stream runs the careful loop
+    int32_t v[4][NCP];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      decode_entry<NCP, T, TG, DUMP, MODE, TAB, false, SPLIT>(rl, geom, pp, prev, v[j], dptr, dump, (uint64_t)g * 4 + j);
+    store_group4<NCP>(pp, store, dsize, optr, (uint64_t)g * 4, v);
+    rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
+    cp_async_wait<1>();
+  }
+  // ---- per-lane tail: exact `off > 0` handling ----
+  for (uint32_t e = g * 4u; e < n_entries; ++e) {
+    int32_t v[NCP];
+    decode_entry<NCP, T, TG, DUMP, MODE, TAB, true, SPLIT>(rl, geom, pp, prev, v, dptr, dump, e);
+    store_entry<NCP>(pp, store, dsize, optr, e, v);
+    rl.template top_up<(3 * NCP + 15) / 16 + 1>();
+    cp_async_wait<0>();
+  }
+}
+
 template <int NCP, typename T, bool DUMP, bool TABLE_GLOBAL, int MODE, int TAB>
 __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                             const uint32_t *__restrict__ order, uint32_t n_streams,
@@ -126,12 +168,15 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
 
   RansLane<T, TABLE_GLOBAL> rl;
   uint32_t n_entries = 0;
+  T *lut = nullptr, *ent = nullptr;
+  uint8_t *lutb = nullptr;
+  uint32_t *blk = nullptr;
+  bool split_ok = true;  // idle lanes do not veto
   if (have) {
     const StreamDesc &d = *dp;
     n_entries = d.n_entries;
     int status = DCB_OK;
     if (n_entries > 0) {
-      T *lut, *ent;
       uint32_t ent_off;
       if (TABLE_GLOBAL) {
         // per launch slot: [LUT region | entry region] in the global scratch arena
@@ -146,24 +191,36 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
         rl.lut0 = nullptr;
         rl.ent0 = smem + lay.ent0;
         rl.lut_base = smem_base + lay.lut0 + lane * geom.lut_bytes;
+        rl.lutb_addr = smem_base + lay.lutb0 + lane * geom.lutb_bytes;
+        rl.blk_addr = smem_base + lay.blk0 + lane * geom.blk_bytes;
+        blk = reinterpret_cast<uint32_t *>(smem + lay.blk0 + (size_t)lane * geom.blk_bytes);
         ent_off = lane * geom.ent_bytes;
+        rl.cum_addr = smem_base + lay.ent0 + ent_off;
         lut = reinterpret_cast<T *>(smem + lay.lut0 + (size_t)lane * geom.lut_bytes);
+        lutb = smem + lay.lutb0 + (size_t)lane * geom.lutb_bytes;
         ent = reinterpret_cast<T *>(smem + lay.ent0 + (size_t)lane * geom.ent_bytes);
       }
-      status = rl.build(arena, d, geom, lut, ent, ent_off);
+      status = rl.build(arena, d, geom, ent, ent_off);
       if (status == DCB_OK) status = rl.init_state(arena, d);
-      if (status == DCB_OK) rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
+      if (status == DCB_OK) split_ok = rl.split_ok && !(dump & 0x80000000u);
     }
     if (status != DCB_OK) {
       dp->status = status;
       n_entries = 0;
     }
   }
+  // the branch-free two-region LUT is used when every stream of the warp can have one
+  const bool use_split = __all_sync(0xffffffffu, split_ok);
+  if ((dump & 0x40000000u) && blockIdx.x < 2 && have && n_entries)
+    printf("[dcb kernel] cta %u lane %u: split_ok=%d use_split=%d t_split=%u kA=%u base_b=%u ne=%u dprefix=%u\n", blockIdx.x, lane,
+           (int)rl.split_ok, (int)use_split, rl.t_split, rl.a_sh + 1u, rl.blk_mask, rl.n_entries_tab, rl.dprefix);
   // groups of 4 entries every active lane of the warp can run without per-lane bounds checks
   uint32_t g_min = n_entries ? (n_entries >> 2) : 0xFFFFFFFFu;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) g_min = min(g_min, __shfl_xor_sync(0xffffffffu, g_min, o));
   if (n_entries == 0) return;  // idle lane, empty or failed stream (no warp-level operation below)
+  rl.fill_lut(geom, lut, lutb, blk, ent, use_split);
+  rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
 
   PostParams pp;
   pp.load(*dp);
@@ -175,32 +232,10 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
     pp.store = STORE_NARROW;
     pp.dsize = 4;
   }
-  const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp);
-  int32_t prev[NCP];
-#pragma unroll
-  for (int c = 0; c < NCP; ++c) prev[c] = 0;
-
-  // ---- main loop: 4 entries (4 * NCP symbols) per iteration, renormalisation bounds checked once per group ----
-  constexpr uint32_t kGroupBytes = 4u * NCP * 3u;
-  uint32_t g = 0;
-  for (; g < g_min; ++g) {
-    if (rl.bytes_left() < kGroupBytes) break;  // per lane: the rest of this stream runs the careful loop
-    int32_t v[4][NCP];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      decode_entry<NCP, T, TABLE_GLOBAL, DUMP, MODE, TAB, false>(rl, geom, pp, prev, v[j], dptr, dump, (uint64_t)g * 4 + j);
-    store_group4<NCP>(pp, store, dsize, optr, (uint64_t)g * 4, v);
-    rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
-    cp_async_wait<1>();
-  }
-  // ---- per-lane tail: exact `off > 0` handling ----
-  for (uint32_t e = g * 4u; e < n_entries; ++e) {
-    int32_t v[NCP];
-    decode_entry<NCP, T, TABLE_GLOBAL, DUMP, MODE, TAB, true>(rl, geom, pp, prev, v, dptr, dump, e);
-    store_entry<NCP>(pp, store, dsize, optr, e, v);
-    rl.template top_up<(3 * NCP + 15) / 16 + 1>();
-    cp_async_wait<0>();
-  }
+  if (use_split)
+    run_stream<NCP, T, DUMP, TABLE_GLOBAL, MODE, TAB, true>(rl, geom, pp, optr, dptr, dump, n_entries, g_min);
+  else
+    run_stream<NCP, T, DUMP, TABLE_GLOBAL, MODE, TAB, false>(rl, geom, pp, optr, dptr, dump, n_entries, g_min);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -230,9 +265,10 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
   rl.lut0 = nullptr;
   rl.ent0 = smem + lay.ent0;
   rl.lut_base = smem_base + lay.lut0 + lane * geom.lut_bytes;
-  int status = rl.build(arena, d, geom, reinterpret_cast<T *>(smem + lay.lut0 + (size_t)lane * geom.lut_bytes),
-                        reinterpret_cast<T *>(smem + lay.ent0 + (size_t)lane * geom.ent_bytes), lane * geom.ent_bytes);
+  T *ent = reinterpret_cast<T *>(smem + lay.ent0 + (size_t)lane * geom.ent_bytes);
+  int status = rl.build(arena, d, geom, ent, lane * geom.ent_bytes);
   if (status == DCB_OK) status = rl.init_state(arena, d);
+  if (status == DCB_OK) rl.fill_lut(geom, reinterpret_cast<T *>(smem + lay.lut0 + (size_t)lane * geom.lut_bytes), nullptr, nullptr, ent, false);
   if (status != DCB_OK) {
     dp->status = status;
     dp->bits_total = 0;
@@ -247,7 +283,7 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
     if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
     uint32_t t[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = ((rl.step<false>() - rl.ent_off) >> 1) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+    for (int j = 0; j < 4; ++j) t[j] = ((rl.step<false, false>() - rl.ent_off) >> 1) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
     const uint32_t tmax = max(max(t[0], t[1]), max(t[2], t[3]));
     const uint64_t nbits = bits + (uint64_t)(t[0] + t[1] + t[2] + t[3]) * ncp;
     if (tmax > 32u || nbits > avail_bits) {
@@ -269,7 +305,7 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
   // ---- careful tail (exact `off > 0` handling, per-point checks) ----
   for (; status == DCB_OK && e < n_entries; ++e) {
     if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-    const uint32_t tag = ((rl.step<true>() - rl.ent_off) >> 1) & 0xFFu;
+    const uint32_t tag = ((rl.step<true, false>() - rl.ent_off) >> 1) & 0xFFu;
     if (tag > 32u) {
       status = DCB_ERR_TAG;
       break;
@@ -769,8 +805,12 @@ __global__ void copy_kernel(const uint8_t *__restrict__ arena, StreamDesc *strea
 static TableGeom geom_of(const RansLaunch &p) {
   TableGeom g;
   g.lut_bytes = p.lut_bytes;
+  g.lutb_bytes = p.lutb_bytes;
+  g.blk_bytes = p.lutb_bytes ? (((1u << p.prec_bits) >> 7) << 2) : 0u;
+  if (g.blk_bytes && g.blk_bytes < 16u) g.blk_bytes = 16u;
   g.ent_bytes = p.ent_bytes;
   g.cap_entries = p.cap_entries;
+  g.cap_exc = p.cap_exc;
   g.lut_shift = p.lut_shift;
   g.compact = p.compact;
   g.zig = p.zig;
@@ -780,7 +820,10 @@ static TableGeom geom_of(const RansLaunch &p) {
 uint32_t dcb_rans_smem_bytes(const RansLaunch &p, bool table_global) {
   // worst-case alignment slack + LUTs + rings + entries (see smem_layout)
   uint32_t b = DCB_RING_BYTES + p.lanes_per_warp * DCB_RING_BYTES;
-  if (!table_global) b += p.lut_bytes + p.lanes_per_warp * (p.lut_bytes + p.ent_bytes);
+  if (!table_global) {
+    const uint32_t blk = p.lutb_bytes ? std::max(16u, ((1u << p.prec_bits) >> 7) << 2) : 0u;
+    b += p.lut_bytes + blk + 16u + p.lanes_per_warp * (p.lut_bytes + p.lutb_bytes + blk + p.ent_bytes);
+  }
   return b;
 }
 
@@ -794,7 +837,7 @@ static cudaError_t launch_raw_t(const RansLaunch &p, const DevArenas &a, cudaStr
   }
   const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
   k<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, geom_of(p), a.out, a.dbg,
-                                  a.aux, a.tab, p.dump);
+                                  a.aux, a.tab, p.dump | (getenv("DCB_NO_SPLIT") ? 0x80000000u : 0u) | (getenv("DCB_DEBUG_KERNEL") ? 0x40000000u : 0u));
   return cudaGetLastError();
 }
 

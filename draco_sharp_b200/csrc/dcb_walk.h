@@ -65,9 +65,11 @@ DCB_HD uint64_t wr_varint(WalkRd &r) {
 }
 
 // RANS_TABLE: validates it and advances past it.  Entropy/RAnsSymbolDecoder.cs:12-51 + RAnsDecoder.cs:69-88
-DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint32_t &n_active) {
+DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint32_t &n_active, uint32_t &dense_prefix) {
   num_symbols = 0;
   n_active = 0;
+  dense_prefix = 0;  // number of leading symbols that all have non-zero probability
+  bool gap = false;
   const uint64_t ns = wr_varint(r);
   if (r.err) return r.err;
   if (ns > (r.end - r.pos) * 64u || ns > (1u << 24)) return DCB_ERR_EOF;  // cannot be backed by data
@@ -81,12 +83,18 @@ DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint
     if (token == 3u) {
       const uint32_t off = pd >> 2;
       if (i + off >= num_symbols) return DCB_ERR_TABLE;  // RAnsSymbolDecoder.cs:31
+      gap = true;
       i += off;
     } else {
       uint32_t prob = pd >> 2;
       for (uint32_t b = 0; b < token; ++b) prob |= wr_u8(r) << (8 * (b + 1) - 2);
       if (r.err) return r.err;
-      if (prob) ++n_active;
+      if (prob) {
+        ++n_active;
+        if (!gap) ++dense_prefix;
+      } else {
+        gap = true;
+      }
       sum += prob;
     }
   }
@@ -222,7 +230,7 @@ DCB_HD int walk_portable(WalkRd &r, const BufWalk &w, StreamDesc &s, int *st) {
         return 0;
       }
       s.table_off = r.pos;
-      e = walk_rans_table(r, s.prec_bits, s.num_symbols, s.n_active);
+      e = walk_rans_table(r, s.prec_bits, s.num_symbols, s.n_active, s.dense_prefix);
       if (!e && s.num_symbols == 0) e = DCB_ERR_NUM_SYMBOLS;
       if (!e) e = walk_rans_payload(r, s.prec_bits, s.payload_off, s.payload_len);
       if (e) { *st = e; return 0; }
