@@ -681,7 +681,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   // ---- Tagged streams: decode tags, resume the walks behind their bit areas ----
   for (;;) {
     Group g{};
-    g.kind = 1; g.ncp = 1; g.wide = false; g.compact = 0; g.prec_bits = 12; g.entries = 0; g.zig = 0; g.mode = 0;
+    g.kind = 1; g.ncp = 1; g.wide = false; g.compact = 1; g.prec_bits = 12; g.entries = 0; g.exc = 0; g.zig = 0; g.mode = 0;
     std::vector<uint32_t> blocked;
     for (size_t bi = 0; bi < sh.walks.size(); ++bi) {
       const BufWalk &w = sh.walks[bi];
@@ -690,7 +690,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       if (sh.tags_launched[si]) continue;
       sh.tags_launched[si] = 1;
       g.order.push_back(si);
-      g.entries = std::max(g.entries, sh.streams[si].num_symbols);
+      g.entries = std::max(g.entries, sh.streams[si].n_active);
+      g.exc = std::max(g.exc, sh.streams[si].n_active - std::min(sh.streams[si].n_active, sh.streams[si].dense_prefix));
       g.total_symbols += sh.streams[si].n_entries;
       blocked.push_back((uint32_t)bi);
     }
@@ -705,8 +706,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(sh.d_order, g.order.data(), g.order.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(sh.d_order + g.order.size(), blocked.data(), blocked.size() * 4, cudaMemcpyHostToDevice, st));
-    RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.lut_bytes, 0, g.ent_bytes, g.entries, 0,
-                 g.lut_shift, g.prec_bits, dump, 0, 0, 0};
+    RansLaunch L{sh.d_streams, sh.d_order, (uint32_t)g.order.size(), g.lanes, g.lut_bytes, g.lutb_bytes, g.ent_bytes,
+                 g.entries, g.exc, g.lut_shift, g.prec_bits, dump, 1, 0, 0};
     const bool time_tag = timed && dev_index == 0 && !ctx->ev_tag;
     if (time_tag) {
       CUDA_TRY(cudaEventRecord(ctx->ev[4], st));

@@ -244,37 +244,16 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
 // TAG_CHUNK points (for the parallel bit-field extraction) and bits_total; fails the stream on
 // tag > 32 (DecoderBuffer.cs:141) or when the bit area would run past the buffer.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
-                                                      const uint32_t *__restrict__ order, uint32_t n_streams,
-                                                      uint32_t lanes, TableGeom geom, uint8_t *__restrict__ aux) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  typedef uint16_t T;
-  const uint32_t lane = threadIdx.x;
-  const uint32_t slot = blockIdx.x * lanes + lane;
-  if (lane >= lanes || slot >= n_streams) return;
-  StreamDesc *dp = &streams[order[slot]];
+template <bool SPLIT>
+__device__ __forceinline__ void run_tags(RansLane<uint16_t, false> &rl, const TableGeom &geom, StreamDesc *dp, uint8_t *aux) {
   const StreamDesc &d = *dp;
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-  const SmemLayout lay = smem_layout(smem_base, lanes, geom, false);
-  RansLane<T, false> rl;
   const uint32_t n_entries = d.n_entries;
   const uint32_t ncp = d.ncp;
   const uint64_t avail_bits = (d.buf_end - d.bits_off) * 8ull;
   uint8_t *tags = aux + d.tag_off;
   uint64_t *chunk_bits = reinterpret_cast<uint64_t *>(aux + d.tag_off + (((uint64_t)n_entries + 15ull) & ~15ull));
-  rl.lut0 = nullptr;
-  rl.ent0 = smem + lay.ent0;
-  rl.lut_base = smem_base + lay.lut0 + lane * geom.lut_bytes;
-  T *ent = reinterpret_cast<T *>(smem + lay.ent0 + (size_t)lane * geom.ent_bytes);
-  int status = rl.build(arena, d, geom, ent, lane * geom.ent_bytes);
-  if (status == DCB_OK) status = rl.init_state(arena, d);
-  if (status == DCB_OK) rl.fill_lut(geom, reinterpret_cast<T *>(smem + lay.lut0 + (size_t)lane * geom.lut_bytes), nullptr, nullptr, ent, false);
-  if (status != DCB_OK) {
-    dp->status = status;
-    dp->bits_total = 0;
-    return;
-  }
-  rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
+  const bool compact = geom.compact != 0;
+  int status = DCB_OK;
   uint64_t bits = 0;
   uint32_t e = 0;
   // ---- groups of 4 tags, no per-symbol branches; errors are sorted out when the group is left ----
@@ -283,7 +262,8 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
     if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
     uint32_t t[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = ((rl.step<false, false>() - rl.ent_off) >> 1) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+    for (int j = 0; j < 4; ++j)
+      t[j] = (uint32_t)rl.value(rl.template step<false, SPLIT>(), compact, false) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
     const uint32_t tmax = max(max(t[0], t[1]), max(t[2], t[3]));
     const uint64_t nbits = bits + (uint64_t)(t[0] + t[1] + t[2] + t[3]) * ncp;
     if (tmax > 32u || nbits > avail_bits) {
@@ -305,7 +285,7 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
   // ---- careful tail (exact `off > 0` handling, per-point checks) ----
   for (; status == DCB_OK && e < n_entries; ++e) {
     if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-    const uint32_t tag = ((rl.step<true, false>() - rl.ent_off) >> 1) & 0xFFu;
+    const uint32_t tag = (uint32_t)rl.value(rl.template step<true, SPLIT>(), compact, false) & 0xFFu;
     if (tag > 32u) {
       status = DCB_ERR_TAG;
       break;
@@ -321,6 +301,47 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
   }
   dp->bits_total = bits;
   if (status != DCB_OK) dp->status = status;
+}
+
+__global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+                                                      const uint32_t *__restrict__ order, uint32_t n_streams,
+                                                      uint32_t lanes, TableGeom geom, uint8_t *__restrict__ aux) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  typedef uint16_t T;
+  const uint32_t lane = threadIdx.x;
+  const uint32_t slot = blockIdx.x * lanes + lane;
+  const bool have = lane < lanes && slot < n_streams;
+  StreamDesc *dp = have ? &streams[order[slot]] : nullptr;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const SmemLayout lay = smem_layout(smem_base, lanes, geom, false);
+  RansLane<T, false> rl;
+  T *ent = reinterpret_cast<T *>(smem + lay.ent0 + (size_t)lane * geom.ent_bytes);
+  bool alive = false, split_ok = true;
+  if (have) {
+    rl.lut0 = nullptr;
+    rl.ent0 = smem + lay.ent0;
+    rl.lut_base = smem_base + lay.lut0 + lane * geom.lut_bytes;
+    rl.lutb_addr = smem_base + lay.lutb0 + lane * geom.lutb_bytes;
+    rl.blk_addr = smem_base + lay.blk0 + lane * geom.blk_bytes;
+    rl.cum_addr = smem_base + lay.ent0 + lane * geom.ent_bytes;
+    int status = rl.build(arena, *dp, geom, ent, lane * geom.ent_bytes);
+    if (status == DCB_OK) status = rl.init_state(arena, *dp);
+    if (status != DCB_OK) {
+      dp->status = status;
+      dp->bits_total = 0;
+    } else {
+      alive = true;
+      split_ok = rl.split_ok;
+    }
+  }
+  const bool use_split = __all_sync(0xffffffffu, split_ok);
+  if (!alive) return;
+  rl.fill_lut(geom, reinterpret_cast<T *>(smem + lay.lut0 + (size_t)lane * geom.lut_bytes),
+              smem + lay.lutb0 + (size_t)lane * geom.lutb_bytes,
+              reinterpret_cast<uint32_t *>(smem + lay.blk0 + (size_t)lane * geom.blk_bytes), ent, use_split);
+  rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
+  if (use_split) run_tags<true>(rl, geom, dp, aux);
+  else run_tags<false>(rl, geom, dp, aux);
 }
 
 // ---------------------------------------------------------------------------------------------
