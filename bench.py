@@ -110,6 +110,7 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
@@ -125,6 +126,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -135,7 +140,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw = [], [], []
         reasons = set()
-        for ln in self.lines:
+        lines = self.lines[self.first:] if len(self.lines) - self.first >= 2 else self.lines[-3:]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -240,7 +246,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -299,6 +305,8 @@ def main():
     def step():
         dec.decode_resident(batch, dev_out=d_out.data_ptr())
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs ~0.5 s to come up: start it before the warm-up, keep the samples under load
     for _ in range(args.warmup):
         step()
     # parity gate before any number is reported: word checksums of a sample of decoded attributes
@@ -312,11 +320,10 @@ def main():
     bad = sum(1 for k in range(n_bufs) if batch.status(k) != 0)
     assert bad == 0, "%d buffers failed" % bad
 
-    sampler = ClockSampler(local_rank)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    sampler.start()
+    sampler.mark()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     dom_ms = []

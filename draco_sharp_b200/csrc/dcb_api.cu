@@ -885,7 +885,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       stats.smem_per_stream = (uint64_t)g->lut_bytes + g->lutb_bytes + g->ent_bytes + DCB_RING_BYTES;
       RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, 0, g->compact, g->zig, g->mode};
       const uint32_t cta_smem = dcb_rans_smem_bytes(Ls, g->table_global) + kSmemPerCtaReserve;
-      const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, kSmemPerSM / cta_smem)) * g->lanes;
+      const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, (kSmemPerSM + 1024u) / cta_smem)) * g->lanes;
       stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);
       snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_fused<ncp=%d,%s,%s,mode=%u,k=%u,%s>", g->ncp,
                g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->mode, g->lut_shift,
