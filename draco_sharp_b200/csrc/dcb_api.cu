@@ -93,6 +93,10 @@ struct dcb_ctx {
   std::vector<cudaStream_t> streams;
   std::vector<bool> own_stream;
   std::vector<int> num_sms;
+  // side streams: independent rANS groups of one decode run concurrently (their CTAs share the SMs)
+  std::vector<std::vector<cudaStream_t>> side;
+  std::vector<cudaEvent_t> fork_ev;
+  std::vector<std::vector<cudaEvent_t>> join_ev;
   dcb_launch_stats stats{};
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_raw = false, ev_tag = false, ev_par = false;
@@ -518,6 +522,10 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms) {
     uint32_t kmin = g.prec_bits > le + 2 ? g.prec_bits - le - 2 : 0;
     kmin = std::max(kmin, kfloor);
     kcap[i] = std::max(kmin, std::min<uint32_t>(g.prec_bits - 4, g.prec_bits > le ? g.prec_bits - le + 2 : 2));
+    // compact u16 tables decode through the two-region byte LUT; the uniform LUT is only their fallback, keep it
+    // small (2^prec / 16 bytes: also the capacity of the byte LUT's wide region) and spend the memory on region B
+    if (!g.wide && g.compact) kmin = std::max(kmin, std::min<uint32_t>(5u, g.prec_bits - 4));
+    kcap[i] = std::max(kcap[i], kmin);
     g.lut_shift = kmin;
   }
   auto total_for = [&]() {
@@ -840,9 +848,24 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   for (Group *g : rgs)
     if (!dom || g->total_symbols > dom->total_symbols) dom = g;
   // ---- launches ----
+  // independent smem-table groups go to side streams so that their chains overlap (c3: positions, normals, colours)
+  const bool fan_out = rgs.size() > 1 && !getenv("DCB_NO_FANOUT");
+  if (fan_out) {
+    CUDA_TRY(cudaEventRecord(ctx->fork_ev[dev_index], st));
+    for (cudaStream_t ss : ctx->side[dev_index]) CUDA_TRY(cudaStreamWaitEvent(ss, ctx->fork_ev[dev_index], 0));
+  }
+  bool side_used[3] = {false, false, false};
+  size_t gi = 0;
+  const cudaStream_t st_main = st;
   for (Group *g : rgs) {
     const uint32_t n = (uint32_t)g->order.size();
     const bool is_dom = timed && dev_index == 0 && g == dom;
+    cudaStream_t st = st_main;
+    if (fan_out && !g->table_global && g != dom) {
+      const size_t k = gi++ % 3;
+      st = ctx->side[dev_index][k];
+      side_used[k] = true;
+    }
     if (getenv("DCB_DEBUG_PLAN"))
       fprintf(stderr, "[dcb plan] raw group ncp=%d wide=%d compact=%u prec=%u entries=%u mode=%u zig=%u: %u streams, %llu symbols, "
                       "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u global=%d\n",
@@ -893,6 +916,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     stats.n_streams += (int32_t)n;
   }
+  for (int k = 0; k < 3; ++k)
+    if (side_used[k]) {
+      CUDA_TRY(cudaEventRecord(ctx->join_ev[dev_index][k], ctx->side[dev_index][k]));
+      CUDA_TRY(cudaStreamWaitEvent(st, ctx->join_ev[dev_index][k], 0));
+    }
   for (int n = 1; n <= 4; ++n) {
     if (!post[n].order.empty()) {
       CUDA_TRY(dcb_launch_serial_post(sh.d_streams, sh.d_order + post[n].order_off, (uint32_t)post[n].order.size(), n, dump, 0, A, st));
@@ -1123,6 +1151,17 @@ int dcb_create(const int *device_ids, int n_devices, dcb_ctx **out) {
     }
     c->streams.push_back(st);
     c->own_stream.push_back(true);
+    std::vector<cudaStream_t> side(3, nullptr);
+    std::vector<cudaEvent_t> jev(3, nullptr);
+    cudaEvent_t fev = nullptr;
+    for (int k = 0; k < 3; ++k) {
+      cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&jev[k], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&fev, cudaEventDisableTiming);
+    c->side.push_back(side);
+    c->join_ev.push_back(jev);
+    c->fork_ev.push_back(fev);
     c->num_sms.push_back(p.multiProcessorCount > 0 ? p.multiProcessorCount : (int)kNumSMsDefault);
   }
   cudaSetDevice(c->devices[0]);
@@ -1140,6 +1179,12 @@ void dcb_destroy(dcb_ctx *ctx) {
     }
   for (auto &e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  for (size_t i = 0; i < ctx->side.size(); ++i) {
+    cudaSetDevice(ctx->devices[i]);
+    for (auto &s : ctx->side[i]) if (s) cudaStreamDestroy(s);
+    for (auto &e : ctx->join_ev[i]) if (e) cudaEventDestroy(e);
+    if (ctx->fork_ev[i]) cudaEventDestroy(ctx->fork_ev[i]);
+  }
   delete ctx;
 }
 

@@ -47,31 +47,33 @@ __device__ __forceinline__ int32_t abs32(int32_t v) { return v < 0 ? neg32(v) : 
 __device__ __forceinline__ bool oct_in_diamond(const OctBox &t, int32_t s, int32_t u) {
   return (uint32_t)abs32(s) + (uint32_t)abs32(u) <= (uint32_t)t.center;
 }
+// The octahedron helpers are written as straight-line select code: every lane of a warp decodes a different
+// stream, so any data-dependent branch here would be divergent on almost every entry.
 __device__ __forceinline__ void oct_invert_diamond(const OctBox &t, int32_t &s, int32_t &u) {
-  int32_t ss, su;
-  if (s >= 0 && u >= 0) { ss = 1; su = 1; }
-  else if (s <= 0 && u <= 0) { ss = -1; su = -1; }
-  else { ss = s > 0 ? 1 : -1; su = u > 0 ? 1 : -1; }
-  const int32_t cs = ss * t.center, cu = su * t.center;
-  int32_t us = (int32_t)((uint32_t)s + (uint32_t)s - (uint32_t)cs);
-  int32_t uu = (int32_t)((uint32_t)u + (uint32_t)u - (uint32_t)cu);
-  const int32_t tmp = us;
-  if (ss * su >= 0) { us = neg32(uu); uu = neg32(tmp); }
-  else { us = uu; uu = tmp; }
+  const bool a = (s >= 0) & (u >= 0);
+  const bool b = (s <= 0) & (u <= 0);
+  const int32_t ss = a ? 1 : (b ? -1 : (s > 0 ? 1 : -1));
+  const int32_t su = a ? 1 : (b ? -1 : (u > 0 ? 1 : -1));
+  const int32_t cs = ss > 0 ? t.center : neg32(t.center), cu = su > 0 ? t.center : neg32(t.center);
+  const int32_t us0 = (int32_t)((uint32_t)s + (uint32_t)s - (uint32_t)cs);
+  const int32_t uu0 = (int32_t)((uint32_t)u + (uint32_t)u - (uint32_t)cu);
+  const bool same = (ss == su);  // ss * su >= 0
+  int32_t us = same ? neg32(uu0) : uu0;
+  int32_t uu = same ? neg32(us0) : us0;
   us = (int32_t)((uint32_t)us + (uint32_t)cs);
   uu = (int32_t)((uint32_t)uu + (uint32_t)cu);
   s = us / 2;  // truncating, as C#
   u = uu / 2;
 }
 __device__ __forceinline__ int32_t oct_mod_max(const OctBox &t, int32_t x) {
-  if (x > t.center) return (int32_t)((uint32_t)x - (uint32_t)t.max_q);
-  return x < -t.center ? (int32_t)((uint32_t)x + (uint32_t)t.max_q) : x;
+  const int32_t hi = (int32_t)((uint32_t)x - (uint32_t)t.max_q);
+  const int32_t lo = (int32_t)((uint32_t)x + (uint32_t)t.max_q);
+  return x > t.center ? hi : (x < -t.center ? lo : x);
 }
 __device__ __forceinline__ void oct_rotate(int32_t &a, int32_t &b, int rot) {
-  const int32_t x = a, y = b;
-  if (rot == 1) { a = y; b = neg32(x); }
-  else if (rot == 2) { a = neg32(x); b = neg32(y); }
-  else if (rot == 3) { a = neg32(y); b = x; }
+  const int32_t x = a, y = b, nx = neg32(a), ny = neg32(b);
+  a = rot == 1 ? y : (rot == 2 ? nx : (rot == 3 ? ny : x));
+  b = rot == 1 ? nx : (rot == 2 ? ny : (rot == 3 ? x : y));
 }
 // pred (p0io,p1io) + correction (c0,c1) -> original, in place
 __device__ __forceinline__ void oct_original(const OctBox &t, bool canonical, int32_t &p0io, int32_t &p1io,
@@ -79,20 +81,26 @@ __device__ __forceinline__ void oct_original(const OctBox &t, bool canonical, in
   int32_t p0 = (int32_t)((uint32_t)p0io - (uint32_t)t.center);
   int32_t p1 = (int32_t)((uint32_t)p1io - (uint32_t)t.center);
   const bool in_diamond = oct_in_diamond(t, p0, p1);
-  if (!in_diamond) oct_invert_diamond(t, p0, p1);
-  bool bottom_left = true;
-  int rot = 0;
-  if (canonical) {
-    bottom_left = (p0 == 0 && p1 == 0) ? true : (p0 < 0 && p1 <= 0);
-    if (p0 == 0) rot = p1 == 0 ? 0 : (p1 > 0 ? 3 : 1);
-    else if (p0 > 0) rot = p1 >= 0 ? 2 : 1;
-    else rot = p1 <= 0 ? 0 : 3;
-    if (!bottom_left) oct_rotate(p0, p1, rot);
+  {
+    int32_t q0 = p0, q1 = p1;
+    oct_invert_diamond(t, q0, q1);
+    p0 = in_diamond ? p0 : q0;
+    p1 = in_diamond ? p1 : q1;
   }
+  // canonicalized transform: rotate the prediction into the bottom-left quadrant
+  const bool bottom_left = ((p0 == 0) & (p1 == 0)) | ((p0 < 0) & (p1 <= 0));
+  int rot = p0 == 0 ? (p1 == 0 ? 0 : (p1 > 0 ? 3 : 1)) : (p0 > 0 ? (p1 >= 0 ? 2 : 1) : (p1 <= 0 ? 0 : 3));
+  rot = (canonical && !bottom_left) ? rot : 0;
+  oct_rotate(p0, p1, rot);
   int32_t o0 = oct_mod_max(t, (int32_t)((uint32_t)p0 + (uint32_t)c0));
   int32_t o1 = oct_mod_max(t, (int32_t)((uint32_t)p1 + (uint32_t)c1));
-  if (canonical && !bottom_left) oct_rotate(o0, o1, (4 - rot) & 3);
-  if (!in_diamond) oct_invert_diamond(t, o0, o1);
+  oct_rotate(o0, o1, (4 - rot) & 3);
+  {
+    int32_t q0 = o0, q1 = o1;
+    oct_invert_diamond(t, q0, q1);
+    o0 = in_diamond ? o0 : q0;
+    o1 = in_diamond ? o1 : q1;
+  }
   p0io = (int32_t)((uint32_t)o0 + (uint32_t)t.center);
   p1io = (int32_t)((uint32_t)o1 + (uint32_t)t.center);
 }
