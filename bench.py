@@ -243,6 +243,60 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_sweep(args, rank, local_rank):
+    """BASELINE configs[4]: points-per-buffer sweep (total points fixed) and batch-size sweep (points per buffer fixed).
+    Kernel-only numbers (inputs resident), one JSON line per cell; not the headline."""
+    import torch
+    import draco_sharp_b200 as D
+    from draco_sharp_b200 import synth_gen as G
+    torch.cuda.set_device(local_rank)
+    dec = D.DracoBatchDecoder([local_rank])
+    stream = torch.cuda.current_stream()
+    dec.set_stream(0, stream.cuda_stream)
+    peak, _ = measured_peak()
+    cells = [("points_per_buffer", n, max(1, 200_000_000 // n)) for n in (1000, 10_000, 100_000, 1_000_000, 10_000_000)]
+    cells += [("batch_size", 100_000, b) for b in (1, 16, 256, 4096, 16384)]
+    for scheme, sname in ((1, "raw"), (0, "tagged")):
+        for axis, n, b in cells:
+            uniq = min(b, max(1, 20_000_000 // n))
+            spec = G.make_spec(n, seed=rank_seed(rank) + n, pos_bits=14, scheme=scheme)
+            arena_u, offs_u, lens_u, sums_u, schemes_u, used_u = G.synth_batch(spec, uniq, n_threads=host_cores())
+            reps = (b + uniq - 1) // uniq
+            stride = (used_u + 15) // 16 * 16
+            arena = np.empty(stride * reps, dtype=np.uint8)
+            offs = np.zeros(b, dtype=np.uint64)
+            lens = np.zeros(b, dtype=np.uint64)
+            for j in range(reps):
+                arena[j * stride: j * stride + used_u] = arena_u[:used_u]
+                lo, hi = j * uniq, min(b, (j + 1) * uniq)
+                offs[lo:hi] = offs_u[: hi - lo] + np.uint64(j * stride)
+                lens[lo:hi] = lens_u[: hi - lo]
+            batch = dec.index_arena(arena, offs, lens)
+            dec.upload(batch)
+            d_out = torch.empty(batch.out_bytes, dtype=torch.uint8, device="cuda")
+            for _ in range(3):
+                dec.decode_resident(batch, dev_out=d_out.data_ptr())
+            ai = batch.attr_info(0, 0)
+            ok = G.word_checksum(d_out[ai.out_off: ai.out_off + ai.out_bytes].cpu().numpy()) == int(sums_u[0, 0])
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = 5
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(steps):
+                dec.decode_resident(batch, dev_out=d_out.data_ptr())
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / steps
+            st = dec.stats()
+            print(json.dumps({"sweep": axis, "scheme": sname, "points_per_buffer": n, "buffers": b, "ms_per_step": ms,
+                              "points_per_s": batch.points / (ms * 1e-3), "algorithmic_GBps": batch.algo_bytes / (ms * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": batch.algo_bytes / (ms * 1e-3) / 1e9 / peak, "parity_ok": bool(ok),
+                              "launches": st.n_launches, "stage_ms": {"raw": st.ms_raw, "tag": st.ms_tag, "par": st.ms_par}}), flush=True)
+            batch.free()
+            del d_out
+    dec.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,12 +307,15 @@ def main():
     ap.add_argument("--unique", type=int, default=2048, help="distinct clouds generated per rank (0 = all distinct)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: points-per-buffer and batch-size sweep (one JSON line per cell)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.sweep:
+        return run_sweep(args, rank, local_rank)
     args.warmup = max(args.warmup, 3)
 
     import torch
