@@ -98,6 +98,7 @@ struct dcb_ctx {
   std::vector<cudaEvent_t> fork_ev;
   std::vector<std::vector<cudaEvent_t>> join_ev;
   dcb_launch_stats stats{};
+  uint32_t epoch = 0;  // tags the look-back words of par_post_kernel: no clearing between decodes
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_raw = false, ev_tag = false, ev_par = false;
   uint64_t algo_raw = 0, algo_tag = 0, algo_par = 0;
@@ -364,10 +365,10 @@ void layout_shard(Shard &sh) {
       if (w.status) continue;
       if (s.seq_type != SEQ_GENERIC &&
           (s.scheme == SCHEME_TAGGED || s.scheme == SCHEME_UNCOMPRESSED || (any_unready && s.state < ST_READY))) {
-        // tags u8[n] | bit offset per chunk u64[nch + 1] | correction sums per chunk u32[nch][4]
+        // tags u8[n] | bit offset per chunk u64[nch + 1] | look-back state words per chunk u64[nch][4]
         const uint64_t nch = (s.n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
         s.tag_off = aux;
-        aux = align_up(aux + align_up(s.n_entries, 16) + 8ull * (nch + 1) + 16ull * nch, 16);
+        aux = align_up(aux + align_up(s.n_entries, 16) + 8ull * (nch + 1) + 32ull * nch, 16);
       }
       if (s.seq_type != SEQ_GENERIC && s.has_maps && (s.recon == RECON_PARA_WRAP || s.state < ST_READY)) {
         s.aux_off = aux;
@@ -654,7 +655,10 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   }
   if (!sh.streams.empty()) CUDA_TRY(cudaMalloc(&sh.d_streams, sh.streams.size() * sizeof(StreamDesc)));
   if (!sh.walks.empty()) CUDA_TRY(cudaMalloc(&sh.d_walks, sh.walks.size() * sizeof(BufWalk)));
-  if (sh.aux_bytes) CUDA_TRY(cudaMalloc(&sh.d_aux, sh.aux_bytes));
+  if (sh.aux_bytes) {
+    CUDA_TRY(cudaMalloc(&sh.d_aux, sh.aux_bytes));
+    CUDA_TRY(cudaMemsetAsync(sh.d_aux, 0, sh.aux_bytes, st));  // look-back words start with epoch 0 (never a live epoch)
+  }
   sh.uploaded = true;
   sh.dirty = true;
   return DCB_OK;
@@ -938,8 +942,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         }
       }
       CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, np,
-                                   (par[n].max_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK, n, par_delta[n], dump, A, st));
-      stats.n_launches += par_delta[n] ? 3 : 1;
+                                   (par[n].max_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK, n, dump, ++ctx->epoch, A, st));
+      stats.n_launches += 1;
       if (par_delta[n]) {
         // streams whose corrections break the modular-sum condition fall back to the exact serial recurrence
         CUDA_TRY(dcb_launch_serial_post(sh.d_streams, sh.d_order + par[n].order_off, np, n, dump, 1, A, st));

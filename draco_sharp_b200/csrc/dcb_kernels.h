@@ -31,7 +31,7 @@ cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_orde
                                    uint32_t only_irregular, const DevArenas &a, cudaStream_t st);
 // point-parallel path behind Tagged / uncompressed sources (recon none or delta + wrap)
 cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_chunks, int ncp,
-                                bool any_delta, uint32_t dump, const DevArenas &a, cudaStream_t st);
+                                uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
                             uint32_t dump, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_oct_unit(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries,
