@@ -256,19 +256,24 @@ __device__ __forceinline__ void run_tags(RansLane<uint16_t, false> &rl, const Ta
   int status = DCB_OK;
   uint64_t bits = 0;
   uint32_t e = 0;
-  // ---- groups of 4 tags, no per-symbol branches; errors are sorted out when the group is left ----
-  for (; e + 4 <= n_entries; e += 4) {
-    if (rl.bytes_left() < 12u) break;  // renormalisation may run out of bytes: careful loop below
+  // ---- groups of 16 tags, no per-symbol branches; errors are sorted out when the group is left ----
+  for (; e + 16 <= n_entries; e += 16) {
+    if (rl.bytes_left() < 48u) break;  // renormalisation may run out of bytes: careful loop below
     if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-    uint32_t t[4];
+    uint32_t t[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 16; ++j)
       t[j] = (uint32_t)rl.value(rl.template step<false, SPLIT>(), compact, false) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
-    const uint32_t tmax = max(max(t[0], t[1]), max(t[2], t[3]));
-    const uint64_t nbits = bits + (uint64_t)(t[0] + t[1] + t[2] + t[3]) * ncp;
+    uint32_t tmax = 0, tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      tmax = max(tmax, t[j]);
+      tsum += t[j];
+    }
+    const uint64_t nbits = bits + (uint64_t)tsum * ncp;
     if (tmax > 32u || nbits > avail_bits) {
       // first failing point decides the status, as in the sequential reference loop
-      for (int j = 0; j < 4 && status == DCB_OK; ++j) {
+      for (int j = 0; j < 16 && status == DCB_OK; ++j) {
         if (t[j] > 32u) status = DCB_ERR_TAG;
         else {
           bits += (uint64_t)t[j] * ncp;
@@ -277,9 +282,14 @@ __device__ __forceinline__ void run_tags(RansLane<uint16_t, false> &rl, const Ta
       }
       break;
     }
-    *reinterpret_cast<uint32_t *>(tags + e) = t[0] | (t[1] << 8) | (t[2] << 16) | (t[3] << 24);
+    uint4 pk;
+    pk.x = t[0] | (t[1] << 8) | (t[2] << 16) | (t[3] << 24);
+    pk.y = t[4] | (t[5] << 8) | (t[6] << 16) | (t[7] << 24);
+    pk.z = t[8] | (t[9] << 8) | (t[10] << 16) | (t[11] << 24);
+    pk.w = t[12] | (t[13] << 8) | (t[14] << 16) | (t[15] << 24);
+    *reinterpret_cast<uint4 *>(tags + e) = pk;
     bits = nbits;
-    rl.top_up<1>();
+    rl.template top_up<4>();
     cp_async_wait<1>();
   }
   // ---- careful tail (exact `off > 0` handling, per-point checks) ----
