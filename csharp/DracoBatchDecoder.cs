@@ -64,6 +64,9 @@ public sealed class DracoBatchDecoder : IDisposable
     [DllImport(Lib)] private static extern int dcb_set_attr_section(IntPtr batch, int buf, ulong attrSectionOff, uint nPoints);
     [DllImport(Lib)] private static extern int dcb_set_mesh_maps(IntPtr batch, int buf, int attrDecoder, uint[] opposite, uint[] cornerToVertex,
         ulong nCorners, uint[] dataToCorner, ulong nEntries, int[] vertexToData, ulong nVertices);
+    [DllImport(Lib)] private static extern int dcb_host_connectivity(IntPtr batch, int buf);
+    [DllImport(Lib)] private static extern int dcb_mesh_faces(IntPtr batch, int buf, uint[]? faces, ulong capFaces, out ulong nFaces);
+    [DllImport(Lib)] private static extern int dcb_mesh_map(IntPtr batch, int buf, int attrDecoder, int which, uint[]? dst, ulong cap, out ulong n);
     [DllImport(Lib)] private static extern int dcb_index_finish(IntPtr ctx, IntPtr batch);
     [DllImport(Lib)] private static extern unsafe int dcb_decode_scatter(IntPtr ctx, IntPtr batch, byte** outs, int nOuts, uint flags);
     [DllImport(Lib)] private static extern int dcb_status(IntPtr batch, int buf);
@@ -116,7 +119,13 @@ public sealed class DracoBatchDecoder : IDisposable
                 Check(dcb_get_buffer_info(batch, k, out var bi));
                 if (bi.Status != 0 || bi.NeedsConnectivity == 0) continue;
                 anyMesh = true;
-                if (Connectivity == null) continue; // stays unresolved -> DCB_ERR_CONNECTIVITY -> NotSupported
+                if (Connectivity == null)
+                {
+                    // no C# hook installed: the library's own host Edgebreaker decoder (still CPU work, still
+                    // MeshEdgeBreakerDecoder.DecodeConnectivity's algorithm); faces come back through dcb_mesh_faces
+                    Check(dcb_host_connectivity(batch, k));
+                    continue;
+                }
                 var hc = Connectivity.DecodeConnectivity(buffers[k]);
                 hostMeshes[k] = hc.Mesh;
                 Check(dcb_set_attr_section(batch, k, (ulong)hc.AttributesSectionOffset, (uint)hc.Mesh.PointsCount));

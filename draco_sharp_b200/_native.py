@@ -88,6 +88,9 @@ EXPORTS = [
     ("dcb_batch_algo_bytes", C.c_uint64, [_P]),
     ("dcb_set_attr_section", C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint32]),
     ("dcb_set_mesh_maps", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_uint64, _P, C.c_uint64, _P, C.c_uint64]),
+    ("dcb_host_connectivity", C.c_int, [_P, C.c_int]),
+    ("dcb_mesh_faces", C.c_int, [_P, C.c_int, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("dcb_mesh_map", C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("dcb_index_finish", C.c_int, [_P, _P]),
     ("dcb_decode", C.c_int, [_P, _P, _P, _P, C.c_uint32]),
     ("dcb_decode_scatter", C.c_int, [_P, _P, C.POINTER(_P), C.c_int, C.c_uint32]),

@@ -43,7 +43,7 @@ def build_lib(force=False):
     srcs.append(os.path.join(ROOT, "include", "dracob200.h"))
     if force or _newer(LIB, srcs):
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cu = [os.path.join(CSRC, f) for f in ("dcb_api.cu", "dcb_kernels.cu")]
+        cu = [os.path.join(CSRC, f) for f in ("dcb_api.cu", "dcb_kernels.cu", "dcb_mesh_host.cu")]
         _run([nvcc] + NVCC_FLAGS + ["-o", LIB] + cu)
     return LIB
 

@@ -23,6 +23,7 @@
 
 #include "dcb_internal.h"
 #include "dcb_kernels.h"
+#include "dcb_mesh_host.h"
 #include "dcb_walk.h"
 
 namespace {
@@ -52,6 +53,8 @@ struct BufRec {
   dcb_buffer_info info{};
   bool is_eb = false;
   std::vector<MeshMapsHost> maps;  // per attributes decoder
+  std::vector<uint32_t> faces;     // dcb_host_connectivity: 3 point ids per face
+  uint64_t conn_off = 0;           // meshes: first byte after header + metadata
   std::vector<uint32_t> dec_entries;
 };
 
@@ -212,6 +215,7 @@ void parse_header(BufRec &b) {
     inf.n_points = (uint32_t)np;
     inf.attr_section_off = r.pos;
   } else if (inf.geometry_type == 1) {
+    b.conn_off = r.pos;
     if (inf.encoder_method == 1) {
       // Edgebreaker: connectivity is host work (DracoDecoder.cs:80-88 -> MeshEdgeBreakerDecoder); the
       // caller reports where ATTRIBUTES starts with dcb_set_attr_section + dcb_set_mesh_maps.
@@ -1287,6 +1291,63 @@ int dcb_set_mesh_maps(dcb_batch *b, int buf, int attr_decoder, const uint32_t *o
   m.data_to_corner.assign(data_to_corner, data_to_corner + n_entries);
   m.vertex_to_data.assign(vertex_to_data, vertex_to_data + n_vertices);
   m.set = true;
+  return DCB_OK;
+}
+
+int dcb_host_connectivity(dcb_batch *b, int buf) {
+  if (!b || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+  BufRec &r = b->bufs[buf];
+  if (!r.info.needs_connectivity) return DCB_ERR_STATE;
+  if (r.info.status != DCB_OK) return DCB_OK;
+  if (!r.is_eb) {  // sequential mesh connectivity (MeshSequentialDecoder.cs:8-118): SURVEY 8f-4, not built yet
+    r.info.status = DCB_ERR_UNSUPPORTED;
+    return DCB_OK;
+  }
+  std::vector<DcbHostMaps> maps;
+  uint64_t attr_off = 0;
+  uint32_t n_points = 0;
+  const int st = dcb_host_edgebreaker(r.src, r.len, r.conn_off, &attr_off, &n_points, &maps, &r.faces);
+  if (st != DCB_OK) {  // the buffer fails alone, like an exception in the reference's DecodeConnectivity
+    r.info.status = st;
+    return DCB_OK;
+  }
+  r.info.attr_section_off = attr_off;
+  r.info.n_points = n_points;
+  r.maps.assign(maps.size(), MeshMapsHost{});
+  for (size_t d = 0; d < maps.size(); ++d) {
+    r.maps[d].opposite.swap(maps[d].opposite);
+    r.maps[d].corner_to_vertex.swap(maps[d].corner_to_vertex);
+    r.maps[d].data_to_corner.swap(maps[d].data_to_corner);
+    r.maps[d].vertex_to_data.swap(maps[d].vertex_to_data);
+    r.maps[d].set = true;
+  }
+  return DCB_OK;
+}
+
+int dcb_mesh_faces(const dcb_batch *b, int buf, uint32_t *faces, uint64_t cap_faces, uint64_t *n_faces) {
+  if (!b || buf < 0 || buf >= (int)b->bufs.size() || !n_faces) return DCB_ERR_ARG;
+  const BufRec &r = b->bufs[buf];
+  *n_faces = r.faces.size() / 3;
+  if (faces) {
+    if (cap_faces < *n_faces) return DCB_ERR_ARG;
+    memcpy(faces, r.faces.data(), r.faces.size() * 4);
+  }
+  return DCB_OK;
+}
+
+int dcb_mesh_map(const dcb_batch *b, int buf, int attr_decoder, int which, uint32_t *dst, uint64_t cap, uint64_t *n) {
+  if (!b || buf < 0 || buf >= (int)b->bufs.size() || !n || which < 0 || which > 3) return DCB_ERR_ARG;
+  const BufRec &r = b->bufs[buf];
+  if (attr_decoder < 0 || attr_decoder >= (int)r.maps.size() || !r.maps[attr_decoder].set) return DCB_ERR_STATE;
+  const MeshMapsHost &m = r.maps[attr_decoder];
+  const void *src = which == 0 ? (const void *)m.opposite.data() : which == 1 ? (const void *)m.corner_to_vertex.data()
+                  : which == 2 ? (const void *)m.data_to_corner.data() : (const void *)m.vertex_to_data.data();
+  *n = which == 0 ? m.opposite.size() : which == 1 ? m.corner_to_vertex.size()
+     : which == 2 ? m.data_to_corner.size() : m.vertex_to_data.size();
+  if (dst) {
+    if (cap < *n) return DCB_ERR_ARG;
+    memcpy(dst, src, *n * 4);
+  }
   return DCB_OK;
 }
 

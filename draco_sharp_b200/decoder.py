@@ -56,6 +56,7 @@ class Draco:  # src/Draco/Draco.cs:9-15
     status: int
     points_count: int = 0
     attributes: List[PointAttribute] = field(default_factory=list)
+    faces: Optional[np.ndarray] = None  # meshes: (n_faces, 3) point ids, Mesh.cs:5-19
 
     @property
     def ok(self):
@@ -131,6 +132,27 @@ class Batch:
         v = np.ascontiguousarray(vertex_to_data, dtype=np.int32)
         N.check(N.lib().dcb_set_mesh_maps(self.h, k, dec, o.ctypes.data, c.ctypes.data, o.size, d.ctypes.data, d.size,
                                           v.ctypes.data, v.size))
+
+    def host_connectivity(self, k):
+        """Decode the Edgebreaker connectivity of mesh buffer k on the host (dcb_host_connectivity)."""
+        N.check(N.lib().dcb_host_connectivity(self.h, k))
+
+    def faces(self, k):
+        n = C.c_uint64(0)
+        N.check(N.lib().dcb_mesh_faces(self.h, k, None, 0, C.byref(n)))
+        f = np.zeros((n.value, 3), dtype=np.uint32)
+        if n.value:
+            N.check(N.lib().dcb_mesh_faces(self.h, k, f.ctypes.data, n.value, C.byref(n)))
+        return f
+
+    def mesh_map(self, k, attr_decoder, which):
+        """which: 0 opposite, 1 corner_to_vertex, 2 data_to_corner (uint32), 3 vertex_to_data (int32)."""
+        n = C.c_uint64(0)
+        N.check(N.lib().dcb_mesh_map(self.h, k, attr_decoder, which, None, 0, C.byref(n)))
+        m = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            N.check(N.lib().dcb_mesh_map(self.h, k, attr_decoder, which, m.ctypes.data, n.value, C.byref(n)))
+        return m.view(np.int32) if which == 3 else m
 
     def finish(self):
         N.check(N.lib().dcb_index_finish(self._dec.ctx if self._dec else None, self.h))
@@ -224,6 +246,11 @@ class DracoBatchDecoder:
         attributes (the reference would have thrown for that buffer alone)."""
         batch = self.index(buffers)
         try:
+            meshes = [k for k in range(batch.n_bufs) if batch.buffer_info(k).needs_connectivity]
+            for k in meshes:
+                batch.host_connectivity(k)  # connectivity stays on the host (SURVEY 8f-1)
+            if meshes:
+                batch.finish()
             out, _ = self.decode(batch)
             return self.wrap(batch, out)
         finally:
@@ -237,6 +264,9 @@ class DracoBatchDecoder:
             if bi.status not in (-1, -2) or bi.version_major:
                 hdr = DracoHeader(bi.version_major, bi.version_minor, bi.geometry_type, bi.encoder_method, bi.flags)
             d = Draco(header=hdr, status=bi.status, points_count=bi.n_points)
+            if bi.status == 0 and bi.geometry_type == 1:
+                f = batch.faces(k)
+                d.faces = f if f.shape[0] else None  # None: the caller supplied the connectivity itself
             if bi.status == 0:
                 for a in range(bi.n_attrs):
                     ai = batch.attr_info(k, a)

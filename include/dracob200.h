@@ -147,6 +147,19 @@ int dcb_set_attr_section(dcb_batch *b, int buf, uint64_t attr_section_off, uint3
 int dcb_set_mesh_maps(dcb_batch *b, int buf, int attr_decoder, const uint32_t *opposite,
                       const uint32_t *corner_to_vertex, uint64_t n_corners, const uint32_t *data_to_corner,
                       uint64_t n_entries, const int32_t *vertex_to_data, uint64_t n_vertices);
+/* Host helper for callers without the C# host: decodes the Edgebreaker connectivity of mesh buffer
+ * `buf` ON THE CPU -- the part of the reference that stays on the host, MeshEdgeBreakerDecoder.DecodeConnectivity
+ * (Mesh/MeshEdgeBreakerDecoder.cs:25-638), the standard / valence traversal decoders and the depth-first attribute
+ * traversal (Mesh/Traverser/DepthFirstTraverser.cs:9-99) -- and installs what dcb_set_attr_section +
+ * dcb_set_mesh_maps would.  A buffer whose connectivity is invalid or unsupported gets its own status. */
+int dcb_host_connectivity(dcb_batch *b, int buf);
+/* Faces (3 point ids each) of a mesh decoded by dcb_host_connectivity (Mesh.SetFace, MeshEdgeBreakerDecoder.cs:622-636).
+ * faces == NULL: only *n_faces is written. */
+int dcb_mesh_faces(const dcb_batch *b, int buf, uint32_t *faces, uint64_t cap_faces, uint64_t *n_faces);
+/* Read back one installed map of an attributes decoder: which = 0 opposite, 1 corner_to_vertex, 2 data_to_corner,
+ * 3 vertex_to_data (int32 bit patterns).  dst == NULL: only *n is written.  What a host needs to build the
+ * reference's CornerTable / MeshAttributeIndicesEncodingData from dcb_host_connectivity's result. */
+int dcb_mesh_map(const dcb_batch *b, int buf, int attr_decoder, int which, uint32_t *dst, uint64_t cap, uint64_t *n);
 /* Re-run the attribute indexing of mesh buffers once their maps are set. */
 int dcb_index_finish(dcb_ctx *ctx, dcb_batch *b);
 

@@ -112,3 +112,48 @@ def test_mesh_without_maps_fails_cleanly(gpu_decoder):
     batch.finish()
     assert batch.status(0) == -14          # DCB_ERR_MAPS
     batch.free()
+
+
+def _house_positions_only():
+    """house_04's header + Edgebreaker connectivity, bytes verbatim, followed by an ATTRIBUTES section that keeps
+    only the position attribute (also verbatim): a complete, valid Edgebreaker mesh the product decodes alone."""
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    a = o.attrs[0]
+    start = a.table_off - 5
+    end = a.payload_off + a.payload_len + 8
+    section = (bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
+               + bytes(b[start:end]) + bytes(b[end:end + 17]))
+    return bytes(b[:1158]) + section, o
+
+
+def test_house_mesh_end_to_end_through_product_host_helper(gpu_decoder):
+    """No oracle on the decode path: dcb_host_connectivity (product, host) -> dcb_index_finish -> CUDA
+    parallelogram kernels.  Positions and faces against the SHA-256 goldens / the OBJ the asset was made from."""
+    buf, o = _house_positions_only()
+    (d,) = gpu_decoder.decode_batch([buf])
+    assert d.ok and d.points_count == 3220 and d.header.geometry_type == 1
+    pos = d.get_named_attribute(0)
+    assert pos.unique_entries_count == 1775
+    assert sha(pos.buffer) == "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
+    assert d.faces.shape == (2588, 3) and np.array_equal(d.faces, o.faces)
+    # every decoded vertex within half a quantisation step of a vertex of the source OBJ
+    obj = np.load(os.path.join(GOLD, "house_04_obj_vertices.npy")).astype(np.float64)
+    v = pos.values.astype(np.float64)
+    dist = np.abs(v[:, None, :] - obj[None, :, :]).max(axis=2).min(axis=1)
+    assert dist.max() < 0.49094
+
+
+def test_mixed_batch_meshes_and_clouds(gpu_decoder):
+    """Meshes (host connectivity) and point clouds in one batch; a mesh with broken connectivity fails alone."""
+    from draco_sharp_b200 import synth_gen as G
+    buf, o = _house_positions_only()
+    bad = bytearray(buf)
+    bad[20:60] = bytes(40)
+    cloud, tr = G.synth_cloud(G.make_spec(5000, seed=3))
+    res = gpu_decoder.decode_batch([cloud, buf, bytes(bad), buf, cloud])
+    assert [r.ok for r in res] == [True, True, False, True, True]
+    assert sha(res[1].attributes[0].buffer) == sha(res[3].attributes[0].buffer) == \
+        "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
+    assert G.word_checksum(res[0].attributes[0].buffer) == tr["sums"][0]
+    assert np.array_equal(res[0].attributes[0].buffer, res[4].attributes[0].buffer)
