@@ -135,6 +135,11 @@ def synth():
         s.synth_cloud.argtypes = [C.POINTER(SynthSpec), _P, C.c_uint64, C.POINTER(SynthTruth)]
         s.synth_batch.restype = C.c_int64
         s.synth_batch.argtypes = [C.POINTER(SynthSpec), C.c_uint32, C.c_int, _P, C.c_uint64, _P, _P, _P, _P]
+        s.synth_grid_topology.restype = C.c_int64
+        s.synth_grid_topology.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P]
+        s.synth_grid_mesh.restype = C.c_int64
+        s.synth_grid_mesh.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_uint64,
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _P, C.POINTER(C.c_int32)]
         s.synth_word_checksum.restype = C.c_uint64
         s.synth_word_checksum.argtypes = [_P, C.c_uint64]
         _synth = s

@@ -571,5 +571,168 @@ int64_t synth_batch(const synth_spec *base, uint32_t n_bufs, int n_threads, uint
   return (int64_t)pos;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BASELINE configs[3]: a triangulated w x h grid surface (2 (w-1)(h-1) faces).  The Edgebreaker connectivity itself
+// is the host's business (an opaque blob in the buffer); what the attribute path consumes is the corner table and the
+// depth-first traversal maps, built here the way CornerTable / DepthFirstTraverser define them
+// (IO/Mesh/CornerTable.cs:59-83, IO/Mesh/Traverser/DepthFirstTraverser.cs:9-99,
+// MeshAttributeIndicesEncodingObserver.cs:14-21).
+// ---------------------------------------------------------------------------------------------
+static inline uint32_t cnext(uint32_t c) { return c % 3u == 2u ? c - 2u : c + 1u; }
+static inline uint32_t cprev(uint32_t c) { return c % 3u == 0u ? c + 2u : c - 1u; }
+
+// opposite / corner_to_vertex: [3F]; data_to_corner: [V]; vertex_to_data: [V].  Returns the number of entries (== V).
+int64_t synth_grid_topology(uint32_t w, uint32_t h, uint32_t *opposite, uint32_t *c2v, uint32_t *d2c, int32_t *v2d) {
+  if (w < 2 || h < 2) return -1;
+  const uint32_t V = w * h, F = 2u * (w - 1) * (h - 1), INV = 0xFFFFFFFFu;
+  uint32_t f = 0;
+  for (uint32_t j = 0; j + 1 < h; ++j)
+    for (uint32_t i = 0; i + 1 < w; ++i) {
+      const uint32_t v00 = j * w + i, v10 = v00 + 1, v01 = v00 + w, v11 = v01 + 1;
+      c2v[3 * f] = v00; c2v[3 * f + 1] = v10; c2v[3 * f + 2] = v11; ++f;
+      c2v[3 * f] = v00; c2v[3 * f + 1] = v11; c2v[3 * f + 2] = v01; ++f;
+    }
+  // opposite corners: the two corners facing the same undirected edge
+  std::vector<std::pair<uint64_t, uint32_t>> edges(3ull * F);
+  for (uint32_t c = 0; c < 3 * F; ++c) {
+    uint32_t a = c2v[cnext(c)], b = c2v[cprev(c)];
+    if (a > b) std::swap(a, b);
+    edges[c] = {((uint64_t)a << 32) | b, c};
+    opposite[c] = INV;
+  }
+  std::sort(edges.begin(), edges.end());
+  for (size_t k = 0; k + 1 < edges.size(); ++k)
+    if (edges[k].first == edges[k + 1].first) {
+      opposite[edges[k].second] = edges[k + 1].second;
+      opposite[edges[k + 1].second] = edges[k].second;
+      ++k;
+    }
+  auto on_boundary = [&](uint32_t v) { const uint32_t i = v % w, j = v / w; return i == 0 || j == 0 || i == w - 1 || j == h - 1; };
+  auto right = [&](uint32_t c) { return opposite[cnext(c)]; };
+  auto left = [&](uint32_t c) { return opposite[cprev(c)]; };
+  std::vector<uint8_t> fvis(F, 0), vvis(V, 0);
+  std::vector<uint32_t> stk;
+  uint32_t n = 0;
+  for (uint32_t v = 0; v < V; ++v) v2d[v] = -1;
+  auto visit = [&](uint32_t v, uint32_t c) { vvis[v] = 1; v2d[v] = (int32_t)n; d2c[n++] = c; };
+  for (uint32_t f0 = 0; f0 < F; ++f0) {
+    if (fvis[f0]) continue;
+    uint32_t corner = 3 * f0;
+    stk.assign(1, corner);
+    const uint32_t nv = c2v[cnext(corner)], pv = c2v[cprev(corner)];
+    if (!vvis[nv]) visit(nv, cnext(corner));
+    if (!vvis[pv]) visit(pv, cprev(corner));
+    while (!stk.empty()) {
+      corner = stk.back();
+      if (corner == INV || fvis[corner / 3]) { stk.pop_back(); continue; }
+      for (;;) {
+        fvis[corner / 3] = 1;
+        const uint32_t v = c2v[corner];
+        if (!vvis[v]) {
+          const bool b = on_boundary(v);
+          visit(v, corner);
+          if (!b) { corner = right(corner); continue; }
+        }
+        const uint32_t rc = right(corner), lc = left(corner);
+        const bool rvis = rc == INV || fvis[rc / 3], lvis = lc == INV || fvis[lc / 3];
+        if (rvis) {
+          if (lvis) { stk.pop_back(); break; }
+          corner = lc;
+        } else {
+          if (lvis) corner = rc;
+          else { stk.back() = lc; stk.push_back(rc); break; }
+        }
+      }
+    }
+  }
+  return (int64_t)n;
+}
+
+// One mesh over that topology: jittered grid in x / y, a smooth height field in z, `pos_bits`-bit quantization,
+// parallelogram prediction (MeshPredictionSchemeParallelogramEncoder semantics = the decoder's
+// MeshPredictionSchemeParallelogramDecoder.cs:29-89 read backwards) + wrap transform.  `out` receives the whole .drc
+// buffer; *attr_off the ATTRIBUTES section offset, *sum the checksum of the expected output floats (entry order),
+// pos_q (nullable, [V*3]) the quantized positions in entry order.  Returns bytes, or -(needed).
+int64_t synth_grid_mesh(uint32_t w, uint32_t h, uint64_t seed, int32_t pos_bits, int32_t scheme, const uint32_t *opposite,
+                        const uint32_t *c2v, const uint32_t *d2c, const int32_t *v2d, uint8_t *out, uint64_t cap,
+                        uint64_t *attr_off, uint64_t *sum, int32_t *pos_q, int32_t *scheme_used) {
+  const uint32_t V = w * h, INV = 0xFFFFFFFFu;
+  const int32_t maxq = (1 << pos_bits) - 1;
+  Rng rng(seed);
+  const double fx = 0.004 + 0.004 * (double)(rng.u32() % 1000u) / 1000.0, fy = 0.003 + 0.005 * (double)(rng.u32() % 1000u) / 1000.0;
+  const double ph = (double)(rng.u32() % 6283u) / 1000.0;
+  std::vector<int32_t> q((size_t)V * 3);  // entry order
+  for (uint32_t p = 0; p < V; ++p) {
+    const uint32_t v = c2v[d2c[p]], i = v % w, j = v / w;
+    const double gx = (double)i * (double)(maxq - 8) / (double)(w - 1) + 4.0, gy = (double)j * (double)(maxq - 8) / (double)(h - 1) + 4.0;
+    const uint32_t r = rng.u32();
+    int32_t x = (int32_t)std::lround(gx) + (int32_t)(r % 5u) - 2, y = (int32_t)std::lround(gy) + (int32_t)((r >> 8) % 5u) - 2;
+    int32_t z = (int32_t)std::lround(0.5 * maxq + 0.45 * maxq * std::sin(fx * i + ph) * std::cos(fy * j)) + (int32_t)((r >> 16) % 3u) - 1;
+    q[3ull * p] = x < 0 ? 0 : (x > maxq ? maxq : x);
+    q[3ull * p + 1] = y < 0 ? 0 : (y > maxq ? maxq : y);
+    q[3ull * p + 2] = z < 0 ? 0 : (z > maxq ? maxq : z);
+  }
+  int32_t mn = q[0], mx = q[0];
+  for (size_t k = 1; k < q.size(); ++k) { mn = std::min(mn, q[k]); mx = std::max(mx, q[k]); }
+  const int32_t max_diff = 1 + mx - mn;
+  int32_t max_corr = max_diff / 2, min_corr = -max_corr;
+  if ((max_diff & 1) == 0) max_corr -= 1;
+  std::vector<uint32_t> sym((size_t)V * 3);
+  for (uint32_t p = 0; p < V; ++p) {
+    int32_t pred[3] = {0, 0, 0};
+    if (p > 0) {
+      bool para = false;
+      const uint32_t oc = opposite[d2c[p]];
+      if (oc != INV) {
+        const int32_t a = v2d[c2v[oc]], b = v2d[c2v[cnext(oc)]], c = v2d[c2v[cprev(oc)]];
+        if (a >= 0 && b >= 0 && c >= 0 && a < (int32_t)p && b < (int32_t)p && c < (int32_t)p) {
+          para = true;
+          for (int k = 0; k < 3; ++k) pred[k] = q[3ull * b + k] + q[3ull * c + k] - q[3ull * a + k];
+        }
+      }
+      if (!para) for (int k = 0; k < 3; ++k) pred[k] = q[3ull * (p - 1) + k];
+    }
+    for (int k = 0; k < 3; ++k) {
+      const int32_t pr = pred[k] > mx ? mx : (pred[k] < mn ? mn : pred[k]);
+      int32_t corr = q[3ull * p + k] - pr;
+      if (corr < min_corr) corr += max_diff; else if (corr > max_corr) corr -= max_diff;
+      sym[3ull * p + k] = zigzag_enc(corr);
+    }
+  }
+  Out o;
+  o.bytes("DRACO", 5);
+  o.u8(2); o.u8(2);
+  o.u8(1);   // TRIANGULAR_MESH
+  o.u8(1);   // MESH_EDGEBREAKER_ENCODING
+  o.u16(0);
+  o.u8(0);   // standard traversal; the connectivity payload proper is decoded by the host and not part of this path
+  for (int k = 0; k < 15; ++k) o.u8(0xEB);
+  const uint64_t aoff = o.b.size();
+  o.u8(1);                        // one attributes decoder
+  o.u8(0xFF); o.u8(0); o.u8(0);   // att_data_id -1 (position), MESH_VERTEX_ATTRIBUTE, depth-first traversal
+  o.varint(1);
+  o.u8(0); o.u8(9); o.u8(3); o.u8(0); o.varint(0);
+  o.u8(2);                        // SEQUENTIAL_ATTRIBUTE_ENCODER_QUANTIZATION
+  o.u8(1);                        // MESH_PREDICTION_PARALLELOGRAM
+  o.u8(1);                        // PREDICTION_TRANSFORM_WRAP
+  o.u8(1);
+  const int sch = encode_symbols(o, sym, 3, scheme);
+  o.i32(mn); o.i32(mx);
+  const float pos_min[3] = {-1.0f, -1.0f, -1.0f}, range = 2.0f;
+  o.f32(pos_min[0]); o.f32(pos_min[1]); o.f32(pos_min[2]); o.f32(range); o.u8((uint8_t)pos_bits);
+  if (scheme_used) *scheme_used = sch;
+  if (attr_off) *attr_off = aoff;
+  if (sum) {
+    const float delta = range / (float)maxq;
+    std::vector<float> fl((size_t)V * 3);
+    for (size_t k = 0; k < fl.size(); ++k) { volatile float t = (float)q[k] * delta; fl[k] = t + pos_min[k % 3]; }
+    *sum = word_checksum(fl.data(), fl.size() * 4);
+  }
+  if (pos_q) memcpy(pos_q, q.data(), q.size() * 4);
+  if (o.b.size() > cap) return -(int64_t)o.b.size();
+  memcpy(out, o.b.data(), o.b.size());
+  return (int64_t)o.b.size();
+}
+
 uint64_t synth_word_checksum(const void *p, uint64_t nbytes) { return word_checksum(p, (size_t)nbytes); }
 }

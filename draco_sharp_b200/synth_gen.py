@@ -60,6 +60,36 @@ def synth_batch(spec, n_bufs, n_threads=None, arena=None):
     return arena, offs, lens, sums, schemes, int(used)
 
 
+def grid_topology(w, h):
+    """Corner table + depth-first traversal maps of a triangulated w x h grid (BASELINE configs[3]).  The dict has
+    the keys dcb_set_mesh_maps / the oracle take; `faces` is corner_to_vertex reshaped."""
+    nf, nv = 2 * (w - 1) * (h - 1), w * h
+    m = dict(opposite=np.zeros(3 * nf, dtype=np.uint32), corner_to_vertex=np.zeros(3 * nf, dtype=np.uint32),
+             data_to_corner=np.zeros(nv, dtype=np.uint32), vertex_to_data=np.zeros(nv, dtype=np.int32))
+    n = N.synth().synth_grid_topology(w, h, m["opposite"].ctypes.data, m["corner_to_vertex"].ctypes.data,
+                                      m["data_to_corner"].ctypes.data, m["vertex_to_data"].ctypes.data)
+    if n != nv:
+        raise RuntimeError("grid traversal reached %d of %d vertices" % (n, nv))
+    return m
+
+
+def grid_mesh(w, h, maps, seed=0xD5AC4000, pos_bits=14, scheme=-1, want_q=False):
+    """One Edgebreaker-mesh .drc buffer over grid_topology(w, h): positions, parallelogram + wrap, rANS.
+    Returns (buffer, attr_section_off, checksum of the expected output floats, scheme used, pos_q or None)."""
+    nv = w * h
+    cap = 4096 + nv * 3 * 4
+    out = np.empty(cap, dtype=np.uint8)
+    aoff, sm, sch = C.c_uint64(0), C.c_uint64(0), C.c_int32(0)
+    q = np.zeros(nv * 3, dtype=np.int32) if want_q else None
+    sz = N.synth().synth_grid_mesh(w, h, seed, pos_bits, scheme, maps["opposite"].ctypes.data,
+                                   maps["corner_to_vertex"].ctypes.data, maps["data_to_corner"].ctypes.data,
+                                   maps["vertex_to_data"].ctypes.data, out.ctypes.data, cap, C.byref(aoff), C.byref(sm),
+                                   q.ctypes.data if want_q else None, C.byref(sch))
+    if sz < 0:
+        raise RuntimeError("grid mesh needs %d bytes" % -sz)
+    return out[:sz].copy(), int(aoff.value), int(sm.value), int(sch.value), q
+
+
 def word_checksum(a):
     a = np.ascontiguousarray(a)
     return int(N.synth().synth_word_checksum(a.ctypes.data, a.nbytes))

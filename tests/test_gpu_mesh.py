@@ -132,7 +132,7 @@ def test_house_mesh_end_to_end_through_product_host_helper(gpu_decoder):
     parallelogram kernels.  Positions and faces against the SHA-256 goldens / the OBJ the asset was made from."""
     buf, o = _house_positions_only()
     (d,) = gpu_decoder.decode_batch([buf])
-    assert d.ok and d.points_count == 3220 and d.header.geometry_type == 1
+    assert d.ok and d.points_count == 3220 and d.header.encoder_type == 1
     pos = d.get_named_attribute(0)
     assert pos.unique_entries_count == 1775
     assert sha(pos.buffer) == "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
