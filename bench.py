@@ -43,6 +43,13 @@ WORKLOADS = {
     "small": (1024, 100000, dict(pos_bits=14, scheme=-1), "CI-sized configs[1]: 1,024 clouds x 100k points"),
     "tiny": (64, 20000, dict(pos_bits=14, scheme=-1), "smoke-sized"),
 }
+# BASELINE configs[3]: meshes per GPU, grid side (side^2 vertices each), description
+MESH_WORKLOADS = {
+    "c4": (64, 1000, "BASELINE configs[3]: Edgebreaker meshes of 1,000 x 1,000 vertices (1,996,002 faces), connectivity maps "
+                     "from the host, 14-bit positions, parallelogram + wrap, rANS (upstream scheme rule)", -1),
+    "c4tagged": (64, 1000, "configs[3] with the Tagged scheme forced", 0),
+    "c4s": (8, 300, "configs[3] at CI size: 8 meshes of 300 x 300 vertices", -1),
+}
 METRIC = "decoded points/sec"
 UNIT = "points/s"
 
@@ -218,7 +225,11 @@ def run_reference(args, rank, world):
     """Reference arm: the reference's own algorithm on the host CPU (oracle port; the C# needs .NET, absent)."""
     if rank != 0:
         return
-    n_sample, n_points, threads, run, results = cpu_oracle_rate(args.workload, seconds_target=20.0)
+    mesh = args.workload in MESH_WORKLOADS
+    if mesh:
+        n_sample, n_points, threads, run, results = cpu_mesh_rate(args.workload)
+    else:
+        n_sample, n_points, threads, run, results = cpu_oracle_rate(args.workload, seconds_target=20.0)
     for _ in range(max(1, min(args.warmup, 1))):
         run()
     times = [run() for _ in range(max(1, args.steps))]
@@ -226,12 +237,13 @@ def run_reference(args, rank, world):
     pts = sum(r[0] for r in results)
     outb = sum(r[1] for r in results)
     val = pts / dt
-    n_bufs = WORKLOADS[args.workload][0]
+    n_bufs = (MESH_WORKLOADS if mesh else WORKLOADS)[args.workload][0]
+    desc = MESH_WORKLOADS[args.workload][2] if mesh else WORKLOADS[args.workload][3]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32->f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3],
+        "config": {"workload": args.workload, "description": desc,
                    "clouds_per_gpu": n_bufs, "points_per_cloud": n_points},
         "output_GBps": outb / dt / 1e9,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
@@ -241,6 +253,180 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def make_meshes(name, rank, n_meshes=None):
+    from concurrent.futures import ThreadPoolExecutor
+    from draco_sharp_b200 import synth_gen as G
+    m, side, _, scheme = MESH_WORKLOADS[name]
+    m = n_meshes or m
+    topo = G.grid_topology(side, side)
+    with ThreadPoolExecutor(max_workers=host_cores()) as ex:
+        meshes = list(ex.map(lambda k: G.grid_mesh(side, side, topo, seed=rank_seed(rank) + 0x4000 + k, scheme=scheme), range(m)))
+    return topo, meshes, side * side
+
+
+def cpu_mesh_rate(name, threads=None):
+    """CPU oracle on the mesh workload: one mesh per thread, maps handed over exactly as to the GPU path."""
+    from oracle import pyoracle as O  # cpu_baseline / reference arm only
+    from draco_sharp_b200 import build as B
+    B.build_oracle()
+    O.lib()
+    threads = threads or host_cores()
+    topo, meshes, nv = make_meshes(name, 0, n_meshes=threads)
+    results = [None] * threads
+
+    def work(t):
+        buf, aoff, sm, _, _ = meshes[t]
+        r = O.decode(buf, [topo], aoff, nv)
+        assert r.status == 0
+        results[t] = (nv, r.attrs[0].out.nbytes)
+
+    def run():
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    return threads, nv, threads, run, results
+
+
+def run_mesh(args, rank, local_rank, world):
+    """configs[3]: a batch of large meshes.  Connectivity (corner table + traversal maps) comes from the host, the
+    symbol decode, parallelogram inverse prediction, wrap and dequantisation run on the GPU."""
+    import torch
+    import draco_sharp_b200 as D
+    from draco_sharp_b200 import build as B
+    from draco_sharp_b200 import synth_gen as G
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "draco_sharp_b200", "libdracob200.so")):
+        B.build_all()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the decode path is CUDA only (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    args.warmup = max(args.warmup, 3)
+    t0 = time.perf_counter()
+    topo, meshes, nv = make_meshes(args.workload, rank, args.meshes or None)
+    gen_s = time.perf_counter() - t0
+    bufs = [m[0] for m in meshes]
+    dec = D.DracoBatchDecoder([local_rank])
+    stream = torch.cuda.current_stream()
+    dec.set_stream(0, stream.cuda_stream)
+
+    def indexed():
+        b = dec.index(bufs)
+        for k, m in enumerate(meshes):
+            b.set_attr_section(k, m[1], nv)
+            b.set_mesh_maps(k, 0, topo["opposite"], topo["corner_to_vertex"], topo["data_to_corner"], topo["vertex_to_data"])
+        b.finish()
+        return b
+
+    batch = indexed()
+    n_bufs, points, out_bytes, in_bytes, algo_bytes = batch.n_bufs, batch.points, batch.out_bytes, batch.in_bytes, batch.algo_bytes
+    maps_bytes = sum(int(v.nbytes) for v in topo.values()) * n_bufs
+    dec.upload(batch)
+    d_out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+
+    def step():
+        dec.decode_resident(batch, dev_out=d_out.data_ptr())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    for k in range(n_bufs):
+        assert batch.status(k) == 0, "mesh %d failed: %d" % (k, batch.status(k))
+        ai = batch.attr_info(k, 0)
+        got = d_out[ai.out_off: ai.out_off + ai.out_bytes].cpu().numpy()
+        assert G.word_checksum(got) == meshes[k][2], "decoded positions of mesh %d do not match the generator" % k
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler.mark()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dom_ms, launches = [], 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        st = dec.stats()
+        dom_ms.append(st.ms_dominant)
+        launches += st.n_launches
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms, (total_points, total_out, total_launches) = reduce_over_ranks(dist, "cuda", ev0.elapsed_time(ev1), [points, out_bytes, launches])
+    ms_per_step = ms / args.steps
+    stats = dec.stats()
+    # e2e: index + maps + H2D (buffers and maps) + kernels + D2H
+    h_out = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    e2e_ms = []
+    for i in range(args.e2e_steps + 1):
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        b2 = indexed()
+        dec.decode(b2, out_ptr=h_out.data_ptr())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        b2.free()
+        if i > 0:
+            e2e_ms.append(dt)
+    e2e_t = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
+    e2e_t, _ = reduce_over_ranks(dist, "cuda", e2e_t, [0.0])
+    if e2e_ms:
+        ai = batch.attr_info(n_bufs // 2, 0)
+        assert G.word_checksum(h_out.numpy()[ai.out_off: ai.out_off + ai.out_bytes]) == meshes[n_bufs // 2][2]
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        dom = float(np.mean(dom_ms)) if dom_ms else 0.0
+        dom_bytes = int(stats.algo_bytes_dominant) or algo_bytes
+        achieved = (dom_bytes / (dom * 1e-3) / 1e9) if dom > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": total_points / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i32->f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": MESH_WORKLOADS[args.workload][2], "meshes_per_gpu": n_bufs,
+                       "vertices_per_mesh": nv, "faces_per_mesh": int(topo["opposite"].size // 3),
+                       "symbol_scheme_of_positions": {0: "tagged", 1: "raw"}.get(meshes[0][3], "n/a"),
+                       "compressed_bytes_per_gpu": in_bytes, "output_bytes_per_gpu": out_bytes, "map_bytes_per_gpu": maps_bytes,
+                       "l2": "inputs+outputs+maps (%.1f GB per step) exceed the 126 MB L2" % ((in_bytes + out_bytes + maps_bytes) / 1e9),
+                       "generate_s": round(gen_s, 1)},
+            "output_GBps": total_out / (ms_per_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": profile_traffic(args.workload), "peak_source": peak_src,
+                         "kernel": stats.dominant_name.decode(), "kernel_ms": dom, "algorithmic_bytes_per_launch": dom_bytes,
+                         "algorithmic_bytes_per_step": algo_bytes,
+                         "stage_ms": {"raw_fused": stats.ms_raw, "tag_rans": stats.ms_tag, "par_post": stats.ms_par,
+                                      "parallelogram": stats.ms_para, "all_kernels": stats.ms_total},
+                         "note": "one serial rANS chain of %d symbols and one serial parallelogram chain per mesh "
+                                 "(dependency depth of a depth-first traversal ~ 0.86 n): %d chains in flight" % (3 * nv, n_bufs)},
+            "e2e": {"value": total_points / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + maps_bytes,
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_t, "steps": args.e2e_steps,
+                    "what": "dcb_index + dcb_set_mesh_maps + dcb_index_finish + dcb_decode: host indexing, H2D of buffers and maps, kernels, D2H"},
+            "gpu_launches": int(total_launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_sample, n_points, threads, run, results = cpu_mesh_rate(args.workload)
+            run()
+            dt = run()
+            line["cpu_baseline"] = {"value": sum(r[0] for r in results) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d meshes x %d vertices of the same workload, one mesh per thread, C oracle -O2" % (n_sample, n_points)}
+        print(json.dumps(line))
+    batch.free()
+    dec.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_sweep(args, rank, local_rank):
@@ -303,9 +489,10 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(MESH_WORKLOADS))
     ap.add_argument("--unique", type=int, default=2048, help="distinct clouds generated per rank (0 = all distinct)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--meshes", type=int, default=0, help="mesh workloads: meshes per GPU (0 = the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: points-per-buffer and batch-size sweep (one JSON line per cell)")
     args = ap.parse_args()
@@ -316,6 +503,8 @@ def main():
         return run_reference(args, rank, world)
     if args.sweep:
         return run_sweep(args, rank, local_rank)
+    if args.workload in MESH_WORKLOADS:
+        return run_mesh(args, rank, local_rank, world)
     args.warmup = max(args.warmup, 3)
 
     import torch

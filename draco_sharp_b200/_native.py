@@ -48,7 +48,7 @@ class LaunchStats(C.Structure):
     _fields_ = [
         ("n_launches", C.c_int32), ("n_streams", C.c_int32), ("n_waves", C.c_int32), ("lanes_per_warp", C.c_int32),
         ("smem_per_stream", C.c_uint64), ("ms_total", C.c_float), ("ms_dominant", C.c_float),
-        ("ms_raw", C.c_float), ("ms_tag", C.c_float), ("ms_par", C.c_float), ("reserved", C.c_float),
+        ("ms_raw", C.c_float), ("ms_tag", C.c_float), ("ms_par", C.c_float), ("ms_para", C.c_float),
         ("algo_bytes_dominant", C.c_uint64), ("dominant_name", C.c_char * 96),
     ]
 

@@ -102,8 +102,8 @@ struct dcb_ctx {
   std::vector<std::vector<cudaEvent_t>> join_ev;
   dcb_launch_stats stats{};
   uint32_t epoch = 0;  // tags the look-back words of par_post_kernel: no clearing between decodes
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool ev_raw = false, ev_tag = false, ev_par = false;
+  cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_raw = false, ev_tag = false, ev_par = false, ev_para = false;
   uint64_t algo_raw = 0, algo_tag = 0, algo_par = 0;
   char raw_name[96] = {0};
 };
@@ -793,7 +793,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         if (key.compact) g.exc = std::max(g.exc, s.n_active - std::min(s.n_active, s.dense_prefix));
         g.total_symbols += (uint64_t)s.n_entries * s.ncp;
         g.order.push_back(si);
-      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP) && !getenv("DCB_NO_PAR_POST")) {
+      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP) && !getenv("DCB_NO_PAR_POST")) {
         // Tagged / uncompressed source, scan-able reconstruction: point-parallel kernels
         par[s.ncp].max_entries = std::max(par[s.ncp].max_entries, s.n_entries);
         par[s.ncp].order.push_back(si);
@@ -969,9 +969,15 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   }
   for (int n = 1; n <= 4; ++n)
     if (!para[n].order.empty()) {
+      const bool time_para = timed && dev_index == 0 && !ctx->ev_para;
+      if (time_para) CUDA_TRY(cudaEventRecord(ctx->ev[8], st));
       CUDA_TRY(dcb_launch_para(sh.d_streams, sh.d_order + para[n].order_off, (uint32_t)para[n].order.size(), n,
                                para[n].max_entries, dump, A, st));
       stats.n_launches += 2;
+      if (time_para) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[9], st));
+        ctx->ev_para = true;
+      }
     }
   if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
   if (has_para) {
@@ -1007,7 +1013,7 @@ int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_
   for (const BufRec &r : b->bufs)
     if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;  // dcb_index_finish not run
   memset(&ctx->stats, 0, sizeof ctx->stats);
-  ctx->ev_raw = ctx->ev_tag = ctx->ev_par = false;
+  ctx->ev_raw = ctx->ev_tag = ctx->ev_par = ctx->ev_para = false;
   ctx->algo_raw = ctx->algo_tag = ctx->algo_par = 0;
   ctx->raw_name[0] = 0;
   for (int d = 0; d < b->n_devices; ++d) {
@@ -1061,6 +1067,7 @@ void finish_stats(dcb_ctx *ctx) {
   if (ctx->ev_raw && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) st.ms_raw = ms;
   if (ctx->ev_tag && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) st.ms_tag = ms;
   if (ctx->ev_par && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) st.ms_par = ms;
+  if (ctx->ev_para && cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess) st.ms_para = ms;
   cudaGetLastError();
   if (st.ms_raw >= st.ms_tag && st.ms_raw >= st.ms_par && ctx->ev_raw) {
     st.ms_dominant = st.ms_raw;

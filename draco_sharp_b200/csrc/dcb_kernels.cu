@@ -675,14 +675,20 @@ __global__ void __launch_bounds__(kParThreads) par_post_kernel(const uint8_t *__
       if (d.irregular) continue;  // the serial kernel re-runs this stream (it also overwrites anything stored so far)
     }
     // ---- store ----
-    if (DUMP && (dump & DCB_DUMP_QINTS)) {
+    if (DUMP && (dump & DCB_DUMP_QINTS) && recon != RECON_PARA_WRAP) {
 #pragma unroll
       for (uint32_t j = 0; j < kParPts; ++j)
         if (j < mine_cnt)
 #pragma unroll
           for (int c = 0; c < NCP; ++c) dptr[(size_t)(e0 + p0 + j) * NCP + c] = v[j][c];
     }
-    if (mine_cnt) store_run<NCP>(pp, out + d.out_off, (uint64_t)e0 + p0, mine_cnt, v);
+    uint8_t *obase = out + d.out_off;
+    if (recon == RECON_PARA_WRAP) {  // corrections for the parallelogram chain: int32 into the stream's scratch
+      pp.store = STORE_NARROW;
+      pp.dsize = 4;
+      obase = aux + d.aux_off;
+    }
+    if (mine_cnt) store_run<NCP>(pp, obase, (uint64_t)e0 + p0, mine_cnt, v);
   }
 }
 
@@ -737,74 +743,139 @@ __global__ void para_deps_kernel(StreamDesc *streams, const uint32_t *__restrict
   }
 }
 
-// The recurrence itself: serial per stream, one stream per lane.  The last DCB_PARA_RING entries
-// live in the lane's shared-memory ring (98.6 % of the dependencies of a depth-first traversal fall
-// inside 32 entries); older ones are re-read from the quantized-int scratch in HBM/L2.
+// The recurrence itself.  Its dependency graph is a chain in practice (a depth-first traversal predicts almost every
+// entry from the one decoded just before it: dependency depth 1,529 of 1,775 entries on the reference's sample mesh), so
+// the "wavefront" is one entry wide inside a stream and the parallelism is across streams: ONE WARP PER STREAM.
+//   lanes 0..NCP-1  walk the chain, one component each (components never mix), branch-free: the value of entry p-1
+//                   stays in a register, the operands of entry p+1 are fetched from shared memory while entry p is
+//                   computed -- recent ones from a history ring, older ones from a staging area
+//   all 32 lanes    run two blocks ahead of the chain: cp.async the dependencies / corrections of block b+2 and GATHER
+//                   the old operands of block b+1 (anything decoded before block b started is already in the
+//                   quantized-int scratch) into the staging area, so no global-memory latency is left on the chain;
+//                   then dequantise and store the finished block with coalesced writes
+constexpr uint32_t kParaBlock = 64;    // entries per staged block
+constexpr uint32_t kParaHist = 128;    // history ring: the block being decoded and the one before it
+
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ int32_t lds32(uint32_t smem_addr) {
+  int32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(smem_addr) : "memory");
+  return v;
+}
+
 template <int NCP, bool DUMP>
 __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
                                                         uint32_t n_streams, uint8_t *__restrict__ out,
                                                         uint8_t *__restrict__ dbg, uint8_t *__restrict__ aux,
                                                         uint32_t dump) {
-  __shared__ int32_t ring[32][DCB_PARA_RING][NCP];
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_streams) return;
-  StreamDesc &d = streams[order[slot]];
-  if (d.status != DCB_OK) return;
-  const uint32_t n = d.n_entries;
-  PostParams pp;
-  pp.load(d);
-  uint8_t *optr = out + d.out_off;
-  int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
-  const int32_t *corr = reinterpret_cast<const int32_t *>(aux + d.aux_off);
-  int32_t *qints = reinterpret_cast<int32_t *>(aux + d.aux_off) + (uint64_t)n * NCP;
-  const int32_t *deps = qints + (uint64_t)n * NCP;
-  int32_t(*my)[NCP] = ring[threadIdx.x];
-  int32_t prev[NCP];
+  __shared__ int32_t s_dep[3][kParaBlock * 3];          // (opp, next, prev) entry ids; -1 = predict from entry p-1
+  __shared__ int32_t s_cor[3][kParaBlock * NCP];        // corrections
+  __shared__ int32_t s_far[2][kParaBlock * 3 * NCP];    // gathered operands older than the history ring
+  __shared__ int32_t s_hist[kParaHist * NCP];
+  const uint32_t lane = threadIdx.x;
+  const uint32_t a_hist = (uint32_t)__cvta_generic_to_shared(s_hist) + 4u * lane;
+  for (uint32_t si = blockIdx.x; si < n_streams; si += gridDim.x) {
+    StreamDesc &d = streams[order[si]];
+    if (d.status != DCB_OK) continue;
+    const uint32_t n = d.n_entries;
+    if (n == 0) continue;
+    PostParams pp;
+    pp.load(d);
+    uint8_t *optr = out + d.out_off;
+    int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
+    const int32_t *corr = reinterpret_cast<const int32_t *>(aux + d.aux_off);
+    int32_t *qints = reinterpret_cast<int32_t *>(aux + d.aux_off) + (uint64_t)n * NCP;
+    const int32_t *deps = qints + (uint64_t)n * NCP;
+    const uint32_t n_blocks = (n + kParaBlock - 1) / kParaBlock;
+    auto stage = [&](uint32_t blk) {  // all lanes: dependencies + corrections of block blk -> shared memory
+      if (blk >= n_blocks) return;
+      const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0), b = blk % 3u;
+      for (uint32_t i = lane; i < cnt * 3; i += 32)
+        cp_async4((uint32_t)__cvta_generic_to_shared(&s_dep[b][i]), deps + 3ull * e0 + i);
+      for (uint32_t i = lane; i < cnt * NCP; i += 32)
+        cp_async4((uint32_t)__cvta_generic_to_shared(&s_cor[b][i]), corr + (uint64_t)e0 * NCP + i);
+    };
+    auto gather = [&](uint32_t blk) {  // all lanes: operands of block blk decoded before block blk-1 started
+      if (blk >= n_blocks || blk < 2) return;
+      const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0), b = blk % 3u, limit = e0 - kParaBlock;
+      for (uint32_t i = lane; i < cnt * 3; i += 32) {
+        const int32_t e = s_dep[b][i];
+        if (s_dep[b][i - i % 3u] >= 0 && (uint32_t)e < limit) {
 #pragma unroll
-  for (int c = 0; c < NCP; ++c) prev[c] = 0;
-  int32_t dn_o = -1, dn_n = -1, dn_p = -1;
-  for (uint32_t p = 0; p < n; ++p) {
-    const int32_t e_o = dn_o, e_n = dn_n, e_p = dn_p;
-    if (p + 1 < n) {  // prefetch the next entry's dependencies
-      dn_o = deps[3ull * (p + 1)];
-      dn_n = deps[3ull * (p + 1) + 1];
-      dn_p = deps[3ull * (p + 1) + 2];
-    }
-    int32_t v[NCP];
-#pragma unroll
-    for (int c = 0; c < NCP; ++c) v[c] = corr[(uint64_t)p * NCP + c];
-    int32_t pred[NCP];
-    if (e_o >= 0) {
-      int32_t a[NCP], b[NCP], o[NCP];
-      auto fetch = [&](int32_t e, int32_t *dst) {
-        if (p - (uint32_t)e <= DCB_PARA_RING) {
-#pragma unroll
-          for (int c = 0; c < NCP; ++c) dst[c] = my[(uint32_t)e % DCB_PARA_RING][c];
-        } else {
-#pragma unroll
-          for (int c = 0; c < NCP; ++c) dst[c] = qints[(uint64_t)e * NCP + c];
+          for (int c = 0; c < NCP; ++c)
+            cp_async4((uint32_t)__cvta_generic_to_shared(&s_far[blk & 1u][i * NCP + c]), qints + (uint64_t)(uint32_t)e * NCP + c);
         }
-      };
-      fetch(e_n, a);
-      fetch(e_p, b);
-      fetch(e_o, o);
+      }
+    };
+    __syncwarp();
+    stage(0);
+    stage(1);
+    cp_async_commit();
+    int32_t prev = 0;  // lanes < NCP: value of entry p-1, component `lane`
+    for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+      cp_async_wait<0>();  // issued one whole block ago: block blk's operands, block blk+1's dependencies
+      __syncwarp();
+      stage(blk + 2);
+      gather(blk + 1);     // the scratch holds every entry before block blk (stored at the end of block blk-1)
+      cp_async_commit();
+      const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0), b = blk % 3u;
+      if (lane < NCP) {
+        const int32_t *sd = s_dep[b];
+        const int32_t *sc = s_cor[b];
+        const uint32_t a_far = (uint32_t)__cvta_generic_to_shared(s_far[blk & 1u]) + 4u * lane;
+        const uint32_t limit = e0 >= kParaBlock ? e0 - kParaBlock : 0u;
+        struct Ops { int32_t va, vb, vo, corr; bool para, fa, fb, fo; };
+        auto fetch = [&](uint32_t p, uint32_t j) {
+          Ops o;
+          const int32_t e_o = sd[3 * j], e_n = sd[3 * j + 1], e_p = sd[3 * j + 2];
+          o.corr = sc[j * NCP + lane];
+          o.para = e_o >= 0;
+          auto get = [&](int32_t e, uint32_t k, bool &flag) -> int32_t {
+            flag = (uint32_t)e + 1u == p;
+            // one shared-memory load, address selected: staging area (old) or history ring (recent; entry p-1 may
+            // not be there yet -- then the flag makes the caller take the register instead)
+            const uint32_t a = (uint32_t)e < limit ? a_far + (3u * j + k) * (4u * NCP)
+                                                    : a_hist + ((uint32_t)e & (kParaHist - 1u)) * (4u * NCP);
+            return lds32(a);
+          };
+          o.vo = get(e_o, 0, o.fo);
+          o.va = get(e_n, 1, o.fa);
+          o.vb = get(e_p, 2, o.fb);
+          return o;
+        };
+        Ops cur = fetch(e0, 0);
+        for (uint32_t j = 0; j < cnt; ++j) {
+          const uint32_t p = e0 + j;
+          Ops nxt = cur;
+          if (j + 1 < cnt) nxt = fetch(p + 1, j + 1);
+          const int32_t va = cur.fa ? prev : cur.va, vb = cur.fb ? prev : cur.vb, vo = cur.fo ? prev : cur.vo;
+          const int32_t pred = cur.para ? (int32_t)((uint32_t)va + (uint32_t)vb - (uint32_t)vo) : prev;  // :84 / :36,:49-50
+          prev = wrap_original(pred, cur.corr, pp.mn, pp.mx, pp.max_diff);
+          asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(a_hist + (p & (kParaHist - 1u)) * (4u * NCP)), "r"(prev) : "memory");
+          cur = nxt;
+        }
+      }
+      __syncwarp();
+      // all lanes: the finished block -> quantized-int scratch (later gathers read it), dump, typed output
+      for (uint32_t j = lane; j < cnt; j += 32) {
+        const uint32_t p = e0 + j;
+        int32_t v[NCP];
 #pragma unroll
-      for (int c = 0; c < NCP; ++c) pred[c] = (int32_t)((uint32_t)a[c] + (uint32_t)b[c] - (uint32_t)o[c]);  // :84
-    } else {
+        for (int c = 0; c < NCP; ++c) v[c] = s_hist[(p & (kParaHist - 1u)) * NCP + c];
 #pragma unroll
-      for (int c = 0; c < NCP; ++c) pred[c] = prev[c];  // :36 (p == 0: zeros) and :49-50 (entry p-1)
+        for (int c = 0; c < NCP; ++c) qints[(uint64_t)p * NCP + c] = v[c];
+        if (DUMP && (dump & DCB_DUMP_QINTS)) {
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) dptr[(size_t)p * NCP + c] = v[c];
+        }
+        store_entry<NCP>(pp, pp.store, pp.dsize, optr, p, v);
+      }
+      __syncwarp();
     }
-#pragma unroll
-    for (int c = 0; c < NCP; ++c) {
-      prev[c] = wrap_original(pred[c], v[c], pp.mn, pp.mx, pp.max_diff);
-      my[p % DCB_PARA_RING][c] = prev[c];
-      qints[(uint64_t)p * NCP + c] = prev[c];
-    }
-    if (DUMP && (dump & DCB_DUMP_QINTS)) {
-#pragma unroll
-      for (int c = 0; c < NCP; ++c) dptr[(size_t)p * NCP + c] = prev[c];
-    }
-    store_entry<NCP>(pp, pp.store, pp.dsize, optr, p, prev);
+    cp_async_wait<0>();
+    __syncwarp();
   }
 }
 
@@ -1000,7 +1071,7 @@ cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint
   para_deps_kernel<<<dim3(gx, n > 65535u ? 65535u : n), 256, 0, st>>>(d_streams, d_order, n, a.maps, a.aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const uint32_t grid = (n + 31) / 32;
+  const uint32_t grid = n < 148u * 32u ? n : 148u * 32u;  // one warp per stream
 #define DCB_CASE(N)                                                                                     \
   case N:                                                                                               \
     if (dump)                                                                                           \

@@ -6,7 +6,6 @@
 #include "dcb_internal.h"
 
 #define DCB_TAG_CHUNK 1024u  // points per bit-offset checkpoint of a Tagged stream
-#define DCB_PARA_RING 64u
 #define DCB_RING_BYTES 128u   // per-lane shared-memory ring of compressed bytes (rANS kernels)    // entries of the per-stream shared-memory ring of the parallelogram chain
 
 // device arenas of one shard

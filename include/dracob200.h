@@ -197,7 +197,7 @@ typedef struct dcb_launch_stats {
   float ms_raw;              /* largest Raw rANS fused kernel */
   float ms_tag;              /* tag rANS kernels + walk resolve (Tagged streams) */
   float ms_par;              /* point-parallel bit extraction / scan / store passes (Tagged, uncompressed) */
-  float reserved;
+  float ms_para;             /* parallelogram dependency + chain kernels (mesh attributes) */
   uint64_t algo_bytes_dominant; /* algorithmic bytes of the dominant kernel (compulsory reads + writes) */
   char dominant_name[96];
 } dcb_launch_stats;

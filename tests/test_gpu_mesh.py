@@ -157,3 +157,26 @@ def test_mixed_batch_meshes_and_clouds(gpu_decoder):
         "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
     assert G.word_checksum(res[0].attributes[0].buffer) == tr["sums"][0]
     assert np.array_equal(res[0].attributes[0].buffer, res[4].attributes[0].buffer)
+
+
+@pytest.mark.parametrize("w,h,scheme", [(2, 2, -1), (3, 2, 1), (17, 9, 0), (64, 64, 1), (300, 300, -1), (300, 300, 0)])
+def test_grid_meshes_match_oracle_and_generator(gpu_decoder, w, h, scheme):
+    """BASELINE configs[3] shape at test size: a batch of grid meshes sharing one topology, parallelogram + wrap."""
+    from draco_sharp_b200 import synth_gen as G
+    topo = G.grid_topology(w, h)
+    meshes = [G.grid_mesh(w, h, topo, seed=100 + k, scheme=scheme, want_q=True) for k in range(5)]
+    batch = gpu_decoder.index([m[0] for m in meshes])
+    for k, m in enumerate(meshes):
+        batch.set_attr_section(k, m[1], w * h)
+        batch.set_mesh_maps(k, 0, topo["opposite"], topo["corner_to_vertex"], topo["data_to_corner"], topo["vertex_to_data"])
+    batch.finish()
+    out, dbg = gpu_decoder.decode(batch, flags=N.DCB_DUMP_QINTS)
+    for k, (buf, aoff, sm, sch, q) in enumerate(meshes):
+        assert batch.status(k) == 0
+        ai = batch.attr_info(k, 0)
+        ref = O.decode(buf, [topo], aoff, w * h)
+        assert ref.status == 0 and np.array_equal(ref.attrs[0].qints, q)
+        assert np.array_equal(dbg[ai.dbg_off: ai.dbg_off + 4 * q.size].view(np.int32), q)
+        got = out[ai.out_off: ai.out_off + ai.out_bytes]
+        assert np.array_equal(got, ref.attrs[0].out) and G.word_checksum(got) == sm
+    batch.free()

@@ -93,3 +93,22 @@ def test_uncompressed_and_generic_attributes():
     assert r.status == 0
     assert np.array_equal(r.attrs[0].out.view(np.int32), v.astype(np.int32))
     assert np.array_equal(r.attrs[1].out, gen)
+
+
+@pytest.mark.parametrize("w,h", [(2, 2), (3, 2), (17, 9), (120, 77)])
+@pytest.mark.parametrize("scheme", [-1, 0, 1])
+def test_grid_mesh_generator_roundtrip(w, h, scheme):
+    """configs[3] generator: corner table + depth-first maps of a grid, parallelogram corrections written by the
+    generator, decoded back by the oracle's MeshPredictionSchemeParallelogramDecoder restatement."""
+    topo = G.grid_topology(w, h)
+    nv = w * h
+    assert sorted(topo["vertex_to_data"].tolist()) == list(range(nv))           # every vertex reached exactly once
+    assert np.array_equal(topo["corner_to_vertex"][topo["data_to_corner"]][topo["vertex_to_data"]], np.arange(nv))
+    opp = topo["opposite"]
+    inner = opp != 0xFFFFFFFF
+    assert np.array_equal(opp[opp[inner]], np.nonzero(inner)[0])               # opposite is an involution
+    assert int((~inner).sum()) == 2 * (w - 1) + 2 * (h - 1)                      # boundary edges
+    buf, aoff, sm, sch, q = G.grid_mesh(w, h, topo, seed=w * 31 + h, scheme=scheme, want_q=True)
+    r = O.decode(buf, [topo], aoff, nv)
+    assert r.status == 0 and np.array_equal(r.attrs[0].qints, q) and G.word_checksum(r.attrs[0].out) == sm
+    assert r.attrs[0].pred_method == 1
