@@ -826,12 +826,22 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
         const int32_t *sc = s_cor[b];
         const uint32_t a_far = (uint32_t)__cvta_generic_to_shared(s_far[blk & 1u]) + 4u * lane;
         const uint32_t limit = e0 >= kParaBlock ? e0 - kParaBlock : 0u;
+        // two-deep software pipeline: the dependency ids of entry p+2 and the operand values of entry p+1 are in
+        // flight while entry p is computed, so neither shared-memory latency sits on the chain
+        struct Ids { int32_t e_o, e_n, e_p, corr; };
         struct Ops { int32_t va, vb, vo, corr; bool para, fa, fb, fo; };
-        auto fetch = [&](uint32_t p, uint32_t j) {
+        auto ids = [&](uint32_t j) {
+          Ids r;
+          r.e_o = sd[3 * j];
+          r.e_n = sd[3 * j + 1];
+          r.e_p = sd[3 * j + 2];
+          r.corr = sc[j * NCP + lane];
+          return r;
+        };
+        auto values = [&](const Ids &r, uint32_t p, uint32_t j) {
           Ops o;
-          const int32_t e_o = sd[3 * j], e_n = sd[3 * j + 1], e_p = sd[3 * j + 2];
-          o.corr = sc[j * NCP + lane];
-          o.para = e_o >= 0;
+          o.corr = r.corr;
+          o.para = r.e_o >= 0;
           auto get = [&](int32_t e, uint32_t k, bool &flag) -> int32_t {
             flag = (uint32_t)e + 1u == p;
             // one shared-memory load, address selected: staging area (old) or history ring (recent; entry p-1 may
@@ -840,21 +850,24 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
                                                     : a_hist + ((uint32_t)e & (kParaHist - 1u)) * (4u * NCP);
             return lds32(a);
           };
-          o.vo = get(e_o, 0, o.fo);
-          o.va = get(e_n, 1, o.fa);
-          o.vb = get(e_p, 2, o.fb);
+          o.vo = get(r.e_o, 0, o.fo);
+          o.va = get(r.e_n, 1, o.fa);
+          o.vb = get(r.e_p, 2, o.fb);
           return o;
         };
-        Ops cur = fetch(e0, 0);
+        Ids i1 = ids(0);
+        Ops cur = values(i1, e0, 0);
+        i1 = ids(cnt > 1 ? 1 : 0);
         for (uint32_t j = 0; j < cnt; ++j) {
           const uint32_t p = e0 + j;
-          Ops nxt = cur;
-          if (j + 1 < cnt) nxt = fetch(p + 1, j + 1);
+          const Ids i2 = ids(j + 2 < cnt ? j + 2 : j);               // harmless re-read at the end of the block
+          const Ops nxt = values(i1, p + 1, j + 1 < cnt ? j + 1 : j);  // reads history up to p-1; p itself is flagged
           const int32_t va = cur.fa ? prev : cur.va, vb = cur.fb ? prev : cur.vb, vo = cur.fo ? prev : cur.vo;
           const int32_t pred = cur.para ? (int32_t)((uint32_t)va + (uint32_t)vb - (uint32_t)vo) : prev;  // :84 / :36,:49-50
           prev = wrap_original(pred, cur.corr, pp.mn, pp.mx, pp.max_diff);
           asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(a_hist + (p & (kParaHist - 1u)) * (4u * NCP)), "r"(prev) : "memory");
           cur = nxt;
+          i1 = i2;
         }
       }
       __syncwarp();
