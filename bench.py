@@ -492,6 +492,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(MESH_WORKLOADS))
     ap.add_argument("--unique", type=int, default=2048, help="distinct clouds generated per rank (0 = all distinct)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-slices", type=int, default=1, help="pipeline slices of the e2e leg (dcb_create with the device listed K times; measured: no gain, the leg is D2H-bound)")
     ap.add_argument("--meshes", type=int, default=0, help="mesh workloads: meshes per GPU (0 = the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: points-per-buffer and batch-size sweep (one JSON line per cell)")
@@ -594,25 +595,30 @@ def main():
     stats = dec.stats()
 
     # ---- e2e: host buffers in, host buffers out, through the public call (index + H2D + kernels + D2H) ----
+    # the same device listed K times = K pipeline slices: H2D, kernels and D2H of neighbouring slices overlap
     h_out = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    dec_e2e = D.DracoBatchDecoder([local_rank] * max(1, args.e2e_slices)) if args.e2e_slices > 1 else dec
     e2e_ms = []
     for i in range(args.e2e_steps + 1):
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         t0 = time.perf_counter()
-        b2 = dec.index_arena(arena, offs, lens)
-        dec.decode(b2, out_ptr=h_out.data_ptr())
+        b2 = dec_e2e.index_arena(arena, offs, lens)
+        dec_e2e.decode(b2, out_ptr=h_out.data_ptr())
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
+        if i == 0:
+            e2e_offs = [(b2.attr_info(k, 0).out_off, b2.attr_info(k, 0).out_bytes) for k in (0, n_bufs // 2, n_bufs - 1)]
         b2.free()
         if i > 0:
             e2e_ms.append(dt)
     e2e_t = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
     e2e_t, _ = reduce_over_ranks(dist, "cuda", e2e_t, [0.0])
-    k = n_bufs // 2
-    ai = batch.attr_info(k, 0)
-    assert nocheck or G.word_checksum(h_out.numpy()[ai.out_off: ai.out_off + ai.out_bytes]) == int(sums[k, 0])
+    for k, (oo, ob) in zip((0, n_bufs // 2, n_bufs - 1), e2e_offs):
+        assert nocheck or G.word_checksum(h_out.numpy()[oo: oo + ob]) == int(sums[k, 0]), "e2e output of buffer %d is wrong" % k
+    if dec_e2e is not dec:
+        dec_e2e.close()
     e2e_value = total_points / (e2e_t * 1e-3)
 
     if rank == 0:
@@ -641,7 +647,7 @@ def main():
                          "note": "serial rANS chains: %d streams x %d symbols; residency waves %d, %d lanes/warp, %d B smem/stream"
                                  % (n_bufs, WORKLOADS[args.workload][1] * 3, stats.n_waves, stats.lanes_per_warp, stats.smem_per_stream)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                    "ms_per_step": e2e_t, "steps": args.e2e_steps,
+                    "ms_per_step": e2e_t, "steps": args.e2e_steps, "pipeline_slices": args.e2e_slices,
                     "what": "dcb_index_arena + dcb_decode: host indexing, H2D from pinned memory, kernels, D2H to pinned memory"},
             "gpu_launches": total_launches,
             "clocks": clocks,

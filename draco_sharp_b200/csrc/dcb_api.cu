@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <chrono>
 #include <stdlib.h>
 #include <string.h>
 
@@ -70,6 +71,9 @@ struct Group {            // one kernel launch (or a few, for global tables)
 };
 
 struct Shard {
+  bool direct = false;  // the shard's buffers are one 16-byte aligned range of the caller's arena: upload it as is
+  uint64_t direct_lo = 0, direct_hi = 0;
+  int share = 1;        // shards of this batch living on the same physical device (pipeline slices)
   int device = 0;
   std::vector<int> bufs;
   std::vector<StreamDesc> streams, streams0;
@@ -100,6 +104,12 @@ struct dcb_ctx {
   std::vector<std::vector<cudaStream_t>> side;
   std::vector<cudaEvent_t> fork_ev;
   std::vector<std::vector<cudaEvent_t>> join_ev;
+  // pipeline slices (one device listed several times): the slices' bulk copies go through ONE stream per direction
+  // and device, in slice order, so that slice k computes while slice k+1 uploads and slice k-1 downloads -- on
+  // separate streams the copy engines would share the link and every slice would finish its copy at the same time
+  std::vector<cudaStream_t> copy_in, copy_out;  // per ctx device entry; replicas share the handles
+  std::vector<bool> own_copy;
+  std::vector<cudaEvent_t> in_ev, out_ev;
   dcb_launch_stats stats{};
   uint32_t epoch = 0;  // tags the look-back words of par_post_kernel: no clearing between decodes
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -112,8 +122,6 @@ struct dcb_batch {
   std::vector<BufRec> bufs;
   std::vector<Shard> shards;
   const uint8_t *host_arena = nullptr;  // dcb_index_arena: buffers live in one host arena
-  bool direct = false;                  // single shard + 16-byte aligned offsets: upload the arena as is
-  uint64_t direct_lo = 0, direct_hi = 0;
   uint64_t total_out = 0, total_dbg = 0, total_in = 0, total_points = 0, algo_bytes = 0;
   int n_devices = 1;
 };
@@ -407,11 +415,27 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
     if (!r.src && r.len) { delete b; return DCB_ERR_ARG; }
     parse_header(r);
   }
-  // shard by buffer: longest-processing-time-first on compressed bytes; no collective
+  // shard by buffer; no collective.  Distinct devices: longest-processing-time-first on compressed bytes.
+  // The same device listed K times (dcb_create): K pipeline slices -- contiguous runs of buffers with equal bytes, so
+  // that each slice uploads one arena range and H2D / kernels / D2H of neighbouring slices overlap.
   std::vector<int> idx((size_t)n_bufs);
   for (int k = 0; k < n_bufs; ++k) idx[k] = k;
   std::vector<uint64_t> load((size_t)b->n_devices, 0);
-  if (b->n_devices > 1) {
+  bool replicas = b->n_devices > 1;
+  for (int d = 1; d < b->n_devices; ++d) replicas = replicas && b->shards[d].device == b->shards[0].device;
+  for (int d = 0; d < b->n_devices; ++d) {
+    int share = 0;
+    for (int e = 0; e < b->n_devices; ++e) share += b->shards[e].device == b->shards[d].device;
+    b->shards[d].share = share;
+  }
+  if (replicas) {
+    uint64_t total = 0, run = 0;
+    for (int k = 0; k < n_bufs; ++k) total += b->bufs[k].len + 64;
+    for (int k = 0; k < n_bufs; ++k) {
+      b->bufs[k].shard = (int)std::min<uint64_t>((uint64_t)b->n_devices - 1, run * (uint64_t)b->n_devices / std::max<uint64_t>(total, 1));
+      run += b->bufs[k].len + 64;
+    }
+  } else if (b->n_devices > 1) {
     std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return b->bufs[x].len > b->bufs[y].len; });
     for (int k : idx) {
       int best = 0;
@@ -427,19 +451,26 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
     b->bufs[k].info.device = b->bufs[k].shard;
     sh.bufs.push_back(k);
   }
-  b->direct = aligned && b->n_devices == 1 && n_bufs > 0;
-  if (b->direct) {
-    uint64_t lo = ~0ull, hi = 0;
-    for (int k = 0; k < n_bufs; ++k) {
-      lo = std::min(lo, offs[k]);
-      hi = std::max(hi, offs[k] + lens[k]);
+  for (Shard &sh : b->shards) {
+    sh.direct = aligned && !sh.bufs.empty() && (b->n_devices == 1 || replicas);
+    if (sh.direct) {
+      uint64_t lo = ~0ull, hi = 0;
+      for (int k : sh.bufs) {
+        lo = std::min(lo, offs[k]);
+        hi = std::max(hi, offs[k] + lens[k]);
+      }
+      // a slice must not drag foreign bytes along: its range may only hold its own buffers (arena in buffer order)
+      uint64_t own = 0;
+      for (int k : sh.bufs) own += lens[k];
+      if (b->n_devices > 1 && hi - lo > own + 64ull * sh.bufs.size()) sh.direct = false;
+      if (sh.direct) {
+        sh.direct_lo = lo;
+        sh.direct_hi = hi;
+        for (int k : sh.bufs) b->bufs[k].arena_off = kFrontPad + (offs[k] - lo);
+        sh.in_bytes = kFrontPad + (hi - lo) + kBackPad;
+      }
     }
-    b->direct_lo = lo;
-    b->direct_hi = hi;
-    for (int k = 0; k < n_bufs; ++k) b->bufs[k].arena_off = kFrontPad + (offs[k] - lo);
-    b->shards[0].in_bytes = kFrontPad + (hi - lo) + kBackPad;
-  } else {
-    for (Shard &sh : b->shards) {
+    if (!sh.direct) {
       uint64_t pos = kFrontPad;
       for (int k : sh.bufs) {
         b->bufs[k].arena_off = pos;
@@ -515,8 +546,11 @@ uint32_t lane_bytes_for(const Group &g, uint32_t k) { return lut_bytes_for(g, k)
 // Choose LUT granularity, lanes per warp-CTA and the table home for every rANS group of a shard so
 // that as many streams as possible are resident at once: the chains are serial, so the batch time
 // is (waves) x (longest chain) and a second wave doubles it.
-void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms) {
-  const uint32_t budget = kSmemPerSM - 10 * kSmemPerCtaReserve;
+// `share`: shards decoding on the same device at the same time (pipeline slices); each plans for its part of an SM
+void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share = 1) {
+  share = std::max(1u, share);
+  const uint32_t sm_bytes = kSmemPerSM / share;
+  const uint32_t budget = sm_bytes - std::min(sm_bytes / 2, std::max(10 * kSmemPerCtaReserve / share, 2 * kSmemPerCtaReserve + 512));
   std::vector<uint32_t> per_sm(gs.size()), kcap(gs.size());
   for (size_t i = 0; i < gs.size(); ++i) {
     Group &g = *gs[i];
@@ -587,7 +621,9 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms) {
     if (!g.wide && g.compact) {
       const uint32_t ctas_per_sm = std::max<uint32_t>(1u, (want + g.lanes - 1) / g.lanes);
       const uint32_t blk = std::max(16u, ((1u << g.prec_bits) >> 7) << 2);
-      const uint64_t cta_budget = (kSmemPerSM + 1024) / ctas_per_sm - kSmemPerCtaReserve - g.lut_bytes - blk - 256;
+      const uint64_t cta_raw = (sm_bytes + 1024 / share) / ctas_per_sm;
+      const uint64_t cta_fixed = (uint64_t)kSmemPerCtaReserve + g.lut_bytes + blk + 256;
+      const uint64_t cta_budget = cta_raw > cta_fixed ? cta_raw - cta_fixed : 0;
       const uint64_t used = (uint64_t)g.lanes * (lane_bytes + blk);
       if (cta_budget > used) {
         const uint64_t spare = (cta_budget - used) / g.lanes;
@@ -614,9 +650,14 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   CUDA_TRY(cudaMalloc(&sh.d_in, sh.in_bytes));
   CUDA_TRY(cudaMemsetAsync(sh.d_in, 0, kFrontPad, st));
   CUDA_TRY(cudaMemsetAsync(sh.d_in + sh.in_bytes - kBackPad, 0, kBackPad, st));
-  if (b->direct) {
-    CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, b->host_arena + b->direct_lo, b->direct_hi - b->direct_lo,
-                             cudaMemcpyHostToDevice, st));
+  if (sh.direct) {
+    cudaStream_t cs = sh.share > 1 ? ctx->copy_in[dev_index] : st;
+    CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, b->host_arena + sh.direct_lo, sh.direct_hi - sh.direct_lo,
+                             cudaMemcpyHostToDevice, cs));
+    if (cs != st) {
+      CUDA_TRY(cudaEventRecord(ctx->in_ev[dev_index], cs));
+      CUDA_TRY(cudaStreamWaitEvent(st, ctx->in_ev[dev_index], 0));
+    }
   } else if (!sh.bufs.empty()) {
     CUDA_TRY(cudaMallocHost(&sh.h_stage, sh.in_bytes));
     for (int k : sh.bufs) memcpy(sh.h_stage + b->bufs[k].arena_off, b->bufs[k].src, b->bufs[k].len);
@@ -656,6 +697,12 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
         }
       }
     }
+  }
+  // every allocation of a decode happens here, before any kernel is launched: a cudaMalloc issued between two
+  // launches keeps them from running concurrently (pipeline slices, side streams)
+  {
+    int rc = ensure_order(sh, 4 * (uint64_t)sh.streams.size() + sh.bufs.size() + 1024);
+    if (rc) return rc;
   }
   if (!sh.streams.empty()) CUDA_TRY(cudaMalloc(&sh.d_streams, sh.streams.size() * sizeof(StreamDesc)));
   if (!sh.walks.empty()) CUDA_TRY(cudaMalloc(&sh.d_walks, sh.walks.size() * sizeof(BufWalk)));
@@ -716,7 +763,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     std::stable_sort(g.order.begin(), g.order.end(),
                      [&](uint32_t x, uint32_t y) { return sh.streams[x].n_entries > sh.streams[y].n_entries; });
     std::vector<Group *> gs{&g};
-    plan_rans_groups(gs, num_sms);
+    plan_rans_groups(gs, num_sms, (uint32_t)sh.share);
     if (g.table_global) return DCB_ERR_STATE;  // cannot happen: tag alphabets are tiny (<= 2^24 guarded by table size)
     int rc = ensure_order(sh, g.order.size() + blocked.size());
     if (rc) return rc;
@@ -813,7 +860,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   // the groups run one after another on the shard's stream: each one may use the whole SM
   for (Group *g : rgs) {
     std::vector<Group *> one{g};
-    plan_rans_groups(one, num_sms);
+    plan_rans_groups(one, num_sms, (uint32_t)sh.share);
   }
   // device order lists
   uint64_t n_order = 0;
@@ -1004,7 +1051,29 @@ void collect_status(dcb_batch *b) {
   }
 }
 
-int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags) {
+// D2H of one shard's arenas (asynchronous).  Pipeline slices: in slice order on the device's download stream.
+int download_shard(dcb_ctx *ctx, dcb_batch *b, int d, uint8_t *host_out, uint8_t *host_dbg) {
+  Shard &sh = b->shards[d];
+  CUDA_TRY(cudaSetDevice(sh.device));
+  if (host_out && sh.ext_out && sh.out_bytes) {
+    if (sh.share > 1) {  // the slice's own stream then waits for the copy, so that sync_all covers it
+      cudaStream_t cs = ctx->copy_out[d];
+      CUDA_TRY(cudaEventRecord(ctx->out_ev[d], ctx->streams[d]));
+      CUDA_TRY(cudaStreamWaitEvent(cs, ctx->out_ev[d], 0));
+      CUDA_TRY(cudaMemcpyAsync(host_out + sh.out_base, sh.ext_out, sh.out_bytes, cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(cudaEventRecord(ctx->out_ev[d], cs));
+      CUDA_TRY(cudaStreamWaitEvent(ctx->streams[d], ctx->out_ev[d], 0));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(host_out + sh.out_base, sh.ext_out, sh.out_bytes, cudaMemcpyDeviceToHost, ctx->streams[d]));
+    }
+  }
+  if (host_dbg && sh.ext_dbg && sh.dbg_bytes)
+    CUDA_TRY(cudaMemcpyAsync(host_dbg + sh.dbg_base, sh.ext_dbg, sh.dbg_bytes, cudaMemcpyDeviceToHost, ctx->streams[d]));
+  return DCB_OK;
+}
+
+int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags, uint8_t *host_out = nullptr,
+               uint8_t *host_dbg = nullptr) {
   if (!ctx || !b) return DCB_ERR_ARG;
   if ((int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
   if ((dev_out || dev_dbg) && b->n_devices != 1) return DCB_ERR_ARG;
@@ -1016,6 +1085,7 @@ int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_
   ctx->ev_raw = ctx->ev_tag = ctx->ev_par = ctx->ev_para = false;
   ctx->algo_raw = ctx->algo_tag = ctx->algo_par = 0;
   ctx->raw_name[0] = 0;
+  const auto t_up = std::chrono::steady_clock::now();
   for (int d = 0; d < b->n_devices; ++d) {
     Shard &sh = b->shards[d];
     int rc = upload_shard(ctx, b, sh, d);
@@ -1043,10 +1113,23 @@ int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_
     }
     sh.ext_dbg = g;
   }
+  const bool dbg_t = getenv("DCB_DEBUG_TIMING") != nullptr;
+  if (dbg_t)
+    fprintf(stderr, "[dcb timing] uploads issued in %.1f ms\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count());
+  const auto t0 = std::chrono::steady_clock::now();
   for (int d = 0; d < b->n_devices; ++d) {
     Shard &sh = b->shards[d];
     int rc = decode_shard(ctx, b, sh, d, sh.ext_out, sh.ext_dbg, flags, true);
     if (rc) return rc;
+    if (host_out || host_dbg) {  // host-buffer decode: this shard's results start travelling while the next one decodes
+      rc = download_shard(ctx, b, d, host_out, host_dbg);
+      if (rc) return rc;
+    }
+    if (dbg_t)
+      fprintf(stderr, "[dcb timing]   shard %d launched at +%.1f ms (direct=%d in=%.1f MB out=%.1f MB)\n", d,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), (int)sh.direct,
+              sh.in_bytes / 1e6, sh.out_bytes / 1e6);
   }
   return DCB_OK;
 }
@@ -1177,6 +1260,24 @@ int dcb_create(const int *device_ids, int n_devices, dcb_ctx **out) {
     c->side.push_back(side);
     c->join_ev.push_back(jev);
     c->fork_ev.push_back(fev);
+    {
+      cudaStream_t ci = nullptr, co = nullptr;
+      bool own = true;
+      for (size_t e = 0; e + 1 < c->streams.size(); ++e)
+        if (c->devices[e] == dev) { ci = c->copy_in[e]; co = c->copy_out[e]; own = false; break; }
+      if (own) {
+        cudaStreamCreateWithFlags(&ci, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&co, cudaStreamNonBlocking);
+      }
+      c->copy_in.push_back(ci);
+      c->copy_out.push_back(co);
+      c->own_copy.push_back(own);
+      cudaEvent_t ie = nullptr, oe = nullptr;
+      cudaEventCreateWithFlags(&ie, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&oe, cudaEventDisableTiming);
+      c->in_ev.push_back(ie);
+      c->out_ev.push_back(oe);
+    }
     c->num_sms.push_back(p.multiProcessorCount > 0 ? p.multiProcessorCount : (int)kNumSMsDefault);
   }
   cudaSetDevice(c->devices[0]);
@@ -1199,6 +1300,12 @@ void dcb_destroy(dcb_ctx *ctx) {
     for (auto &s : ctx->side[i]) if (s) cudaStreamDestroy(s);
     for (auto &e : ctx->join_ev[i]) if (e) cudaEventDestroy(e);
     if (ctx->fork_ev[i]) cudaEventDestroy(ctx->fork_ev[i]);
+    if (i < ctx->own_copy.size() && ctx->own_copy[i]) {
+      if (ctx->copy_in[i]) cudaStreamDestroy(ctx->copy_in[i]);
+      if (ctx->copy_out[i]) cudaStreamDestroy(ctx->copy_out[i]);
+    }
+    if (i < ctx->in_ev.size() && ctx->in_ev[i]) cudaEventDestroy(ctx->in_ev[i]);
+    if (i < ctx->out_ev.size() && ctx->out_ev[i]) cudaEventDestroy(ctx->out_ev[i]);
   }
   delete ctx;
 }
@@ -1404,12 +1511,8 @@ int dcb_decode_resident(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg
 int dcb_download(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg) {
   if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
   for (int d = 0; d < b->n_devices; ++d) {
-    Shard &sh = b->shards[d];
-    CUDA_TRY(cudaSetDevice(sh.device));
-    if (host_out && sh.ext_out && sh.out_bytes)
-      CUDA_TRY(cudaMemcpyAsync(host_out + sh.out_base, sh.ext_out, sh.out_bytes, cudaMemcpyDeviceToHost, ctx->streams[d]));
-    if (host_dbg && sh.ext_dbg && sh.dbg_bytes)
-      CUDA_TRY(cudaMemcpyAsync(host_dbg + sh.dbg_base, sh.ext_dbg, sh.dbg_bytes, cudaMemcpyDeviceToHost, ctx->streams[d]));
+    int rc = download_shard(ctx, b, d, host_out, host_dbg);
+    if (rc) return rc;
   }
   return sync_all(ctx);
 }
@@ -1417,10 +1520,16 @@ int dcb_download(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_db
 int dcb_decode(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg, uint32_t flags) {
   if (!host_out && b && b->total_out) return DCB_ERR_ARG;
   if ((flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS)) && !host_dbg) return DCB_ERR_ARG;
-  int rc = decode_all(ctx, b, nullptr, nullptr, flags);
+  const bool dbg_t = getenv("DCB_DEBUG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
+  int rc = decode_all(ctx, b, nullptr, nullptr, flags, host_out, host_dbg);
   if (rc) return rc;
-  rc = dcb_download(ctx, b, host_out, host_dbg);
+  const double t_dec = ms();
+  rc = sync_all(ctx);
   if (rc) return rc;
+  if (dbg_t) fprintf(stderr, "[dcb timing] decode_all issued %.1f ms, download done %.1f ms\n", t_dec, ms());
   finish_stats(ctx);
   collect_status(b);
   return DCB_OK;

@@ -965,6 +965,9 @@ static cudaError_t launch_raw_t(const RansLaunch &p, const DevArenas &a, cudaStr
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
   }
+  // the whole SM as shared memory, whatever this launch needs: CTAs of other launches (pipeline slices, side-stream
+  // groups) can only move in next to ours when the carve-out already holds them
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
   k<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, geom_of(p), a.out, a.dbg,
                                   a.aux, a.tab, p.dump | (getenv("DCB_NO_SPLIT") ? 0x80000000u : 0u) | (getenv("DCB_DEBUG_KERNEL") ? 0x40000000u : 0u));
@@ -1015,6 +1018,7 @@ cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, cudaStr
     cudaError_t e = cudaFuncSetAttribute(rans_tag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
   }
+  cudaFuncSetAttribute(rans_tag_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
   rans_tag_kernel<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, geom_of(p),
                                                 a.aux);

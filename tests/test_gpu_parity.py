@@ -113,3 +113,37 @@ def test_resident_decode_into_torch_tensor(gpu_decoder):
             ai = batch.attr_info(k, a)
             assert np.array_equal(first[ai.out_off: ai.out_off + ai.out_bytes], host[ai.out_off: ai.out_off + ai.out_bytes])
     batch.free()
+
+
+@pytest.mark.parametrize("scheme", [-1, 0])
+@pytest.mark.parametrize("slices", [3, 8])
+def test_pipeline_slices_match_single_shard(gpu_decoder, scheme, slices):
+    """The same device listed K times in dcb_create = K pipeline slices (contiguous buffer runs, own streams, own
+    arenas): every decoded byte and status equals the single-shard decode."""
+    import draco_sharp_b200 as D
+    sp = G.make_spec(20000, seed=0xD5AC0100, scheme=scheme, normal_bits=10, colors=1)
+    arena, offs, lens, sums, schemes, used = G.synth_batch(sp, 37)
+    arena = arena.copy()
+    arena[int(offs[5]) + 40] ^= 0x55  # one damaged buffer: must fail alone, in its own slice
+    one = gpu_decoder.index_arena(arena, offs, lens)
+    ref, _ = gpu_decoder.decode(one)
+    dec = D.DracoBatchDecoder([0] * slices)
+    try:
+        many = dec.index_arena(arena, offs, lens)
+        out, _ = dec.decode(many)
+        assert many.out_bytes == out.nbytes
+        devs = set()
+        for k in range(37):
+            assert many.status(k) == one.status(k)
+            devs.add(many.buffer_info(k).device)
+            if one.status(k):
+                continue
+            for a in range(3):
+                x, y = one.attr_info(k, a), many.attr_info(k, a)
+                assert x.out_bytes == y.out_bytes
+                assert np.array_equal(ref[x.out_off: x.out_off + x.out_bytes], out[y.out_off: y.out_off + y.out_bytes]), (k, a)
+        assert len(devs) == slices
+        many.free()
+    finally:
+        dec.close()
+        one.free()
