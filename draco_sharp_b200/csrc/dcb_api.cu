@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <chrono>
+#include <string>
 #include <stdlib.h>
 #include <string.h>
 
@@ -110,6 +111,8 @@ struct dcb_ctx {
   std::vector<cudaStream_t> copy_in, copy_out;  // per ctx device entry; replicas share the handles
   std::vector<bool> own_copy;
   std::vector<cudaEvent_t> in_ev, out_ev;
+  // DCB_DEBUG_TIMING: per-launch events of the last decode (name, begin, end), printed by finish_stats
+  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timeline;
   dcb_launch_stats stats{};
   uint32_t epoch = 0;  // tags the look-back words of par_post_kernel: no clearing between decodes
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -547,9 +550,12 @@ uint32_t lane_bytes_for(const Group &g, uint32_t k) { return lut_bytes_for(g, k)
 // that as many streams as possible are resident at once: the chains are serial, so the batch time
 // is (waves) x (longest chain) and a second wave doubles it.
 // `share`: shards decoding on the same device at the same time (pipeline slices); each plans for its part of an SM
-void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share = 1) {
+// `corun`: bytes of every SM left free for the CTAs of kernels that run NEXT TO the rANS kernels (oct_chain, oct_unit on
+// a side stream): a CTA needs its 1 KB system reservation even when it declares no shared memory, so an SM whose
+// shared memory the rANS CTAs fill to the brim holds nothing else.
+void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share = 1, uint32_t corun = 0) {
   share = std::max(1u, share);
-  const uint32_t sm_bytes = kSmemPerSM / share;
+  const uint32_t sm_bytes = (kSmemPerSM - corun) / share;
   const uint32_t budget = sm_bytes - std::min(sm_bytes / 2, std::max(10 * kSmemPerCtaReserve / share, 2 * kSmemPerCtaReserve + 512));
   std::vector<uint32_t> per_sm(gs.size()), kcap(gs.size());
   for (size_t i = 0; i < gs.size(); ++i) {
@@ -739,6 +745,18 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   sh.tags_launched.assign(sh.streams.size(), 0);
   DevArenas A{sh.d_in, d_out, d_dbg, sh.d_aux, sh.d_tab, sh.d_maps};
   const uint32_t dump = flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS);
+  const bool dbg_tl = timed && dev_index == 0 && getenv("DCB_DEBUG_TIMING") != nullptr;
+  auto tl_begin = [&](const char *name, cudaStream_t s) {
+    if (!dbg_tl) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    ctx->timeline.push_back({name, {a, b}});
+  };
+  auto tl_end = [&](cudaStream_t s) {
+    if (dbg_tl) cudaEventRecord(ctx->timeline.back().second.second, s);
+  };
   if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
   // ---- Tagged streams: decode tags, resume the walks behind their bit areas ----
@@ -814,7 +832,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         continue;
       }
       if (s.n_entries == 0) continue;
-      if (s.store == STORE_OCT_UNIT) {
+      // normals behind a Raw stream: the rANS kernel leaves corrections, oct_chain + oct_unit follow on its stream
+      const bool raw_normals = s.scheme == SCHEME_RAW && s.ncp == 2 && s.store == STORE_OCT_UNIT &&
+                               (s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON);
+      if (s.store == STORE_OCT_UNIT && !raw_normals) {
         octs.order.push_back(si);
         octs.max_entries = std::max(octs.max_entries, s.n_entries);
       }
@@ -830,7 +851,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         key.mode = 0;
         if (s.recon == RECON_DELTA_WRAP && s.store == STORE_DEQUANT) key.mode = 1;
         else if (s.recon == RECON_DELTA_WRAP && s.store == STORE_NARROW && dcb_dtype_len(s.data_type) == 1) key.mode = 2;
-        else if (s.recon == RECON_DELTA_OCT_CANON && s.store == STORE_OCT_UNIT) key.mode = 3;
+        else if (raw_normals) key.mode = 3;
         Group &g = raw[key];
         if (g.order.empty()) {
           g.kind = 0; g.ncp = key.ncp; g.wide = key.wide != 0; g.compact = (uint32_t)key.compact; g.prec_bits = (uint32_t)key.prec;
@@ -839,6 +860,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         g.entries = std::max(g.entries, entries);
         if (key.compact) g.exc = std::max(g.exc, s.n_active - std::min(s.n_active, s.dense_prefix));
         g.total_symbols += (uint64_t)s.n_entries * s.ncp;
+        g.max_entries = std::max(g.max_entries, s.n_entries);
         g.order.push_back(si);
       } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP) && !getenv("DCB_NO_PAR_POST")) {
         // Tagged / uncompressed source, scan-able reconstruction: point-parallel kernels
@@ -858,9 +880,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   std::vector<Group *> rgs;
   for (auto &kv : raw) rgs.push_back(&kv.second);
   // the groups run one after another on the shard's stream: each one may use the whole SM
+  bool side_followers = false;
+  for (Group *g : rgs) side_followers = side_followers || (g->mode == 3 && rgs.size() > 1);
   for (Group *g : rgs) {
     std::vector<Group *> one{g};
-    plan_rans_groups(one, num_sms, (uint32_t)sh.share);
+    plan_rans_groups(one, num_sms, (uint32_t)sh.share, side_followers ? 6u * 1024u : 0u);
   }
   // device order lists
   uint64_t n_order = 0;
@@ -949,8 +973,20 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     } else {
       RansLaunch L{sh.d_streams, sh.d_order + g->order_off, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes,
                    g->entries, g->exc, g->lut_shift, g->prec_bits, dump, g->compact, g->zig, g->mode};
+      tl_begin(g->mode == 1 ? "rans mode1" : g->mode == 2 ? "rans mode2" : g->mode == 3 ? "rans mode3" : "rans mode0", st);
       CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
+      tl_end(st);
       stats.n_launches++;
+    }
+    if (g->mode == 3) {
+      // same stream, right behind the corrections; no shared memory, so they run next to the other groups' rANS kernels
+      tl_begin("oct_chain", st);
+      CUDA_TRY(dcb_launch_oct_chain(sh.d_streams, sh.d_order + g->order_off, n, dump, A, st));
+      tl_end(st);
+      tl_begin("oct_unit", st);
+      CUDA_TRY(dcb_launch_oct_unit(sh.d_streams, sh.d_order + g->order_off, n, g->max_entries, A, st));
+      tl_end(st);
+      stats.n_launches += 2;
     }
     if (is_dom) {
       CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
@@ -1145,6 +1181,15 @@ int sync_all(dcb_ctx *ctx) {
 void finish_stats(dcb_ctx *ctx) {
   dcb_launch_stats &st = ctx->stats;
   float ms = 0.0f;
+  for (auto &t : ctx->timeline) {
+    float a = 0.0f, b = 0.0f;
+    cudaEventElapsedTime(&a, ctx->ev[0], t.second.first);
+    cudaEventElapsedTime(&b, ctx->ev[0], t.second.second);
+    fprintf(stderr, "[dcb timeline] %-12s %8.2f -> %8.2f ms\n", t.first.c_str(), a, b);
+    cudaEventDestroy(t.second.first);
+    cudaEventDestroy(t.second.second);
+  }
+  ctx->timeline.clear();
   if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) st.ms_total = ms;
   else cudaGetLastError();
   if (ctx->ev_raw && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) st.ms_raw = ms;

@@ -43,10 +43,12 @@ namespace {
 // compile time for the hot shapes
 //   1  delta + wrap  -> dequantise to float      (quantized positions / tex coords)
 //   2  delta + wrap  -> narrow to uint8          (colours)
-//   3  delta + canonicalized octahedron -> unit vector (normals)
+//   3  normals: the unsigned corrections go to the int32 scratch as they are; the octahedral recurrence is a chain of
+//      its own (~120 dependent-ish instructions per entry) and runs in oct_chain_kernel, next to the rANS kernels of
+//      the batch's other attributes instead of in front of them
 template <int MODE>
 __device__ __forceinline__ int recon_of(const PostParams &pp) {
-  return (MODE == 1 || MODE == 2) ? (int)RECON_DELTA_WRAP : (MODE == 3 ? (int)RECON_DELTA_OCT_CANON : pp.recon);
+  return (MODE == 1 || MODE == 2) ? (int)RECON_DELTA_WRAP : (MODE == 3 ? (int)RECON_NONE : pp.recon);
 }
 template <int MODE>
 __device__ __forceinline__ int store_of(const PostParams &pp) {
@@ -115,7 +117,7 @@ __device__ __forceinline__ void decode_entry(RansLane<T, TG> &rl, const TableGeo
       v[NCP - 1] = prev[NCP - 1];
     }
   }
-  if (DUMP && (dump & DCB_DUMP_QINTS)) {
+  if (DUMP && MODE != 3 && (dump & DCB_DUMP_QINTS)) {
 #pragma unroll
     for (int c = 0; c < NCP; ++c) dptr[e * NCP + c] = v[c];
   }
@@ -227,8 +229,12 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   uint8_t *optr = out + dp->out_off;
   int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + dp->dbg_off) : nullptr;
   if (MODE == 3 || (MODE == 0 && (pp.recon == RECON_PARA_WRAP || pp.store == STORE_OCT_UNIT))) {
-    // int32 scratch: corrections for the parallelogram kernel / quantized (s, t) for oct_unit_kernel
+    // int32 scratch: corrections for the parallelogram kernel / for oct_chain_kernel
     optr = aux + dp->aux_off;
+    if (NCP == 2 && pp.store == STORE_OCT_UNIT) {  // normals: the recurrence and its quantized-int dump run in oct_chain_kernel
+      pp.recon = RECON_NONE;
+      dump &= ~(uint32_t)DCB_DUMP_QINTS;
+    }
     pp.store = STORE_NARROW;
     pp.dsize = 4;
   }
@@ -892,6 +898,58 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
   }
 }
 
+// PredictionSchemeDeltaDecoder over PredictionSchemeNormalOctahedron(Canonicalized)DecodingTransform
+// (ComputeOriginalValue, :34-78): orig[i] = f(orig[i-1], corr[i]) on the int32 pairs the Raw rANS kernel (MODE 3) left
+// in the stream's scratch, in place.  One stream per lane, no shared memory: the kernel shares the SMs with whatever
+// rANS kernels of the batch are running.  Four entries per iteration, the next four prefetched.
+template <bool DUMP>
+__global__ void __launch_bounds__(32) oct_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
+                                                       uint32_t n_streams, uint8_t *__restrict__ aux,
+                                                       uint8_t *__restrict__ dbg, uint32_t dump) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_streams) return;
+  const StreamDesc &d = streams[order[slot]];
+  if (d.status != DCB_OK) return;
+  const uint32_t n = d.n_entries;
+  PostParams pp;
+  pp.load(d);
+  const bool canonical = d.recon == RECON_DELTA_OCT_CANON;
+  int4 *st = reinterpret_cast<int4 *>(aux + d.aux_off);  // two (s, t) pairs per int4; scratch offsets are 16-byte aligned
+  int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
+  int32_t p0 = 0, p1 = 0;
+  const uint32_t n4 = n / 4;
+  int4 a = make_int4(0, 0, 0, 0), b = a;
+  if (n4) { a = st[0]; b = st[1]; }
+  for (uint32_t g = 0; g < n4; ++g) {
+    int4 na = a, nb = b;
+    if (g + 1 < n4) { na = st[2 * g + 2]; nb = st[2 * g + 3]; }
+    oct_original(pp.box, canonical, p0, p1, a.x, a.y);
+    a.x = p0; a.y = p1;
+    oct_original(pp.box, canonical, p0, p1, a.z, a.w);
+    a.z = p0; a.w = p1;
+    oct_original(pp.box, canonical, p0, p1, b.x, b.y);
+    b.x = p0; b.y = p1;
+    oct_original(pp.box, canonical, p0, p1, b.z, b.w);
+    b.z = p0; b.w = p1;
+    st[2 * g] = a;
+    st[2 * g + 1] = b;
+    if (DUMP && (dump & DCB_DUMP_QINTS)) {
+      reinterpret_cast<int4 *>(dptr)[2 * g] = a;
+      reinterpret_cast<int4 *>(dptr)[2 * g + 1] = b;
+    }
+    a = na;
+    b = nb;
+  }
+  int2 *s2 = reinterpret_cast<int2 *>(aux + d.aux_off);
+  for (uint32_t e = n4 * 4; e < n; ++e) {
+    int2 c = s2[e];
+    oct_original(pp.box, canonical, p0, p1, c.x, c.y);
+    c.x = p0; c.y = p1;
+    s2[e] = c;
+    if (DUMP && (dump & DCB_DUMP_QINTS)) reinterpret_cast<int2 *>(dptr)[e] = c;
+  }
+}
+
 // AttributeOctahedronTransform.InverseTransformAttribute (:82-102): quantized octahedral (s, t) -> unit vector,
 // one thread per entry, reading the int32 pairs the serial kernels left in scratch
 __global__ void oct_unit_kernel(StreamDesc *streams, const uint32_t *__restrict__ order, uint32_t n_streams,
@@ -1108,11 +1166,32 @@ cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint
   return cudaGetLastError();
 }
 
+// Kernels that run next to the rANS kernels (side streams) must ask for the same shared-memory carve-out: an SM
+// cannot hold CTAs of two carve-out configurations at once, it would drain first.
+template <typename K>
+static void same_carveout(K k) {
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
+cudaError_t dcb_launch_oct_chain(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t dump,
+                                 const DevArenas &a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const uint32_t grid = (n + 31) / 32;
+  same_carveout(oct_chain_kernel<true>);
+  same_carveout(oct_chain_kernel<false>);
+  if (dump)
+    oct_chain_kernel<true><<<grid, 32, 0, st>>>(d_streams, d_order, n, a.aux, a.dbg, dump);
+  else
+    oct_chain_kernel<false><<<grid, 32, 0, st>>>(d_streams, d_order, n, a.aux, a.dbg, dump);
+  return cudaGetLastError();
+}
+
 cudaError_t dcb_launch_oct_unit(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries,
                                 const DevArenas &a, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   uint32_t gx = (max_entries + 255) / 256;
   gx = gx < 1 ? 1 : (gx > 4096 ? 4096 : gx);
+  same_carveout(oct_unit_kernel);
   oct_unit_kernel<<<dim3(gx, n > 65535u ? 65535u : n), 256, 0, st>>>(d_streams, d_order, n, a.out, a.aux);
   return cudaGetLastError();
 }

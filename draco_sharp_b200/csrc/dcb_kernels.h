@@ -33,6 +33,8 @@ cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, 
                                 uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
                             uint32_t dump, const DevArenas &a, cudaStream_t st);
+cudaError_t dcb_launch_oct_chain(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t dump,
+                                 const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_oct_unit(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries,
                                 const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_copy(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint64_t max_bytes,
