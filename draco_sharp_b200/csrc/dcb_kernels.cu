@@ -213,9 +213,6 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   }
   // the branch-free two-region LUT is used when every stream of the warp can have one
   const bool use_split = __all_sync(0xffffffffu, split_ok);
-  if ((dump & 0x40000000u) && blockIdx.x < 2 && have && n_entries)
-    printf("[dcb kernel] cta %u lane %u: split_ok=%d use_split=%d t_split=%u kA=%u base_b=%u ne=%u dprefix=%u\n", blockIdx.x, lane,
-           (int)rl.split_ok, (int)use_split, rl.t_split, rl.a_sh + 1u, rl.blk_mask, rl.n_entries_tab, rl.dprefix);
   // groups of 4 entries every active lane of the warp can run without per-lane bounds checks
   uint32_t g_min = n_entries ? (n_entries >> 2) : 0xFFFFFFFFu;
 #pragma unroll
@@ -1015,6 +1012,12 @@ uint32_t dcb_rans_smem_bytes(const RansLaunch &p, bool table_global) {
   return b;
 }
 
+// DCB_NO_SPLIT=1 forces the uniform-LUT probe (tests of the fallback path); bit 31 of the kernel's `dump` word
+static uint32_t no_split_bit() {
+  static const uint32_t bit = getenv("DCB_NO_SPLIT") ? 0x80000000u : 0u;
+  return bit;
+}
+
 template <int NCP, typename T, bool DUMP, bool TG, int MODE, int TAB = 0>
 static cudaError_t launch_raw_t(const RansLaunch &p, const DevArenas &a, cudaStream_t st) {
   auto k = rans_raw_fused_kernel<NCP, T, DUMP, TG, MODE, TAB>;
@@ -1028,7 +1031,7 @@ static cudaError_t launch_raw_t(const RansLaunch &p, const DevArenas &a, cudaStr
   cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
   k<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, geom_of(p), a.out, a.dbg,
-                                  a.aux, a.tab, p.dump | (getenv("DCB_NO_SPLIT") ? 0x80000000u : 0u) | (getenv("DCB_DEBUG_KERNEL") ? 0x40000000u : 0u));
+                                  a.aux, a.tab, p.dump | no_split_bit());
   return cudaGetLastError();
 }
 

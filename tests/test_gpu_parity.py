@@ -147,3 +147,20 @@ def test_pipeline_slices_match_single_shard(gpu_decoder, scheme, slices):
     finally:
         dec.close()
         one.free()
+
+
+def test_uniform_lut_fallback_path_is_bit_exact_too():
+    """DCB_NO_SPLIT=1 forces every Raw stream through the uniform-LUT probe (the path tables take when they cannot
+    satisfy the two-region LUT); the switch is read once per process, so the parity cases re-run in a child."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DCB_NO_SPLIT"):
+        pytest.skip("already the child")
+    env = dict(os.environ, DCB_NO_SPLIT="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "positions_small_sizes or positions_normals_colors or ragged_batch or wide_alphabets"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
