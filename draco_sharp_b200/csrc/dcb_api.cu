@@ -75,6 +75,7 @@ struct Shard {
   bool direct = false;  // the shard's buffers are one 16-byte aligned range of the caller's arena: upload it as is
   uint64_t direct_lo = 0, direct_hi = 0;
   int share = 1;        // shards of this batch living on the same physical device (pipeline slices)
+  bool arena_pending = false;
   int device = 0;
   std::vector<int> bufs;
   std::vector<StreamDesc> streams, streams0;
@@ -649,6 +650,25 @@ int ensure_order(Shard &sh, uint64_t n) {
   return DCB_OK;
 }
 
+void tl_mark(dcb_ctx *ctx, const std::string &name, cudaStream_t s, bool begin);
+
+// Pipeline slices: the slice's compressed bytes, on the device's upload stream (slice order = issue order); the
+// slice's own stream waits for them.  Issued slice by slice, interleaved with the slices' launches, so that the small
+// descriptor copies of slice k are not queued behind the bulk copies of slices k+1.. on the copy engine.
+int issue_arena_copy(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
+  if (!sh.arena_pending) return DCB_OK;
+  sh.arena_pending = false;
+  cudaStream_t st = ctx->streams[dev_index], cs = ctx->copy_in[dev_index];
+  CUDA_TRY(cudaSetDevice(sh.device));
+  tl_mark(ctx, "h2d s" + std::to_string(dev_index), cs, true);
+  CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, b->host_arena + sh.direct_lo, sh.direct_hi - sh.direct_lo,
+                           cudaMemcpyHostToDevice, cs));
+  tl_mark(ctx, "", cs, false);
+  CUDA_TRY(cudaEventRecord(ctx->in_ev[dev_index], cs));
+  CUDA_TRY(cudaStreamWaitEvent(st, ctx->in_ev[dev_index], 0));
+  return DCB_OK;
+}
+
 int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   if (sh.uploaded) return DCB_OK;
   cudaStream_t st = ctx->streams[dev_index];
@@ -656,14 +676,11 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   CUDA_TRY(cudaMalloc(&sh.d_in, sh.in_bytes));
   CUDA_TRY(cudaMemsetAsync(sh.d_in, 0, kFrontPad, st));
   CUDA_TRY(cudaMemsetAsync(sh.d_in + sh.in_bytes - kBackPad, 0, kBackPad, st));
-  if (sh.direct) {
-    cudaStream_t cs = sh.share > 1 ? ctx->copy_in[dev_index] : st;
+  if (sh.direct && sh.share > 1) {
+    sh.arena_pending = true;  // pipeline slices: issue_arena_copy, right before the slice's kernels are launched
+  } else if (sh.direct) {
     CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, b->host_arena + sh.direct_lo, sh.direct_hi - sh.direct_lo,
-                             cudaMemcpyHostToDevice, cs));
-    if (cs != st) {
-      CUDA_TRY(cudaEventRecord(ctx->in_ev[dev_index], cs));
-      CUDA_TRY(cudaStreamWaitEvent(st, ctx->in_ev[dev_index], 0));
-    }
+                             cudaMemcpyHostToDevice, st));
   } else if (!sh.bufs.empty()) {
     CUDA_TRY(cudaMallocHost(&sh.h_stage, sh.in_bytes));
     for (int k : sh.bufs) memcpy(sh.h_stage + b->bufs[k].arena_off, b->bufs[k].src, b->bufs[k].len);
@@ -745,14 +762,14 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   sh.tags_launched.assign(sh.streams.size(), 0);
   DevArenas A{sh.d_in, d_out, d_dbg, sh.d_aux, sh.d_tab, sh.d_maps};
   const uint32_t dump = flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS);
-  const bool dbg_tl = timed && dev_index == 0 && getenv("DCB_DEBUG_TIMING") != nullptr;
+  const bool dbg_tl = timed && sh.device == ctx->devices[0] && getenv("DCB_DEBUG_TIMING") != nullptr;
   auto tl_begin = [&](const char *name, cudaStream_t s) {
     if (!dbg_tl) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     cudaEventRecord(a, s);
-    ctx->timeline.push_back({name, {a, b}});
+    ctx->timeline.push_back({std::string(name) + " s" + std::to_string(dev_index), {a, b}});
   };
   auto tl_end = [&](cudaStream_t s) {
     if (dbg_tl) cudaEventRecord(ctx->timeline.back().second.second, s);
@@ -1087,6 +1104,19 @@ void collect_status(dcb_batch *b) {
   }
 }
 
+void tl_mark(dcb_ctx *ctx, const std::string &name, cudaStream_t s, bool begin) {
+  if (!getenv("DCB_DEBUG_TIMING")) return;
+  if (begin) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    ctx->timeline.push_back({name, {a, b}});
+  } else {
+    cudaEventRecord(ctx->timeline.back().second.second, s);
+  }
+}
+
 // D2H of one shard's arenas (asynchronous).  Pipeline slices: in slice order on the device's download stream.
 int download_shard(dcb_ctx *ctx, dcb_batch *b, int d, uint8_t *host_out, uint8_t *host_dbg) {
   Shard &sh = b->shards[d];
@@ -1096,7 +1126,9 @@ int download_shard(dcb_ctx *ctx, dcb_batch *b, int d, uint8_t *host_out, uint8_t
       cudaStream_t cs = ctx->copy_out[d];
       CUDA_TRY(cudaEventRecord(ctx->out_ev[d], ctx->streams[d]));
       CUDA_TRY(cudaStreamWaitEvent(cs, ctx->out_ev[d], 0));
+      tl_mark(ctx, "d2h s" + std::to_string(d), cs, true);
       CUDA_TRY(cudaMemcpyAsync(host_out + sh.out_base, sh.ext_out, sh.out_bytes, cudaMemcpyDeviceToHost, cs));
+      tl_mark(ctx, "", cs, false);
       CUDA_TRY(cudaEventRecord(ctx->out_ev[d], cs));
       CUDA_TRY(cudaStreamWaitEvent(ctx->streams[d], ctx->out_ev[d], 0));
     } else {
@@ -1156,7 +1188,9 @@ int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_
   const auto t0 = std::chrono::steady_clock::now();
   for (int d = 0; d < b->n_devices; ++d) {
     Shard &sh = b->shards[d];
-    int rc = decode_shard(ctx, b, sh, d, sh.ext_out, sh.ext_dbg, flags, true);
+    int rc = issue_arena_copy(ctx, b, sh, d);
+    if (rc) return rc;
+    rc = decode_shard(ctx, b, sh, d, sh.ext_out, sh.ext_dbg, flags, true);
     if (rc) return rc;
     if (host_out || host_dbg) {  // host-buffer decode: this shard's results start travelling while the next one decodes
       rc = download_shard(ctx, b, d, host_out, host_dbg);
@@ -1538,6 +1572,8 @@ int dcb_upload(dcb_ctx *ctx, dcb_batch *b) {
     if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;
   for (int d = 0; d < b->n_devices; ++d) {
     int rc = upload_shard(ctx, b, b->shards[d], d);
+    if (rc) return rc;
+    rc = issue_arena_copy(ctx, b, b->shards[d], d);
     if (rc) return rc;
   }
   return sync_all(ctx);
