@@ -648,6 +648,7 @@ def main():
                                  % (n_bufs, WORKLOADS[args.workload][1] * 3, stats.n_waves, stats.lanes_per_warp, stats.smem_per_stream)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": e2e_t, "steps": args.e2e_steps, "pipeline_slices": args.e2e_slices,
+                    "ms_each": [round(x, 1) for x in e2e_ms],
                     "what": "dcb_index_arena + dcb_decode: host indexing, H2D from pinned memory, kernels, D2H to pinned memory"},
             "gpu_launches": total_launches,
             "clocks": clocks,

@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <chrono>
+#include <memory>
 #include <string>
 #include <stdlib.h>
 #include <string.h>
@@ -38,6 +39,21 @@ constexpr uint32_t kSmemPerCtaReserve = 1024;
 constexpr uint64_t kTabArenaBudget = 1ull << 30;
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// Device-memory cache of a context: the big per-batch arenas (input, output, scratch, maps) are returned here when a
+// batch is freed and reused by the next one -- a cudaMalloc / cudaFree pair of 15 GB costs 10-100 ms, more than the
+// kernels of the batch.  Blocks are handed out when they are at most twice the size asked for; the cache is capped.
+struct PoolBlock {
+  void *p;
+  uint64_t bytes;
+  int device;
+};
+struct DevPool {
+  std::vector<PoolBlock> free_blocks;
+  uint64_t cached = 0;
+};
+constexpr uint64_t kPoolCap = 96ull << 30;
+constexpr uint64_t kPoolMin = 1ull << 20;  // smaller allocations go straight to cudaMalloc
 
 struct MeshMapsHost {
   std::vector<uint32_t> opposite, corner_to_vertex, data_to_corner;
@@ -76,6 +92,8 @@ struct Shard {
   uint64_t direct_lo = 0, direct_hi = 0;
   int share = 1;        // shards of this batch living on the same physical device (pipeline slices)
   bool arena_pending = false;
+  std::shared_ptr<DevPool> pool;  // the owning context's cache (outlives the context if batches are freed late)
+  uint64_t cap_in = 0, cap_out = 0, cap_aux = 0, cap_maps = 0;
   int device = 0;
   std::vector<int> bufs;
   std::vector<StreamDesc> streams, streams0;
@@ -112,6 +130,7 @@ struct dcb_ctx {
   std::vector<cudaStream_t> copy_in, copy_out;  // per ctx device entry; replicas share the handles
   std::vector<bool> own_copy;
   std::vector<cudaEvent_t> in_ev, out_ev;
+  std::shared_ptr<DevPool> pool = std::make_shared<DevPool>();
   // DCB_DEBUG_TIMING: per-launch events of the last decode (name, begin, end), printed by finish_stats
   std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timeline;
   dcb_launch_stats stats{};
@@ -340,15 +359,65 @@ void parse_attr_section(BufRec &b, Shard &sh, int buf_index) {
   finish(w.status);
 }
 
+cudaError_t pool_alloc(const std::shared_ptr<DevPool> &pool, int device, uint64_t bytes, uint8_t **out, uint64_t *cap) {
+  *out = nullptr;
+  *cap = 0;
+  if (bytes == 0) return cudaSuccess;
+  if (pool && bytes >= kPoolMin) {
+    int best = -1;
+    for (size_t i = 0; i < pool->free_blocks.size(); ++i) {
+      const PoolBlock &k = pool->free_blocks[i];
+      if (k.device != device || k.bytes < bytes || k.bytes > 2 * bytes) continue;
+      if (best < 0 || k.bytes < pool->free_blocks[best].bytes) best = (int)i;
+    }
+    if (best >= 0) {
+      *out = (uint8_t *)pool->free_blocks[best].p;
+      *cap = pool->free_blocks[best].bytes;
+      pool->cached -= *cap;
+      pool->free_blocks.erase(pool->free_blocks.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  const uint64_t want = bytes >= kPoolMin ? align_up(bytes, 2ull << 20) : bytes;
+  cudaError_t e = cudaMalloc(out, want);
+  if (e != cudaSuccess && pool && !pool->free_blocks.empty()) {  // out of memory with a warm cache: drop it and retry
+    cudaGetLastError();
+    for (PoolBlock &k : pool->free_blocks) { cudaSetDevice(k.device); cudaFree(k.p); }
+    pool->free_blocks.clear();
+    pool->cached = 0;
+    cudaSetDevice(device);
+    e = cudaMalloc(out, want);
+  }
+  if (e == cudaSuccess) *cap = want;
+  return e;
+}
+
+void pool_free(const std::shared_ptr<DevPool> &pool, int device, void *p, uint64_t cap) {
+  if (!p) return;
+  if (pool && cap >= kPoolMin && pool->cached + cap <= kPoolCap) {
+    pool->free_blocks.push_back({p, cap, device});
+    pool->cached += cap;
+    return;
+  }
+  cudaFree(p);
+}
+
+void pool_trim(const std::shared_ptr<DevPool> &pool) {
+  if (!pool) return;
+  for (PoolBlock &k : pool->free_blocks) { cudaSetDevice(k.device); cudaFree(k.p); }
+  pool->free_blocks.clear();
+  pool->cached = 0;
+}
+
 void free_shard_device(Shard &sh) {
   if (!sh.d_in && !sh.d_streams && !sh.h_stage && !sh.d_out) return;
   cudaSetDevice(sh.device);
-  cudaFree(sh.d_in);
-  if (sh.own_out) cudaFree(sh.d_out);
+  pool_free(sh.pool, sh.device, sh.d_in, sh.cap_in);
+  if (sh.own_out) pool_free(sh.pool, sh.device, sh.d_out, sh.cap_out);
   cudaFree(sh.d_dbg);
-  cudaFree(sh.d_aux);
+  pool_free(sh.pool, sh.device, sh.d_aux, sh.cap_aux);
   cudaFree(sh.d_tab);
-  cudaFree(sh.d_maps);
+  pool_free(sh.pool, sh.device, sh.d_maps, sh.cap_maps);
   cudaFree(sh.d_streams);
   cudaFree(sh.d_walks);
   cudaFree(sh.d_order);
@@ -673,7 +742,8 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   if (sh.uploaded) return DCB_OK;
   cudaStream_t st = ctx->streams[dev_index];
   CUDA_TRY(cudaSetDevice(sh.device));
-  CUDA_TRY(cudaMalloc(&sh.d_in, sh.in_bytes));
+  sh.pool = ctx->pool;
+  CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.in_bytes, &sh.d_in, &sh.cap_in));
   CUDA_TRY(cudaMemsetAsync(sh.d_in, 0, kFrontPad, st));
   CUDA_TRY(cudaMemsetAsync(sh.d_in + sh.in_bytes - kBackPad, 0, kBackPad, st));
   if (sh.direct && sh.share > 1) {
@@ -700,7 +770,7 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
       }
   sh.maps_bytes = mbytes;
   if (mbytes) {
-    CUDA_TRY(cudaMalloc(&sh.d_maps, mbytes));
+    CUDA_TRY(pool_alloc(sh.pool, sh.device, mbytes, &sh.d_maps, &sh.cap_maps));
     for (int k : sh.bufs)
       for (MeshMapsHost &m : b->bufs[k].maps)
         if (m.set) {
@@ -730,7 +800,7 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   if (!sh.streams.empty()) CUDA_TRY(cudaMalloc(&sh.d_streams, sh.streams.size() * sizeof(StreamDesc)));
   if (!sh.walks.empty()) CUDA_TRY(cudaMalloc(&sh.d_walks, sh.walks.size() * sizeof(BufWalk)));
   if (sh.aux_bytes) {
-    CUDA_TRY(cudaMalloc(&sh.d_aux, sh.aux_bytes));
+    CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.aux_bytes, &sh.d_aux, &sh.cap_aux));
     CUDA_TRY(cudaMemsetAsync(sh.d_aux, 0, sh.aux_bytes, st));  // look-back words start with epoch 0 (never a live epoch)
   }
   sh.uploaded = true;
@@ -1162,7 +1232,7 @@ int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_
     uint8_t *o = (uint8_t *)dev_out;
     if (!o) {
       if (!sh.d_out && sh.out_bytes) {
-        CUDA_TRY(cudaMalloc(&sh.d_out, sh.out_bytes));
+        CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.out_bytes, &sh.d_out, &sh.cap_out));
         sh.own_out = true;
       }
       o = sh.d_out;
@@ -1367,6 +1437,8 @@ int dcb_create(const int *device_ids, int n_devices, dcb_ctx **out) {
 
 void dcb_destroy(dcb_ctx *ctx) {
   if (!ctx) return;
+  pool_trim(ctx->pool);
+  ctx->pool->cached = kPoolCap + 1;  // batches freed after their context: straight to cudaFree
   for (size_t i = 0; i < ctx->streams.size(); ++i)
     if (ctx->own_stream[i]) {
       cudaSetDevice(ctx->devices[i]);
