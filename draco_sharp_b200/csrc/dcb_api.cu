@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <chrono>
+#include <thread>
 #include <memory>
 #include <string>
 #include <stdlib.h>
@@ -486,7 +487,6 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
     r.len = lens[k];
     if (arena && (offs[k] & 15)) aligned = false;
     if (!r.src && r.len) { delete b; return DCB_ERR_ARG; }
-    parse_header(r);
   }
   // shard by buffer; no collective.  Distinct devices: longest-processing-time-first on compressed bytes.
   // The same device listed K times (dcb_create): K pipeline slices -- contiguous runs of buffers with equal bytes, so
@@ -521,7 +521,6 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
   for (int k = 0; k < n_bufs; ++k) {
     Shard &sh = b->shards[b->bufs[k].shard];
     b->bufs[k].local = (int)sh.bufs.size();
-    b->bufs[k].info.device = b->bufs[k].shard;
     sh.bufs.push_back(k);
   }
   for (Shard &sh : b->shards) {
@@ -553,9 +552,22 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
     }
   }
   for (Shard &sh : b->shards) sh.walks.resize(sh.bufs.size());
-  for (int k = 0; k < n_bufs; ++k) {
-    BufRec &r = b->bufs[k];
-    parse_attr_section(r, b->shards[r.shard], k);
+  // header + attribute indexing: a shard's buffers in order (the shard's stream list is append-only), shards in
+  // parallel when there are several -- nothing is shared between them
+  auto index_shard = [&](Shard &sh) {
+    for (int k : sh.bufs) {
+      BufRec &r = b->bufs[k];
+      parse_header(r);
+      r.info.device = r.shard;
+      parse_attr_section(r, sh, k);
+    }
+  };
+  if (b->n_devices > 1 && n_bufs >= 16) {
+    std::vector<std::thread> th;
+    for (Shard &sh : b->shards) th.emplace_back(index_shard, std::ref(sh));
+    for (std::thread &t : th) t.join();
+  } else {
+    for (Shard &sh : b->shards) index_shard(sh);
   }
   *out = b;
   return DCB_OK;
