@@ -10,6 +10,8 @@ workload  N=1: BASELINE.json configs[1] -- 10,000 synthetic point clouds x 100,0
 step      one pass of the attribute-decode hot path over the whole batch
 value     inputs (compressed bytes + stream descriptors) resident in HBM when the timed region starts
 e2e       the same metric through the public call with HOST buffers: index + H2D + kernels + D2H per step
+          (the device listed 8 times in dcb_create = 8 pipeline slices; --e2e-slices)
+other     --workload c2tagged|c3|c4|c4tagged (BASELINE configs[1] Tagged, [2], [3]); --sweep (configs[4])
 roofline  algorithmic bytes (compressed in + decoded out) of the dominant kernel / its CUDA-event
           duration measured inside the timed steps, against MEASURED_PEAKS.json
 cpu_baseline  the CPU oracle (a linear-time port of the reference's algorithm; the C# itself cannot run: no .NET

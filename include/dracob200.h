@@ -120,7 +120,11 @@ int dcb_version(void);
 int dcb_device_count(void);
 const char *dcb_error_string(int code);
 
-/* device_ids == NULL / n_devices == 0: use the current CUDA device only. */
+/* device_ids == NULL / n_devices == 0: use the current CUDA device only.
+ * Distinct ids: a batch is sharded by buffer across the GPUs (longest-processing-time-first on compressed bytes; no
+ * collective).  The SAME id listed K times: K pipeline slices on that GPU -- contiguous runs of buffers with
+ * their own streams and arenas, so that in a host-buffer decode (dcb_decode / dcb_decode_scatter) slice k decodes while
+ * slice k+1 uploads and slice k-1 downloads.  The context caches the device arenas of freed batches. */
 int dcb_create(const int *device_ids, int n_devices, dcb_ctx **out);
 void dcb_destroy(dcb_ctx *ctx);
 /* Launch on a caller-owned CUDA stream (cudaStream_t) of device `dev_index` instead of the ctx's own. */
