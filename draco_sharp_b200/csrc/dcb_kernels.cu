@@ -46,19 +46,20 @@ namespace {
 //   3  normals: the unsigned corrections go to the int32 scratch as they are; the octahedral recurrence is a chain of
 //      its own (~120 dependent-ish instructions per entry) and runs in oct_chain_kernel, next to the rANS kernels of
 //      the batch's other attributes instead of in front of them
+//   4  parallelogram streams: zig-zag decoded corrections to the int32 scratch (para_chain_kernel does the rest)
 template <int MODE>
 __device__ __forceinline__ int recon_of(const PostParams &pp) {
-  return (MODE == 1 || MODE == 2) ? (int)RECON_DELTA_WRAP : (MODE == 3 ? (int)RECON_NONE : pp.recon);
+  return (MODE == 1 || MODE == 2) ? (int)RECON_DELTA_WRAP : ((MODE == 3 || MODE == 4) ? (int)RECON_NONE : pp.recon);
 }
 template <int MODE>
 __device__ __forceinline__ int store_of(const PostParams &pp) {
   // normals leave the serial kernels as quantized (s, t) pairs: the unit-vector conversion (double precision
   // 1/sqrt, as the C#) runs in oct_unit_kernel, point-parallel, instead of stretching the serial chain
-  return MODE == 1 ? (int)STORE_DEQUANT : ((MODE == 2 || MODE == 3) ? (int)STORE_NARROW : pp.store);
+  return MODE == 1 ? (int)STORE_DEQUANT : ((MODE == 2 || MODE == 3 || MODE == 4) ? (int)STORE_NARROW : pp.store);
 }
 template <int MODE>
 __device__ __forceinline__ int dsize_of(const PostParams &pp) {
-  return MODE == 2 ? 1 : (MODE == 3 ? 4 : pp.dsize);
+  return MODE == 2 ? 1 : ((MODE == 3 || MODE == 4) ? 4 : pp.dsize);
 }
 
 // shared-memory carve-up of a warp-CTA (see RansLane)
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   pp.load(*dp);
   uint8_t *optr = out + dp->out_off;
   int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + dp->dbg_off) : nullptr;
-  if (MODE == 3 || (MODE == 0 && (pp.recon == RECON_PARA_WRAP || pp.store == STORE_OCT_UNIT))) {
+  if (MODE == 3 || MODE == 4 || (MODE == 0 && (pp.recon == RECON_PARA_WRAP || pp.store == STORE_OCT_UNIT))) {
     // int32 scratch: corrections for the parallelogram kernel / for oct_chain_kernel
     optr = aux + dp->aux_off;
     if (NCP == 2 && pp.store == STORE_OCT_UNIT) {  // normals: the recurrence and its quantized-int dump run in oct_chain_kernel
@@ -1056,6 +1057,8 @@ cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool ta
     DCB_SPEC(2, 3)
     DCB_SPEC(2, 4)
     DCB_SPEC(3, 2)
+    DCB_SPEC(4, 3)
+    DCB_SPEC(4, 2)
 #undef DCB_SPEC
   }
 #define DCB_CASE(N)                                                       \
