@@ -86,6 +86,16 @@ struct Group {            // one kernel launch (or a few, for global tables)
   uint32_t max_entries;
   std::vector<uint32_t> order;
   uint64_t order_off;     // offset (in uint32) inside the shard's device order array
+  // earliest / latest 128-slot block (over the group's streams) holding the first entry narrower than 2^k slots
+  uint32_t nb_min[8], nb_max[8];
+  bool nb_any;
+  void note_table(const StreamDesc &s) {
+    for (int k = 1; k <= 7; ++k) {
+      nb_min[k] = nb_any ? std::min<uint32_t>(nb_min[k], s.narrow_blk[k]) : s.narrow_blk[k];
+      nb_max[k] = nb_any ? std::max<uint32_t>(nb_max[k], s.narrow_blk[k]) : s.narrow_blk[k];
+    }
+    nb_any = true;
+  }
 };
 
 struct Shard {
@@ -717,6 +727,21 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
         const uint64_t spare = (cta_budget - used) / g.lanes;
         g.lutb_bytes = (uint32_t)std::min<uint64_t>((1u << g.prec_bits) >> 1, spare / 16 * 16);
       }
+      // ... but no more than the group's tables need: region B covers the slots from the first entry narrower than
+      // 2^k on, for the k whose wide region still fits the LUT.  What is not taken stays free for the CTAs of the
+      // batch's other groups, which then run next to this one instead of behind it.
+      if (g.nb_any && g.lutb_bytes) {
+        uint32_t need = 0xFFFFFFFFu;
+        const uint32_t prec = 1u << g.prec_bits;
+        for (uint32_t k = 1; k <= 7; ++k) {
+          if (k + 7 > g.prec_bits) continue;
+          const uint32_t t_max = std::min(prec, g.nb_max[k] << 7), t_min = std::min(prec, g.nb_min[k] << 7);
+          if ((t_max >> k) > g.lut_bytes) continue;
+          need = std::min(need, (prec - t_min) >> 1);
+        }
+        if (need != 0xFFFFFFFFu && !getenv("DCB_LUTB_FULL"))
+          g.lutb_bytes = std::min<uint32_t>(g.lutb_bytes, std::max<uint32_t>(16u, (uint32_t)align_up(need, 16)));
+      }
     }
   }
 }
@@ -873,6 +898,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       g.entries = std::max(g.entries, sh.streams[si].n_active);
       g.exc = std::max(g.exc, sh.streams[si].n_active - std::min(sh.streams[si].n_active, sh.streams[si].dense_prefix));
       g.total_symbols += sh.streams[si].n_entries;
+      g.note_table(sh.streams[si]);
       blocked.push_back((uint32_t)bi);
     }
     if (g.order.empty()) break;
@@ -961,6 +987,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         if (key.compact) g.exc = std::max(g.exc, s.n_active - std::min(s.n_active, s.dense_prefix));
         g.total_symbols += (uint64_t)s.n_entries * s.ncp;
         g.max_entries = std::max(g.max_entries, s.n_entries);
+        g.note_table(s);
         g.order.push_back(si);
       } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP) && !getenv("DCB_NO_PAR_POST")) {
         // Tagged / uncompressed source, scan-able reconstruction: point-parallel kernels
@@ -1040,8 +1067,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     const uint32_t n = (uint32_t)g->order.size();
     const bool is_dom = timed && dev_index == 0 && g == dom;
     cudaStream_t st = st_main;
-    if (fan_out && !g->table_global && g != dom) {
-      const size_t k = gi++ % 3;
+    if (fan_out && !g->table_global && (g != dom || g->mode == 3)) {
+      const size_t k = g->mode == 3 ? 0 : 1 + gi++ % 2;
       st = ctx->side[dev_index][k];
       side_used[k] = true;
     }
@@ -1414,8 +1441,13 @@ int dcb_create(const int *device_ids, int n_devices, dcb_ctx **out) {
     std::vector<cudaStream_t> side(3, nullptr);
     std::vector<cudaEvent_t> jev(3, nullptr);
     cudaEvent_t fev = nullptr;
+    // side[0] outranks the others: it carries the group whose chain goes on after its rANS kernel (normals:
+    // oct_chain, oct_unit), the longest dependent sequence of a batch
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int k = 0; k < 3; ++k) {
-      cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking);
+      if (k == 0) cudaStreamCreateWithPriority(&side[k], cudaStreamNonBlocking, prio_hi);
+      else cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking);
       cudaEventCreateWithFlags(&jev[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&fev, cudaEventDisableTiming);

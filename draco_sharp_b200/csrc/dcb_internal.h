@@ -93,6 +93,9 @@ struct StreamDesc {
   uint8_t compressed;
   uint8_t has_maps;              // host supplied connectivity maps for this attribute's decoder
   uint8_t pad_[1];
+  // narrow_blk[k] (k = 1..7): 128-slot block holding the first table entry narrower than 2^k slots (2^prec >> 7 when
+  // there is none) -- what the launch planner needs to size the narrow region of the two-region LUT
+  uint16_t narrow_blk[8];
 };
 
 // Resumable container walk of one buffer (runs on the host; continues on the device behind Tagged

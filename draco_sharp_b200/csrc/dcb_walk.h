@@ -65,11 +65,14 @@ DCB_HD uint64_t wr_varint(WalkRd &r) {
 }
 
 // RANS_TABLE: validates it and advances past it.  Entropy/RAnsSymbolDecoder.cs:12-51 + RAnsDecoder.cs:69-88
-DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint32_t &n_active, uint32_t &dense_prefix) {
+DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint32_t &n_active, uint32_t &dense_prefix,
+                           uint16_t *narrow_blk) {
   num_symbols = 0;
   n_active = 0;
   dense_prefix = 0;  // number of leading symbols that all have non-zero probability
   bool gap = false;
+  const uint32_t none_blk = (uint32_t)((1ull << prec_bits) >> 7) > 0xFFFFu ? 0xFFFFu : (uint32_t)((1ull << prec_bits) >> 7);
+  for (int k = 0; k < 8; ++k) narrow_blk[k] = (uint16_t)none_blk;
   const uint64_t ns = wr_varint(r);
   if (r.err) return r.err;
   if (ns > (r.end - r.pos) * 64u || ns > (1u << 24)) return DCB_ERR_EOF;  // cannot be backed by data
@@ -92,6 +95,8 @@ DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint
       if (prob) {
         ++n_active;
         if (!gap) ++dense_prefix;
+        for (int k = 1; k <= 7; ++k)
+          if (prob < (1u << k) && narrow_blk[k] == (uint16_t)none_blk && (sum >> 7) < none_blk) narrow_blk[k] = (uint16_t)(sum >> 7);
       } else {
         gap = true;
       }
@@ -230,7 +235,7 @@ DCB_HD int walk_portable(WalkRd &r, const BufWalk &w, StreamDesc &s, int *st) {
         return 0;
       }
       s.table_off = r.pos;
-      e = walk_rans_table(r, s.prec_bits, s.num_symbols, s.n_active, s.dense_prefix);
+      e = walk_rans_table(r, s.prec_bits, s.num_symbols, s.n_active, s.dense_prefix, s.narrow_blk);
       if (!e && s.num_symbols == 0) e = DCB_ERR_NUM_SYMBOLS;
       if (!e) e = walk_rans_payload(r, s.prec_bits, s.payload_off, s.payload_len);
       if (e) { *st = e; return 0; }
