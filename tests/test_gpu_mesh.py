@@ -180,3 +180,26 @@ def test_grid_meshes_match_oracle_and_generator(gpu_decoder, w, h, scheme):
         got = out[ai.out_off: ai.out_off + ai.out_bytes]
         assert np.array_equal(got, ref.attrs[0].out) and G.word_checksum(got) == sm
     batch.free()
+
+
+@pytest.mark.parametrize("scheme", [-1, 0])
+def test_million_vertex_mesh_full_size(gpu_decoder, scheme):
+    """BASELINE configs[3] at full size: one 1,000 x 1,000 grid mesh (3M-symbol chains, dependencies ~1,000 entries
+    back): every quantized int and output byte against the oracle, the output checksum against the generator."""
+    from draco_sharp_b200 import synth_gen as G
+    w = h = 1000
+    topo = G.grid_topology(w, h)
+    buf, aoff, sm, sch, q = G.grid_mesh(w, h, topo, seed=77, scheme=scheme, want_q=True)
+    batch = gpu_decoder.index([buf])
+    batch.set_attr_section(0, aoff, w * h)
+    batch.set_mesh_maps(0, 0, topo["opposite"], topo["corner_to_vertex"], topo["data_to_corner"], topo["vertex_to_data"])
+    batch.finish()
+    out, dbg = gpu_decoder.decode(batch, flags=N.DCB_DUMP_QINTS)
+    assert batch.status(0) == 0
+    ai = batch.attr_info(0, 0)
+    assert np.array_equal(dbg[ai.dbg_off: ai.dbg_off + 4 * q.size].view(np.int32), q)
+    got = out[ai.out_off: ai.out_off + ai.out_bytes]
+    assert G.word_checksum(got) == sm
+    ref = O.decode(buf, [topo], aoff, w * h)
+    assert ref.status == 0 and np.array_equal(got, ref.attrs[0].out)
+    batch.free()
