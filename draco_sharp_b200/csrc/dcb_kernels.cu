@@ -749,15 +749,19 @@ __global__ void para_deps_kernel(StreamDesc *streams, const uint32_t *__restrict
 
 // The recurrence itself.  Its dependency graph is a chain in practice (a depth-first traversal predicts almost every
 // entry from the one decoded just before it: dependency depth 1,529 of 1,775 entries on the reference's sample mesh), so
-// the "wavefront" is one entry wide inside a stream and the parallelism is across streams: ONE WARP PER STREAM.
-//   lanes 0..NCP-1  walk the chain, one component each (components never mix), branch-free: the value of entry p-1
-//                   stays in a register, the operands of entry p+1 are fetched from shared memory while entry p is
-//                   computed -- recent ones from a history ring, older ones from a staging area
-//   all 32 lanes    run two blocks ahead of the chain: cp.async the dependencies / corrections of block b+2 and GATHER
-//                   the old operands of block b+1 (anything decoded before block b started is already in the
-//                   quantized-int scratch) into the staging area, so no global-memory latency is left on the chain;
-//                   then dequantise and store the finished block with coalesced writes
-constexpr uint32_t kParaBlock = 64;    // entries per staged block
+// the "wavefront" is one entry wide inside a stream and the parallelism is across streams: ONE CTA OF TWO WARPS PER
+// STREAM, in lock step over blocks of 64 entries.
+//   chain warp   lanes 0..NCP-1 walk the chain, one component each (components never mix).  Per entry and component the
+//                helper has prepared a record {address of operand opp, next, prev, correction} and a coefficient k:
+//                pred = v(next) + v(prev) - v(opp) + k * value(p-1).  An operand that IS entry p-1 points at a zero
+//                word and counts in k, so the value of entry p-1 never leaves its register; an entry predicted from
+//                p-1 alone (no parallelogram) has three zero operands and k = 1.  No branch, no select, ~20
+//                instructions per entry; records of entry p+2 and operands of p+1 are in flight while p is computed.
+//   helper warp  runs around the chain: stores the finished block b-1 (quantized ints for later gathers, dequantised
+//                output, coalesced), cp.asyncs the dependencies / corrections of block b+2, GATHERS the operands of
+//                block b+1 that were decoded before block b started (anything older than the 128-entry history ring)
+//                from the quantized-int scratch, and writes block b+1's records.
+constexpr uint32_t kParaBlock = 64;    // entries per block
 constexpr uint32_t kParaHist = 128;    // history ring: the block being decoded and the one before it
 
 __device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void *gsrc) {
@@ -768,21 +772,30 @@ __device__ __forceinline__ int32_t lds32(uint32_t smem_addr) {
   asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(smem_addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
+  return v;
+}
 
 template <int NCP, bool DUMP>
-__global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
+__global__ void __launch_bounds__(64) para_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
                                                         uint32_t n_streams, uint8_t *__restrict__ out,
                                                         uint8_t *__restrict__ dbg, uint8_t *__restrict__ aux,
                                                         uint32_t dump) {
-  __shared__ int32_t s_dep[3][kParaBlock * 3];          // (opp, next, prev) entry ids; -1 = predict from entry p-1
-  __shared__ int32_t s_cor[3][kParaBlock * NCP];        // corrections
-  __shared__ int32_t s_far[2][kParaBlock * 3 * NCP];    // gathered operands older than the history ring
+  __shared__ int32_t s_dep[3][kParaBlock * 3];           // (opp, next, prev) entry ids; -1 = predict from entry p-1
+  __shared__ int32_t s_cor[3][kParaBlock * NCP];         // corrections
+  __shared__ int32_t s_far[2][kParaBlock * 3 * NCP];     // gathered operands older than the history ring
+  __shared__ __align__(16) uint4 s_rec[2][kParaBlock * NCP];  // {addr opp, addr next, addr prev, correction}
+  __shared__ int32_t s_k[2][kParaBlock];                 // coefficient of value(p-1)
   __shared__ int32_t s_hist[kParaHist * NCP];
-  const uint32_t lane = threadIdx.x;
-  const uint32_t a_hist = (uint32_t)__cvta_generic_to_shared(s_hist) + 4u * lane;
+  __shared__ int32_t s_zero;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t a_hist0 = (uint32_t)__cvta_generic_to_shared(s_hist);
+  const uint32_t a_zero = (uint32_t)__cvta_generic_to_shared(&s_zero);
   for (uint32_t si = blockIdx.x; si < n_streams; si += gridDim.x) {
     StreamDesc &d = streams[order[si]];
-    if (d.status != DCB_OK) continue;
+    if (d.status != DCB_OK) continue;   // uniform over the CTA
     const uint32_t n = d.n_entries;
     if (n == 0) continue;
     PostParams pp;
@@ -793,7 +806,8 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
     int32_t *qints = reinterpret_cast<int32_t *>(aux + d.aux_off) + (uint64_t)n * NCP;
     const int32_t *deps = qints + (uint64_t)n * NCP;
     const uint32_t n_blocks = (n + kParaBlock - 1) / kParaBlock;
-    auto stage = [&](uint32_t blk) {  // all lanes: dependencies + corrections of block blk -> shared memory
+    // ---- helper warp's pieces ----
+    auto stage = [&](uint32_t blk) {  // dependencies + corrections of block blk -> shared memory
       if (blk >= n_blocks) return;
       const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0), b = blk % 3u;
       for (uint32_t i = lane; i < cnt * 3; i += 32)
@@ -801,7 +815,7 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
       for (uint32_t i = lane; i < cnt * NCP; i += 32)
         cp_async4((uint32_t)__cvta_generic_to_shared(&s_cor[b][i]), corr + (uint64_t)e0 * NCP + i);
     };
-    auto gather = [&](uint32_t blk) {  // all lanes: operands of block blk decoded before block blk-1 started
+    auto gather = [&](uint32_t blk) {  // operands of block blk decoded before block blk-1 started
       if (blk >= n_blocks || blk < 2) return;
       const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0), b = blk % 3u, limit = e0 - kParaBlock;
       for (uint32_t i = lane; i < cnt * 3; i += 32) {
@@ -813,69 +827,33 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
         }
       }
     };
-    __syncwarp();
-    stage(0);
-    stage(1);
-    cp_async_commit();
-    int32_t prev = 0;  // lanes < NCP: value of entry p-1, component `lane`
-    for (uint32_t blk = 0; blk < n_blocks; ++blk) {
-      cp_async_wait<0>();  // issued one whole block ago: block blk's operands, block blk+1's dependencies
-      __syncwarp();
-      stage(blk + 2);
-      gather(blk + 1);     // the scratch holds every entry before block blk (stored at the end of block blk-1)
-      cp_async_commit();
+    auto records = [&](uint32_t blk) {  // block blk's operand addresses and coefficients (needs its dependencies)
+      if (blk >= n_blocks) return;
       const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0), b = blk % 3u;
-      if (lane < NCP) {
-        const int32_t *sd = s_dep[b];
-        const int32_t *sc = s_cor[b];
-        const uint32_t a_far = (uint32_t)__cvta_generic_to_shared(s_far[blk & 1u]) + 4u * lane;
-        const uint32_t limit = e0 >= kParaBlock ? e0 - kParaBlock : 0u;
-        // two-deep software pipeline: the dependency ids of entry p+2 and the operand values of entry p+1 are in
-        // flight while entry p is computed, so neither shared-memory latency sits on the chain
-        struct Ids { int32_t e_o, e_n, e_p, corr; };
-        struct Ops { int32_t va, vb, vo, corr; bool para, fa, fb, fo; };
-        auto ids = [&](uint32_t j) {
-          Ids r;
-          r.e_o = sd[3 * j];
-          r.e_n = sd[3 * j + 1];
-          r.e_p = sd[3 * j + 2];
-          r.corr = sc[j * NCP + lane];
-          return r;
+      const uint32_t limit = e0 >= kParaBlock ? e0 - kParaBlock : 0u;
+      const uint32_t a_far = (uint32_t)__cvta_generic_to_shared(s_far[blk & 1u]);
+      for (uint32_t i = lane; i < cnt * NCP; i += 32) {
+        const uint32_t j = i / NCP, c = i - j * NCP, p = e0 + j;
+        const int32_t e_o = s_dep[b][3 * j], e_n = s_dep[b][3 * j + 1], e_p = s_dep[b][3 * j + 2];
+        const bool para = e_o >= 0;
+        int32_t k = para ? 0 : 1;
+        auto addr = [&](int32_t e, uint32_t which, int32_t sign) -> uint32_t {
+          if (!para) return a_zero;
+          if ((uint32_t)e + 1u == p) { k += sign; return a_zero; }
+          if ((uint32_t)e < limit) return a_far + ((3u * j + which) * NCP + c) * 4u;
+          return a_hist0 + (((uint32_t)e & (kParaHist - 1u)) * NCP + c) * 4u;
         };
-        auto values = [&](const Ids &r, uint32_t p, uint32_t j) {
-          Ops o;
-          o.corr = r.corr;
-          o.para = r.e_o >= 0;
-          auto get = [&](int32_t e, uint32_t k, bool &flag) -> int32_t {
-            flag = (uint32_t)e + 1u == p;
-            // one shared-memory load, address selected: staging area (old) or history ring (recent; entry p-1 may
-            // not be there yet -- then the flag makes the caller take the register instead)
-            const uint32_t a = (uint32_t)e < limit ? a_far + (3u * j + k) * (4u * NCP)
-                                                    : a_hist + ((uint32_t)e & (kParaHist - 1u)) * (4u * NCP);
-            return lds32(a);
-          };
-          o.vo = get(r.e_o, 0, o.fo);
-          o.va = get(r.e_n, 1, o.fa);
-          o.vb = get(r.e_p, 2, o.fb);
-          return o;
-        };
-        Ids i1 = ids(0);
-        Ops cur = values(i1, e0, 0);
-        i1 = ids(cnt > 1 ? 1 : 0);
-        for (uint32_t j = 0; j < cnt; ++j) {
-          const uint32_t p = e0 + j;
-          const Ids i2 = ids(j + 2 < cnt ? j + 2 : j);               // harmless re-read at the end of the block
-          const Ops nxt = values(i1, p + 1, j + 1 < cnt ? j + 1 : j);  // reads history up to p-1; p itself is flagged
-          const int32_t va = cur.fa ? prev : cur.va, vb = cur.fb ? prev : cur.vb, vo = cur.fo ? prev : cur.vo;
-          const int32_t pred = cur.para ? (int32_t)((uint32_t)va + (uint32_t)vb - (uint32_t)vo) : prev;  // :84 / :36,:49-50
-          prev = wrap_original(pred, cur.corr, pp.mn, pp.mx, pp.max_diff);
-          asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(a_hist + (p & (kParaHist - 1u)) * (4u * NCP)), "r"(prev) : "memory");
-          cur = nxt;
-          i1 = i2;
-        }
+        uint4 r;
+        r.x = addr(e_o, 0, -1);
+        r.y = addr(e_n, 1, 1);
+        r.z = addr(e_p, 2, 1);
+        r.w = (uint32_t)s_cor[b][i];
+        s_rec[blk & 1u][i] = r;
+        if (c == 0) s_k[blk & 1u][j] = k;
       }
-      __syncwarp();
-      // all lanes: the finished block -> quantized-int scratch (later gathers read it), dump, typed output
+    };
+    auto output = [&](uint32_t blk) {  // finished block -> quantized-int scratch (later gathers read it), dump, typed output
+      const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0);
       for (uint32_t j = lane; j < cnt; j += 32) {
         const uint32_t p = e0 + j;
         int32_t v[NCP];
@@ -889,10 +867,60 @@ __global__ void __launch_bounds__(32) para_chain_kernel(StreamDesc *streams, con
         }
         store_entry<NCP>(pp, pp.store, pp.dsize, optr, p, v);
       }
+    };
+    __syncthreads();  // the previous stream's last block has left shared memory
+    if (threadIdx.x == 0) s_zero = 0;
+    if (warp == 1) {
+      stage(0);
+      stage(1);
+      cp_async_commit();
+      cp_async_wait<0>();
       __syncwarp();
+      records(0);
     }
-    cp_async_wait<0>();
-    __syncwarp();
+    __syncthreads();
+    int32_t prev = 0;  // chain lanes: value of entry p-1, component `lane`
+    for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+      if (warp == 0) {
+        if (lane < NCP) {
+          const uint32_t e0 = blk * kParaBlock, cnt = min(kParaBlock, n - e0);
+          const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(s_rec[blk & 1u]) + 16u * lane;
+          const uint32_t a_k = (uint32_t)__cvta_generic_to_shared(s_k[blk & 1u]);
+          const uint32_t a_st = a_hist0 + ((e0 & (kParaHist - 1u)) * NCP + lane) * 4u;  // a block never wraps the ring
+          // two-deep software pipeline: record of entry j+2 and operands of entry j+1 in flight while j is computed
+          uint4 r1 = lds128(a_rec);
+          int32_t k1 = lds32(a_k);
+          int32_t vo = lds32(r1.x), va = lds32(r1.y), vb = lds32(r1.z), co = (int32_t)r1.w, kk = k1;
+          const uint32_t j1 = cnt > 1 ? 1u : 0u;
+          r1 = lds128(a_rec + j1 * (16u * NCP));
+          k1 = lds32(a_k + 4u * j1);
+          for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t j2 = j + 2 < cnt ? j + 2 : j;  // harmless re-read at the end of the block
+            const uint4 r2 = lds128(a_rec + j2 * (16u * NCP));
+            const int32_t k2 = lds32(a_k + 4u * j2);
+            // operands of entry j+1: history up to entry j-1 is in shared memory, entry j itself rides in k
+            const int32_t nvo = lds32(r1.x), nva = lds32(r1.y), nvb = lds32(r1.z);
+            const int32_t sum = (int32_t)((uint32_t)va + (uint32_t)vb - (uint32_t)vo);
+            const int32_t pred = (int32_t)((uint32_t)sum + (uint32_t)kk * (uint32_t)prev);  // :84 / :36,:49-50
+            prev = wrap_original(pred, co, pp.mn, pp.mx, pp.max_diff);
+            asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(a_st + j * (4u * NCP)), "r"(prev) : "memory");
+            vo = nvo; va = nva; vb = nvb; co = (int32_t)r1.w; kk = k1;
+            r1 = r2; k1 = k2;
+          }
+        }
+      } else {
+        if (blk > 0) output(blk - 1);
+        __syncwarp();
+        stage(blk + 2);
+        gather(blk + 1);   // the scratch now holds every entry before block blk
+        cp_async_commit();
+        records(blk + 1);
+        cp_async_wait<0>();
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+    if (warp == 1) output(n_blocks - 1);
   }
 }
 
@@ -1156,9 +1184,9 @@ cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint
 #define DCB_CASE(N)                                                                                     \
   case N:                                                                                               \
     if (dump)                                                                                           \
-      para_chain_kernel<N, true><<<grid, 32, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump);  \
+      para_chain_kernel<N, true><<<grid, 64, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump);  \
     else                                                                                                \
-      para_chain_kernel<N, false><<<grid, 32, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump); \
+      para_chain_kernel<N, false><<<grid, 64, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump); \
     break;
   switch (ncp) {
     DCB_CASE(1)
