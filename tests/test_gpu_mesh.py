@@ -203,3 +203,28 @@ def test_million_vertex_mesh_full_size(gpu_decoder, scheme):
     ref = O.decode(buf, [topo], aoff, w * h)
     assert ref.status == 0 and np.array_equal(got, ref.attrs[0].out)
     batch.free()
+
+
+def test_meshes_and_clouds_through_pipeline_slices(gpu_decoder):
+    """Pipeline slices (the device listed three times) with meshes in the batch: host connectivity, maps upload and the
+    parallelogram kernels per slice; same bytes as the single-shard decode."""
+    import draco_sharp_b200 as D
+    from draco_sharp_b200 import synth_gen as G
+    mesh, o = _house_positions_only()
+    bufs = []
+    for k in range(18):
+        bufs.append(mesh if k % 3 == 1 else G.synth_cloud(G.make_spec(3000 + 100 * k, seed=40 + k, scheme=k % 2, colors=1))[0])
+    one = gpu_decoder.decode_batch(bufs)
+    dec = D.DracoBatchDecoder([0, 0, 0])
+    try:
+        many = dec.decode_batch(bufs)
+    finally:
+        dec.close()
+    for k, (x, y) in enumerate(zip(one, many)):
+        assert x.ok and y.ok, k
+        assert len(x.attributes) == len(y.attributes)
+        for a, b in zip(x.attributes, y.attributes):
+            assert np.array_equal(a.buffer, b.buffer), k
+        if k % 3 == 1:
+            assert np.array_equal(x.faces, y.faces) and sha(y.attributes[0].buffer) == \
+                "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
