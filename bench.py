@@ -502,7 +502,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(MESH_WORKLOADS))
     ap.add_argument("--unique", type=int, default=2048, help="distinct clouds generated per rank (0 = all distinct)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-slices", type=int, default=8, help="pipeline slices of the e2e leg (dcb_create with the device listed K times)")
     ap.add_argument("--meshes", type=int, default=0, help="mesh workloads: meshes per GPU (0 = the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
