@@ -263,7 +263,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def make_meshes(name, rank, n_meshes=None):
@@ -432,7 +432,7 @@ def run_mesh(args, rank, local_rank, world):
             dt = run()
             line["cpu_baseline"] = {"value": sum(r[0] for r in results) / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d meshes x %d vertices of the same workload, one mesh per thread, C oracle -O2" % (n_sample, n_points)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     batch.free()
     dec.close()
     if dist:
@@ -672,7 +672,7 @@ def main():
             line["cpu_baseline"] = {
                 "value": sum(r[0] for r in results) / dt, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": "%d clouds x %d points of the same workload, one buffer per thread, C oracle -O2" % (n_sample, n_points)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     batch.free()
     dec.close()
     if dist:
