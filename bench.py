@@ -11,7 +11,8 @@ step      one pass of the attribute-decode hot path over the whole batch
 value     inputs (compressed bytes + stream descriptors) resident in HBM when the timed region starts
 e2e       the same metric through the public call with HOST buffers: index + H2D + kernels + D2H per step
           (the device listed 8 times in dcb_create = 8 pipeline slices; --e2e-slices)
-other     --workload c2tagged|c3|c4|c4tagged (BASELINE configs[1] Tagged, [2], [3]); --sweep (configs[4])
+other     --workload c1 (configs[0], the real asset) | c2tagged | c3 | c4 | c4tagged (configs[1] Tagged, [2], [3]);
+          --sweep (configs[4])
 roofline  algorithmic bytes (compressed in + decoded out) of the dominant kernel / its CUDA-event
           duration measured inside the timed steps, against MEASURED_PEAKS.json
 cpu_baseline  the CPU oracle (a linear-time port of the reference's algorithm; the C# itself cannot run: no .NET
@@ -236,6 +237,26 @@ def run_reference(args, rank, world):
     """Reference arm: the reference's own algorithm on the host CPU (oracle port; the C# needs .NET, absent)."""
     if rank != 0:
         return
+    if args.workload == "c1":
+        from oracle import pyoracle as O
+        from draco_sharp_b200 import build as B
+        B.build_oracle()
+        buf = np.fromfile(os.path.join(ROOT, "tests", "golden", "house_04_positions_only.drc"), dtype=np.uint8)
+        r = O.decode(buf)
+        steps = max(args.steps, 20)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.decode(buf)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        n = int(r.attrs[0].n_entries)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "i32->f32", "data": "real asset",
+                          "config": {"workload": "c1", "description": "house_04.obj.drc, position attribute, 1 buffer"},
+                          "cpu_baseline": {"value": n / (ms * 1e-3), "unit": UNIT, "cores": 1, "kind": "port", "sample": "the whole buffer"},
+                          "e2e": {"value": n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     mesh = args.workload in MESH_WORKLOADS
     if mesh:
         n_sample, n_points, threads, run, results = cpu_mesh_rate(args.workload)
@@ -440,6 +461,53 @@ def run_mesh(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_real_asset(args, rank, local_rank):
+    """BASELINE configs[0]: the reference's one real asset (house_04.obj.drc: Edgebreaker mesh, 11-bit positions,
+    parallelogram + wrap, Raw rANS), reduced to its position attribute (tests/golden/make_house_positions_only.py) --
+    the other two attributes need predictors outside the path.  Whole decode through the public call: host Edgebreaker
+    connectivity (CPU by design), indexing, H2D, kernels, D2H.  1,775 entries: latency, not throughput."""
+    if rank != 0:
+        return
+    import torch
+    import draco_sharp_b200 as D
+    from oracle import pyoracle as O  # cpu_baseline only
+    from draco_sharp_b200 import build as B
+    B.build_all()
+    buf = np.fromfile(os.path.join(ROOT, "tests", "golden", "house_04_positions_only.drc"), dtype=np.uint8)
+    torch.cuda.set_device(local_rank)
+    dec = D.DracoBatchDecoder([local_rank])
+    ref = O.decode(buf)
+    assert ref.status == 0
+    for _ in range(max(3, args.warmup)):
+        (d,) = dec.decode_batch([buf])
+    assert d.ok and np.array_equal(d.attributes[0].buffer, ref.attrs[0].out), "GPU decode differs from the oracle"
+    steps = max(args.steps, 20)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dec.decode_batch([buf])
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    st = dec.stats()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.decode(buf)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / steps
+    n = int(ref.attrs[0].n_entries)
+    print(json.dumps({
+        "metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32->f32", "data": "real asset",
+        "config": {"workload": "c1", "description": "BASELINE configs[0]: house_04.obj.drc (reference sample), position attribute, "
+                   "1 buffer, %d entries, %d faces" % (n, len(d.faces))},
+        "e2e": {"value": n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(buf.nbytes), "d2h_bytes_per_step": int(ref.attrs[0].out.nbytes),
+                "ms_per_step": ms, "what": "dcb_index + dcb_host_connectivity + dcb_index_finish + dcb_decode"},
+        "roofline": {"bound": "hbm", "achieved": None, "peak": measured_peak()[0], "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "one 1,775-entry stream: launch latency and host work, kernels %.3f ms of %.3f ms" % (st.ms_total, ms)},
+        "cpu_baseline": {"value": n / (cpu_ms * 1e-3), "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "the same buffer, C oracle -O2 (connectivity + attribute), %.3f ms per decode" % cpu_ms},
+        "gpu_launches": int(st.n_launches) * steps}), flush=True)
+    dec.close()
+
+
 def run_sweep(args, rank, local_rank):
     """BASELINE configs[4]: points-per-buffer sweep (total points fixed) and batch-size sweep (points per buffer fixed).
     Kernel-only numbers (inputs resident), one JSON line per cell; not the headline."""
@@ -500,7 +568,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(MESH_WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(MESH_WORKLOADS) + ["c1"])
     ap.add_argument("--unique", type=int, default=2048, help="distinct clouds generated per rank (0 = all distinct)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-slices", type=int, default=8, help="pipeline slices of the e2e leg (dcb_create with the device listed K times)")
@@ -515,6 +583,8 @@ def main():
         return run_reference(args, rank, world)
     if args.sweep:
         return run_sweep(args, rank, local_rank)
+    if args.workload == "c1":
+        return run_real_asset(args, rank, local_rank)
     if args.workload in MESH_WORKLOADS:
         return run_mesh(args, rank, local_rank, world)
     args.warmup = max(args.warmup, 3)
