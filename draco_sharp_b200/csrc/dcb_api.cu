@@ -51,10 +51,11 @@ struct PoolBlock {
 };
 struct DevPool {
   std::vector<PoolBlock> free_blocks;
+  std::vector<PoolBlock> free_pinned;  // page-locked staging buffers (device = -1)
   uint64_t cached = 0;
 };
 constexpr uint64_t kPoolCap = 96ull << 30;
-constexpr uint64_t kPoolMin = 1ull << 20;  // smaller allocations go straight to cudaMalloc
+constexpr uint64_t kPoolMin = 0;  // every arena goes through the cache: a small batch pays for each cudaMalloc / cudaFree too
 
 struct MeshMapsHost {
   std::vector<uint32_t> opposite, corner_to_vertex, data_to_corner;
@@ -104,7 +105,7 @@ struct Shard {
   int share = 1;        // shards of this batch living on the same physical device (pipeline slices)
   bool arena_pending = false;
   std::shared_ptr<DevPool> pool;  // the owning context's cache (outlives the context if batches are freed late)
-  uint64_t cap_in = 0, cap_out = 0, cap_aux = 0, cap_maps = 0;
+  uint64_t cap_in = 0, cap_out = 0, cap_aux = 0, cap_maps = 0, cap_stage = 0, cap_streams = 0, cap_walks = 0, cap_order = 0;
   int device = 0;
   std::vector<int> bufs;
   std::vector<StreamDesc> streams, streams0;
@@ -389,7 +390,7 @@ cudaError_t pool_alloc(const std::shared_ptr<DevPool> &pool, int device, uint64_
       return cudaSuccess;
     }
   }
-  const uint64_t want = bytes >= kPoolMin ? align_up(bytes, 2ull << 20) : bytes;
+  const uint64_t want = bytes >= (1ull << 20) ? align_up(bytes, 2ull << 20) : align_up(bytes, 512);
   cudaError_t e = cudaMalloc(out, want);
   if (e != cudaSuccess && pool && !pool->free_blocks.empty()) {  // out of memory with a warm cache: drop it and retry
     cudaGetLastError();
@@ -416,8 +417,34 @@ void pool_free(const std::shared_ptr<DevPool> &pool, int device, void *p, uint64
 void pool_trim(const std::shared_ptr<DevPool> &pool) {
   if (!pool) return;
   for (PoolBlock &k : pool->free_blocks) { cudaSetDevice(k.device); cudaFree(k.p); }
+  for (PoolBlock &k : pool->free_pinned) cudaFreeHost(k.p);
   pool->free_blocks.clear();
+  pool->free_pinned.clear();
   pool->cached = 0;
+}
+
+cudaError_t pinned_alloc(const std::shared_ptr<DevPool> &pool, uint64_t bytes, uint8_t **out, uint64_t *cap) {
+  if (pool)
+    for (size_t i = 0; i < pool->free_pinned.size(); ++i) {
+      const PoolBlock k = pool->free_pinned[i];
+      if (k.bytes >= bytes && k.bytes <= 2 * bytes + 4096) {
+        *out = (uint8_t *)k.p;
+        *cap = k.bytes;
+        pool->free_pinned.erase(pool->free_pinned.begin() + i);
+        return cudaSuccess;
+      }
+    }
+  *cap = align_up(bytes, 4096);
+  return cudaMallocHost(out, *cap);
+}
+
+void pinned_free(const std::shared_ptr<DevPool> &pool, void *p, uint64_t cap) {
+  if (!p) return;
+  if (pool && pool->cached <= kPoolCap && pool->free_pinned.size() < 64) {
+    pool->free_pinned.push_back({p, cap, -1});
+    return;
+  }
+  cudaFreeHost(p);
 }
 
 void free_shard_device(Shard &sh) {
@@ -429,10 +456,10 @@ void free_shard_device(Shard &sh) {
   pool_free(sh.pool, sh.device, sh.d_aux, sh.cap_aux);
   cudaFree(sh.d_tab);
   pool_free(sh.pool, sh.device, sh.d_maps, sh.cap_maps);
-  cudaFree(sh.d_streams);
-  cudaFree(sh.d_walks);
-  cudaFree(sh.d_order);
-  if (sh.h_stage) cudaFreeHost(sh.h_stage);
+  pool_free(sh.pool, sh.device, sh.d_streams, sh.cap_streams);
+  pool_free(sh.pool, sh.device, sh.d_walks, sh.cap_walks);
+  pool_free(sh.pool, sh.device, sh.d_order, sh.cap_order);
+  if (sh.h_stage) pinned_free(sh.pool, sh.h_stage, sh.cap_stage);
   sh.d_in = sh.d_out = sh.d_dbg = sh.d_aux = sh.d_tab = sh.d_maps = nullptr;
   sh.d_streams = nullptr;
   sh.d_walks = nullptr;
@@ -748,10 +775,12 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
 
 int ensure_order(Shard &sh, uint64_t n) {
   if (n <= sh.order_cap) return DCB_OK;
-  cudaFree(sh.d_order);
+  pool_free(sh.pool, sh.device, sh.d_order, sh.cap_order);
   sh.d_order = nullptr;
   sh.order_cap = 0;
-  CUDA_TRY(cudaMalloc(&sh.d_order, std::max<uint64_t>(n, 1024) * 4));
+  uint8_t *p = nullptr;
+  CUDA_TRY(pool_alloc(sh.pool, sh.device, std::max<uint64_t>(n, 1024) * 4, &p, &sh.cap_order));
+  sh.d_order = reinterpret_cast<uint32_t *>(p);
   sh.order_cap = std::max<uint64_t>(n, 1024);
   return DCB_OK;
 }
@@ -789,7 +818,7 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
     CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, b->host_arena + sh.direct_lo, sh.direct_hi - sh.direct_lo,
                              cudaMemcpyHostToDevice, st));
   } else if (!sh.bufs.empty()) {
-    CUDA_TRY(cudaMallocHost(&sh.h_stage, sh.in_bytes));
+    CUDA_TRY(pinned_alloc(sh.pool, sh.in_bytes, &sh.h_stage, &sh.cap_stage));
     for (int k : sh.bufs) memcpy(sh.h_stage + b->bufs[k].arena_off, b->bufs[k].src, b->bufs[k].len);
     CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, sh.h_stage + kFrontPad, sh.in_bytes - kFrontPad - kBackPad,
                              cudaMemcpyHostToDevice, st));
@@ -834,8 +863,16 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
     int rc = ensure_order(sh, 4 * (uint64_t)sh.streams.size() + sh.bufs.size() + 1024);
     if (rc) return rc;
   }
-  if (!sh.streams.empty()) CUDA_TRY(cudaMalloc(&sh.d_streams, sh.streams.size() * sizeof(StreamDesc)));
-  if (!sh.walks.empty()) CUDA_TRY(cudaMalloc(&sh.d_walks, sh.walks.size() * sizeof(BufWalk)));
+  if (!sh.streams.empty()) {
+    uint8_t *p = nullptr;
+    CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.streams.size() * sizeof(StreamDesc), &p, &sh.cap_streams));
+    sh.d_streams = reinterpret_cast<StreamDesc *>(p);
+  }
+  if (!sh.walks.empty()) {
+    uint8_t *p = nullptr;
+    CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.walks.size() * sizeof(BufWalk), &p, &sh.cap_walks));
+    sh.d_walks = reinterpret_cast<BufWalk *>(p);
+  }
   if (sh.aux_bytes) {
     CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.aux_bytes, &sh.d_aux, &sh.cap_aux));
     CUDA_TRY(cudaMemsetAsync(sh.d_aux, 0, sh.aux_bytes, st));  // look-back words start with epoch 0 (never a live epoch)
