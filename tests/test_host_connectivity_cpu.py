@@ -76,3 +76,22 @@ def test_helper_refuses_point_clouds_and_bad_indices():
         bt.host_connectivity(0)
     assert N.lib().dcb_host_connectivity(bt.h, 5) == -100
     bt.free()
+
+
+def test_positions_only_fixture_is_a_complete_mesh():
+    """tests/golden/house_04_positions_only.drc (bench.py --workload c1): the product's host helper walks its
+    connectivity, the indexer accepts every attribute, and the oracle decodes it to the golden floats."""
+    b = np.fromfile(os.path.join(GOLD, "house_04_positions_only.drc"), dtype=np.uint8)
+    assert bytes(b[:1158]) == bytes(_house()[:1158])          # header + connectivity verbatim
+    bt = D.index_only([b])
+    bt.host_connectivity(0)
+    bt.finish()
+    bi = bt.buffer_info(0)
+    assert bi.status == 0 and bi.n_attrs == 1 and bi.n_points == 3220
+    ai = bt.attr_info(0, 0)
+    assert ai.n_entries == 1775 and ai.pred_method == 1 and ai.out_bytes == 1775 * 12
+    assert bt.faces(0).shape == (2588, 3)
+    bt.free()
+    r = O.decode(b)
+    assert r.status == 0
+    assert hashlib.sha256(r.attrs[0].out.tobytes()).hexdigest() == "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
