@@ -414,6 +414,107 @@ int orc_parallelogram_wrap(const int32_t *corr, uint32_t n, int nc, int32_t mn, 
   return ORC_OK;
 }
 
+/* MeshPredictionSchemeTexCoordsPortableDecoder.ComputeOriginalValues (:49-66) over
+ * MeshPredictionSchemeTexCoordsPortablePredictor.ComputePredictedValue (:52-150) and the wrap transform.
+ * uv: maps of the attribute's own decoder; pos_q / pm: quantized positions (portable parent attribute) and the maps of
+ * ITS decoder -- GetPositionForEntryId (:34-39) goes entry -> point -> position value, i.e. through the corner the
+ * entry was first reached at.  orient[0..n_or): flags in decoding order; the predictor pops them from the BACK (:127).
+ * Where the C# would throw (assertions, negative indices) the stream is invalid: ORC_ERR_PRED / ORC_ERR_MAPS. */
+int orc_texcoords_portable_wrap(const int32_t *corr, uint32_t n, int32_t mn, int32_t mx, const orc_mesh_maps *uv,
+                                const int32_t *pos_q, uint32_t n_pos, const orc_mesh_maps *pm, const uint8_t *orient,
+                                uint32_t n_or, int32_t *out) {
+  int32_t max_diff = (int32_t)(1u + (uint32_t)mx - (uint32_t)mn);
+  if (n == 0) return ORC_OK;
+  if (!uv || !pm || uv->n_entries < n) return ORC_ERR_MAPS;
+  uint32_t left = n_or;
+  for (uint32_t p = 0; p < n; ++p) {
+    uint32_t corner = uv->data_to_corner[p];
+    if (corner == 0xFFFFFFFFu || corner >= uv->n_corners) return ORC_ERR_MAPS;
+    uint32_t nx = (corner % 3u == 2u) ? corner - 2u : corner + 1u;
+    uint32_t pv = (corner % 3u == 0u) ? corner + 2u : corner - 1u;
+    uint32_t v_n = uv->corner_to_vertex[nx], v_p = uv->corner_to_vertex[pv];
+    if (v_n >= uv->n_vertices || v_p >= uv->n_vertices) return ORC_ERR_MAPS;
+    int32_t nd = uv->vertex_to_data[v_n], pd = uv->vertex_to_data[v_p]; /* :58-59 */
+    int64_t pred[2] = {0, 0};
+    int done = 0;
+    if (pd < (int32_t)p && nd < (int32_t)p) { /* :61 */
+      if (pd < 0 || nd < 0) return ORC_ERR_MAPS;
+      int64_t n_uv[2] = {out[2ull * nd], out[2ull * nd + 1]}, p_uv[2] = {out[2ull * pd], out[2ull * pd + 1]};
+      if (p_uv[0] == n_uv[0] && p_uv[1] == n_uv[1]) { /* :66-71 */
+        pred[0] = p_uv[0];
+        pred[1] = p_uv[1];
+        done = 1;
+      } else {
+        int64_t P[3][3]; /* tip, next, prev */
+        const uint32_t ids[3] = {p, (uint32_t)nd, (uint32_t)pd};
+        for (int k = 0; k < 3; ++k) {
+          uint32_t c = uv->data_to_corner[ids[k]];
+          if (c >= pm->n_corners) return ORC_ERR_MAPS;
+          uint32_t v = pm->corner_to_vertex[c];
+          if (v >= pm->n_vertices) return ORC_ERR_MAPS;
+          int32_t e = pm->vertex_to_data[v];
+          if (e < 0 || (uint32_t)e >= n_pos) return ORC_ERR_MAPS;
+          for (int j = 0; j < 3; ++j) P[k][j] = pos_q[3ull * (uint32_t)e + j];
+        }
+        int64_t pn[3], cn[3], pn2 = 0, cdp = 0;
+        for (int j = 0; j < 3; ++j) {
+          pn[j] = P[2][j] - P[1][j];
+          cn[j] = P[0][j] - P[1][j];
+          pn2 += pn[j] * pn[j];
+          cdp += pn[j] * cn[j];
+        }
+        if (pn2 != 0) { /* :78 */
+          int64_t pn_uv[2] = {p_uv[0] - n_uv[0], p_uv[1] - n_uv[1]};
+          int64_t a0 = n_uv[0] < 0 ? -n_uv[0] : n_uv[0], a1 = n_uv[1] < 0 ? -n_uv[1] : n_uv[1];
+          if ((a0 > a1 ? a0 : a1) > INT64_MAX / pn2) return ORC_ERR_PRED; /* :85 */
+          int64_t b0 = pn_uv[0] < 0 ? -pn_uv[0] : pn_uv[0], b1 = pn_uv[1] < 0 ? -pn_uv[1] : pn_uv[1];
+          if (cdp > INT64_MAX / (b0 > b1 ? b0 : b1)) return ORC_ERR_PRED; /* :87 */
+          int64_t x_uv[2] = {n_uv[0] * pn2 + cdp * pn_uv[0], n_uv[1] * pn2 + cdp * pn_uv[1]};
+          int64_t m = 0;
+          for (int j = 0; j < 3; ++j) {
+            int64_t t = pn[j] < 0 ? -pn[j] : pn[j];
+            if (t > m) m = t;
+          }
+          if (cdp > INT64_MAX / m) return ORC_ERR_PRED; /* :90 */
+          int64_t cx2 = 0;
+          for (int j = 0; j < 3; ++j) {
+            int64_t xp = P[1][j] + (cdp * pn[j]) / pn2; /* :91, truncating */
+            int64_t dlt = P[0][j] - xp;
+            cx2 += dlt * dlt;
+          }
+          int64_t nrm = (int64_t)orc_int_sqrt((uint64_t)(cx2 * pn2)); /* :94 */
+          int64_t cx_uv[2] = {pn_uv[1] * nrm, -pn_uv[0] * nrm};
+          if (left == 0) return ORC_ERR_PRED; /* :125 */
+          int o = orient[--left];             /* :126-127: Last() + PopBack() */
+          for (int j = 0; j < 2; ++j) pred[j] = (o ? x_uv[j] + cx_uv[j] : x_uv[j] - cx_uv[j]) / pn2; /* :128 */
+          done = 1;
+        }
+      }
+    }
+    if (!done) { /* :135-160 */
+      int64_t off;
+      int have = 1;
+      off = 0;
+      if (pd < (int32_t)p) off = (int64_t)pd * 2;
+      if (nd < (int32_t)p) {
+        off = (int64_t)nd * 2;
+      } else if (p > 0) {
+        off = (int64_t)(p - 1) * 2;
+      } else {
+        have = 0;
+      }
+      if (have) {
+        if (off < 0) return ORC_ERR_MAPS;
+        pred[0] = out[off];
+        pred[1] = out[off + 1];
+      }
+    }
+    for (int c = 0; c < 2; ++c)
+      out[2ull * p + c] = wrap_original((int32_t)pred[c], corr[2ull * p + c], mn, mx, max_diff);
+  }
+  return ORC_OK;
+}
+
 /* Octahedron tool box: D/IO/Attributes/OctahedronToolBox.cs:13-21,144-212 */
 typedef struct {
   int32_t bits, max_q, max_value, center;
@@ -625,6 +726,7 @@ static void skip_metadata(rd_t *r) {
 int orc_eb_decode_connectivity(const uint8_t *buf, uint64_t len, uint64_t *pos, int traversal_type, orc_result *res);
 int orc_eb_build_maps(orc_result *res, const uint8_t *dec_ids, int n_dec);
 int orc_seq_mesh_connectivity(const uint8_t *buf, uint64_t len, uint64_t *pos, orc_result *res);
+int orc_rabs_bits(const uint8_t *buf, uint64_t len, uint64_t *pos, uint32_t n_bits, uint8_t *bits_out);
 
 /* PORTABLE(int-like): D/IO/Attributes/SequentialIntegerAttributeDecoder.cs:23-101 */
 static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh_maps *maps, int n_maps) {
@@ -661,8 +763,10 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
     /* Edgebreaker meshes have corner table + encoding data: mesh schemes apply */
     if (a->pred_method == 1)
       mesh_scheme = 1;
+    else if (a->pred_method == 5 && a->nc_portable == 2 && a->transform == 1)
+      mesh_scheme = 5; /* TexCoordsPortable: oracle only so far, the CUDA path reports UNSUPPORTED */
     else if (a->pred_method != 0)
-      return ORC_ERR_UNSUPPORTED; /* multi-/constrained-/texcoords/geometric-normal: SURVEY 8f-3 */
+      return ORC_ERR_UNSUPPORTED; /* multi-/constrained-parallelogram, deprecated texcoords, geometric normal: SURVEY 8f-3 */
   }
   int ncp = a->nc_portable;
   uint64_t nv = (uint64_t)n * ncp;
@@ -694,15 +798,43 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
     return ORC_OK;
   }
   /* PRED_DATA :93 */
+  uint8_t *orient = NULL;
+  uint32_t n_or = 0;
+  if (mesh_scheme == 5) { /* MeshPredictionSchemeTexCoordsPortableDecoder.DecodePredictionData :68-84, before the transform data */
+    int32_t no = rd_i32(r);
+    if (r->err) return r->err;
+    if (no < 0 || (uint64_t)no > nv + 1) return ORC_ERR_PRED; /* at most one flag per entry is ever consumed */
+    n_or = (uint32_t)no;
+    orient = (uint8_t *)malloc(n_or ? n_or : 1);
+    int st = orc_rabs_bits(r->p, r->len, &r->pos, n_or, orient);
+    if (st) { free(orient); return st; }
+    int last = 1;
+    for (uint32_t i = 0; i < n_or; ++i) { /* :76-82 */
+      if (orient[i] == 0) last = !last;
+      orient[i] = (uint8_t)last;
+    }
+  }
   if (a->transform == 1) { /* PredictionSchemeWrapDecodingTransform.cs:69-75 */
     a->xf_a = rd_i32(r);
     a->xf_b = rd_i32(r);
-    if (r->err) return r->err;
-    if (a->xf_a > a->xf_b) return ORC_ERR_WRAP;
     int64_t diff = (int64_t)a->xf_b - (int64_t)a->xf_a; /* WrapTransform.cs:90-91 (int overflow -> negative) */
-    if ((int32_t)diff < 0 || diff >= 2147483647ll) return ORC_ERR_WRAP;
+    if (r->err || a->xf_a > a->xf_b || (int32_t)diff < 0 || diff >= 2147483647ll) {
+      free(orient);
+      return r->err ? r->err : ORC_ERR_WRAP;
+    }
     if (nv > 0) {
-      if (mesh_scheme) {
+      if (mesh_scheme == 5) {
+        if (!maps || a->decoder_id >= n_maps) { free(orient); return ORC_ERR_MAPS; }
+        const orc_attr *pos = NULL; /* parent attribute: the (already decoded) position attribute, portable form */
+        for (int i = 0; i < res->n_attrs && &res->attrs[i] != a; ++i)
+          if (res->attrs[i].att_type == 0 && res->attrs[i].nc_portable == 3 && res->attrs[i].qints) pos = &res->attrs[i];
+        if (!pos || pos->decoder_id >= n_maps) { free(orient); return ORC_ERR_PRED; }
+        int st = orc_texcoords_portable_wrap(a->corr, n, a->xf_a, a->xf_b, &maps[a->decoder_id], pos->qints, pos->n_entries,
+                                             &maps[pos->decoder_id], orient, n_or, a->qints);
+        free(orient);
+        orient = NULL;
+        if (st) return st;
+      } else if (mesh_scheme) {
         if (!maps || a->decoder_id >= n_maps) return ORC_ERR_MAPS;
         int st = orc_parallelogram_wrap(a->corr, n, ncp, a->xf_a, a->xf_b, &maps[a->decoder_id], a->qints);
         if (st) return st;
@@ -710,6 +842,7 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
         orc_delta_wrap(a->corr, n, ncp, a->xf_a, a->xf_b, a->qints);
       }
     }
+    free(orient);
   } else { /* octahedron transforms */
     a->xf_a = rd_i32(r); /* max_quantized_value */
     if (a->transform == 3) a->xf_b = rd_i32(r); /* center_value (ignored) ...CanonicalizedDecodingTransform.cs:80-84 */

@@ -92,6 +92,19 @@ static uint32_t rabs_bit(rabs_t *a) { /* AnsDecoder.RAbsRead */
   return (uint32_t)val;
 }
 
+/* rABS-coded bit sequence at *pos (u8 prob_zero, varint size, data), as RAnsBitDecoder.StartDecoding / DecodeNextBit /
+ * EndDecoding read it (D/IO/BitCoders/RAnsBitDecoder.cs:12-35).  Used by prediction schemes that carry flag streams
+ * (MeshPredictionSchemeTexCoordsPortableDecoder.DecodePredictionData :68-84).  *pos ends behind the data. */
+int orc_rabs_bits(const uint8_t *buf, uint64_t len, uint64_t *pos, uint32_t n_bits, uint8_t *bits_out) {
+  rd_t r = {buf, len, *pos, 0};
+  rabs_t a;
+  int st = rabs_start(&a, &r);
+  if (st) return st;
+  for (uint32_t i = 0; i < n_bits; ++i) bits_out[i] = (uint8_t)rabs_bit(&a);
+  *pos = r.pos;
+  return ORC_OK;
+}
+
 /* ---- corner table ---- */
 typedef struct {
   uint32_t *c2v, *opp;   /* [n_corners] */

@@ -94,8 +94,8 @@ def test_house_container_and_connectivity(house):
     assert r.n_faces == 2588          # `f` lines of house_04.obj
     assert r.attr_section_off == 1158
     assert r.n_decoders == 3 and r.n_attrs == 3
-    # attribute 1 uses the TexCoordsPortable predictor: outside the hot path, reported as such
-    assert r.status == -3
+    # the oracle decodes the whole sample, TexCoordsPortable (attribute 1) included
+    assert r.status == 0 and r.end_off == len(b)
     m = r.maps[0]
     assert m["data_to_corner"].size == 1775 and m["opposite"].size == 3 * 2588
     assert m["data_to_corner"][:8].tolist() == [1, 2, 0, 4, 8, 10, 11, 9]
@@ -143,3 +143,21 @@ def test_house_positions_match_the_source_obj(house):
     half_step = 2009.9021 / 2047 / 2
     assert d.max() < half_step
     assert d.max() == pytest.approx(0.48928, abs=1e-4)
+
+
+def test_house_texcoords_match_the_obj(house):
+    """SURVEY 8f-3 groundwork: the oracle's TexCoordsPortable predictor (MeshPredictionSchemeTexCoordsPortable
+    Decoder / Predictor) on the reference's sample.  Ground truth that does not come from us: every dequantised
+    (u, v) lies within half a quantisation step of a `vt` line of house_04.obj, and the rABS-coded orientation
+    flags are consumed exactly (a wrong flag order or a wrong parent position would miss by whole texels)."""
+    b, r = house
+    a = r.attrs[1]
+    assert (a.att_type, a.data_type, a.nc, a.seq_type) == (3, 9, 2, 2)
+    assert (a.pred_method, a.transform, a.n_entries) == (5, 1, 3220)
+    vts = np.load(os.path.join(GOLD, "house_04_obj_texcoords.npy"))
+    uv = a.out.view(np.float32).reshape(-1, 2).astype(np.float64)
+    half_step = float(a.qrange) / ((1 << a.qbits) - 1) / 2
+    d = np.abs(uv[:, None, :] - vts[None, :, :]).max(axis=2).min(axis=1)
+    assert d.max() < half_step, (d.max(), half_step)
+    # the third attribute (generic, parallelogram) decodes too: the whole file is consumed
+    assert r.attrs[2].out.nbytes == 1775 and r.status == 0
