@@ -20,7 +20,9 @@
  *     self-check (0 bytes left, final state == 4*2^precision), the position
  *     attribute's symbols / corrections / quantized ints / floats match the
  *     SHA-256 goldens of SURVEY.md Appendix C, and every dequantised position
- *     lies within half a quantisation step of a `v` line of house_04.obj.
+ *     lies within half a quantisation step of a `v` line of house_04.obj; its texture
+ *     coordinates (TexCoordsPortable predictor, rABS orientation flags) decode to within half a
+ *     quantisation step of the `vt` lines.
  * The Tagged symbol scheme is anchored by no upstream artefact (it crashes in the
  * C#, Appendix B-3): for it and for the octahedral transforms parity is
  * "unpinned by reference artefacts" and rests on the mirrored encoder/decoder
