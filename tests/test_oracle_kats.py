@@ -161,3 +161,6 @@ def test_house_texcoords_match_the_obj(house):
     assert d.max() < half_step, (d.max(), half_step)
     # the third attribute (generic, parallelogram) decodes too: the whole file is consumed
     assert r.attrs[2].out.nbytes == 1775 and r.status == 0
+    # goldens for the GPU kernel to come (quantized ints and floats of the tex-coord attribute, little endian)
+    assert sha(a.qints.astype("<i4")) == "a243b8cf61c7145d3f75eda19721098918e735e925822b6a211ae6686a6d2990"
+    assert sha(a.out) == "26bd6cc9ae35d081caba5b2061dd9d6d049a66c9050f7c5b9cfdc345c3c8449a"
