@@ -19,8 +19,9 @@ SYNTH_LIB = os.path.join(HERE, "synth", "libdrcsynth.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _newer(target, sources):
@@ -39,12 +40,20 @@ def _run(cmd, cwd=None):
 
 
 def build_lib(force=False):
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
-    srcs.append(os.path.join(ROOT, "include", "dracob200.h"))
-    if force or _newer(LIB, srcs):
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cu = [os.path.join(CSRC, f) for f in ("dcb_api.cu", "dcb_kernels.cu", "dcb_mesh_host.cu")]
-        _run([nvcc] + NVCC_FLAGS + ["-o", LIB] + cu)
+    """One object per .cu (compiled in parallel, rebuilt only when it or a header changed), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(ROOT, "include", "dracob200.h"))
+    cus = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = [os.path.join(OBJ_DIR, os.path.basename(c)[:-3] + ".o") for c in cus]
+    todo = [(c, o) for c, o in zip(cus, objs) if force or _newer(o, [c] + headers)]
+    if todo:
+        with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+            list(ex.map(lambda co: _run([nvcc] + NVCC_FLAGS + ["-c", "-o", co[1], co[0]]), todo))
+    if todo or _newer(LIB, objs):
+        _run([nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + objs)
     return LIB
 
 

@@ -41,6 +41,27 @@ constexpr uint64_t kTabArenaBudget = 1ull << 30;
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+// experiment / test switches, read once per process (never per stream or per decode)
+struct EnvFlags {
+  bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_v1, no_direct;
+  int ctas_per_sm, pairs;
+  EnvFlags() {
+    no_par_post = getenv("DCB_NO_PAR_POST") != nullptr;
+    no_fanout = getenv("DCB_NO_FANOUT") != nullptr;
+    debug_plan = getenv("DCB_DEBUG_PLAN") != nullptr;
+    debug_timing = getenv("DCB_DEBUG_TIMING") != nullptr;
+    lutb_full = getenv("DCB_LUTB_FULL") != nullptr;
+    rans_v1 = getenv("DCB_RANS_V1") != nullptr;      // single-warp rANS kernels (round 1) instead of warp pairs
+    no_direct = getenv("DCB_NO_DIRECT") != nullptr;  // never plan the direct slot LUT
+    ctas_per_sm = getenv("DCB_CTAS_PER_SM") ? atoi(getenv("DCB_CTAS_PER_SM")) : 0;
+    pairs = getenv("DCB_PAIRS") ? atoi(getenv("DCB_PAIRS")) : 0;
+  }
+};
+const EnvFlags &env_flags() {
+  static const EnvFlags f;
+  return f;
+}
+
 // Device-memory cache of a context: the big per-batch arenas (input, output, scratch, maps) are returned here when a
 // batch is freed and reused by the next one -- a cudaMalloc / cudaFree pair of 15 GB costs 10-100 ms, more than the
 // kernels of the batch.  Blocks are handed out when they are at most twice the size asked for; the cache is capped.
@@ -83,6 +104,8 @@ struct Group {            // one kernel launch (or a few, for global tables)
   int ncp;
   bool wide, table_global;
   uint32_t compact, prec_bits, entries, exc, lut_shift, lut_bytes, lutb_bytes, ent_bytes, lanes, zig, mode;
+  uint32_t pairs;         // chain/consumer warp pairs per CTA (0: the single-warp kernels of dcb_kernels.cu)
+  uint32_t ctas_per_sm;   // planned residency (reporting)
   uint64_t total_symbols, max_bytes;
   uint32_t max_entries;
   std::vector<uint32_t> order;
@@ -733,8 +756,66 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
       const uint64_t my = (uint64_t)budget * ((uint64_t)per_sm[i] * lane_bytes) / total;
       want = std::max<uint32_t>(1u, (uint32_t)(my / lane_bytes));
     }
+    g.pairs = 0;
+    g.ctas_per_sm = 0;
+    // what the group's tables need of the two-region LUT's narrow region: it covers the slots from the first entry
+    // narrower than 2^k on, for the k whose wide region still fits the LUT
+    auto lutb_need = [&]() -> uint32_t {
+      uint32_t need = 0xFFFFFFFFu;
+      if (!g.nb_any) return need;
+      const uint32_t prec = 1u << g.prec_bits;
+      for (uint32_t k = 1; k <= 7; ++k) {
+        if (k + 7 > g.prec_bits) continue;
+        const uint32_t t_max = std::min(prec, g.nb_max[k] << 7), t_min = std::min(prec, g.nb_min[k] << 7);
+        if ((t_max >> k) > g.lut_bytes) continue;
+        need = std::min(need, (prec - t_min) >> 1);
+      }
+      return need == 0xFFFFFFFFu ? need : std::max<uint32_t>(16u, (uint32_t)align_up(need, 16));
+    };
+    if (!g.wide && !env_flags().rans_v1) {
+      // ---- chain / consumer warp pairs (dcb_rans_pc.cu): `pairs` pairs per CTA, `lanes` streams per pair ----
+      // Four pairs per SM put one chain warp and one consumer warp on every sub-partition; pipeline slices share
+      // the SM, so each plans for its part of those four.
+      const uint32_t ksym = g.kind == 1 ? 16u : 4u * (uint32_t)g.ncp;
+      auto cta_bytes = [&](uint32_t pairs, uint32_t lanes, uint32_t lutb) -> uint64_t {
+        RansLaunch L{};
+        L.lanes_per_warp = lanes;
+        L.lut_bytes = g.lut_bytes;
+        L.lutb_bytes = lutb;
+        L.ent_bytes = g.ent_bytes;
+        L.prec_bits = g.prec_bits;
+        L.pairs = pairs;
+        return (uint64_t)dcb_rans_pc_smem_bytes(L, ksym) + kSmemPerCtaReserve;
+      };
+      const uint64_t sm_cap = (uint64_t)sm_bytes + 1024 / share;
+      uint32_t target = std::max<uint32_t>(1u, 4u / share);
+      if (env_flags().pairs > 0) target = (uint32_t)env_flags().pairs;  // experiments
+      const uint32_t lutb_min = g.compact ? 16u : 0u;
+      uint32_t pairs = 1, lanes = 1, ctas = 1;
+      for (;; --want) {
+        uint32_t nw = std::max<uint32_t>((want + 31) / 32, std::min<uint32_t>(target, want));
+        if (!g.wide)
+          while ((uint64_t)((want + nw - 1) / nw) * g.ent_bytes > 65535) ++nw;  // 16-bit entry offsets inside a pair
+        ctas = (nw + 3) / 4;
+        pairs = (nw + ctas - 1) / ctas;
+        lanes = (want + pairs * ctas - 1) / (pairs * ctas);
+        if (ctas * cta_bytes(pairs, lanes, lutb_min) <= sm_cap || want <= 1) break;
+      }
+      g.lanes = lanes;
+      g.pairs = pairs;
+      g.ctas_per_sm = ctas;
+      g.lutb_bytes = 0;
+      if (g.compact) {
+        const uint64_t base = ctas * cta_bytes(pairs, lanes, lutb_min);
+        const uint64_t spare = sm_cap > base ? (sm_cap - base) / ((uint64_t)ctas * pairs * (lanes + 1)) : 0;
+        g.lutb_bytes = (uint32_t)std::min<uint64_t>((1u << g.prec_bits) >> 1, lutb_min + spare / 16 * 16);
+        const uint32_t need = lutb_need();
+        if (need != 0xFFFFFFFFu && !env_flags().lutb_full) g.lutb_bytes = std::min(g.lutb_bytes, need);
+      }
+      continue;
+    }
     uint32_t ctas = (want + 31) / 32;
-    if (const char *e = getenv("DCB_CTAS_PER_SM")) ctas = std::max<uint32_t>(ctas, (uint32_t)atoi(e));  // experiments
+    if (env_flags().ctas_per_sm > 0) ctas = std::max<uint32_t>(ctas, (uint32_t)env_flags().ctas_per_sm);  // experiments
     g.lanes = std::max<uint32_t>(1u, std::min<uint32_t>(32u, (want + ctas - 1) / ctas));
     // a CTA must fit an SM (with its alignment slack) and, for u16 tables, address its entries with 16 bits
     while (g.lanes > 1 && ((uint64_t)g.lanes * lane_bytes + g.lut_bytes + 256 > kSmemPerSM - kSmemPerCtaReserve ||
@@ -757,17 +838,9 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
       // ... but no more than the group's tables need: region B covers the slots from the first entry narrower than
       // 2^k on, for the k whose wide region still fits the LUT.  What is not taken stays free for the CTAs of the
       // batch's other groups, which then run next to this one instead of behind it.
-      if (g.nb_any && g.lutb_bytes) {
-        uint32_t need = 0xFFFFFFFFu;
-        const uint32_t prec = 1u << g.prec_bits;
-        for (uint32_t k = 1; k <= 7; ++k) {
-          if (k + 7 > g.prec_bits) continue;
-          const uint32_t t_max = std::min(prec, g.nb_max[k] << 7), t_min = std::min(prec, g.nb_min[k] << 7);
-          if ((t_max >> k) > g.lut_bytes) continue;
-          need = std::min(need, (prec - t_min) >> 1);
-        }
-        if (need != 0xFFFFFFFFu && !getenv("DCB_LUTB_FULL"))
-          g.lutb_bytes = std::min<uint32_t>(g.lutb_bytes, std::max<uint32_t>(16u, (uint32_t)align_up(need, 16)));
+      if (g.lutb_bytes) {
+        const uint32_t need = lutb_need();
+        if (need != 0xFFFFFFFFu && !env_flags().lutb_full) g.lutb_bytes = std::min<uint32_t>(g.lutb_bytes, need);
       }
     }
   }
@@ -906,7 +979,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   sh.tags_launched.assign(sh.streams.size(), 0);
   DevArenas A{sh.d_in, d_out, d_dbg, sh.d_aux, sh.d_tab, sh.d_maps};
   const uint32_t dump = flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS);
-  const bool dbg_tl = timed && sh.device == ctx->devices[0] && getenv("DCB_DEBUG_TIMING") != nullptr;
+  const bool dbg_tl = timed && sh.device == ctx->devices[0] && env_flags().debug_timing;
   auto tl_begin = [&](const char *name, cudaStream_t s) {
     if (!dbg_tl) return;
     cudaEvent_t a, b;
@@ -956,7 +1029,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
       for (uint32_t si : g.order) ctx->algo_tag += sh.streams[si].payload_len + sh.streams[si].n_entries;
     }
-    CUDA_TRY(dcb_launch_rans_tag(L, A, st));
+    L.pairs = g.pairs;
+    CUDA_TRY(g.pairs ? dcb_launch_rans_tag_pc(L, A, st) : dcb_launch_rans_tag(L, A, st));
     if (time_tag) {
       CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
       ctx->ev_tag = true;
@@ -1026,7 +1100,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         g.max_entries = std::max(g.max_entries, s.n_entries);
         g.note_table(s);
         g.order.push_back(si);
-      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP) && !getenv("DCB_NO_PAR_POST")) {
+      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP) && !env_flags().no_par_post) {
         // Tagged / uncompressed source, scan-able reconstruction: point-parallel kernels
         par[s.ncp].max_entries = std::max(par[s.ncp].max_entries, s.n_entries);
         par[s.ncp].order.push_back(si);
@@ -1092,7 +1166,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     if (!dom || g->total_symbols > dom->total_symbols) dom = g;
   // ---- launches ----
   // independent smem-table groups go to side streams so that their chains overlap (c3: positions, normals, colours)
-  const bool fan_out = rgs.size() > 1 && !getenv("DCB_NO_FANOUT");
+  const bool fan_out = rgs.size() > 1 && !env_flags().no_fanout;
   if (fan_out) {
     CUDA_TRY(cudaEventRecord(ctx->fork_ev[dev_index], st));
     for (cudaStream_t ss : ctx->side[dev_index]) CUDA_TRY(cudaStreamWaitEvent(ss, ctx->fork_ev[dev_index], 0));
@@ -1109,11 +1183,12 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       st = ctx->side[dev_index][k];
       side_used[k] = true;
     }
-    if (getenv("DCB_DEBUG_PLAN"))
+    if (env_flags().debug_plan)
       fprintf(stderr, "[dcb plan] raw group ncp=%d wide=%d compact=%u prec=%u entries=%u mode=%u zig=%u: %u streams, %llu symbols, "
-                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u global=%d\n",
+                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u pairs=%u ctas/sm=%u global=%d\n",
               g->ncp, (int)g->wide, g->compact, g->prec_bits, g->entries, g->mode, g->zig, n,
-              (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->lanes, (int)g->table_global);
+              (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->lanes, g->pairs,
+              g->ctas_per_sm, (int)g->table_global);
     if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (g->table_global) {
       const uint64_t slot_bytes = (uint64_t)g->lut_bytes + g->ent_bytes;
@@ -1138,7 +1213,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       RansLaunch L{sh.d_streams, sh.d_order + g->order_off, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes,
                    g->entries, g->exc, g->lut_shift, g->prec_bits, dump, g->compact, g->zig, g->mode};
       tl_begin(g->mode == 1 ? "rans mode1" : g->mode == 2 ? "rans mode2" : g->mode == 3 ? "rans mode3" : g->mode == 4 ? "rans mode4" : "rans mode0", st);
-      CUDA_TRY(dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
+      L.pairs = g->pairs;
+      CUDA_TRY(g->pairs ? dcb_launch_rans_raw_pc(L, g->ncp, A, st) : dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
       tl_end(st);
       stats.n_launches++;
     }
@@ -1161,13 +1237,17 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       }
       stats.lanes_per_warp = (int32_t)g->lanes;
       stats.smem_per_stream = (uint64_t)g->lut_bytes + g->lutb_bytes + g->ent_bytes + DCB_RING_BYTES;
-      RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, 0, g->compact, g->zig, g->mode};
-      const uint32_t cta_smem = dcb_rans_smem_bytes(Ls, g->table_global) + kSmemPerCtaReserve;
-      const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, (kSmemPerSM + 1024u) / cta_smem)) * g->lanes;
+      RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, 0, g->compact, g->zig, g->mode, g->pairs};
+      const uint32_t cta_smem = (g->pairs ? dcb_rans_pc_smem_bytes(Ls, 4u * (uint32_t)g->ncp) : dcb_rans_smem_bytes(Ls, g->table_global)) + kSmemPerCtaReserve;
+      const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, (kSmemPerSM + 1024u) / cta_smem)) * g->lanes * std::max(1u, g->pairs);
       stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);
-      snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_fused<ncp=%d,%s,%s,mode=%u,k=%u,%s>", g->ncp,
-               g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->mode, g->lut_shift,
-               g->compact ? "compact" : "dense");
+      if (g->pairs)
+        snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_pc<ncp=%d,u16,smem,mode=%u,k=%u,%s,%ux%u lanes>", g->ncp, g->mode,
+                 g->lut_shift, g->compact ? "compact" : "dense", g->pairs, g->lanes);
+      else
+        snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_fused<ncp=%d,%s,%s,mode=%u,k=%u,%s>", g->ncp,
+                 g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->mode, g->lut_shift,
+                 g->compact ? "compact" : "dense");
     }
     stats.n_streams += (int32_t)n;
   }
@@ -1252,7 +1332,7 @@ void collect_status(dcb_batch *b) {
 }
 
 void tl_mark(dcb_ctx *ctx, const std::string &name, cudaStream_t s, bool begin) {
-  if (!getenv("DCB_DEBUG_TIMING")) return;
+  if (!env_flags().debug_timing) return;
   if (begin) {
     cudaEvent_t a, b;
     cudaEventCreate(&a);
@@ -1328,7 +1408,7 @@ int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_
     }
     sh.ext_dbg = g;
   }
-  const bool dbg_t = getenv("DCB_DEBUG_TIMING") != nullptr;
+  const bool dbg_t = env_flags().debug_timing;
   if (dbg_t)
     fprintf(stderr, "[dcb timing] uploads issued in %.1f ms\n",
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count());
@@ -1755,7 +1835,7 @@ int dcb_download(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_db
 int dcb_decode(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg, uint32_t flags) {
   if (!host_out && b && b->total_out) return DCB_ERR_ARG;
   if ((flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS)) && !host_dbg) return DCB_ERR_ARG;
-  const bool dbg_t = getenv("DCB_DEBUG_TIMING") != nullptr;
+  const bool dbg_t = env_flags().debug_timing;
   const auto t0 = std::chrono::steady_clock::now();
   auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;

@@ -620,4 +620,93 @@ struct RansLane {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// pieces shared by the lane-per-stream rANS kernels (dcb_kernels.cu, dcb_rans_pc.cu)
+// ---------------------------------------------------------------------------------------------
+// post-processing mode of a launch: 0 = per-stream (runtime) recon/store kinds; the others pin them at
+// compile time for the hot shapes
+//   1  delta + wrap  -> dequantise to float      (quantized positions / tex coords)
+//   2  delta + wrap  -> narrow to uint8          (colours)
+//   3  normals: the unsigned corrections go to the int32 scratch as they are; the octahedral recurrence is a chain of
+//      its own (~120 dependent-ish instructions per entry) and runs in oct_chain_kernel, next to the rANS kernels of
+//      the batch's other attributes instead of in front of them
+//   4  parallelogram streams: zig-zag decoded corrections to the int32 scratch (para_chain_kernel does the rest)
+template <int MODE>
+__device__ __forceinline__ int recon_of(const PostParams &pp) {
+  return (MODE == 1 || MODE == 2) ? (int)RECON_DELTA_WRAP : ((MODE == 3 || MODE == 4) ? (int)RECON_NONE : pp.recon);
+}
+template <int MODE>
+__device__ __forceinline__ int store_of(const PostParams &pp) {
+  // normals leave the serial kernels as quantized (s, t) pairs: the unit-vector conversion (double precision
+  // 1/sqrt, as the C#) runs in oct_unit_kernel, point-parallel, instead of stretching the serial chain
+  return MODE == 1 ? (int)STORE_DEQUANT : ((MODE == 2 || MODE == 3 || MODE == 4) ? (int)STORE_NARROW : pp.store);
+}
+template <int MODE>
+__device__ __forceinline__ int dsize_of(const PostParams &pp) {
+  return MODE == 2 ? 1 : ((MODE == 3 || MODE == 4) ? 4 : pp.dsize);
+}
+
+// shared-memory carve-up of a warp-CTA (see RansLane)
+struct SmemLayout {
+  uint32_t lut0, ring0, blk0, lutb0, ent0;  // byte offsets from the dynamic shared-memory base
+};
+__device__ __forceinline__ SmemLayout smem_layout(uint32_t base_addr, uint32_t lanes, const TableGeom &g, bool table_global) {
+  SmemLayout l;
+  uint32_t a = base_addr;
+  if (!table_global) {
+    a = (a + g.lut_bytes - 1u) & ~(g.lut_bytes - 1u);
+    l.lut0 = a - base_addr;
+    a += lanes * g.lut_bytes;
+  } else {
+    l.lut0 = 0;
+  }
+  a = (a + DCB_RING_BYTES - 1u) & ~(DCB_RING_BYTES - 1u);
+  l.ring0 = a - base_addr;
+  a += lanes * DCB_RING_BYTES;
+  l.blk0 = l.lutb0 = a - base_addr;
+  if (!table_global && g.lutb_bytes) {
+    a = (a + g.blk_bytes - 1u) & ~(g.blk_bytes - 1u);
+    l.blk0 = a - base_addr;
+    a += lanes * g.blk_bytes;
+    l.lutb0 = a - base_addr;
+    a += (lanes * g.lutb_bytes + 15u) & ~15u;
+  }
+  l.ent0 = a - base_addr;
+  return l;
+}
+
+// decode one entry: NCP symbols -> corrections -> prediction; leaves the portable ints in v and prev
+// TAB: 0 = table kind (dense / compact) read from the launch geometry, 1 = dense, 2 = compact
+template <int NCP, typename T, bool TG, bool DUMP, int MODE, int TAB, bool CAREFUL, bool SPLIT>
+__device__ __forceinline__ void decode_entry(RansLane<T, TG> &rl, const TableGeom &g, const PostParams &pp, int32_t *prev,
+                                             int32_t *v, int32_t *dptr, uint32_t dump, uint64_t e) {
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) {
+    const uint32_t o = rl.template step<CAREFUL, SPLIT>();
+    const bool compact = TAB == 0 ? g.compact != 0 : TAB == 2;
+    const bool zig = MODE == 0 ? g.zig != 0 : MODE != 3;
+    v[c] = rl.value(o, compact, zig);
+    if (DUMP && (dump & DCB_DUMP_SYMBOLS)) dptr[e * NCP + c] = (int32_t)rl.symbol(o, g);
+  }
+  const int recon = recon_of<MODE>(pp);
+  if (recon == RECON_DELTA_WRAP) {
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) {
+      prev[c] = wrap_original(prev[c], v[c], pp.mn, pp.mx, pp.max_diff);
+      v[c] = prev[c];
+    }
+  } else if (recon == RECON_DELTA_OCT || recon == RECON_DELTA_OCT_CANON) {
+    if (NCP == 2) {
+      oct_original(pp.box, recon == RECON_DELTA_OCT_CANON, prev[0], prev[NCP - 1], v[0], v[NCP - 1]);
+      v[0] = prev[0];
+      v[NCP - 1] = prev[NCP - 1];
+    }
+  }
+  if (DUMP && MODE != 3 && (dump & DCB_DUMP_QINTS)) {
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) dptr[e * NCP + c] = v[c];
+  }
+}
+
+
 }  // namespace dcb

@@ -143,5 +143,6 @@ struct RansLaunch {
   uint32_t dump;                  // DCB_DUMP_* flags
   uint32_t compact;               // 1: tables indexed by active-symbol rank (+ value map), 0: by symbol id
   uint32_t zig;                   // symbols are zig-zag coded corrections
-  uint32_t mode;                  // 0 generic post-processing, 1..3 specialised (dcb_kernels.cu)
+  uint32_t mode;                  // 0 generic post-processing, 1..4 specialised (dcb_device.cuh)
+  uint32_t pairs;                 // chain/consumer warp pairs per CTA (dcb_rans_pc.cu); 0 = the single-warp kernels
 };

@@ -6,7 +6,17 @@
 #include "dcb_internal.h"
 
 #define DCB_TAG_CHUNK 1024u  // points per bit-offset checkpoint of a Tagged stream
-#define DCB_RING_BYTES 128u   // per-lane shared-memory ring of compressed bytes (rANS kernels)    // entries of the per-stream shared-memory ring of the parallelogram chain
+#define DCB_RING_BYTES 128u   // per-lane shared-memory ring of compressed bytes (rANS kernels)
+// chain / consumer warp pairs (dcb_rans_pc.cu): shared memory of one pair beyond its lanes' tables
+#define DCB_PC_STAGES 4u       // queue depth in groups
+#define DCB_PC_ROW_BYTES 64u   // one queue row: symbol j of all 32 lanes, 2 bytes each
+#define DCB_PC_CTL_BYTES 96u   // mbarriers full[4] empty[4] setup handoff + flag[4]
+#define DCB_PC_HAND_BYTES 40u  // per-lane hand-over record
+struct PcGeom {
+  uint32_t tab_bytes;    // table part of a pair's slice (worst-case alignment slack included)
+  uint32_t slice_bytes;  // whole slice
+  uint32_t q_off, ctl_off, hand_off;  // offsets inside the slice
+};
 
 // device arenas of one shard
 struct DevArenas {
@@ -22,6 +32,11 @@ uint32_t dcb_rans_smem_bytes(const RansLaunch &p, bool table_global);
 // Raw-scheme rANS decode fused with inverse prediction + transform + store; one stream per lane.
 cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool table_global, const DevArenas &a,
                                 cudaStream_t st);
+// the same two kernels as chain / consumer warp pairs (u16 tables in shared memory only)
+PcGeom dcb_pc_geom(const RansLaunch &p, uint32_t syms_per_group);
+uint32_t dcb_rans_pc_smem_bytes(const RansLaunch &p, uint32_t syms_per_group);
+cudaError_t dcb_launch_rans_raw_pc(const RansLaunch &p, int ncp, const DevArenas &a, cudaStream_t st);
+cudaError_t dcb_launch_rans_tag_pc(const RansLaunch &p, const DevArenas &a, cudaStream_t st);
 // tag stream of Tagged attributes; one stream per lane
 cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_resolve(const DevArenas &a, BufWalk *d_walks, const uint32_t *d_list, uint32_t n,
