@@ -62,8 +62,10 @@ public sealed class DracoBatchDecoder : IDisposable
     [DllImport(Lib)] private static extern int dcb_get_attr_info(IntPtr batch, int buf, int attr, out AttrInfo info);
     [DllImport(Lib)] private static extern ulong dcb_batch_out_bytes(IntPtr batch);
     [DllImport(Lib)] private static extern int dcb_set_attr_section(IntPtr batch, int buf, ulong attrSectionOff, uint nPoints);
-    [DllImport(Lib)] private static extern int dcb_set_mesh_maps(IntPtr batch, int buf, int attrDecoder, uint[] opposite, uint[] cornerToVertex,
-        ulong nCorners, uint[] dataToCorner, ulong nEntries, int[] vertexToData, ulong nVertices);
+    [DllImport(Lib)] private static extern int dcb_set_limits(IntPtr ctx, ulong maxPointsPerBuffer, ulong pointsPerByte);
+    // the four arrays are BORROWED by the library until the decode call returns: raw pointers of pinned arrays
+    [DllImport(Lib)] private static extern unsafe int dcb_set_mesh_maps(IntPtr batch, int buf, int attrDecoder, uint* opposite, uint* cornerToVertex,
+        ulong nCorners, uint* dataToCorner, ulong nEntries, int* vertexToData, ulong nVertices);
     [DllImport(Lib)] private static extern int dcb_host_connectivity(IntPtr batch, int buf);
     [DllImport(Lib)] private static extern int dcb_mesh_faces(IntPtr batch, int buf, uint[]? faces, ulong capFaces, out ulong nFaces);
     [DllImport(Lib)] private static extern int dcb_mesh_map(IntPtr batch, int buf, int attrDecoder, int which, uint[]? dst, ulong cap, out ulong n);
@@ -85,7 +87,10 @@ public sealed class DracoBatchDecoder : IDisposable
         }
     }
 
-    /// <summary>Host connectivity hook for meshes; null = meshes are reported as NotSupported.</summary>
+    /// <summary>Per-buffer plausibility limits (dcb_set_limits): a forged point count fails its own buffer.</summary>
+    public void SetLimits(ulong maxPointsPerBuffer = 0, ulong pointsPerByte = 4096) => Check(dcb_set_limits(_ctx, maxPointsPerBuffer, pointsPerByte));
+
+    /// <summary>Host connectivity hook for meshes; null = the library's own host Edgebreaker helper is used.</summary>
     public IHostConnectivity? Connectivity { get; set; }
 
     /// <summary>
@@ -98,8 +103,11 @@ public sealed class DracoBatchDecoder : IDisposable
         var result = new Draco?[n];
         errors = new Exception?[n];
         var pins = new System.Buffers.MemoryHandle[n];
-        var ptrs = stackalloc byte*[Math.Max(n, 1)];
-        var lens = stackalloc ulong[Math.Max(n, 1)];
+        // heap, not stack: batches of 200,000 buffers are a normal case (BASELINE configs[4])
+        var ptrs = (byte**)NativeMemory.Alloc((nuint)Math.Max(n, 1), (nuint)sizeof(byte*));
+        var lens = (ulong*)NativeMemory.Alloc((nuint)Math.Max(n, 1), (nuint)sizeof(ulong));
+        byte** outs = null;
+        var mapPins = new List<GCHandle>();  // connectivity maps stay pinned until the decode has consumed them
         IntPtr batch = IntPtr.Zero;
         try
         {
@@ -126,14 +134,31 @@ public sealed class DracoBatchDecoder : IDisposable
                     Check(dcb_host_connectivity(batch, k));
                     continue;
                 }
-                var hc = Connectivity.DecodeConnectivity(buffers[k]);
+                HostConnectivity hc;
+                try
+                {
+                    hc = Connectivity.DecodeConnectivity(buffers[k]);
+                }
+                catch (Exception e)
+                {
+                    // one malformed mesh fails alone: without an attribute section the library reports
+                    // DCB_ERR_CONNECTIVITY for this buffer after dcb_index_finish; keep the host's own exception
+                    errors[k] = e;
+                    continue;
+                }
                 hostMeshes[k] = hc.Mesh;
                 Check(dcb_set_attr_section(batch, k, (ulong)hc.AttributesSectionOffset, (uint)hc.Mesh.PointsCount));
                 for (int d = 0; d < hc.Decoders.Count; ++d)
                 {
                     var m = hc.Decoders[d];
-                    Check(dcb_set_mesh_maps(batch, k, d, m.Opposite, m.CornerToVertex, (ulong)m.Opposite.Length,
-                        m.DataToCorner, (ulong)m.DataToCorner.Length, m.VertexToData, (ulong)m.VertexToData.Length));
+                    uint* Pin<T>(T[] a) where T : unmanaged
+                    {
+                        var h = GCHandle.Alloc(a, GCHandleType.Pinned);
+                        mapPins.Add(h);
+                        return (uint*)h.AddrOfPinnedObject();
+                    }
+                    Check(dcb_set_mesh_maps(batch, k, d, Pin(m.Opposite), Pin(m.CornerToVertex), (ulong)m.Opposite.Length,
+                        Pin(m.DataToCorner), (ulong)m.DataToCorner.Length, (int*)Pin(m.VertexToData), (ulong)m.VertexToData.Length));
                 }
             }
             if (anyMesh) Check(dcb_index_finish(_ctx, batch));
@@ -152,7 +177,7 @@ public sealed class DracoBatchDecoder : IDisposable
             }
             try
             {
-                var outs = stackalloc byte*[Math.Max(attrs.Count, 1)];
+                outs = (byte**)NativeMemory.Alloc((nuint)Math.Max(attrs.Count, 1), (nuint)sizeof(byte*));
                 for (int i = 0; i < attrs.Count; ++i)
                     outs[i] = attrs[i].data.Length > 0 ? (byte*)attrs[i].pin.AddrOfPinnedObject() : null;
                 Check(dcb_decode_scatter(_ctx, batch, outs, attrs.Count, 0));
@@ -172,7 +197,7 @@ public sealed class DracoBatchDecoder : IDisposable
                 cursor += bi.NAttrs;
                 if (status != 0)
                 {
-                    errors[k] = ToException(status);
+                    errors[k] ??= ToException(status);  // a host connectivity exception, if any, is the more precise one
                     continue;
                 }
                 PointCloud.PointCloud pc = hostMeshes[k] ?? (bi.GeometryType == 1 ? new Mesh.Mesh() : new PointCloud.PointCloud());
@@ -208,7 +233,11 @@ public sealed class DracoBatchDecoder : IDisposable
         finally
         {
             if (batch != IntPtr.Zero) dcb_batch_free(batch);
+            foreach (var h in mapPins) h.Free();
             foreach (var p in pins) p.Dispose();
+            NativeMemory.Free(ptrs);
+            NativeMemory.Free(lens);
+            if (outs != null) NativeMemory.Free(outs);
         }
     }
 

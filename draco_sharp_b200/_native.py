@@ -77,6 +77,7 @@ EXPORTS = [
     ("dcb_create", C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     ("dcb_destroy", None, [_P]),
     ("dcb_set_stream", C.c_int, [_P, C.c_int, _P]),
+    ("dcb_set_limits", C.c_int, [_P, C.c_uint64, C.c_uint64]),
     ("dcb_index", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.c_int, C.POINTER(_P)]),
     ("dcb_index_arena", C.c_int, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int, C.POINTER(_P)]),
     ("dcb_get_buffer_info", C.c_int, [_P, C.c_int, C.POINTER(BufferInfo)]),

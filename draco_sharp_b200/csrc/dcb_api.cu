@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <new>
 #include <tuple>
@@ -38,6 +39,7 @@ constexpr uint32_t kNumSMsDefault = 148;
 constexpr uint32_t kSmemPerSM = 227 * 1024;
 constexpr uint32_t kSmemPerCtaReserve = 1024;
 constexpr uint64_t kTabArenaBudget = 1ull << 30;
+constexpr uint64_t kDefaultPointsPerByte = 4096;
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
@@ -78,11 +80,17 @@ struct DevPool {
 constexpr uint64_t kPoolCap = 96ull << 30;
 constexpr uint64_t kPoolMin = 0;  // every arena goes through the cache: a small batch pays for each cudaMalloc / cudaFree too
 
+// Connectivity maps of one attributes decoder.  The arrays are BORROWED from the caller (dcb_set_mesh_maps: they must
+// stay valid until the decode / upload call that consumes them returns) -- 56 bytes per vertex that are only read once,
+// by the H2D copy; the library's own host helper (dcb_host_connectivity) parks its results in `own`.
 struct MeshMapsHost {
-  std::vector<uint32_t> opposite, corner_to_vertex, data_to_corner;
-  std::vector<int32_t> vertex_to_data;
+  const uint32_t *opposite = nullptr, *corner_to_vertex = nullptr, *data_to_corner = nullptr;
+  const int32_t *vertex_to_data = nullptr;
+  uint64_t n_corners = 0, n_entries = 0, n_vertices = 0;
+  std::shared_ptr<DcbHostMaps> own;
   bool set = false;
   uint64_t dev_off[4] = {0, 0, 0, 0};
+  uint64_t bytes() const { return 4ull * (2 * n_corners + n_entries + n_vertices); }
 };
 
 struct BufRec {
@@ -127,6 +135,7 @@ struct Shard {
   uint64_t direct_lo = 0, direct_hi = 0;
   int share = 1;        // shards of this batch living on the same physical device (pipeline slices)
   bool arena_pending = false;
+  bool maps_pending = false;  // mesh maps allocated on the device, not copied yet
   std::shared_ptr<DevPool> pool;  // the owning context's cache (outlives the context if batches are freed late)
   uint64_t cap_in = 0, cap_out = 0, cap_aux = 0, cap_maps = 0, cap_stage = 0, cap_streams = 0, cap_walks = 0, cap_order = 0;
   int device = 0;
@@ -164,12 +173,16 @@ struct dcb_ctx {
   // separate streams the copy engines would share the link and every slice would finish its copy at the same time
   std::vector<cudaStream_t> copy_in, copy_out;  // per ctx device entry; replicas share the handles
   std::vector<bool> own_copy;
-  std::vector<cudaEvent_t> in_ev, out_ev;
+  std::vector<cudaEvent_t> in_ev, out_ev, maps_ev;
   std::shared_ptr<DevPool> pool = std::make_shared<DevPool>();
   // DCB_DEBUG_TIMING: per-launch events of the last decode (name, begin, end), printed by finish_stats
   std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timeline;
   dcb_launch_stats stats{};
   uint32_t epoch = 0;  // tags the look-back words of par_post_kernel: no clearing between decodes
+  // plausibility limits of one buffer (dcb_set_limits): a forged point / entry count must fail its own buffer instead
+  // of sizing a 25 GB arena for the whole batch
+  uint64_t max_points = 0;                          // absolute cap per buffer, 0 = none
+  uint64_t points_per_byte = kDefaultPointsPerByte; // n_points <= 65536 + points_per_byte * buffer_len, 0 = unchecked
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_raw = false, ev_tag = false, ev_par = false, ev_para = false;
   uint64_t algo_raw = 0, algo_tag = 0, algo_par = 0;
@@ -182,6 +195,7 @@ struct dcb_batch {
   const uint8_t *host_arena = nullptr;  // dcb_index_arena: buffers live in one host arena
   uint64_t total_out = 0, total_dbg = 0, total_in = 0, total_points = 0, algo_bytes = 0;
   int n_devices = 1;
+  uint64_t max_points = 0, points_per_byte = 0;  // plausibility limits (dcb_set_limits), copied from the context
 };
 
 namespace {
@@ -298,8 +312,20 @@ void parse_header(BufRec &b) {
   }
 }
 
+// A point / entry count that the buffer's own size cannot plausibly back fails THIS buffer (DCB_ERR_ATTR) before it
+// sizes any arena.  The rule is deliberately loose -- a constant attribute legitimately costs ~0 bits per point -- and
+// caller-settable (dcb_set_limits).
+bool implausible(const dcb_batch &b, uint64_t n_points, uint64_t len) {
+  if (b.max_points && n_points > b.max_points) return true;
+  if (b.points_per_byte && n_points > 65536 + b.points_per_byte * len) return true;
+  return false;
+}
+void check_plausible(const dcb_batch &b, BufRec &r) {
+  if (r.info.status == DCB_OK && implausible(b, r.info.n_points, r.len)) r.info.status = DCB_ERR_ATTR;
+}
+
 // DEC_ID + DEC_DATA: creates the StreamDescs of one buffer (appended to sh.streams) and its BufWalk.
-void parse_attr_section(BufRec &b, Shard &sh, int buf_index) {
+void parse_attr_section(BufRec &b, Shard &sh, int buf_index, const dcb_batch *batch = nullptr) {
   dcb_buffer_info &inf = b.info;
   BufWalk w;
   memset(&w, 0, sizeof w);
@@ -371,16 +397,17 @@ void parse_attr_section(BufRec &b, Shard &sh, int buf_index) {
     bool has_maps = false;
     if (b.is_eb) {
       if ((size_t)d >= b.maps.size() || !b.maps[d].set) return finish(DCB_ERR_MAPS);
-      n_entries = (uint32_t)b.maps[d].data_to_corner.size();
+      n_entries = (uint32_t)b.maps[d].n_entries;
       has_maps = true;
+      if (batch && implausible(*batch, n_entries, b.len)) return finish(DCB_ERR_ATTR);
     }
     for (uint64_t i = 0; i < na; ++i) {
       StreamDesc &s = sh.streams[first + i];
       s.n_entries = n_entries;
       s.has_maps = has_maps ? 1 : 0;
       if (has_maps) {
-        s.n_corners = (uint32_t)b.maps[d].opposite.size();
-        s.n_vertices = (uint32_t)b.maps[d].vertex_to_data.size();
+        s.n_corners = (uint32_t)b.maps[d].n_corners;
+        s.n_vertices = (uint32_t)b.maps[d].n_vertices;
       }
       const uint64_t esz = (s.seq_type == SEQ_NORMALS) ? 12ull : (uint64_t)dcb_dtype_len(s.data_type) * s.nc;
       s.out_bytes = esz * n_entries;
@@ -503,12 +530,17 @@ void layout_shard(Shard &sh) {
     }
     for (int i = 0; i < w.stream_count; ++i) {
       StreamDesc &s = sh.streams[w.stream_first + i];
+      if (w.status) {  // a buffer that failed while indexing reserves no output, debug or scratch space
+        s.out_off = out;
+        s.dbg_off = dbg;
+        s.out_bytes = 0;
+        continue;
+      }
       s.out_off = out;
       out = align_up(out + s.out_bytes, 128);
       const uint64_t nv = (uint64_t)s.n_entries * (s.ncp ? s.ncp : s.nc);
       s.dbg_off = dbg;
       dbg = align_up(dbg + nv * 4, 16);
-      if (w.status) continue;
       if (s.seq_type != SEQ_GENERIC &&
           (s.scheme == SCHEME_TAGGED || s.scheme == SCHEME_UNCOMPRESSED || (any_unready && s.state < ST_READY))) {
         // tags u8[n] | bit offset per chunk u64[nch + 1] | look-back state words per chunk u64[nch][4]
@@ -533,8 +565,11 @@ void layout_shard(Shard &sh) {
 int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, const uint64_t *offs,
                const uint64_t *lens, int n_bufs, dcb_batch **out) {
   if (!out || n_bufs < 0 || (n_bufs > 0 && !lens) || (n_bufs > 0 && !arena && !ptrs)) return DCB_ERR_ARG;
-  dcb_batch *b = new (std::nothrow) dcb_batch();
+  std::unique_ptr<dcb_batch> owner(new (std::nothrow) dcb_batch());
+  dcb_batch *b = owner.get();
   if (!b) return DCB_ERR_OOM;
+  b->max_points = ctx ? ctx->max_points : 0;
+  b->points_per_byte = ctx ? ctx->points_per_byte : kDefaultPointsPerByte;
   b->n_devices = ctx ? (int)ctx->devices.size() : 1;
   b->host_arena = arena;
   b->bufs.resize((size_t)n_bufs);
@@ -546,7 +581,7 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
     r.src = arena ? arena + offs[k] : ptrs[k];
     r.len = lens[k];
     if (arena && (offs[k] & 15)) aligned = false;
-    if (!r.src && r.len) { delete b; return DCB_ERR_ARG; }
+    if (!r.src && r.len) return DCB_ERR_ARG;
   }
   // shard by buffer; no collective.  Distinct devices: longest-processing-time-first on compressed bytes.
   // The same device listed K times (dcb_create): K pipeline slices -- contiguous runs of buffers with equal bytes, so
@@ -614,12 +649,18 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
   for (Shard &sh : b->shards) sh.walks.resize(sh.bufs.size());
   // header + attribute indexing: a shard's buffers in order (the shard's stream list is append-only), shards in
   // parallel when there are several -- nothing is shared between them
+  std::atomic<bool> index_oom{false};
   auto index_shard = [&](Shard &sh) {
-    for (int k : sh.bufs) {
-      BufRec &r = b->bufs[k];
-      parse_header(r);
-      r.info.device = r.shard;
-      parse_attr_section(r, sh, k);
+    try {
+      for (int k : sh.bufs) {
+        BufRec &r = b->bufs[k];
+        parse_header(r);
+        r.info.device = r.shard;
+        check_plausible(*b, r);
+        parse_attr_section(r, sh, k, b);
+      }
+    } catch (...) {  // std::bad_alloc inside a worker thread must not reach std::terminate
+      index_oom = true;
     }
   };
   if (b->n_devices > 1 && n_bufs >= 16) {
@@ -629,7 +670,8 @@ int make_batch(dcb_ctx *ctx, const uint8_t *arena, const uint8_t *const *ptrs, c
   } else {
     for (Shard &sh : b->shards) index_shard(sh);
   }
-  *out = b;
+  if (index_oom) return DCB_ERR_OOM;
+  *out = owner.release();
   return DCB_OK;
 }
 
@@ -659,7 +701,7 @@ void finalize_layout(dcb_batch *b) {
       const BufWalk &w = sh.walks[r.local];
       for (int i = 0; i < w.stream_count; ++i) b->algo_bytes += sh.streams[w.stream_first + i].out_bytes;
       for (const MeshMapsHost &m : r.maps)
-        if (m.set) b->algo_bytes += 4ull * (m.opposite.size() + m.corner_to_vertex.size() + m.data_to_corner.size() + m.vertex_to_data.size());
+        if (m.set) b->algo_bytes += m.bytes();
     }
   }
 }
@@ -877,6 +919,31 @@ int issue_arena_copy(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   return DCB_OK;
 }
 
+// Mesh connectivity maps (56 bytes per vertex, read by para_deps_kernel only): on the device's upload stream, issued
+// BEHIND the first rANS launch of the decode so that the copy hides behind the symbol chains; `st` then waits for it.
+// From pageable memory cudaMemcpyAsync stages through the driver and holds the calling thread, not the GPU.
+int issue_maps_copy(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
+  if (!sh.maps_pending) return DCB_OK;
+  sh.maps_pending = false;
+  cudaStream_t st = ctx->streams[dev_index], cs = ctx->copy_in[dev_index];
+  CUDA_TRY(cudaSetDevice(sh.device));
+  tl_mark(ctx, "h2d maps s" + std::to_string(dev_index), cs, true);
+  for (int k : sh.bufs)
+    for (const MeshMapsHost &m : b->bufs[k].maps)
+      if (m.set) {
+        if (m.n_corners) {
+          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[0], m.opposite, m.n_corners * 4, cudaMemcpyHostToDevice, cs));
+          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[1], m.corner_to_vertex, m.n_corners * 4, cudaMemcpyHostToDevice, cs));
+        }
+        if (m.n_entries) CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[2], m.data_to_corner, m.n_entries * 4, cudaMemcpyHostToDevice, cs));
+        if (m.n_vertices) CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[3], m.vertex_to_data, m.n_vertices * 4, cudaMemcpyHostToDevice, cs));
+      }
+  tl_mark(ctx, "", cs, false);
+  CUDA_TRY(cudaEventRecord(ctx->maps_ev[dev_index], cs));
+  CUDA_TRY(cudaStreamWaitEvent(st, ctx->maps_ev[dev_index], 0));
+  return DCB_OK;
+}
+
 int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   if (sh.uploaded) return DCB_OK;
   cudaStream_t st = ctx->streams[dev_index];
@@ -896,12 +963,12 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
     CUDA_TRY(cudaMemcpyAsync(sh.d_in + kFrontPad, sh.h_stage + kFrontPad, sh.in_bytes - kFrontPad - kBackPad,
                              cudaMemcpyHostToDevice, st));
   }
-  // mesh maps
+  // mesh maps: laid out and allocated here, copied by issue_maps_copy (behind the first rANS launch of the decode)
   uint64_t mbytes = 0;
   for (int k : sh.bufs)
     for (MeshMapsHost &m : b->bufs[k].maps)
       if (m.set) {
-        const uint64_t sz[4] = {m.opposite.size(), m.corner_to_vertex.size(), m.data_to_corner.size(), m.vertex_to_data.size()};
+        const uint64_t sz[4] = {m.n_corners, m.n_corners, m.n_entries, m.n_vertices};
         for (int j = 0; j < 4; ++j) {
           m.dev_off[j] = mbytes;
           mbytes = align_up(mbytes + sz[j] * 4, 16);
@@ -910,14 +977,7 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   sh.maps_bytes = mbytes;
   if (mbytes) {
     CUDA_TRY(pool_alloc(sh.pool, sh.device, mbytes, &sh.d_maps, &sh.cap_maps));
-    for (int k : sh.bufs)
-      for (MeshMapsHost &m : b->bufs[k].maps)
-        if (m.set) {
-          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[0], m.opposite.data(), m.opposite.size() * 4, cudaMemcpyHostToDevice, st));
-          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[1], m.corner_to_vertex.data(), m.corner_to_vertex.size() * 4, cudaMemcpyHostToDevice, st));
-          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[2], m.data_to_corner.data(), m.data_to_corner.size() * 4, cudaMemcpyHostToDevice, st));
-          CUDA_TRY(cudaMemcpyAsync(sh.d_maps + m.dev_off[3], m.vertex_to_data.data(), m.vertex_to_data.size() * 4, cudaMemcpyHostToDevice, st));
-        }
+    sh.maps_pending = true;
     for (int k : sh.bufs) {
       const BufRec &r = b->bufs[k];
       const BufWalk &w = sh.walks0[r.local];
@@ -1034,6 +1094,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     if (time_tag) {
       CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
       ctx->ev_tag = true;
+    }
+    {  // the maps travel while the tag chains run
+      int rcm = issue_maps_copy(ctx, b, sh, dev_index);
+      if (rcm) return rcm;
     }
     CUDA_TRY(dcb_launch_resolve(A, sh.d_walks, sh.d_order + g.order.size(), (uint32_t)blocked.size(), sh.d_streams, st));
     stats.n_launches += 2;
@@ -1251,6 +1315,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     stats.n_streams += (int32_t)n;
   }
+  {  // mesh maps: behind the rANS launches (their chains hide the copy), in front of the parallelogram kernels
+    int rcm = issue_maps_copy(ctx, b, sh, dev_index);
+    if (rcm) return rcm;
+  }
   for (int k = 0; k < 3; ++k)
     if (side_used[k]) {
       CUDA_TRY(cudaEventRecord(ctx->join_ev[dev_index][k], ctx->side[dev_index][k]));
@@ -1313,7 +1381,6 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     CUDA_TRY(cudaStreamSynchronize(st));
     sh.dirty = true;
   }
-  (void)b;
   return DCB_OK;
 }
 
@@ -1367,8 +1434,27 @@ int download_shard(dcb_ctx *ctx, dcb_batch *b, int d, uint8_t *host_out, uint8_t
   return DCB_OK;
 }
 
+int sync_all(dcb_ctx *ctx);
+int decode_all_impl(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags, uint8_t *host_out, uint8_t *host_dbg);
+
+// An error in the middle of a batch must not leave kernels or copies of the shards launched so far in flight: the
+// caller frees the batch next, and its arenas go back to the context's cache.
 int decode_all(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags, uint8_t *host_out = nullptr,
                uint8_t *host_dbg = nullptr) {
+  const int rc = decode_all_impl(ctx, b, dev_out, dev_dbg, flags, host_out, host_dbg);
+  if (rc != DCB_OK && ctx) {
+    (void)sync_all(ctx);
+    for (size_t d = 0; d < ctx->devices.size(); ++d) {  // side and copy streams too
+      cudaSetDevice(ctx->devices[d]);
+      cudaDeviceSynchronize();
+    }
+    cudaGetLastError();
+  }
+  return rc;
+}
+
+int decode_all_impl(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags, uint8_t *host_out,
+                    uint8_t *host_dbg) {
   if (!ctx || !b) return DCB_ERR_ARG;
   if ((int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
   if ((dev_out || dev_dbg) && b->n_devices != 1) return DCB_ERR_ARG;
@@ -1475,6 +1561,18 @@ void finish_stats(dcb_ctx *ctx) {
 
 }  // namespace
 
+// No C++ exception crosses the C ABI: every entry point that can allocate runs inside this barrier.
+template <typename F>
+static int guarded(F &&f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc &) {
+    return DCB_ERR_OOM;
+  } catch (...) {
+    return DCB_ERR_STATE;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -1524,77 +1622,81 @@ const char *dcb_error_string(int code) {
 }
 
 int dcb_create(const int *device_ids, int n_devices, dcb_ctx **out) {
-  if (!out || n_devices < 0) return DCB_ERR_ARG;
-  *out = nullptr;
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
-    cudaGetLastError();
-    return DCB_ERR_NO_DEVICE;
-  }
-  dcb_ctx *c = new (std::nothrow) dcb_ctx();
-  if (!c) return DCB_ERR_OOM;
-  if (!device_ids || n_devices == 0) {
-    int cur = 0;
-    if (cudaGetDevice(&cur) != cudaSuccess) { delete c; return DCB_ERR_NO_DEVICE; }
-    c->devices.push_back(cur);
-  } else {
-    for (int i = 0; i < n_devices; ++i) c->devices.push_back(device_ids[i]);
-  }
-  for (int dev : c->devices) {
-    cudaDeviceProp p;
-    if (dev < 0 || dev >= count || cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.major != 10) {
+  return guarded([&]() -> int {
+    if (!out || n_devices < 0) return DCB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
       cudaGetLastError();
-      dcb_destroy(c);
-      return DCB_ERR_NO_DEVICE;  // kernels are sm_100a only: no fallback
+      return DCB_ERR_NO_DEVICE;
     }
-    cudaStream_t st = nullptr;
-    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
-      cudaGetLastError();
-      dcb_destroy(c);
-      return DCB_ERR_CUDA;
+    dcb_ctx *c = new (std::nothrow) dcb_ctx();
+    if (!c) return DCB_ERR_OOM;
+    if (!device_ids || n_devices == 0) {
+      int cur = 0;
+      if (cudaGetDevice(&cur) != cudaSuccess) { delete c; return DCB_ERR_NO_DEVICE; }
+      c->devices.push_back(cur);
+    } else {
+      for (int i = 0; i < n_devices; ++i) c->devices.push_back(device_ids[i]);
     }
-    c->streams.push_back(st);
-    c->own_stream.push_back(true);
-    std::vector<cudaStream_t> side(3, nullptr);
-    std::vector<cudaEvent_t> jev(3, nullptr);
-    cudaEvent_t fev = nullptr;
-    // side[0] outranks the others: it carries the group whose chain goes on after its rANS kernel (normals:
-    // oct_chain, oct_unit), the longest dependent sequence of a batch
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    for (int k = 0; k < 3; ++k) {
-      if (k == 0) cudaStreamCreateWithPriority(&side[k], cudaStreamNonBlocking, prio_hi);
-      else cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking);
-      cudaEventCreateWithFlags(&jev[k], cudaEventDisableTiming);
-    }
-    cudaEventCreateWithFlags(&fev, cudaEventDisableTiming);
-    c->side.push_back(side);
-    c->join_ev.push_back(jev);
-    c->fork_ev.push_back(fev);
-    {
-      cudaStream_t ci = nullptr, co = nullptr;
-      bool own = true;
-      for (size_t e = 0; e + 1 < c->streams.size(); ++e)
-        if (c->devices[e] == dev) { ci = c->copy_in[e]; co = c->copy_out[e]; own = false; break; }
-      if (own) {
-        cudaStreamCreateWithFlags(&ci, cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&co, cudaStreamNonBlocking);
+    for (int dev : c->devices) {
+      cudaDeviceProp p;
+      if (dev < 0 || dev >= count || cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.major != 10) {
+        cudaGetLastError();
+        dcb_destroy(c);
+        return DCB_ERR_NO_DEVICE;  // kernels are sm_100a only: no fallback
       }
-      c->copy_in.push_back(ci);
-      c->copy_out.push_back(co);
-      c->own_copy.push_back(own);
-      cudaEvent_t ie = nullptr, oe = nullptr;
-      cudaEventCreateWithFlags(&ie, cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&oe, cudaEventDisableTiming);
-      c->in_ev.push_back(ie);
-      c->out_ev.push_back(oe);
+      cudaStream_t st = nullptr;
+      if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        dcb_destroy(c);
+        return DCB_ERR_CUDA;
+      }
+      c->streams.push_back(st);
+      c->own_stream.push_back(true);
+      std::vector<cudaStream_t> side(3, nullptr);
+      std::vector<cudaEvent_t> jev(3, nullptr);
+      cudaEvent_t fev = nullptr;
+      // side[0] outranks the others: it carries the group whose chain goes on after its rANS kernel (normals:
+      // oct_chain, oct_unit), the longest dependent sequence of a batch
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      for (int k = 0; k < 3; ++k) {
+        if (k == 0) cudaStreamCreateWithPriority(&side[k], cudaStreamNonBlocking, prio_hi);
+        else cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&jev[k], cudaEventDisableTiming);
+      }
+      cudaEventCreateWithFlags(&fev, cudaEventDisableTiming);
+      c->side.push_back(side);
+      c->join_ev.push_back(jev);
+      c->fork_ev.push_back(fev);
+      {
+        cudaStream_t ci = nullptr, co = nullptr;
+        bool own = true;
+        for (size_t e = 0; e + 1 < c->streams.size(); ++e)
+          if (c->devices[e] == dev) { ci = c->copy_in[e]; co = c->copy_out[e]; own = false; break; }
+        if (own) {
+          cudaStreamCreateWithFlags(&ci, cudaStreamNonBlocking);
+          cudaStreamCreateWithFlags(&co, cudaStreamNonBlocking);
+        }
+        c->copy_in.push_back(ci);
+        c->copy_out.push_back(co);
+        c->own_copy.push_back(own);
+        cudaEvent_t ie = nullptr, oe = nullptr, me = nullptr;
+        cudaEventCreateWithFlags(&ie, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&oe, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&me, cudaEventDisableTiming);
+        c->in_ev.push_back(ie);
+        c->out_ev.push_back(oe);
+        c->maps_ev.push_back(me);
+      }
+      c->num_sms.push_back(p.multiProcessorCount > 0 ? p.multiProcessorCount : (int)kNumSMsDefault);
     }
-    c->num_sms.push_back(p.multiProcessorCount > 0 ? p.multiProcessorCount : (int)kNumSMsDefault);
-  }
-  cudaSetDevice(c->devices[0]);
-  for (auto &e : c->ev) cudaEventCreate(&e);
-  *out = c;
-  return DCB_OK;
+    cudaSetDevice(c->devices[0]);
+    for (auto &e : c->ev) cudaEventCreate(&e);
+    *out = c;
+    return DCB_OK;
+  });
 }
 
 void dcb_destroy(dcb_ctx *ctx) {
@@ -1619,71 +1721,89 @@ void dcb_destroy(dcb_ctx *ctx) {
     }
     if (i < ctx->in_ev.size() && ctx->in_ev[i]) cudaEventDestroy(ctx->in_ev[i]);
     if (i < ctx->out_ev.size() && ctx->out_ev[i]) cudaEventDestroy(ctx->out_ev[i]);
+    if (i < ctx->maps_ev.size() && ctx->maps_ev[i]) cudaEventDestroy(ctx->maps_ev[i]);
   }
   delete ctx;
 }
 
 int dcb_set_stream(dcb_ctx *ctx, int dev_index, void *cuda_stream) {
-  if (!ctx || dev_index < 0 || dev_index >= (int)ctx->streams.size()) return DCB_ERR_ARG;
-  if (ctx->own_stream[dev_index]) {
-    cudaSetDevice(ctx->devices[dev_index]);
-    cudaStreamDestroy(ctx->streams[dev_index]);
-  }
-  ctx->streams[dev_index] = (cudaStream_t)cuda_stream;
-  ctx->own_stream[dev_index] = false;
+  return guarded([&]() -> int {
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->streams.size()) return DCB_ERR_ARG;
+    if (ctx->own_stream[dev_index]) {
+      cudaSetDevice(ctx->devices[dev_index]);
+      cudaStreamDestroy(ctx->streams[dev_index]);
+    }
+    ctx->streams[dev_index] = (cudaStream_t)cuda_stream;
+    ctx->own_stream[dev_index] = false;
+    return DCB_OK;
+  });
+}
+
+int dcb_set_limits(dcb_ctx *ctx, uint64_t max_points_per_buffer, uint64_t points_per_byte) {
+  if (!ctx) return DCB_ERR_ARG;
+  ctx->max_points = max_points_per_buffer;
+  ctx->points_per_byte = points_per_byte;
   return DCB_OK;
 }
 
 int dcb_index(dcb_ctx *ctx, const uint8_t *const *bufs, const uint64_t *lens, int n_bufs, dcb_batch **out) {
-  int rc = make_batch(ctx, nullptr, bufs, nullptr, lens, n_bufs, out);
-  if (rc == DCB_OK) finalize_layout(*out);
-  return rc;
+  return guarded([&]() -> int {
+    int rc = make_batch(ctx, nullptr, bufs, nullptr, lens, n_bufs, out);
+    if (rc == DCB_OK) finalize_layout(*out);
+    return rc;
+  });
 }
 
 int dcb_index_arena(dcb_ctx *ctx, const uint8_t *arena, const uint64_t *offs, const uint64_t *lens, int n_bufs,
                     dcb_batch **out) {
-  if (!arena || !offs) return DCB_ERR_ARG;
-  int rc = make_batch(ctx, arena, nullptr, offs, lens, n_bufs, out);
-  if (rc == DCB_OK) finalize_layout(*out);
-  return rc;
+  return guarded([&]() -> int {
+    if (!arena || !offs) return DCB_ERR_ARG;
+    int rc = make_batch(ctx, arena, nullptr, offs, lens, n_bufs, out);
+    if (rc == DCB_OK) finalize_layout(*out);
+    return rc;
+  });
 }
 
 int dcb_get_buffer_info(const dcb_batch *b, int buf, dcb_buffer_info *out) {
-  if (!b || !out || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
-  *out = b->bufs[buf].info;
-  return DCB_OK;
+  return guarded([&]() -> int {
+    if (!b || !out || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+    *out = b->bufs[buf].info;
+    return DCB_OK;
+  });
 }
 
 int dcb_get_attr_info(const dcb_batch *b, int buf, int attr, dcb_attr_info *out) {
-  if (!b || !out || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
-  const BufRec &r = b->bufs[buf];
-  const Shard &sh = b->shards[r.shard];
-  const BufWalk &w = sh.walks[r.local];
-  if (attr < 0 || attr >= w.stream_count) return DCB_ERR_ARG;
-  const StreamDesc &s = sh.streams[w.stream_first + attr];
-  memset(out, 0, sizeof *out);
-  out->att_type = s.att_type;
-  out->data_type = s.data_type;
-  out->num_components = s.nc;
-  out->normalized = s.normalized;
-  out->unique_id = s.unique_id;
-  out->seq_decoder_type = s.seq_type;
-  out->decoder_id = s.decoder_id;
-  out->pred_method = s.pred_method;
-  out->transform = s.transform;
-  out->scheme = (s.scheme == SCHEME_TAGGED || s.scheme == SCHEME_RAW) ? (int32_t)s.scheme : -1;
-  out->precision_bits = s.prec_bits;
-  out->n_entries = s.n_entries;
-  out->out_bytes = s.out_bytes;
-  out->out_off = sh.out_base + s.out_off;
-  out->dbg_off = sh.dbg_base + s.dbg_off;
-  out->xf_a = s.xf_a;
-  out->xf_b = s.xf_b;
-  for (int c = 0; c < 4; ++c) out->q_min[c] = s.q_min[c];
-  out->q_range = s.q_range;
-  out->q_bits = s.q_bits;
-  out->resolved = s.state == ST_READY;
-  return DCB_OK;
+  return guarded([&]() -> int {
+    if (!b || !out || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+    const BufRec &r = b->bufs[buf];
+    const Shard &sh = b->shards[r.shard];
+    const BufWalk &w = sh.walks[r.local];
+    if (attr < 0 || attr >= w.stream_count) return DCB_ERR_ARG;
+    const StreamDesc &s = sh.streams[w.stream_first + attr];
+    memset(out, 0, sizeof *out);
+    out->att_type = s.att_type;
+    out->data_type = s.data_type;
+    out->num_components = s.nc;
+    out->normalized = s.normalized;
+    out->unique_id = s.unique_id;
+    out->seq_decoder_type = s.seq_type;
+    out->decoder_id = s.decoder_id;
+    out->pred_method = s.pred_method;
+    out->transform = s.transform;
+    out->scheme = (s.scheme == SCHEME_TAGGED || s.scheme == SCHEME_RAW) ? (int32_t)s.scheme : -1;
+    out->precision_bits = s.prec_bits;
+    out->n_entries = s.n_entries;
+    out->out_bytes = s.out_bytes;
+    out->out_off = sh.out_base + s.out_off;
+    out->dbg_off = sh.dbg_base + s.dbg_off;
+    out->xf_a = s.xf_a;
+    out->xf_b = s.xf_b;
+    for (int c = 0; c < 4; ++c) out->q_min[c] = s.q_min[c];
+    out->q_range = s.q_range;
+    out->q_bits = s.q_bits;
+    out->resolved = s.state == ST_READY;
+    return DCB_OK;
+  });
 }
 
 uint64_t dcb_batch_out_bytes(const dcb_batch *b) { return b ? b->total_out : 0; }
@@ -1693,184 +1813,229 @@ uint64_t dcb_batch_points(const dcb_batch *b) { return b ? b->total_points : 0; 
 uint64_t dcb_batch_algo_bytes(const dcb_batch *b) { return b ? b->algo_bytes : 0; }
 
 int dcb_set_attr_section(dcb_batch *b, int buf, uint64_t attr_section_off, uint32_t n_points) {
-  if (!b || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
-  BufRec &r = b->bufs[buf];
-  if (!r.info.needs_connectivity) return DCB_ERR_STATE;
-  if (attr_section_off > r.len) return DCB_ERR_ARG;
-  r.info.attr_section_off = attr_section_off;
-  r.info.n_points = n_points;
-  return DCB_OK;
+  return guarded([&]() -> int {
+    if (!b || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+    BufRec &r = b->bufs[buf];
+    if (!r.info.needs_connectivity) return DCB_ERR_STATE;
+    if (attr_section_off > r.len) return DCB_ERR_ARG;
+    r.info.attr_section_off = attr_section_off;
+    r.info.n_points = n_points;
+    return DCB_OK;
+  });
 }
 
 int dcb_set_mesh_maps(dcb_batch *b, int buf, int attr_decoder, const uint32_t *opposite,
                       const uint32_t *corner_to_vertex, uint64_t n_corners, const uint32_t *data_to_corner,
                       uint64_t n_entries, const int32_t *vertex_to_data, uint64_t n_vertices) {
-  if (!b || buf < 0 || buf >= (int)b->bufs.size() || attr_decoder < 0 || attr_decoder > 255) return DCB_ERR_ARG;
-  if ((n_corners && (!opposite || !corner_to_vertex)) || (n_entries && !data_to_corner) || (n_vertices && !vertex_to_data))
-    return DCB_ERR_ARG;
-  if (n_corners > 0xFFFFFFFFull || n_entries > 0xFFFFFFFFull || n_vertices > 0xFFFFFFFFull) return DCB_ERR_ARG;
-  BufRec &r = b->bufs[buf];
-  if (!r.info.needs_connectivity) return DCB_ERR_STATE;
-  if (r.maps.size() <= (size_t)attr_decoder) r.maps.resize((size_t)attr_decoder + 1);
-  MeshMapsHost &m = r.maps[attr_decoder];
-  m.opposite.assign(opposite, opposite + n_corners);
-  m.corner_to_vertex.assign(corner_to_vertex, corner_to_vertex + n_corners);
-  m.data_to_corner.assign(data_to_corner, data_to_corner + n_entries);
-  m.vertex_to_data.assign(vertex_to_data, vertex_to_data + n_vertices);
-  m.set = true;
-  return DCB_OK;
+  return guarded([&]() -> int {
+    if (!b || buf < 0 || buf >= (int)b->bufs.size() || attr_decoder < 0 || attr_decoder > 255) return DCB_ERR_ARG;
+    if ((n_corners && (!opposite || !corner_to_vertex)) || (n_entries && !data_to_corner) || (n_vertices && !vertex_to_data))
+      return DCB_ERR_ARG;
+    if (n_corners > 0xFFFFFFFFull || n_entries > 0xFFFFFFFFull || n_vertices > 0xFFFFFFFFull) return DCB_ERR_ARG;
+    BufRec &r = b->bufs[buf];
+    if (!r.info.needs_connectivity) return DCB_ERR_STATE;
+    if (n_corners % 3 != 0) return DCB_ERR_ARG;  // corners come in triangles (CornerTable.Next / Previous)
+    if (r.maps.size() <= (size_t)attr_decoder) r.maps.resize((size_t)attr_decoder + 1);
+    MeshMapsHost &m = r.maps[attr_decoder];
+    m.own.reset();
+    m.opposite = opposite;
+    m.corner_to_vertex = corner_to_vertex;
+    m.data_to_corner = data_to_corner;
+    m.vertex_to_data = vertex_to_data;
+    m.n_corners = n_corners;
+    m.n_entries = n_entries;
+    m.n_vertices = n_vertices;
+    m.set = true;
+    return DCB_OK;
+  });
 }
 
 int dcb_host_connectivity(dcb_batch *b, int buf) {
-  if (!b || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
-  BufRec &r = b->bufs[buf];
-  if (!r.info.needs_connectivity) return DCB_ERR_STATE;
-  if (r.info.status != DCB_OK) return DCB_OK;
-  if (!r.is_eb) {  // sequential mesh connectivity (MeshSequentialDecoder.cs:8-118): SURVEY 8f-4, not built yet
-    r.info.status = DCB_ERR_UNSUPPORTED;
+  return guarded([&]() -> int {
+    if (!b || buf < 0 || buf >= (int)b->bufs.size()) return DCB_ERR_ARG;
+    BufRec &r = b->bufs[buf];
+    if (!r.info.needs_connectivity) return DCB_ERR_STATE;
+    if (r.info.status != DCB_OK) return DCB_OK;
+    if (!r.is_eb) {  // sequential mesh connectivity (MeshSequentialDecoder.cs:8-118): SURVEY 8f-4, not built yet
+      r.info.status = DCB_ERR_UNSUPPORTED;
+      return DCB_OK;
+    }
+    std::vector<DcbHostMaps> maps;
+    uint64_t attr_off = 0;
+    uint32_t n_points = 0;
+    int st;
+    try {
+      st = dcb_host_edgebreaker(r.src, r.len, r.conn_off, &attr_off, &n_points, &maps, &r.faces);
+    } catch (const std::bad_alloc &) {  // counts the data cannot back: this buffer only
+      st = DCB_ERR_OOM;
+    } catch (...) {
+      st = DCB_ERR_CONNECTIVITY;
+    }
+    if (st != DCB_OK) {  // the buffer fails alone, like an exception in the reference's DecodeConnectivity
+      r.info.status = st;
+      return DCB_OK;
+    }
+    r.info.attr_section_off = attr_off;
+    r.info.n_points = n_points;
+    r.maps.assign(maps.size(), MeshMapsHost{});
+    for (size_t d = 0; d < maps.size(); ++d) {
+      MeshMapsHost &m = r.maps[d];
+      m.own = std::make_shared<DcbHostMaps>();
+      m.own->opposite.swap(maps[d].opposite);
+      m.own->corner_to_vertex.swap(maps[d].corner_to_vertex);
+      m.own->data_to_corner.swap(maps[d].data_to_corner);
+      m.own->vertex_to_data.swap(maps[d].vertex_to_data);
+      m.opposite = m.own->opposite.data();
+      m.corner_to_vertex = m.own->corner_to_vertex.data();
+      m.data_to_corner = m.own->data_to_corner.data();
+      m.vertex_to_data = m.own->vertex_to_data.data();
+      m.n_corners = m.own->opposite.size();
+      m.n_entries = m.own->data_to_corner.size();
+      m.n_vertices = m.own->vertex_to_data.size();
+      m.set = true;
+    }
     return DCB_OK;
-  }
-  std::vector<DcbHostMaps> maps;
-  uint64_t attr_off = 0;
-  uint32_t n_points = 0;
-  const int st = dcb_host_edgebreaker(r.src, r.len, r.conn_off, &attr_off, &n_points, &maps, &r.faces);
-  if (st != DCB_OK) {  // the buffer fails alone, like an exception in the reference's DecodeConnectivity
-    r.info.status = st;
-    return DCB_OK;
-  }
-  r.info.attr_section_off = attr_off;
-  r.info.n_points = n_points;
-  r.maps.assign(maps.size(), MeshMapsHost{});
-  for (size_t d = 0; d < maps.size(); ++d) {
-    r.maps[d].opposite.swap(maps[d].opposite);
-    r.maps[d].corner_to_vertex.swap(maps[d].corner_to_vertex);
-    r.maps[d].data_to_corner.swap(maps[d].data_to_corner);
-    r.maps[d].vertex_to_data.swap(maps[d].vertex_to_data);
-    r.maps[d].set = true;
-  }
-  return DCB_OK;
+  });
 }
 
 int dcb_mesh_faces(const dcb_batch *b, int buf, uint32_t *faces, uint64_t cap_faces, uint64_t *n_faces) {
-  if (!b || buf < 0 || buf >= (int)b->bufs.size() || !n_faces) return DCB_ERR_ARG;
-  const BufRec &r = b->bufs[buf];
-  *n_faces = r.faces.size() / 3;
-  if (faces) {
-    if (cap_faces < *n_faces) return DCB_ERR_ARG;
-    memcpy(faces, r.faces.data(), r.faces.size() * 4);
-  }
-  return DCB_OK;
+  return guarded([&]() -> int {
+    if (!b || buf < 0 || buf >= (int)b->bufs.size() || !n_faces) return DCB_ERR_ARG;
+    const BufRec &r = b->bufs[buf];
+    *n_faces = r.faces.size() / 3;
+    if (faces) {
+      if (cap_faces < *n_faces) return DCB_ERR_ARG;
+      memcpy(faces, r.faces.data(), r.faces.size() * 4);
+    }
+    return DCB_OK;
+  });
 }
 
 int dcb_mesh_map(const dcb_batch *b, int buf, int attr_decoder, int which, uint32_t *dst, uint64_t cap, uint64_t *n) {
-  if (!b || buf < 0 || buf >= (int)b->bufs.size() || !n || which < 0 || which > 3) return DCB_ERR_ARG;
-  const BufRec &r = b->bufs[buf];
-  if (attr_decoder < 0 || attr_decoder >= (int)r.maps.size() || !r.maps[attr_decoder].set) return DCB_ERR_STATE;
-  const MeshMapsHost &m = r.maps[attr_decoder];
-  const void *src = which == 0 ? (const void *)m.opposite.data() : which == 1 ? (const void *)m.corner_to_vertex.data()
-                  : which == 2 ? (const void *)m.data_to_corner.data() : (const void *)m.vertex_to_data.data();
-  *n = which == 0 ? m.opposite.size() : which == 1 ? m.corner_to_vertex.size()
-     : which == 2 ? m.data_to_corner.size() : m.vertex_to_data.size();
-  if (dst) {
-    if (cap < *n) return DCB_ERR_ARG;
-    memcpy(dst, src, *n * 4);
-  }
-  return DCB_OK;
+  return guarded([&]() -> int {
+    if (!b || buf < 0 || buf >= (int)b->bufs.size() || !n || which < 0 || which > 3) return DCB_ERR_ARG;
+    const BufRec &r = b->bufs[buf];
+    if (attr_decoder < 0 || attr_decoder >= (int)r.maps.size() || !r.maps[attr_decoder].set) return DCB_ERR_STATE;
+    const MeshMapsHost &m = r.maps[attr_decoder];
+    const void *src = which == 0 ? (const void *)m.opposite : which == 1 ? (const void *)m.corner_to_vertex
+                    : which == 2 ? (const void *)m.data_to_corner : (const void *)m.vertex_to_data;
+    *n = which == 0 ? m.n_corners : which == 1 ? m.n_corners : which == 2 ? m.n_entries : m.n_vertices;
+    if (dst) {
+      if (cap < *n) return DCB_ERR_ARG;
+      memcpy(dst, src, *n * 4);
+    }
+    return DCB_OK;
+  });
 }
 
 int dcb_index_finish(dcb_ctx *ctx, dcb_batch *b) {
-  (void)ctx;
-  if (!b) return DCB_ERR_ARG;
-  for (Shard &sh : b->shards)
-    if (sh.uploaded) return DCB_ERR_STATE;
-  // rebuild every shard's stream list with the connectivity-dependent buffers included
-  for (Shard &sh : b->shards) {
-    sh.streams.clear();
-    std::fill(sh.walks.begin(), sh.walks.end(), BufWalk{});
-  }
-  for (size_t k = 0; k < b->bufs.size(); ++k) {
-    BufRec &r = b->bufs[k];
-    if (r.info.needs_connectivity && r.info.status == DCB_OK) {
-      if (r.info.attr_section_off == 0) r.info.status = DCB_ERR_CONNECTIVITY;
-      r.info.needs_connectivity = 0;
+  return guarded([&]() -> int {
+    (void)ctx;
+    if (!b) return DCB_ERR_ARG;
+    for (Shard &sh : b->shards)
+      if (sh.uploaded) return DCB_ERR_STATE;
+    // rebuild every shard's stream list with the connectivity-dependent buffers included
+    for (Shard &sh : b->shards) {
+      sh.streams.clear();
+      std::fill(sh.walks.begin(), sh.walks.end(), BufWalk{});
     }
-    parse_attr_section(r, b->shards[r.shard], (int)k);
-  }
-  finalize_layout(b);
-  return DCB_OK;
+    for (size_t k = 0; k < b->bufs.size(); ++k) {
+      BufRec &r = b->bufs[k];
+      if (r.info.needs_connectivity && r.info.status == DCB_OK) {
+        if (r.info.attr_section_off == 0) r.info.status = DCB_ERR_CONNECTIVITY;
+        r.info.needs_connectivity = 0;
+      }
+      check_plausible(*b, r);
+    parse_attr_section(r, b->shards[r.shard], (int)k, b);
+    }
+    finalize_layout(b);
+    return DCB_OK;
+  });
 }
 
 int dcb_upload(dcb_ctx *ctx, dcb_batch *b) {
-  if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
-  for (const BufRec &r : b->bufs)
-    if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;
-  for (int d = 0; d < b->n_devices; ++d) {
-    int rc = upload_shard(ctx, b, b->shards[d], d);
-    if (rc) return rc;
-    rc = issue_arena_copy(ctx, b, b->shards[d], d);
-    if (rc) return rc;
-  }
-  return sync_all(ctx);
+  return guarded([&]() -> int {
+    if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
+    for (const BufRec &r : b->bufs)
+      if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;
+    for (int d = 0; d < b->n_devices; ++d) {
+      int rc = upload_shard(ctx, b, b->shards[d], d);
+      if (rc) return rc;
+      rc = issue_arena_copy(ctx, b, b->shards[d], d);
+      if (rc) return rc;
+      rc = issue_maps_copy(ctx, b, b->shards[d], d);
+      if (rc) return rc;
+    }
+    return sync_all(ctx);
+  });
 }
 
 int dcb_decode_resident(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, uint32_t flags) {
-  int rc = decode_all(ctx, b, dev_out, dev_dbg, flags);
-  if (rc) return rc;
-  rc = sync_all(ctx);
-  if (rc) return rc;
-  finish_stats(ctx);
-  collect_status(b);
-  return DCB_OK;
+  return guarded([&]() -> int {
+    int rc = decode_all(ctx, b, dev_out, dev_dbg, flags);
+    if (rc) return rc;
+    rc = sync_all(ctx);
+    if (rc) return rc;
+    finish_stats(ctx);
+    collect_status(b);
+    return DCB_OK;
+  });
 }
 
 int dcb_download(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg) {
-  if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
-  for (int d = 0; d < b->n_devices; ++d) {
-    int rc = download_shard(ctx, b, d, host_out, host_dbg);
-    if (rc) return rc;
-  }
-  return sync_all(ctx);
+  return guarded([&]() -> int {
+    if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
+    for (int d = 0; d < b->n_devices; ++d) {
+      int rc = download_shard(ctx, b, d, host_out, host_dbg);
+      if (rc) return rc;
+    }
+    return sync_all(ctx);
+  });
 }
 
 int dcb_decode(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg, uint32_t flags) {
-  if (!host_out && b && b->total_out) return DCB_ERR_ARG;
-  if ((flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS)) && !host_dbg) return DCB_ERR_ARG;
-  const bool dbg_t = env_flags().debug_timing;
-  const auto t0 = std::chrono::steady_clock::now();
-  auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
-  if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
-  int rc = decode_all(ctx, b, nullptr, nullptr, flags, host_out, host_dbg);
-  if (rc) return rc;
-  const double t_dec = ms();
-  rc = sync_all(ctx);
-  if (rc) return rc;
-  if (dbg_t) fprintf(stderr, "[dcb timing] decode_all issued %.1f ms, download done %.1f ms\n", t_dec, ms());
-  finish_stats(ctx);
-  collect_status(b);
-  return DCB_OK;
+  return guarded([&]() -> int {
+    if (!host_out && b && b->total_out) return DCB_ERR_ARG;
+    if ((flags & (DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS)) && !host_dbg) return DCB_ERR_ARG;
+    const bool dbg_t = env_flags().debug_timing;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    if (!ctx || !b || (int)ctx->devices.size() != b->n_devices) return DCB_ERR_ARG;
+    int rc = decode_all(ctx, b, nullptr, nullptr, flags, host_out, host_dbg);
+    if (rc) return rc;
+    const double t_dec = ms();
+    rc = sync_all(ctx);
+    if (rc) return rc;
+    if (dbg_t) fprintf(stderr, "[dcb timing] decode_all issued %.1f ms, download done %.1f ms\n", t_dec, ms());
+    finish_stats(ctx);
+    collect_status(b);
+    return DCB_OK;
+  });
 }
 
 int dcb_decode_scatter(dcb_ctx *ctx, dcb_batch *b, uint8_t *const *outs, int n_outs, uint32_t flags) {
-  if (!outs && n_outs) return DCB_ERR_ARG;
-  int rc = decode_all(ctx, b, nullptr, nullptr, flags & ~(DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS));
-  if (rc) return rc;
-  int k = 0;
-  for (const BufRec &r : b->bufs) {
-    const Shard &sh = b->shards[r.shard];
-    const BufWalk &w = sh.walks[r.local];
-    CUDA_TRY(cudaSetDevice(sh.device));
-    for (int i = 0; i < w.stream_count; ++i, ++k) {
-      if (k >= n_outs) break;
-      const StreamDesc &s = sh.streams[w.stream_first + i];
-      if (outs[k] && s.out_bytes && r.info.status == DCB_OK && w.status == DCB_OK)
-        CUDA_TRY(cudaMemcpyAsync(outs[k], sh.ext_out + s.out_off, s.out_bytes, cudaMemcpyDeviceToHost, ctx->streams[r.shard]));
+  return guarded([&]() -> int {
+    if (!outs && n_outs) return DCB_ERR_ARG;
+    int rc = decode_all(ctx, b, nullptr, nullptr, flags & ~(DCB_DUMP_SYMBOLS | DCB_DUMP_QINTS));
+    if (rc) return rc;
+    int k = 0;
+    for (const BufRec &r : b->bufs) {
+      const Shard &sh = b->shards[r.shard];
+      const BufWalk &w = sh.walks[r.local];
+      CUDA_TRY(cudaSetDevice(sh.device));
+      for (int i = 0; i < w.stream_count; ++i, ++k) {
+        if (k >= n_outs) break;
+        const StreamDesc &s = sh.streams[w.stream_first + i];
+        if (outs[k] && s.out_bytes && r.info.status == DCB_OK && w.status == DCB_OK)
+          CUDA_TRY(cudaMemcpyAsync(outs[k], sh.ext_out + s.out_off, s.out_bytes, cudaMemcpyDeviceToHost, ctx->streams[r.shard]));
+      }
     }
-  }
-  rc = sync_all(ctx);
-  if (rc) return rc;
-  finish_stats(ctx);
-  collect_status(b);
-  return DCB_OK;
+    rc = sync_all(ctx);
+    if (rc) return rc;
+    finish_stats(ctx);
+    collect_status(b);
+    return DCB_OK;
+  });
 }
 
 void *dcb_device_out(const dcb_batch *b, int dev_index) {

@@ -261,6 +261,10 @@ int EdgebreakerHost::Decode(const uint8_t *buf, uint64_t len, uint64_t &pos, int
   const uint64_t n_enc_verts = r.varint(), n_faces = r.varint();
   if (r.err) return r.err;
   if (n_faces > (1u << 28) || n_enc_verts > n_faces * 3) return DCB_ERR_CONNECTIVITY;
+  // Counts that the buffer cannot plausibly back fail before anything is allocated from them (the corner table alone
+  // is 24 bytes per face): Edgebreaker symbols cost at least a fraction of a bit each even in the valence coder's
+  // best case, and every mesh carries attribute bytes on top.  Generous: 64 faces per byte of the whole buffer.
+  if (n_faces > 65536 + 64 * len) return DCB_ERR_CONNECTIVITY;
   if (n_faces > 0 && n_enc_verts * (n_enc_verts - 1) / 2 < 3 * n_faces / 2) return DCB_ERR_CONNECTIVITY;
   const uint32_t n_attr_data = r.u8();
   const uint64_t n_symbols = r.varint();

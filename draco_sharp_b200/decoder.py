@@ -130,6 +130,10 @@ class Batch:
         c = np.ascontiguousarray(corner_to_vertex, dtype=np.uint32)
         d = np.ascontiguousarray(data_to_corner, dtype=np.uint32)
         v = np.ascontiguousarray(vertex_to_data, dtype=np.int32)
+        # the library BORROWS the four arrays until the decode / upload call that consumes them returns
+        # (include/dracob200.h): keep them alive with the batch
+        self._borrowed = getattr(self, "_borrowed", {})
+        self._borrowed[(k, dec)] = (o, c, d, v)
         N.check(N.lib().dcb_set_mesh_maps(self.h, k, dec, o.ctypes.data, c.ctypes.data, o.size, d.ctypes.data, d.size,
                                           v.ctypes.data, v.size))
 
@@ -199,6 +203,10 @@ class DracoBatchDecoder:
 
     def set_stream(self, dev_index, cuda_stream):
         N.check(N.lib().dcb_set_stream(self.ctx, dev_index, C.c_void_p(cuda_stream)))
+
+    def set_limits(self, max_points_per_buffer=0, points_per_byte=4096):
+        """Plausibility limits of one buffer (dcb_set_limits): a forged point count fails its own buffer."""
+        N.check(N.lib().dcb_set_limits(self.ctx, max_points_per_buffer, points_per_byte))
 
     # ---- indexing ----
     def index(self, buffers: Sequence) -> Batch:

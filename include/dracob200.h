@@ -130,6 +130,14 @@ void dcb_destroy(dcb_ctx *ctx);
 /* Launch on a caller-owned CUDA stream (cudaStream_t) of device `dev_index` instead of the ctx's own. */
 int dcb_set_stream(dcb_ctx *ctx, int dev_index, void *cuda_stream);
 
+/* Plausibility limits of ONE buffer, applied while indexing (before any arena is sized): a buffer whose header
+ * claims more points (or, for meshes, more attribute entries) than
+ *     max_points_per_buffer            (0 = no absolute cap), or
+ *     65536 + points_per_byte * length (0 = unchecked; default 4096)
+ * gets DCB_ERR_ATTR on its own and reserves nothing, instead of inflating the whole batch.  The reference has no
+ * such check -- it allocates what the header says (PointCloud.cs, DataBuffer.cs) and dies of it. */
+int dcb_set_limits(dcb_ctx *ctx, uint64_t max_points_per_buffer, uint64_t points_per_byte);
+
 /* Phase 1 (host, O(header bytes)): parse containers, locate every stream.  Never reads payloads.
  * The buffers must stay valid until dcb_upload/dcb_decode has returned. */
 int dcb_index(dcb_ctx *ctx, const uint8_t *const *bufs, const uint64_t *lens, int n_bufs, dcb_batch **out);
@@ -146,7 +154,10 @@ uint64_t dcb_batch_points(const dcb_batch *b);     /* sum of n_points over OK bu
 uint64_t dcb_batch_algo_bytes(const dcb_batch *b);
 
 /* Mesh only: where ATTRIBUTES starts (the host decoded connectivity up to there) and, per attributes
- * decoder, the entry count + connectivity-derived arrays.  Arrays are copied. */
+ * decoder, the entry count + connectivity-derived arrays.  The four arrays are BORROWED, not copied: they
+ * must stay valid and unchanged until the dcb_decode* / dcb_upload call that consumes them has returned
+ * (56 bytes per vertex that the library reads exactly once, for the host->device copy; page-locked arrays
+ * travel at full PCIe speed, pageable ones through the driver's staging).  n_corners must be a multiple of 3. */
 int dcb_set_attr_section(dcb_batch *b, int buf, uint64_t attr_section_off, uint32_t n_points);
 int dcb_set_mesh_maps(dcb_batch *b, int buf, int attr_decoder, const uint32_t *opposite,
                       const uint32_t *corner_to_vertex, uint64_t n_corners, const uint32_t *data_to_corner,
