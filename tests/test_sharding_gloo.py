@@ -54,9 +54,9 @@ def test_two_rank_gloo_sharding():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=180) for _ in range(world))
+    res = sorted(q.get(timeout=600) for _ in range(world))
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     (r0, p0, ms0, tp0, to0, f0, c0), (r1, p1, ms1, tp1, to1, f1, c1) = res
     assert p0 == p1 == 8 * 2000
