@@ -45,7 +45,7 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 // experiment / test switches, read once per process (never per stream or per decode)
 struct EnvFlags {
-  bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_v1, no_direct;
+  bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_pc, no_direct;
   int ctas_per_sm, pairs;
   EnvFlags() {
     no_par_post = getenv("DCB_NO_PAR_POST") != nullptr;
@@ -53,7 +53,7 @@ struct EnvFlags {
     debug_plan = getenv("DCB_DEBUG_PLAN") != nullptr;
     debug_timing = getenv("DCB_DEBUG_TIMING") != nullptr;
     lutb_full = getenv("DCB_LUTB_FULL") != nullptr;
-    rans_v1 = getenv("DCB_RANS_V1") != nullptr;      // single-warp rANS kernels (round 1) instead of warp pairs
+    rans_pc = getenv("DCB_RANS_PC") != nullptr;      // chain / consumer warp pairs for every u16 group (experiments)
     no_direct = getenv("DCB_NO_DIRECT") != nullptr;  // never plan the direct slot LUT
     ctas_per_sm = getenv("DCB_CTAS_PER_SM") ? atoi(getenv("DCB_CTAS_PER_SM")) : 0;
     pairs = getenv("DCB_PAIRS") ? atoi(getenv("DCB_PAIRS")) : 0;
@@ -113,6 +113,7 @@ struct Group {            // one kernel launch (or a few, for global tables)
   bool wide, table_global;
   uint32_t compact, prec_bits, entries, exc, lut_shift, lut_bytes, lutb_bytes, ent_bytes, lanes, zig, mode;
   uint32_t pairs;         // chain/consumer warp pairs per CTA (0: the single-warp kernels of dcb_kernels.cu)
+  uint32_t direct;        // direct slot LUT (warp-pair kernels)
   uint32_t ctas_per_sm;   // planned residency (reporting)
   uint64_t total_symbols, max_bytes;
   uint32_t max_entries;
@@ -814,41 +815,59 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
       }
       return need == 0xFFFFFFFFu ? need : std::max<uint32_t>(16u, (uint32_t)align_up(need, 16));
     };
-    if (!g.wide && !env_flags().rans_v1) {
-      // ---- chain / consumer warp pairs (dcb_rans_pc.cu): `pairs` pairs per CTA, `lanes` streams per pair ----
-      // Four pairs per SM put one chain warp and one consumer warp on every sub-partition; pipeline slices share
-      // the SM, so each plans for its part of those four.
-      const uint32_t ksym = g.kind == 1 ? 16u : 4u * (uint32_t)g.ncp;
-      auto cta_bytes = [&](uint32_t pairs, uint32_t lanes, uint32_t lutb) -> uint64_t {
-        RansLaunch L{};
-        L.lanes_per_warp = lanes;
-        L.lut_bytes = g.lut_bytes;
-        L.lutb_bytes = lutb;
-        L.ent_bytes = g.ent_bytes;
-        L.prec_bits = g.prec_bits;
-        L.pairs = pairs;
-        return (uint64_t)dcb_rans_pc_smem_bytes(L, ksym) + kSmemPerCtaReserve;
-      };
-      const uint64_t sm_cap = (uint64_t)sm_bytes + 1024 / share;
+    g.direct = 0;
+    const uint32_t ksym = g.kind == 1 ? 16u : 4u * (uint32_t)g.ncp;
+    const uint64_t sm_cap = (uint64_t)sm_bytes + 1024 / share;
+    auto pc_cta_bytes = [&](uint32_t pairs, uint32_t lanes, uint32_t lut, uint32_t lutb, uint32_t direct) -> uint64_t {
+      RansLaunch L{};
+      L.lanes_per_warp = lanes;
+      L.lut_bytes = lut;
+      L.lutb_bytes = lutb;
+      L.ent_bytes = g.ent_bytes;
+      L.prec_bits = g.prec_bits;
+      L.pairs = pairs;
+      L.direct = direct;
+      return (uint64_t)dcb_rans_pc_smem_bytes(L, ksym) + kSmemPerCtaReserve;
+    };
+    // ---- few streams per SM: direct slot LUT + chain / consumer warp pairs (dcb_rans_pc.cu) ----
+    // The batch time of a handful of long streams is chain latency and nothing else: one dependent shared-memory
+    // access per symbol (slot -> {freq, offset}, 6 bytes per slot) instead of two, and a chain warp that carries
+    // nothing but the chain; its consumer warp sits on another sub-partition (two pairs per CTA: warps 0,1 are
+    // chain warps, 2,3 their consumers).  Taken whenever every stream of the group is resident that way.
+    if (!g.wide && g.prec_bits <= 15 && !env_flags().no_direct && per_sm[i] <= 64 && want == per_sm[i]) {
+      const uint32_t pairs = std::min<uint32_t>(2u, want), lanes = (want + pairs - 1) / pairs;
+      const uint32_t dlut = 6u << g.prec_bits;
+      if ((uint64_t)lanes * g.ent_bytes <= 65535 && pc_cta_bytes(pairs, lanes, dlut, 0, 1) <= sm_cap) {
+        g.direct = 1;
+        g.pairs = pairs;
+        g.lanes = lanes;
+        g.ctas_per_sm = 1;
+        g.lut_bytes = dlut;
+        g.lutb_bytes = 0;
+        continue;
+      }
+    }
+    if (!g.wide && env_flags().rans_pc) {
+      // ---- chain / consumer warp pairs with the two-level tables (experiment: measured slower than one warp per
+      // sub-partition when the SM is full of streams -- the two warps of a pair compete for the same issue port) ----
       uint32_t target = std::max<uint32_t>(1u, 4u / share);
-      if (env_flags().pairs > 0) target = (uint32_t)env_flags().pairs;  // experiments
+      if (env_flags().pairs > 0) target = (uint32_t)env_flags().pairs;
       const uint32_t lutb_min = g.compact ? 16u : 0u;
       uint32_t pairs = 1, lanes = 1, ctas = 1;
       for (;; --want) {
         uint32_t nw = std::max<uint32_t>((want + 31) / 32, std::min<uint32_t>(target, want));
-        if (!g.wide)
-          while ((uint64_t)((want + nw - 1) / nw) * g.ent_bytes > 65535) ++nw;  // 16-bit entry offsets inside a pair
+        while ((uint64_t)((want + nw - 1) / nw) * g.ent_bytes > 65535) ++nw;  // 16-bit entry offsets inside a pair
         ctas = (nw + 3) / 4;
         pairs = (nw + ctas - 1) / ctas;
         lanes = (want + pairs * ctas - 1) / (pairs * ctas);
-        if (ctas * cta_bytes(pairs, lanes, lutb_min) <= sm_cap || want <= 1) break;
+        if (ctas * pc_cta_bytes(pairs, lanes, g.lut_bytes, lutb_min, 0) <= sm_cap || want <= 1) break;
       }
       g.lanes = lanes;
       g.pairs = pairs;
       g.ctas_per_sm = ctas;
       g.lutb_bytes = 0;
       if (g.compact) {
-        const uint64_t base = ctas * cta_bytes(pairs, lanes, lutb_min);
+        const uint64_t base = ctas * pc_cta_bytes(pairs, lanes, g.lut_bytes, lutb_min, 0);
         const uint64_t spare = sm_cap > base ? (sm_cap - base) / ((uint64_t)ctas * pairs * (lanes + 1)) : 0;
         g.lutb_bytes = (uint32_t)std::min<uint64_t>((1u << g.prec_bits) >> 1, lutb_min + spare / 16 * 16);
         const uint32_t need = lutb_need();
@@ -856,8 +875,9 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
       }
       continue;
     }
-    uint32_t ctas = (want + 31) / 32;
-    if (env_flags().ctas_per_sm > 0) ctas = std::max<uint32_t>(ctas, (uint32_t)env_flags().ctas_per_sm);  // experiments
+    // ---- one warp per CTA (dcb_kernels.cu): spread the streams of an SM over its four sub-partitions ----
+    uint32_t ctas = std::max<uint32_t>((want + 31) / 32, std::min<uint32_t>(std::max<uint32_t>(1u, 4u / share), want));
+    if (env_flags().ctas_per_sm > 0) ctas = std::max<uint32_t>((want + 31) / 32, (uint32_t)env_flags().ctas_per_sm);  // experiments
     g.lanes = std::max<uint32_t>(1u, std::min<uint32_t>(32u, (want + ctas - 1) / ctas));
     // a CTA must fit an SM (with its alignment slack) and, for u16 tables, address its entries with 16 bits
     while (g.lanes > 1 && ((uint64_t)g.lanes * lane_bytes + g.lut_bytes + 256 > kSmemPerSM - kSmemPerCtaReserve ||
@@ -1090,6 +1110,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       for (uint32_t si : g.order) ctx->algo_tag += sh.streams[si].payload_len + sh.streams[si].n_entries;
     }
     L.pairs = g.pairs;
+    L.direct = g.direct;
     CUDA_TRY(g.pairs ? dcb_launch_rans_tag_pc(L, A, st) : dcb_launch_rans_tag(L, A, st));
     if (time_tag) {
       CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
@@ -1249,10 +1270,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     if (env_flags().debug_plan)
       fprintf(stderr, "[dcb plan] raw group ncp=%d wide=%d compact=%u prec=%u entries=%u mode=%u zig=%u: %u streams, %llu symbols, "
-                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u pairs=%u ctas/sm=%u global=%d\n",
+                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u pairs=%u direct=%u global=%d\n",
               g->ncp, (int)g->wide, g->compact, g->prec_bits, g->entries, g->mode, g->zig, n,
               (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->lanes, g->pairs,
-              g->ctas_per_sm, (int)g->table_global);
+              g->direct, (int)g->table_global);
     if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (g->table_global) {
       const uint64_t slot_bytes = (uint64_t)g->lut_bytes + g->ent_bytes;
@@ -1278,6 +1299,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
                    g->entries, g->exc, g->lut_shift, g->prec_bits, dump, g->compact, g->zig, g->mode};
       tl_begin(g->mode == 1 ? "rans mode1" : g->mode == 2 ? "rans mode2" : g->mode == 3 ? "rans mode3" : g->mode == 4 ? "rans mode4" : "rans mode0", st);
       L.pairs = g->pairs;
+      L.direct = g->direct;
       CUDA_TRY(g->pairs ? dcb_launch_rans_raw_pc(L, g->ncp, A, st) : dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
       tl_end(st);
       stats.n_launches++;
@@ -1301,13 +1323,13 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       }
       stats.lanes_per_warp = (int32_t)g->lanes;
       stats.smem_per_stream = (uint64_t)g->lut_bytes + g->lutb_bytes + g->ent_bytes + DCB_RING_BYTES;
-      RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, 0, g->compact, g->zig, g->mode, g->pairs};
+      RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, 0, g->compact, g->zig, g->mode, g->pairs, g->direct};
       const uint32_t cta_smem = (g->pairs ? dcb_rans_pc_smem_bytes(Ls, 4u * (uint32_t)g->ncp) : dcb_rans_smem_bytes(Ls, g->table_global)) + kSmemPerCtaReserve;
       const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, (kSmemPerSM + 1024u) / cta_smem)) * g->lanes * std::max(1u, g->pairs);
       stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);
       if (g->pairs)
-        snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_pc<ncp=%d,u16,smem,mode=%u,k=%u,%s,%ux%u lanes>", g->ncp, g->mode,
-                 g->lut_shift, g->compact ? "compact" : "dense", g->pairs, g->lanes);
+        snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_pc<ncp=%d,u16,smem,mode=%u,%s,%s,%ux%u lanes>", g->ncp, g->mode,
+                 g->direct ? "direct slot LUT" : "two-level LUT", g->compact ? "compact" : "dense", g->pairs, g->lanes);
       else
         snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_fused<ncp=%d,%s,%s,mode=%u,k=%u,%s>", g->ncp,
                  g->wide ? "u32" : "u16", g->table_global ? "global" : "smem", g->mode, g->lut_shift,

@@ -288,6 +288,8 @@ struct TableGeom {
   uint32_t lut_shift;   // log2(slots per LUT bucket)
   uint32_t compact;     // 1: entries = symbols with prob > 0 (+ value map), 0: entries = symbol ids
   uint32_t zig;         // value map holds zig-zag decoded values (compact) / apply zig-zag (dense)
+  uint32_t direct_prec; // rANS precision of the launch (direct slot LUT geometry)
+  uint32_t direct;      // 1: direct slot LUT (three u16 arrays of 2^prec slots per lane: freq | offset | entry), lut_bytes = 6 << prec
 };
 
 template <typename T, bool GLOBAL>
@@ -315,6 +317,10 @@ struct RansLane {
   uint32_t cum_addr;    // smem address of the lane's cum[0]
   uint32_t n_entries_tab;  // entries built (ne)
   bool split_ok;        // the two-region LUT fits this lane's LUT capacity
+  // direct slot LUT (low-residency launches): shared-memory addresses of the lane's freq[], offset[] and entry[] arrays
+  // (u16 per slot).  One dependent LDS per symbol instead of two: x' = q * freq[r] + offset[r] (RAnsDecoder.cs:90-99
+  // with lut[] / prob[] / cum[] folded per slot, which is what BuildLookupTable :69-88 itself materialises).
+  uint32_t d_freq, d_off, d_ent;
   const uint8_t *ent0;  // entry region (generic pointer: shared or global)
   const uint8_t *lut0;  // GLOBAL only
   // byte supply
@@ -366,7 +372,8 @@ struct RansLane {
   // L/65536 that x is below, capped by the bytes left.  CAREFUL = false assumes the caller has
   // checked that enough bytes are left for the cap not to bind.
   // Returns the byte offset (from ent0) of cum[entry].
-  template <bool CAREFUL, bool SPLIT>
+  // PROBE: 0 uniform LUT (+ rare search), 1 two-region LUT, 2 direct slot LUT
+  template <bool CAREFUL, int PROBE>
   __device__ __forceinline__ uint32_t step() {
     const uint32_t v = peek();
     uint32_t sh;  // 8 * bytes to shift in
@@ -386,7 +393,16 @@ struct RansLane {
     const uint32_t r = xr & mask;
     const uint32_t q = xr >> prec_bits;
     uint32_t o, c0, c1, c2;
-    if (SPLIT) {
+    if (PROBE == 2) {
+      const uint32_t r2 = r << 1;
+      uint32_t f, off;
+      asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(f) : "r"(d_freq + r2));
+      asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(off) : "r"(d_off + r2));
+      asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(o) : "r"(d_ent + r2));  // off the chain: only the value map wants it
+      x = q * f + off;
+      return o;
+    }
+    if (PROBE == 1) {
       // both regions hold u8 ranks relative to the first entry of their 128-slot block; blk[] holds the
       // shared-memory address of that entry's cum value: one byte load + one word load, issued together
       const uint32_t a_a = ((xr >> a_sh) & a_mask) | lut_base;
@@ -423,6 +439,24 @@ struct RansLane {
     const uint32_t xb = q * (c2 - c1) + (r - c1);
     x = second ? xb : xa;
     return o + (second ? (uint32_t)sizeof(T) : 0u);
+  }
+
+  // direct slot LUT, main loop: returns the SLOT; the consumer warp looks the table entry up (d_ent[slot])
+  __device__ __forceinline__ uint32_t step_direct_slot() {
+    const uint32_t v = peek();
+    const uint32_t sh2 = x < L8 ? 16u : 8u;  // u16 tables: precision <= 15, at most two bytes (see step)
+    const uint32_t sh = x < L ? sh2 : 0u;
+    const uint32_t xr = __funnelshift_l(v, x, sh);
+    p1 -= sh >> 3;
+    prefetch();
+    const uint32_t r = xr & mask;
+    const uint32_t q = xr >> prec_bits;
+    const uint32_t r2 = r << 1;
+    uint32_t f, off;
+    asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(f) : "r"(d_freq + r2));
+    asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(off) : "r"(d_off + r2));
+    x = q * f + off;
+    return r;
   }
 
   // table entry -> symbol value.  dense: the entry index is the symbol id.  compact: entries below the dense
@@ -654,7 +688,8 @@ __device__ __forceinline__ SmemLayout smem_layout(uint32_t base_addr, uint32_t l
   SmemLayout l;
   uint32_t a = base_addr;
   if (!table_global) {
-    a = (a + g.lut_bytes - 1u) & ~(g.lut_bytes - 1u);
+    if (g.direct) a = (a + 15u) & ~15u;
+    else a = (a + g.lut_bytes - 1u) & ~(g.lut_bytes - 1u);
     l.lut0 = a - base_addr;
     a += lanes * g.lut_bytes;
   } else {
@@ -677,12 +712,12 @@ __device__ __forceinline__ SmemLayout smem_layout(uint32_t base_addr, uint32_t l
 
 // decode one entry: NCP symbols -> corrections -> prediction; leaves the portable ints in v and prev
 // TAB: 0 = table kind (dense / compact) read from the launch geometry, 1 = dense, 2 = compact
-template <int NCP, typename T, bool TG, bool DUMP, int MODE, int TAB, bool CAREFUL, bool SPLIT>
+template <int NCP, typename T, bool TG, bool DUMP, int MODE, int TAB, bool CAREFUL, int PROBE>
 __device__ __forceinline__ void decode_entry(RansLane<T, TG> &rl, const TableGeom &g, const PostParams &pp, int32_t *prev,
                                              int32_t *v, int32_t *dptr, uint32_t dump, uint64_t e) {
 #pragma unroll
   for (int c = 0; c < NCP; ++c) {
-    const uint32_t o = rl.template step<CAREFUL, SPLIT>();
+    const uint32_t o = rl.template step<CAREFUL, PROBE>();
     const bool compact = TAB == 0 ? g.compact != 0 : TAB == 2;
     const bool zig = MODE == 0 ? g.zig != 0 : MODE != 3;
     v[c] = rl.value(o, compact, zig);

@@ -145,4 +145,5 @@ struct RansLaunch {
   uint32_t zig;                   // symbols are zig-zag coded corrections
   uint32_t mode;                  // 0 generic post-processing, 1..4 specialised (dcb_device.cuh)
   uint32_t pairs;                 // chain/consumer warp pairs per CTA (dcb_rans_pc.cu); 0 = the single-warp kernels
+  uint32_t direct;                // 1: direct slot LUT (lut_bytes = 6 << prec_bits per lane; warp-pair kernels only)
 };

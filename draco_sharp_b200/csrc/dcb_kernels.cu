@@ -932,7 +932,7 @@ __global__ void copy_kernel(const uint8_t *__restrict__ arena, StreamDesc *strea
 // host launchers
 // ---------------------------------------------------------------------------------------------
 static TableGeom geom_of(const RansLaunch &p) {
-  TableGeom g;
+  TableGeom g{};
   g.lut_bytes = p.lut_bytes;
   g.lutb_bytes = p.lutb_bytes;
   g.blk_bytes = p.lutb_bytes ? (((1u << p.prec_bits) >> 7) << 2) : 0u;
@@ -949,6 +949,7 @@ static TableGeom geom_of(const RansLaunch &p) {
 uint32_t dcb_rans_smem_bytes(const RansLaunch &p, bool table_global) {
   // worst-case alignment slack + LUTs + rings + entries (see smem_layout)
   uint32_t b = DCB_RING_BYTES + p.lanes_per_warp * DCB_RING_BYTES;
+  if (!table_global && p.direct) return b + 32u + p.lanes_per_warp * (p.lut_bytes + p.ent_bytes);  // direct slot LUT: 16-byte alignment only
   if (!table_global) {
     const uint32_t blk = p.lutb_bytes ? std::max(16u, ((1u << p.prec_bits) >> 7) << 2) : 0u;
     b += p.lut_bytes + blk + 16u + p.lanes_per_warp * (p.lut_bytes + p.lutb_bytes + blk + p.ent_bytes);

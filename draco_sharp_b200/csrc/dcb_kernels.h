@@ -10,8 +10,8 @@
 // chain / consumer warp pairs (dcb_rans_pc.cu): shared memory of one pair beyond its lanes' tables
 #define DCB_PC_STAGES 4u       // queue depth in groups
 #define DCB_PC_ROW_BYTES 64u   // one queue row: symbol j of all 32 lanes, 2 bytes each
-#define DCB_PC_CTL_BYTES 96u   // mbarriers full[4] empty[4] setup handoff + flag[4]
-#define DCB_PC_HAND_BYTES 40u  // per-lane hand-over record
+#define DCB_PC_CTL_BYTES 112u  // mbarriers full[4] empty[4] setup handoff filled + flag[4]
+#define DCB_PC_HAND_BYTES 48u  // per-lane hand-over record
 struct PcGeom {
   uint32_t tab_bytes;    // table part of a pair's slice (worst-case alignment slack included)
   uint32_t slice_bytes;  // whole slice

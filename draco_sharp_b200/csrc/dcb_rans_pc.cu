@@ -49,6 +49,8 @@ struct LaneHand {
   int32_t prev[4];      // consumer -> chain: running values of the delta decoder after the last queued group
   int32_t status;       // tags: consumer -> chain
   uint32_t e;           // tags: consumer -> chain: first tag the careful tail has to decode
+  uint32_t ne;          // chain -> both: table entries built (direct slot LUT fill)
+  uint32_t pad_;
   uint64_t bits;        // tags: consumer -> chain: bits consumed in the bit area so far
 };
 static_assert(sizeof(LaneHand) == DCB_PC_HAND_BYTES, "LaneHand size is part of the shared-memory plan");
@@ -104,19 +106,59 @@ __device__ __forceinline__ uint32_t lds_u32m(uint32_t a) {
   return v;
 }
 
-// addresses of a pair's control block (DCB_PC_CTL_BYTES): full[kStages] | empty[kStages] | setup | handoff | flag[kStages]
+// addresses of a pair's control block (DCB_PC_CTL_BYTES): full[kStages] | empty[kStages] | setup | handoff | filled | flag[kStages]
+constexpr uint32_t kNumBarriers = 2u * kStages + 3u;
 struct PairCtl {
   uint32_t base;
   __device__ __forceinline__ uint32_t full(uint32_t s) const { return base + 8u * s; }
   __device__ __forceinline__ uint32_t empty(uint32_t s) const { return base + 8u * (kStages + s); }
   __device__ __forceinline__ uint32_t setup() const { return base + 16u * kStages; }
   __device__ __forceinline__ uint32_t handoff() const { return base + 16u * kStages + 8u; }
-  __device__ __forceinline__ uint32_t flag(uint32_t s) const { return base + 16u * kStages + 16u + 4u * s; }
+  __device__ __forceinline__ uint32_t filled() const { return base + 16u * kStages + 16u; }  // two arrivals: both warps
+  __device__ __forceinline__ uint32_t flag(uint32_t s) const { return base + 8u * kNumBarriers + 4u * s; }
 };
+static_assert(8u * kNumBarriers + 4u * kStages <= DCB_PC_CTL_BYTES, "control block");
+
+// Direct slot LUT of one lane, filled by both warps of the pair (64 threads): for every slot the table entry that owns
+// it -- what RAnsDecoder.BuildLookupTable (RAnsDecoder.cs:69-88) materialises as lut[] -- folded with that entry's
+// frequency and the slot's offset inside it, so that the chain needs ONE dependent shared-memory access per symbol.
+__device__ __forceinline__ void fill_direct(const uint16_t *cum, uint32_t ne, uint32_t prec_bits, uint32_t ent_off,
+                                            uint16_t *freq, uint16_t *off, uint16_t *ent, uint32_t tid, uint32_t nthreads) {
+  const uint32_t n = 1u << prec_bits;
+  for (uint32_t s = tid; s < n; s += nthreads) {
+    uint32_t lo = 0, hi = ne;  // cum[lo] <= s; hi == ne or cum[hi] > s  (zero-width entries of dense tables: the last one wins)
+    while (hi - lo > 1u) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if ((uint32_t)cum[mid] <= s) lo = mid;
+      else hi = mid;
+    }
+    const uint32_t c = cum[lo];
+    freq[s] = (uint16_t)((uint32_t)cum[lo + 1] - c);
+    off[s] = (uint16_t)(s - c);
+    ent[s] = (uint16_t)(ent_off + 2u * lo);
+  }
+}
+// both warps of a pair, after the chain warp has built the tables: fill every active lane's direct LUT, then meet
+__device__ __forceinline__ void fill_direct_all(uint8_t *slice, const SmemLayout &lay, const TableGeom &geom, uint32_t lanes,
+                                                uint32_t hand_off, uint32_t prec_bits, uint32_t tid64, const PairCtl &ctl) {
+  const uint32_t arr = 2u << prec_bits;  // bytes of one u16 array
+  for (uint32_t l = 0; l < lanes; ++l) {
+    const volatile uint32_t *h = reinterpret_cast<const volatile uint32_t *>(slice + hand_off + (size_t)l * DCB_PC_HAND_BYTES);
+    if (h[1] == 0u) continue;  // LaneHand::active
+    const uint32_t ne = h[8];  // LaneHand::ne
+    uint8_t *lut = slice + lay.lut0 + (size_t)l * geom.lut_bytes;
+    fill_direct(reinterpret_cast<const uint16_t *>(slice + lay.ent0 + (size_t)l * geom.ent_bytes), ne, prec_bits, l * geom.ent_bytes,
+                reinterpret_cast<uint16_t *>(lut), reinterpret_cast<uint16_t *>(lut + arr), reinterpret_cast<uint16_t *>(lut + 2u * arr),
+                tid64, 64u);
+  }
+  __syncwarp();
+  if ((tid64 & 31u) == 0u) mbar_arrive(ctl.filled());
+  mbar_wait(ctl.filled(), 0u);
+}
 
 // The chain warp's main loop.  NSYM symbols per group and lane; returns the number of groups queued.
 // `go0`: the warp has at least one full group that every active lane can decode without byte-bound checks.
-template <int NSYM, bool SPLIT>
+template <int NSYM, int PROBE>
 __device__ __forceinline__ uint32_t produce(RansLane<uint16_t, false> &rl, bool active, uint32_t g_min, uint32_t q_addr,
                                             const PairCtl &ctl, uint32_t lane) {
   constexpr uint32_t kGroupBytes = (uint32_t)NSYM * 3u;
@@ -134,7 +176,7 @@ __device__ __forceinline__ uint32_t produce(RansLane<uint16_t, false> &rl, bool 
     if (active) {
 #pragma unroll
       for (int j = 0; j < NSYM; ++j) {
-        const uint32_t o = rl.template step<false, SPLIT>();
+        const uint32_t o = PROBE == 2 ? rl.step_direct_slot() : rl.template step<false, PROBE>();
         sts_u16(qs + (uint32_t)j * kRowBytes, o);
       }
     }
@@ -216,7 +258,7 @@ __global__ void __launch_bounds__(256) rans_raw_pc_kernel(const uint8_t *__restr
   const PairCtl ctl{slice_addr + pc.ctl_off};
   if (role == 0 && lane == 0) {
 #pragma unroll
-    for (uint32_t i = 0; i < 2u * kStages + 2u; ++i) mbar_init(ctl.base + 8u * i, 1u);
+    for (uint32_t i = 0; i < kNumBarriers; ++i) mbar_init(ctl.base + 8u * i, i == 2u * kStages + 2u ? 2u : 1u);
   }
   __syncthreads();
   const uint32_t slot = (blockIdx.x * pairs + pair) * lanes + lane;
@@ -252,6 +294,11 @@ __global__ void __launch_bounds__(256) rans_raw_pc_kernel(const uint8_t *__restr
         lut = reinterpret_cast<T *>(slice + lay.lut0 + (size_t)lane * geom.lut_bytes);
         lutb = slice + lay.lutb0 + (size_t)lane * geom.lutb_bytes;
         ent = reinterpret_cast<T *>(slice + lay.ent0 + (size_t)lane * geom.ent_bytes);
+        if (geom.direct) {
+          rl.d_freq = slice_addr + lay.lut0 + lane * geom.lut_bytes;
+          rl.d_off = rl.d_freq + (2u << d.prec_bits);
+          rl.d_ent = rl.d_off + (2u << d.prec_bits);
+        }
         status = rl.build(arena, d, geom, ent, ent_off);
         if (status == DCB_OK) status = rl.init_state(arena, d);
         if (status == DCB_OK) split_ok = rl.split_ok && !(dump & 0x80000000u);
@@ -267,17 +314,24 @@ __global__ void __launch_bounds__(256) rans_raw_pc_kernel(const uint8_t *__restr
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) g_min = min(g_min, __shfl_xor_sync(0xffffffffu, g_min, o));
     if (active) {
-      rl.fill_lut(geom, lut, lutb, blk, ent, use_split);
+      if (!geom.direct) rl.fill_lut(geom, lut, lutb, blk, ent, use_split);
       rl.init_ring(slice_addr + lay.ring0 + lane * DCB_RING_BYTES);
     }
     if (have) {
       hand->dprefix = rl.dprefix;
       hand->active = active ? 1 : 0;
+      hand->ne = active ? rl.n_entries_tab : 0u;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(ctl.setup());
-    const uint32_t groups = use_split ? produce<kSym, true>(rl, active, g_min, q_addr, ctl, lane)
-                                      : produce<kSym, false>(rl, active, g_min, q_addr, ctl, lane);
+    const int probe = geom.direct ? 2 : (use_split ? 1 : 0);
+    if (geom.direct) {
+      mbar_wait(ctl.setup(), 0u);
+      fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, lane, ctl);
+    }
+    const uint32_t groups = probe == 2 ? produce<kSym, 2>(rl, active, g_min, q_addr, ctl, lane)
+                          : probe == 1 ? produce<kSym, 1>(rl, active, g_min, q_addr, ctl, lane)
+                                       : produce<kSym, 0>(rl, active, g_min, q_addr, ctl, lane);
     mbar_wait(ctl.handoff(), 0u);
     if (!active) return;
     // ---- per-lane tail: exact `off > 0` handling, as RAnsDecoder.Read does it byte by byte ----
@@ -292,8 +346,9 @@ __global__ void __launch_bounds__(256) rans_raw_pc_kernel(const uint8_t *__restr
     for (int c = 0; c < NCP; ++c) prev[c] = hand->prev[c];
     for (uint32_t e = groups * 4u; e < n_entries; ++e) {
       int32_t v[NCP];
-      if (use_split) decode_entry<NCP, T, false, DUMP, MODE, TAB, true, true>(rl, geom, pp, prev, v, dptr, dump, e);
-      else decode_entry<NCP, T, false, DUMP, MODE, TAB, true, false>(rl, geom, pp, prev, v, dptr, dump, e);
+      if (probe == 2) decode_entry<NCP, T, false, DUMP, MODE, TAB, true, 2>(rl, geom, pp, prev, v, dptr, dump, e);
+      else if (probe == 1) decode_entry<NCP, T, false, DUMP, MODE, TAB, true, 1>(rl, geom, pp, prev, v, dptr, dump, e);
+      else decode_entry<NCP, T, false, DUMP, MODE, TAB, true, 0>(rl, geom, pp, prev, v, dptr, dump, e);
       store_entry<NCP>(pp, store, dsize, optr, e, v);
       rl.template top_up<(3 * NCP + 15) / 16 + 1>();
       cp_async_wait<0>();
@@ -311,6 +366,8 @@ __global__ void __launch_bounds__(256) rans_raw_pc_kernel(const uint8_t *__restr
     }
     const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp), recon = recon_of<MODE>(pp);
     mbar_wait(ctl.setup(), 0u);
+    if (geom.direct) fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, 32u + lane, ctl);
+    const uint32_t d_ent = slice_addr + lay.lut0 + lane * geom.lut_bytes + (4u << geom.direct_prec);  // direct LUT: entry[] of this lane
     bool active = false;
     ValMap vm{slice + lay.ent0, lane * geom.ent_bytes, 0u, 0u};
     if (have) {
@@ -332,7 +389,8 @@ __global__ void __launch_bounds__(256) rans_raw_pc_kernel(const uint8_t *__restr
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int c = 0; c < NCP; ++c) {
-            const uint32_t o = lds_u16(qs + (uint32_t)(j * NCP + c) * kRowBytes);
+            uint32_t o = lds_u16(qs + (uint32_t)(j * NCP + c) * kRowBytes);
+            if (geom.direct) o = lds_u16(d_ent + 2u * o);  // the chain queued the slot
             v[j][c] = vm.value(o, compact, zig);
             if (DUMP && (dump & DCB_DUMP_SYMBOLS)) dptr[((uint64_t)g * 4 + j) * NCP + c] = (int32_t)vm.symbol(o, compact, zig);
           }
@@ -393,7 +451,7 @@ __global__ void __launch_bounds__(256) rans_tag_pc_kernel(const uint8_t *__restr
   const PairCtl ctl{slice_addr + pc.ctl_off};
   if (role == 0 && lane == 0) {
 #pragma unroll
-    for (uint32_t i = 0; i < 2u * kStages + 2u; ++i) mbar_init(ctl.base + 8u * i, 1u);
+    for (uint32_t i = 0; i < kNumBarriers; ++i) mbar_init(ctl.base + 8u * i, i == 2u * kStages + 2u ? 2u : 1u);
   }
   __syncthreads();
   const uint32_t slot = (blockIdx.x * pairs + pair) * lanes + lane;
@@ -415,6 +473,11 @@ __global__ void __launch_bounds__(256) rans_tag_pc_kernel(const uint8_t *__restr
       rl.lutb_addr = slice_addr + lay.lutb0 + lane * geom.lutb_bytes;
       rl.blk_addr = slice_addr + lay.blk0 + lane * geom.blk_bytes;
       rl.cum_addr = slice_addr + lay.ent0 + lane * geom.ent_bytes;
+      if (geom.direct) {
+        rl.d_freq = slice_addr + lay.lut0 + lane * geom.lut_bytes;
+        rl.d_off = rl.d_freq + (2u << geom.direct_prec);
+        rl.d_ent = rl.d_off + (2u << geom.direct_prec);
+      }
       int status = rl.build(arena, *dp, geom, ent, lane * geom.ent_bytes);
       if (status == DCB_OK) status = rl.init_state(arena, *dp);
       if (status != DCB_OK) {
@@ -431,19 +494,27 @@ __global__ void __launch_bounds__(256) rans_tag_pc_kernel(const uint8_t *__restr
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) g_min = min(g_min, __shfl_xor_sync(0xffffffffu, g_min, o));
     if (active) {
-      rl.fill_lut(geom, reinterpret_cast<T *>(slice + lay.lut0 + (size_t)lane * geom.lut_bytes),
-                  slice + lay.lutb0 + (size_t)lane * geom.lutb_bytes,
-                  reinterpret_cast<uint32_t *>(slice + lay.blk0 + (size_t)lane * geom.blk_bytes), ent, use_split);
+      if (!geom.direct)
+        rl.fill_lut(geom, reinterpret_cast<T *>(slice + lay.lut0 + (size_t)lane * geom.lut_bytes),
+                    slice + lay.lutb0 + (size_t)lane * geom.lutb_bytes,
+                    reinterpret_cast<uint32_t *>(slice + lay.blk0 + (size_t)lane * geom.blk_bytes), ent, use_split);
       rl.init_ring(slice_addr + lay.ring0 + lane * DCB_RING_BYTES);
     }
     if (have) {
       hand->dprefix = rl.dprefix;
       hand->active = active ? 1 : 0;
+      hand->ne = active ? rl.n_entries_tab : 0u;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(ctl.setup());
-    if (use_split) produce<kSym, true>(rl, active, g_min, q_addr, ctl, lane);
-    else produce<kSym, false>(rl, active, g_min, q_addr, ctl, lane);
+    const int probe = geom.direct ? 2 : (use_split ? 1 : 0);
+    if (geom.direct) {
+      mbar_wait(ctl.setup(), 0u);
+      fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, lane, ctl);
+    }
+    if (probe == 2) produce<kSym, 2>(rl, active, g_min, q_addr, ctl, lane);
+    else if (probe == 1) produce<kSym, 1>(rl, active, g_min, q_addr, ctl, lane);
+    else produce<kSym, 0>(rl, active, g_min, q_addr, ctl, lane);
     mbar_wait(ctl.handoff(), 0u);
     if (!active) return;
     // ---- careful tail (exact `off > 0` handling, per-point checks) ----
@@ -456,7 +527,7 @@ __global__ void __launch_bounds__(256) rans_tag_pc_kernel(const uint8_t *__restr
     uint64_t bits = hand->bits;
     for (uint32_t e = hand->e; status == DCB_OK && e < n_entries; ++e) {
       if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-      const uint32_t o = use_split ? rl.template step<true, true>() : rl.template step<true, false>();
+      const uint32_t o = probe == 2 ? rl.template step<true, 2>() : probe == 1 ? rl.template step<true, 1>() : rl.template step<true, 0>();
       const uint32_t tag = (uint32_t)rl.value(o, compact, false) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
       if (tag > 32u) {
         status = DCB_ERR_TAG;
@@ -487,6 +558,8 @@ __global__ void __launch_bounds__(256) rans_tag_pc_kernel(const uint8_t *__restr
       chunk_bits = reinterpret_cast<uint64_t *>(aux + d.tag_off + (((uint64_t)n_entries + 15ull) & ~15ull));
     }
     mbar_wait(ctl.setup(), 0u);
+    if (geom.direct) fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, 32u + lane, ctl);
+    const uint32_t d_ent = slice_addr + lay.lut0 + lane * geom.lut_bytes + (4u << geom.direct_prec);
     bool active = false;
     ValMap vm{slice + lay.ent0, lane * geom.ent_bytes, 0u, 0u};
     if (have) {
@@ -505,7 +578,11 @@ __global__ void __launch_bounds__(256) rans_tag_pc_kernel(const uint8_t *__restr
       uint32_t t[16];
       if (active) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = (uint32_t)vm.value(lds_u16(qs + (uint32_t)j * kRowBytes), compact, false) & 0xFFu;
+        for (int j = 0; j < 16; ++j) {
+          uint32_t o = lds_u16(qs + (uint32_t)j * kRowBytes);
+          if (geom.direct) o = lds_u16(d_ent + 2u * o);
+          t[j] = (uint32_t)vm.value(o, compact, false) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(ctl.empty(s));
@@ -555,7 +632,9 @@ __global__ void __launch_bounds__(256) rans_tag_pc_kernel(const uint8_t *__restr
 // host side
 // ---------------------------------------------------------------------------------------------
 static TableGeom pc_table_geom(const RansLaunch &p) {
-  TableGeom g;
+  TableGeom g{};
+  g.direct = p.direct;
+  g.direct_prec = p.prec_bits;
   g.lut_bytes = p.lut_bytes;
   g.lutb_bytes = p.lutb_bytes;
   g.blk_bytes = p.lutb_bytes ? (((1u << p.prec_bits) >> 7) << 2) : 0u;

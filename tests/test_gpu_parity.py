@@ -157,10 +157,40 @@ def test_uniform_lut_fallback_path_is_bit_exact_too():
     import sys
     if os.environ.get("DCB_NO_SPLIT"):
         pytest.skip("already the child")
-    env = dict(os.environ, DCB_NO_SPLIT="1")
+    env = dict(os.environ, DCB_NO_SPLIT="1", DCB_NO_DIRECT="1")  # small batches would take the direct slot LUT otherwise
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k",
                         "positions_small_sizes or positions_normals_colors or ragged_batch or wide_alphabets"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+def _rerun_in_child(extra_env, select):
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DCB_TEST_CHILD"):
+        pytest.skip("already the child")
+    env = dict(os.environ, DCB_TEST_CHILD="1", **extra_env)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-k", select],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+_PATH_CASES = ("positions_small_sizes or positions_normals_colors or ragged_batch or wide_alphabets or crafted_streams or "
+               "malformed_buffers or house_positions or grid_meshes or parallelogram_random")
+
+
+def test_two_level_tables_single_warp_kernels_are_bit_exact():
+    """Small batches are planned with the direct slot LUT (few streams per SM); DCB_NO_DIRECT=1 sends the same cases
+    through the two-level tables and the one-warp-per-CTA kernels, the path of the big batches (BASELINE configs[1])."""
+    _rerun_in_child({"DCB_NO_DIRECT": "1"}, _PATH_CASES)
+
+
+def test_two_level_tables_warp_pair_kernels_are_bit_exact():
+    """DCB_RANS_PC=1 + DCB_NO_DIRECT=1: chain / consumer warp pairs over the two-level tables (kept as an experiment
+    path: measured slower than one warp per sub-partition when the SM is full of streams)."""
+    _rerun_in_child({"DCB_NO_DIRECT": "1", "DCB_RANS_PC": "1"}, _PATH_CASES)
