@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <chrono>
 #include <thread>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <stdlib.h>
@@ -45,7 +46,7 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 // experiment / test switches, read once per process (never per stream or per decode)
 struct EnvFlags {
-  bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_pc, no_direct;
+  bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_pc, no_direct, no_fast_tagged, no_threads;
   int ctas_per_sm, pairs;
   EnvFlags() {
     no_par_post = getenv("DCB_NO_PAR_POST") != nullptr;
@@ -55,6 +56,8 @@ struct EnvFlags {
     lutb_full = getenv("DCB_LUTB_FULL") != nullptr;
     rans_pc = getenv("DCB_RANS_PC") != nullptr;      // chain / consumer warp pairs for every u16 group (experiments)
     no_direct = getenv("DCB_NO_DIRECT") != nullptr;  // never plan the direct slot LUT
+    no_threads = getenv("DCB_NO_THREADS") != nullptr;          // multi-device decodes on the calling thread only
+    no_fast_tagged = getenv("DCB_NO_FAST_TAGGED") != nullptr;  // always fetch the resumed walks before classifying
     ctas_per_sm = getenv("DCB_CTAS_PER_SM") ? atoi(getenv("DCB_CTAS_PER_SM")) : 0;
     pairs = getenv("DCB_PAIRS") ? atoi(getenv("DCB_PAIRS")) : 0;
   }
@@ -73,6 +76,7 @@ struct PoolBlock {
   int device;
 };
 struct DevPool {
+  std::mutex mu;  // decode threads of different devices share the context's cache
   std::vector<PoolBlock> free_blocks;
   std::vector<PoolBlock> free_pinned;  // page-locked staging buffers (device = -1)
   uint64_t cached = 0;
@@ -154,6 +158,11 @@ struct Shard {
   uint32_t *d_order = nullptr;
   uint64_t order_cap = 0;
   uint8_t *h_stage = nullptr;  // pinned staging for the packed input
+  uint8_t *h_desc = nullptr;   // pinned staging: device-updated stream descriptors + walks travel back without blocking
+  uint64_t cap_hdesc = 0;
+  bool desc_pending = false;   // h_desc holds a copy-back that absorb_descs folds into streams / walks after the sync
+  std::vector<uint32_t> order_host;  // the order lists of the decode in flight (source of an asynchronous upload)
+  uint32_t epoch = 0;          // tags the look-back words of par_post2_kernel (30 bits, never 0): no clearing between decodes
   bool uploaded = false, dirty = true, own_out = false;
   uint8_t *ext_out = nullptr, *ext_dbg = nullptr;
 };
@@ -179,7 +188,8 @@ struct dcb_ctx {
   // DCB_DEBUG_TIMING: per-launch events of the last decode (name, begin, end), printed by finish_stats
   std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timeline;
   dcb_launch_stats stats{};
-  uint32_t epoch = 0;  // tags the look-back words of par_post_kernel: no clearing between decodes
+  std::vector<dcb_launch_stats> dev_stats;  // per context device entry (entry 0 unused)
+  std::vector<std::pair<const void *, uint32_t>> par_streams;  // (shard, stream): Tagged streams whose bit-area length is device-known
   // plausibility limits of one buffer (dcb_set_limits): a forged point / entry count must fail its own buffer instead
   // of sizing a 25 GB arena for the whole batch
   uint64_t max_points = 0;                          // absolute cap per buffer, 0 = none
@@ -426,6 +436,8 @@ cudaError_t pool_alloc(const std::shared_ptr<DevPool> &pool, int device, uint64_
   *out = nullptr;
   *cap = 0;
   if (bytes == 0) return cudaSuccess;
+  std::unique_lock<std::mutex> lk_;
+  if (pool) lk_ = std::unique_lock<std::mutex>(pool->mu);
   if (pool && bytes >= kPoolMin) {
     int best = -1;
     for (size_t i = 0; i < pool->free_blocks.size(); ++i) {
@@ -457,6 +469,8 @@ cudaError_t pool_alloc(const std::shared_ptr<DevPool> &pool, int device, uint64_
 
 void pool_free(const std::shared_ptr<DevPool> &pool, int device, void *p, uint64_t cap) {
   if (!p) return;
+  std::unique_lock<std::mutex> lk_;
+  if (pool) lk_ = std::unique_lock<std::mutex>(pool->mu);
   if (pool && cap >= kPoolMin && pool->cached + cap <= kPoolCap) {
     pool->free_blocks.push_back({p, cap, device});
     pool->cached += cap;
@@ -467,6 +481,8 @@ void pool_free(const std::shared_ptr<DevPool> &pool, int device, void *p, uint64
 
 void pool_trim(const std::shared_ptr<DevPool> &pool) {
   if (!pool) return;
+  std::unique_lock<std::mutex> lk_;
+  if (pool) lk_ = std::unique_lock<std::mutex>(pool->mu);
   for (PoolBlock &k : pool->free_blocks) { cudaSetDevice(k.device); cudaFree(k.p); }
   for (PoolBlock &k : pool->free_pinned) cudaFreeHost(k.p);
   pool->free_blocks.clear();
@@ -475,6 +491,8 @@ void pool_trim(const std::shared_ptr<DevPool> &pool) {
 }
 
 cudaError_t pinned_alloc(const std::shared_ptr<DevPool> &pool, uint64_t bytes, uint8_t **out, uint64_t *cap) {
+  std::unique_lock<std::mutex> lk_;
+  if (pool) lk_ = std::unique_lock<std::mutex>(pool->mu);
   if (pool)
     for (size_t i = 0; i < pool->free_pinned.size(); ++i) {
       const PoolBlock k = pool->free_pinned[i];
@@ -491,6 +509,8 @@ cudaError_t pinned_alloc(const std::shared_ptr<DevPool> &pool, uint64_t bytes, u
 
 void pinned_free(const std::shared_ptr<DevPool> &pool, void *p, uint64_t cap) {
   if (!p) return;
+  std::unique_lock<std::mutex> lk_;
+  if (pool) lk_ = std::unique_lock<std::mutex>(pool->mu);
   if (pool && pool->cached <= kPoolCap && pool->free_pinned.size() < 64) {
     pool->free_pinned.push_back({p, cap, -1});
     return;
@@ -498,7 +518,13 @@ void pinned_free(const std::shared_ptr<DevPool> &pool, void *p, uint64_t cap) {
   cudaFreeHost(p);
 }
 
+void pinned_free(const std::shared_ptr<DevPool> &pool, void *p, uint64_t cap);
 void free_shard_device(Shard &sh) {
+  if (sh.h_desc) {
+    pinned_free(sh.pool, sh.h_desc, sh.cap_hdesc);
+    sh.h_desc = nullptr;
+    sh.desc_pending = false;
+  }
   if (!sh.d_in && !sh.d_streams && !sh.h_stage && !sh.d_out) return;
   cudaSetDevice(sh.device);
   pool_free(sh.pool, sh.device, sh.d_in, sh.cap_in);
@@ -1026,6 +1052,9 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
     CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.walks.size() * sizeof(BufWalk), &p, &sh.cap_walks));
     sh.d_walks = reinterpret_cast<BufWalk *>(p);
   }
+  if (!sh.h_desc && !sh.streams.empty())
+    CUDA_TRY(pinned_alloc(sh.pool, sh.streams.size() * sizeof(StreamDesc) + sh.walks.size() * sizeof(BufWalk) + 16, &sh.h_desc,
+                          &sh.cap_hdesc));
   if (sh.aux_bytes) {
     CUDA_TRY(pool_alloc(sh.pool, sh.device, sh.aux_bytes, &sh.d_aux, &sh.cap_aux));
     CUDA_TRY(cudaMemsetAsync(sh.d_aux, 0, sh.aux_bytes, st));  // look-back words start with epoch 0 (never a live epoch)
@@ -1033,6 +1062,35 @@ int upload_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   sh.uploaded = true;
   sh.dirty = true;
   return DCB_OK;
+}
+
+// look-back epochs cycle through 1 .. 2^30 - 1: the words carry 30 bits of it and zeroed scratch must never look live
+inline uint32_t next_epoch(Shard &sh) {
+  sh.epoch = sh.epoch >= 0x3FFFFFFEu ? 1u : sh.epoch + 1u;
+  return sh.epoch;
+}
+
+// Stream descriptors and walks as the device left them (statuses, bits_total, the PRED_DATA / XFORM_PARAMS the resumed
+// walks parsed) travel back through pinned memory on the shard's stream; absorb_descs folds them into the host copies
+// once the caller has synchronised.  Nothing here blocks the host thread.
+int queue_desc_copyback(dcb_ctx *ctx, Shard &sh, cudaStream_t st) {
+  const uint64_t nb_s = sh.streams.size() * sizeof(StreamDesc), nb_w = sh.walks.size() * sizeof(BufWalk);
+  if (!sh.h_desc) CUDA_TRY(pinned_alloc(sh.pool, nb_s + nb_w + 16, &sh.h_desc, &sh.cap_hdesc));
+  CUDA_TRY(cudaMemcpyAsync(sh.h_desc, sh.d_streams, nb_s, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(sh.h_desc + nb_s, sh.d_walks, nb_w, cudaMemcpyDeviceToHost, st));
+  sh.desc_pending = true;
+  sh.dirty = true;
+  (void)ctx;
+  return DCB_OK;
+}
+void absorb_descs(dcb_batch *b) {
+  for (Shard &sh : b->shards) {
+    if (!sh.desc_pending) continue;
+    const uint64_t nb_s = sh.streams.size() * sizeof(StreamDesc), nb_w = sh.walks.size() * sizeof(BufWalk);
+    memcpy(sh.streams.data(), sh.h_desc, nb_s);
+    memcpy(sh.walks.data(), sh.h_desc + nb_s, nb_w);
+    sh.desc_pending = false;
+  }
 }
 
 struct Timer {
@@ -1046,7 +1104,9 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   cudaStream_t st = ctx->streams[dev_index];
   CUDA_TRY(cudaSetDevice(sh.device));
   const uint32_t num_sms = (uint32_t)ctx->num_sms[dev_index];
-  dcb_launch_stats &stats = ctx->stats;
+  // device 0 of the context writes the decode's statistics record; the other devices' decode threads count their
+  // launches and streams in records of their own, merged by finish_stats
+  dcb_launch_stats &stats = dev_index == 0 ? ctx->stats : ctx->dev_stats[dev_index];
   if (sh.streams.empty()) return DCB_OK;
   // fresh descriptors: the decode must not depend on what an earlier decode left behind
   if (sh.dirty) {
@@ -1074,6 +1134,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
   // ---- Tagged streams: decode tags, resume the walks behind their bit areas ----
+  bool deferred_descs = false;
   for (;;) {
     Group g{};
     g.kind = 1; g.ncp = 1; g.wide = false; g.compact = 1; g.prec_bits = 12; g.entries = 0; g.exc = 0; g.zig = 0; g.mode = 0;
@@ -1123,6 +1184,36 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     CUDA_TRY(dcb_launch_resolve(A, sh.d_walks, sh.d_order + g.order.size(), (uint32_t)blocked.size(), sh.d_streams, st));
     stats.n_launches += 2;
     stats.n_streams += (int32_t)g.order.size();
+    // Nothing follows a Tagged attribute that closes its buffer, so the host does not need what the resumed walk finds
+    // (wrap bounds, quantisation parameters: they stay in the device descriptors, where the kernels read them) -- only
+    // WHICH kernels to launch, and that follows from the header fields it already has.  No round trip then.
+    bool all_last = !env_flags().no_fast_tagged;
+    for (uint32_t bi : blocked) all_last = all_last && sh.walks[bi].blocked == sh.walks[bi].stream_count - 1;
+    if (all_last) {
+      for (uint32_t bi : blocked) {
+        BufWalk &w = sh.walks[bi];
+        for (int i = 0; i < w.stream_count; ++i) {
+          StreamDesc &s = sh.streams[w.stream_first + i];
+          if (s.state == ST_READY) continue;
+          if (s.state == ST_TAGS_PENDING) {
+            bool has_scheme, mesh_scheme;
+            int e;
+            walk_scheme_kind(w, s, has_scheme, mesh_scheme, e);
+            s.recon = !has_scheme ? (uint8_t)RECON_NONE
+                      : s.transform == XF_WRAP ? (uint8_t)(mesh_scheme ? RECON_PARA_WRAP : RECON_DELTA_WRAP)
+                      : s.transform == XF_OCT_CANON ? (uint8_t)RECON_DELTA_OCT_CANON : (uint8_t)RECON_DELTA_OCT;
+          }
+          if (s.seq_type == SEQ_QUANTIZATION) s.store = STORE_DEQUANT;
+          else if (s.seq_type == SEQ_NORMALS) s.store = STORE_OCT_UNIT;
+          else if (s.seq_type == SEQ_INTEGER) s.store = STORE_NARROW;
+          s.state = ST_READY;
+        }
+        w.blocked = -1;
+        w.phase = 2;
+      }
+      deferred_descs = true;
+      break;
+    }
     CUDA_TRY(cudaMemcpyAsync(sh.streams.data(), sh.d_streams, sh.streams.size() * sizeof(StreamDesc), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(sh.walks.data(), sh.d_walks, sh.walks.size() * sizeof(BufWalk), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1130,8 +1221,9 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
 
   // ---- classify ----
   std::map<RawKey, Group> raw;
-  Group post[5], para[5], par[5], copy{}, octs{};
+  Group post[5], para[5], par[5], copy{}, octs{}, octc{};
   octs.kind = 6;
+  octc.kind = 6;
   bool par_delta[5] = {false, false, false, false, false};
   for (int n = 1; n <= 4; ++n) {
     post[n] = Group{}; post[n].kind = 2; post[n].ncp = n;
@@ -1185,11 +1277,15 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         g.max_entries = std::max(g.max_entries, s.n_entries);
         g.note_table(s);
         g.order.push_back(si);
-      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP) && !env_flags().no_par_post) {
-        // Tagged / uncompressed source, scan-able reconstruction: point-parallel kernels
+      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP ||
+                  ((s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON) && s.ncp == 2 && s.store == STORE_OCT_UNIT)) &&
+                 !env_flags().no_par_post) {
+        // Tagged / uncompressed source: point-parallel extraction; scan-able reconstructions finish there, octahedral
+        // corrections go to the scratch and oct_chain_kernel runs the recurrence (as behind a Raw source)
         par[s.ncp].max_entries = std::max(par[s.ncp].max_entries, s.n_entries);
         par[s.ncp].order.push_back(si);
         if (s.recon == RECON_DELTA_WRAP) par_delta[s.ncp] = true;
+        if (s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON) octc.order.push_back(si);
       } else {
         post[s.ncp].order.push_back(si);
       }
@@ -1223,15 +1319,36 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   for (int n = 1; n <= 4; ++n) { add(post[n]); add(para[n]); add(par[n]); }
   add(copy);
   add(octs);
+  add(octc);
+  // par_post2_kernel: per group the run prefix of its streams (runs of DCB_PAR_RUN chunks) and one ticket word
+  std::vector<uint32_t> par_runs[5];
+  uint64_t par_aux_off[5] = {0, 0, 0, 0, 0};
+  for (int n = 1; n <= 4; ++n) {
+    if (par[n].order.empty()) continue;
+    par_runs[n].reserve(par[n].order.size() + 2);
+    uint64_t acc = 0;
+    for (uint32_t si : par[n].order) {
+      par_runs[n].push_back((uint32_t)acc);
+      const uint64_t nch = ((uint64_t)sh.streams[si].n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
+      acc += (nch + DCB_PAR_RUN - 1) / DCB_PAR_RUN;
+    }
+    if (acc > 0xFFFFFFF0ull) return DCB_ERR_UNSUPPORTED;
+    par_runs[n].push_back((uint32_t)acc);
+    par_runs[n].push_back(0u);  // the ticket
+    par_aux_off[n] = n_order;
+    n_order += par_runs[n].size();
+  }
 
   if (n_order == 0) {
     if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+    if (deferred_descs) return queue_desc_copyback(ctx, sh, st);
     return DCB_OK;
   }
   {
     int rc = ensure_order(sh, n_order);
     if (rc) return rc;
-    std::vector<uint32_t> all;
+    std::vector<uint32_t> &all = sh.order_host;  // outlives the asynchronous upload
+    all.clear();
     all.reserve(n_order);
     for (Group *g : rgs) all.insert(all.end(), g->order.begin(), g->order.end());
     for (int n = 1; n <= 4; ++n) {
@@ -1241,9 +1358,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     all.insert(all.end(), copy.order.begin(), copy.order.end());
     all.insert(all.end(), octs.order.begin(), octs.order.end());
+    all.insert(all.end(), octc.order.begin(), octc.order.end());
+    for (int n = 1; n <= 4; ++n) all.insert(all.end(), par_runs[n].begin(), par_runs[n].end());
 
     CUDA_TRY(cudaMemcpyAsync(sh.d_order, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));  // `all` is a stack vector; the copy is tiny
   }
   // dominant group: most symbols
   Group *dom = nullptr;
@@ -1358,12 +1476,14 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         CUDA_TRY(cudaEventRecord(ctx->ev[6], st));
         for (uint32_t si : par[n].order) {
           const StreamDesc &sd = sh.streams[si];
-          ctx->algo_par += sd.out_bytes + (sd.scheme == SCHEME_TAGGED ? sd.n_entries + (sd.bits_total + 7) / 8
+          ctx->algo_par += sd.out_bytes + (sd.scheme == SCHEME_TAGGED ? sd.n_entries
                                                                        : (uint64_t)sd.n_entries * sd.ncp * sd.raw_num_bytes);
+          if (sd.scheme == SCHEME_TAGGED) ctx->par_streams.push_back({&sh, si});  // + its bit area, once bits_total is back
         }
       }
-      CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, np,
-                                   (par[n].max_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK, n, dump, ++ctx->epoch, A, st));
+      uint32_t *d_runs = sh.d_order + par_aux_off[n];
+      CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, d_runs, np, par_runs[n][np], d_runs + np + 1,
+                                   num_sms, n, dump, next_epoch(sh), A, st));
       stats.n_launches += 1;
       if (par_delta[n]) {
         // streams whose corrections break the modular-sum condition fall back to the exact serial recurrence
@@ -1375,6 +1495,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         ctx->ev_par = true;
       }
     }
+  }
+  if (!octc.order.empty()) {  // octahedral recurrence of the normals whose corrections par_post2 left in the scratch
+    CUDA_TRY(dcb_launch_oct_chain(sh.d_streams, sh.d_order + octc.order_off, (uint32_t)octc.order.size(), dump, A, st));
+    stats.n_launches++;
   }
   if (!octs.order.empty()) {
     CUDA_TRY(dcb_launch_oct_unit(sh.d_streams, sh.d_order + octs.order_off, (uint32_t)octs.order.size(), octs.max_entries, A, st));
@@ -1397,17 +1521,18 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       }
     }
   if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-  if (has_para) {
-    // parallelogram kernels validate the caller's maps on the device: fetch their verdicts
-    CUDA_TRY(cudaMemcpyAsync(sh.streams.data(), sh.d_streams, sh.streams.size() * sizeof(StreamDesc), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    sh.dirty = true;
+  if (has_para || deferred_descs) {
+    // parallelogram kernels validate the caller's maps on the device, resumed walks parse and validate on the device:
+    // their verdicts travel back behind the kernels and are folded in after the caller's synchronisation
+    int rc = queue_desc_copyback(ctx, sh, st);
+    if (rc) return rc;
   }
   return DCB_OK;
 }
 
 // after a decode: fold walk / stream statuses into the buffer records
 void collect_status(dcb_batch *b) {
+  absorb_descs(b);
   for (BufRec &r : b->bufs) {
     if (r.info.status) continue;
     const Shard &sh = b->shards[r.shard];
@@ -1485,6 +1610,8 @@ int decode_all_impl(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, ui
   for (const BufRec &r : b->bufs)
     if (r.info.needs_connectivity && r.info.status == DCB_OK) return DCB_ERR_STATE;  // dcb_index_finish not run
   memset(&ctx->stats, 0, sizeof ctx->stats);
+  ctx->dev_stats.assign(ctx->devices.size(), dcb_launch_stats{});
+  ctx->par_streams.clear();
   ctx->ev_raw = ctx->ev_tag = ctx->ev_par = ctx->ev_para = false;
   ctx->algo_raw = ctx->algo_tag = ctx->algo_par = 0;
   ctx->raw_name[0] = 0;
@@ -1521,7 +1648,7 @@ int decode_all_impl(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, ui
     fprintf(stderr, "[dcb timing] uploads issued in %.1f ms\n",
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count());
   const auto t0 = std::chrono::steady_clock::now();
-  for (int d = 0; d < b->n_devices; ++d) {
+  auto run_shard = [&](int d) -> int {
     Shard &sh = b->shards[d];
     int rc = issue_arena_copy(ctx, b, sh, d);
     if (rc) return rc;
@@ -1535,7 +1662,50 @@ int decode_all_impl(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg, ui
       fprintf(stderr, "[dcb timing]   shard %d launched at +%.1f ms (direct=%d in=%.1f MB out=%.1f MB)\n", d,
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), (int)sh.direct,
               sh.in_bytes / 1e6, sh.out_bytes / 1e6);
+    return DCB_OK;
+  };
+  // One host thread per PHYSICAL device: a shard whose decode needs a round trip (a Tagged attribute followed
+  // by more attributes) holds only its own device's thread.  Pipeline slices of one device stay on one thread, in slice
+  // order -- their bulk copies share one stream per direction.
+  std::vector<std::vector<int>> by_dev;
+  {
+    std::vector<int> ids;
+    for (int d = 0; d < b->n_devices; ++d) {
+      size_t k = 0;
+      while (k < ids.size() && ids[k] != b->shards[d].device) ++k;
+      if (k == ids.size()) { ids.push_back(b->shards[d].device); by_dev.emplace_back(); }
+      by_dev[k].push_back(d);
+    }
   }
+  if (by_dev.size() <= 1 || dbg_t || env_flags().no_threads) {
+    for (int d = 0; d < b->n_devices; ++d) {
+      int rc = run_shard(d);
+      if (rc) return rc;
+    }
+    return DCB_OK;
+  }
+  std::vector<int> rcs(by_dev.size(), DCB_OK);
+  std::vector<std::thread> workers;
+  for (size_t k = 1; k < by_dev.size(); ++k)
+    workers.emplace_back([&, k]() {
+      for (int d : by_dev[k]) {
+        try {
+          rcs[k] = run_shard(d);
+        } catch (const std::bad_alloc &) {
+          rcs[k] = DCB_ERR_OOM;
+        } catch (...) {
+          rcs[k] = DCB_ERR_STATE;
+        }
+        if (rcs[k]) break;
+      }
+    });
+  for (int d : by_dev[0]) {
+    rcs[0] = run_shard(d);
+    if (rcs[0]) break;
+  }
+  for (std::thread &t : workers) t.join();
+  for (int rc : rcs)
+    if (rc) return rc;
   return DCB_OK;
 }
 
@@ -1549,6 +1719,13 @@ int sync_all(dcb_ctx *ctx) {
 
 void finish_stats(dcb_ctx *ctx) {
   dcb_launch_stats &st = ctx->stats;
+  for (size_t d = 1; d < ctx->dev_stats.size(); ++d) {
+    st.n_launches += ctx->dev_stats[d].n_launches;
+    st.n_streams += ctx->dev_stats[d].n_streams;
+  }
+  for (auto &ps : ctx->par_streams)
+    ctx->algo_par += (static_cast<const Shard *>(ps.first)->streams[ps.second].bits_total + 7) / 8;
+  ctx->par_streams.clear();
   float ms = 0.0f;
   for (auto &t : ctx->timeline) {
     float a = 0.0f, b = 0.0f;
@@ -1998,6 +2175,7 @@ int dcb_decode_resident(dcb_ctx *ctx, dcb_batch *b, void *dev_out, void *dev_dbg
     if (rc) return rc;
     rc = sync_all(ctx);
     if (rc) return rc;
+    absorb_descs(b);
     finish_stats(ctx);
     collect_status(b);
     return DCB_OK;
@@ -2029,6 +2207,7 @@ int dcb_decode(dcb_ctx *ctx, dcb_batch *b, uint8_t *host_out, uint8_t *host_dbg,
     rc = sync_all(ctx);
     if (rc) return rc;
     if (dbg_t) fprintf(stderr, "[dcb timing] decode_all issued %.1f ms, download done %.1f ms\n", t_dec, ms());
+    absorb_descs(b);
     finish_stats(ctx);
     collect_status(b);
     return DCB_OK;
@@ -2054,6 +2233,7 @@ int dcb_decode_scatter(dcb_ctx *ctx, dcb_batch *b, uint8_t *const *outs, int n_o
     }
     rc = sync_all(ctx);
     if (rc) return rc;
+    absorb_descs(b);
     finish_stats(ctx);
     collect_status(b);
     return DCB_OK;

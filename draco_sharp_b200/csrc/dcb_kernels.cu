@@ -283,6 +283,11 @@ __global__ void resolve_kernel(const uint8_t *__restrict__ arena, BufWalk *walks
   BufWalk w = walks[list[i]];
   walk_continue(arena, w, streams);
   walks[list[i]] = w;
+  // a walk that failed behind the bit area fails every stream of its buffer: the host may have launched their kernels
+  // without waiting for this verdict (a Tagged attribute that closes its buffer needs no round trip)
+  if (w.status != DCB_OK)
+    for (int k = 0; k < w.stream_count; ++k)
+      if (streams[w.stream_first + k].status == DCB_OK) streams[w.stream_first + k].status = w.status;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,244 +377,7 @@ __global__ void __launch_bounds__(32) serial_post_kernel(const uint8_t *__restri
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// par_post_kernel: the point-parallel path behind a Tagged (or uncompressed) source.
-//
-// Once the tags are known the bit fields are position independent (SymbolDecoding.cs:37-49,
-// DecoderBuffer.cs:138-154): one CTA handles DCB_TAG_CHUNK points -- tags -> exclusive scan of
-// tag * ncp (bit offsets) -> LSB-first extraction -> zig-zag.  Delta + wrap is a prefix sum modulo
-// max_diff when every |correction| < max_diff <= 2^30 (PredictionSchemeWrapDecodingTransform.cs:46-67
-// then reduces to  out = min + (prev - min + corr) mod max_diff); streams that break the condition
-// are flagged `irregular` and re-run by the serial kernel, bit-exact with the reference recurrence.
-// One pass: every CTA reduces its chunk, publishes the aggregate, and picks up the sum of the chunks before it
-// with a decoupled look-back over the per-chunk state words of its stream (state | epoch | value in one 64-bit
-// word, so no fence and no clearing between decodes); then it finishes the scan, dequantises / narrows and stores
-// coalesced.  CTAs of a stream are consecutive in launch order, so predecessors are resident or done.
-// ---------------------------------------------------------------------------------------------
-struct ParChunk {
-  const uint8_t *tags;       // nullptr for uncompressed sources
-  const uint64_t *chunk_bits;
-  unsigned long long *chunk_state;  // [n_chunks][4] look-back words: (epoch << 34) | (state << 32) | sum mod max_diff
-  uint32_t n_chunks;
-};
-__device__ __forceinline__ ParChunk par_chunk_of(const StreamDesc &d, uint8_t *aux) {
-  ParChunk c;
-  const uint64_t n = d.n_entries;
-  c.n_chunks = (uint32_t)((n + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK);
-  uint8_t *base = aux + d.tag_off;
-  c.tags = d.scheme == SCHEME_TAGGED ? base : nullptr;
-  c.chunk_bits = reinterpret_cast<const uint64_t *>(base + ((n + 15ull) & ~15ull));
-  c.chunk_state = reinterpret_cast<unsigned long long *>(base + ((n + 15ull) & ~15ull) + 8ull * (c.n_chunks + 1));
-  return c;
-}
-
-__device__ __forceinline__ uint32_t mod_add(uint32_t a, uint32_t b, uint32_t md) {  // a, b in [0, md), md <= 2^30
-  const uint32_t s = a + b;
-  return s >= md ? s - md : s;
-}
-
-constexpr uint32_t kParThreads = 128;                       // threads per CTA
-constexpr uint32_t kParPts = DCB_TAG_CHUNK / kParThreads;   // consecutive points per thread (8)
-constexpr uint32_t kParWarps = kParThreads / 32;
-
-// Store kParPts consecutive entries starting at entry index e0 (a multiple of 4) as groups of 4
-template <int NCP>
-__device__ __forceinline__ void store_run(const PostParams &pp, uint8_t *optr, uint64_t e0, uint32_t cnt_left,
-                                          int32_t (*v)[NCP]) {
-#pragma unroll
-  for (uint32_t q = 0; q < kParPts / 4; ++q) {
-    if (4 * q + 4 <= cnt_left) {
-      store_group4<NCP>(pp, pp.store, pp.dsize, optr, e0 + 4 * q, v + 4 * q);
-    } else {
-#pragma unroll
-      for (uint32_t j = 0; j < 4; ++j)
-        if (4 * q + j < cnt_left) store_entry<NCP>(pp, pp.store, pp.dsize, optr, e0 + 4 * q + j, v[4 * q + j]);
-    }
-  }
-}
-
-template <int NCP, bool DUMP>
-__global__ void __launch_bounds__(kParThreads) par_post_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
-                                                               const uint32_t *__restrict__ order, uint32_t n_streams,
-                                                               uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
-                                                               uint8_t *__restrict__ aux, uint32_t dump, uint32_t epoch) {
-  extern __shared__ __align__(16) uint32_t sm_bits[];  // the chunk's bit fields, word aligned
-  __shared__ uint32_t warp_sums[kParWarps][NCP];
-  __shared__ uint32_t warp_bits[kParWarps];
-  __shared__ uint32_t chunk_excl[NCP];
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  for (uint32_t slot = blockIdx.y; slot < n_streams; slot += gridDim.y) {
-    StreamDesc &d = streams[order[slot]];
-    if (d.status != DCB_OK) continue;
-    const uint32_t n = d.n_entries;
-    const uint32_t chunk = blockIdx.x;
-    const uint32_t e0 = chunk * DCB_TAG_CHUNK;
-    if (e0 >= n) continue;
-    const ParChunk pc = par_chunk_of(d, aux);
-    const uint32_t cnt = min(DCB_TAG_CHUNK, n - e0);
-    const int recon = d.recon;
-    __syncthreads();  // shared buffers are reused across the slot loop
-
-    // ---- bit lengths of this thread's points ----
-    const uint32_t p0 = tid * kParPts;
-    const uint32_t mine_cnt = p0 < cnt ? min(kParPts, cnt - p0) : 0u;
-    uint32_t tg[kParPts];
-    const uint32_t fixed_bits = 8u * d.raw_num_bytes;
-    if (pc.tags) {
-      // tags are padded to 16 bytes: two aligned words cover the thread's 8 points
-      const uint2 w = p0 < cnt ? *reinterpret_cast<const uint2 *>(pc.tags + e0 + p0) : make_uint2(0u, 0u);
-#pragma unroll
-      for (uint32_t j = 0; j < kParPts; ++j) {
-        const uint32_t ww = j < 4 ? w.x : w.y;
-        tg[j] = j < mine_cnt ? ((ww >> (8 * (j & 3))) & 0xFFu) : 0u;
-      }
-    } else {
-#pragma unroll
-      for (uint32_t j = 0; j < kParPts; ++j) tg[j] = j < mine_cnt ? fixed_bits : 0u;
-    }
-    uint32_t mine = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < kParPts; ++j) mine += tg[j];
-    mine *= NCP;
-    // exclusive scan of the bit counts over the CTA (< 2^18)
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (uint32_t)o) incl += t;
-    }
-    if (lane == 31) warp_bits[warp] = incl;
-    const uint64_t bit_begin = pc.tags ? pc.chunk_bits[chunk] : (uint64_t)e0 * NCP * fixed_bits;
-    const uint64_t byte_begin = (pc.tags ? d.bits_off : d.raw_off) + (bit_begin >> 3);
-    const uint64_t word_begin = byte_begin & ~3ull;
-    PostParams pp;
-    pp.load(d);
-    __syncthreads();
-    uint32_t warp_off = 0, total_bits = 0;
-#pragma unroll
-    for (uint32_t w = 0; w < kParWarps; ++w) {
-      if (w < warp) warp_off += warp_bits[w];
-      total_bits += warp_bits[w];
-    }
-    // chunk bit range -> shared memory (coalesced 32-bit loads from the 4-byte aligned floor)
-    const uint32_t lead = (uint32_t)((byte_begin - word_begin) * 8u + (bit_begin & 7u));  // bits before the first field
-    const uint32_t n_words = (lead + total_bits + 31u) / 32u + 1u;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(arena + word_begin);
-    for (uint32_t i = tid; i < n_words; i += kParThreads) sm_bits[i] = __ldg(src + i);  // arena is padded: over-read is safe
-    __syncthreads();
-
-    // ---- extract + zig-zag ----
-    uint32_t bpos = lead + warp_off + (incl - mine);
-    int32_t v[kParPts][NCP];
-    const bool zig = d.zigzag != 0;
-    int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
-#pragma unroll
-    for (uint32_t j = 0; j < kParPts; ++j) {
-      const uint32_t t = tg[j];
-      const uint32_t msk = t >= 32u ? 0xFFFFFFFFu : ((1u << t) - 1u);
-#pragma unroll
-      for (int c = 0; c < NCP; ++c) {
-        const uint32_t w = bpos >> 5;
-        const uint32_t sym = __funnelshift_r(sm_bits[w], sm_bits[w + 1], bpos) & msk;
-        bpos += t;
-        if (DUMP && (dump & DCB_DUMP_SYMBOLS) && j < mine_cnt) dptr[(size_t)(e0 + p0 + j) * NCP + c] = (int32_t)sym;
-        v[j][c] = zig ? zigzag_dec(sym) : (int32_t)sym;
-      }
-    }
-    if (recon == RECON_DELTA_WRAP) {
-      // ---- corrections as residues modulo max_diff (valid while |corr| < max_diff <= 2^30), block scan ----
-      const uint32_t md = (uint32_t)pp.max_diff;
-      const bool md_ok = md >= 1u && md <= (1u << 30);
-      bool bad = !md_ok;
-      uint32_t tsum[NCP];
-#pragma unroll
-      for (int c = 0; c < NCP; ++c) {
-        tsum[c] = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < kParPts; ++j) {
-          const int32_t x = v[j][c];
-          const uint32_t ax = x < 0 ? 0u - (uint32_t)x : (uint32_t)x;
-          bad |= (j < mine_cnt) & (ax >= md);
-          const uint32_t res = x < 0 ? (uint32_t)x + md : (uint32_t)x;  // residue in [0, md) when not bad
-          v[j][c] = (int32_t)res;
-          tsum[c] = (j < mine_cnt && !bad) ? mod_add(tsum[c], res, md) : tsum[c];
-        }
-      }
-      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(reinterpret_cast<unsigned int *>(&d.irregular), 1u);
-      uint32_t inc[NCP];
-#pragma unroll
-      for (int c = 0; c < NCP; ++c) {
-        inc[c] = tsum[c];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, inc[c], o);
-          if (lane >= (uint32_t)o) inc[c] = mod_add(inc[c], t, md);
-        }
-        if (lane == 31) warp_sums[warp][c] = inc[c];
-      }
-      __syncthreads();
-      // ---- decoupled look-back: one thread per component ----
-      if (tid < NCP) {
-        uint32_t agg = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < kParWarps; ++w) agg = mod_add(agg, warp_sums[w][tid], md);
-        volatile unsigned long long *stw = pc.chunk_state + (size_t)chunk * 4 + tid;
-        const unsigned long long tag_agg = ((unsigned long long)epoch << 34) | (1ull << 32);
-        const unsigned long long tag_pre = ((unsigned long long)epoch << 34) | (2ull << 32);
-        uint32_t excl = 0;
-        if (chunk == 0) {
-          *stw = tag_pre | agg;
-        } else {
-          *stw = tag_agg | agg;
-          uint32_t k = chunk - 1;
-          for (;;) {
-            const unsigned long long wv = *reinterpret_cast<volatile const unsigned long long *>(&pc.chunk_state[(size_t)k * 4 + tid]);
-            if ((wv >> 34) != epoch) continue;  // predecessor has not published in this decode yet
-            excl = mod_add(excl, (uint32_t)wv, md);
-            if (((wv >> 32) & 3ull) == 2ull) break;
-            --k;  // aggregate only: keep walking back (chunk 0 always publishes a prefix)
-          }
-          *stw = tag_pre | mod_add(excl, agg, md);
-        }
-        chunk_excl[tid] = excl;
-      }
-      __syncthreads();
-      // value before this thread's first point = chunks before + warps before + lanes before
-      // first element of the stream: prediction = clamp(0) (PredictionSchemeDeltaDecoder.cs:30 + ClampPredictedValue)
-      const int32_t p0v = 0 > pp.mx ? pp.mx : (0 < pp.mn ? pp.mn : 0);
-#pragma unroll
-      for (int c = 0; c < NCP; ++c) {
-        uint32_t before = mod_add(inc[c], tsum[c] == 0u ? 0u : md - tsum[c], md);
-        before = mod_add(before, chunk_excl[c], md);
-#pragma unroll
-        for (uint32_t w = 0; w < kParWarps; ++w)
-          if (w < warp) before = mod_add(before, warp_sums[w][c], md);
-        uint32_t acc = mod_add(before, (uint32_t)(p0v - pp.mn), md);
-#pragma unroll
-        for (uint32_t j = 0; j < kParPts; ++j) {
-          acc = mod_add(acc, (uint32_t)v[j][c], md);
-          v[j][c] = (int32_t)((uint32_t)pp.mn + acc);
-        }
-      }
-      if (d.irregular) continue;  // the serial kernel re-runs this stream (it also overwrites anything stored so far)
-    }
-    // ---- store ----
-    if (DUMP && (dump & DCB_DUMP_QINTS) && recon != RECON_PARA_WRAP) {
-#pragma unroll
-      for (uint32_t j = 0; j < kParPts; ++j)
-        if (j < mine_cnt)
-#pragma unroll
-          for (int c = 0; c < NCP; ++c) dptr[(size_t)(e0 + p0 + j) * NCP + c] = v[j][c];
-    }
-    uint8_t *obase = out + d.out_off;
-    if (recon == RECON_PARA_WRAP) {  // corrections for the parallelogram chain: int32 into the stream's scratch
-      pp.store = STORE_NARROW;
-      pp.dsize = 4;
-      obase = aux + d.aux_off;
-    }
-    if (mine_cnt) store_run<NCP>(pp, obase, (uint64_t)e0 + p0, mine_cnt, v);
-  }
-}
+// par_post2_kernel (the point-parallel path behind Tagged / uncompressed sources) lives in dcb_par_post.cu.
 
 // ---------------------------------------------------------------------------------------------
 // parallelogram prediction
@@ -1061,31 +829,6 @@ cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_orde
   }
 #undef DCB_CASE
   return cudaGetLastError();
-}
-
-// point-parallel post-processing of Tagged / uncompressed streams: one CTA per 1,024-point chunk
-template <int NCP>
-static cudaError_t launch_par_post_n(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_chunks,
-                                     uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
-  const uint32_t smem = (DCB_TAG_CHUNK * NCP * 32u) / 8u + 64u;  // worst case: 32-bit fields
-  const dim3 grid(max_chunks, n > 65535u ? 65535u : n);
-  if (dump)
-    par_post_kernel<NCP, true><<<grid, kParThreads, smem, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump, epoch);
-  else
-    par_post_kernel<NCP, false><<<grid, kParThreads, smem, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump, epoch);
-  return cudaGetLastError();
-}
-
-cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_chunks, int ncp,
-                                uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
-  if (n == 0 || max_chunks == 0) return cudaSuccess;
-  switch (ncp) {
-    case 1: return launch_par_post_n<1>(d_streams, d_order, n, max_chunks, dump, epoch, a, st);
-    case 2: return launch_par_post_n<2>(d_streams, d_order, n, max_chunks, dump, epoch, a, st);
-    case 3: return launch_par_post_n<3>(d_streams, d_order, n, max_chunks, dump, epoch, a, st);
-    case 4: return launch_par_post_n<4>(d_streams, d_order, n, max_chunks, dump, epoch, a, st);
-    default: return cudaErrorInvalidValue;
-  }
 }
 
 cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
