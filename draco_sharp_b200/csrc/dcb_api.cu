@@ -47,7 +47,7 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 // experiment / test switches, read once per process (never per stream or per decode)
 struct EnvFlags {
   bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_pc, no_direct, no_fast_tagged, no_threads;
-  int ctas_per_sm, pairs;
+  int ctas_per_sm, pairs, par_run;
   EnvFlags() {
     no_par_post = getenv("DCB_NO_PAR_POST") != nullptr;
     no_fanout = getenv("DCB_NO_FANOUT") != nullptr;
@@ -60,6 +60,7 @@ struct EnvFlags {
     no_fast_tagged = getenv("DCB_NO_FAST_TAGGED") != nullptr;  // always fetch the resumed walks before classifying
     ctas_per_sm = getenv("DCB_CTAS_PER_SM") ? atoi(getenv("DCB_CTAS_PER_SM")) : 0;
     pairs = getenv("DCB_PAIRS") ? atoi(getenv("DCB_PAIRS")) : 0;
+    par_run = getenv("DCB_PAR_RUN") ? atoi(getenv("DCB_PAR_RUN")) : 0;  // run length of par_post2_kernel, in chunks
   }
 };
 const EnvFlags &env_flags() {
@@ -1320,17 +1321,33 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   add(copy);
   add(octs);
   add(octc);
-  // par_post2_kernel: per group the run prefix of its streams (runs of DCB_PAR_RUN chunks) and one ticket word
+  // par_post2_kernel: per group the run prefix of its streams (runs of par_run_len chunks) and one ticket word
   std::vector<uint32_t> par_runs[5];
   uint64_t par_aux_off[5] = {0, 0, 0, 0, 0};
+  uint32_t par_run_len[5] = {1, 1, 1, 1, 1}, par_claim[5] = {1, 1, 1, 1, 1};
   for (int n = 1; n <= 4; ++n) {
     if (par[n].order.empty()) continue;
+    // longest streams first: whole-stream runs are handed out by ticket, longest-processing-time first
+    std::stable_sort(par[n].order.begin(), par[n].order.end(),
+                     [&](uint32_t x, uint32_t y) { return sh.streams[x].n_entries > sh.streams[y].n_entries; });
+    uint64_t total_chunks = 0, max_chunks = 0;
+    for (uint32_t si : par[n].order) {
+      const uint64_t nch = ((uint64_t)sh.streams[si].n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
+      total_chunks += nch;
+      max_chunks = std::max(max_chunks, nch);
+    }
+    dcb_par_post_plan((uint32_t)par[n].order.size(), total_chunks, (uint32_t)std::min<uint64_t>(max_chunks, 0xFFFFFFFFull),
+                      par_delta[n], num_sms, n, &par_run_len[n], &par_claim[n]);
+    if (env_flags().par_run > 0) {  // experiments
+      par_run_len[n] = (uint32_t)env_flags().par_run;
+      par_claim[n] = 1;
+    }
     par_runs[n].reserve(par[n].order.size() + 2);
     uint64_t acc = 0;
     for (uint32_t si : par[n].order) {
       par_runs[n].push_back((uint32_t)acc);
       const uint64_t nch = ((uint64_t)sh.streams[si].n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
-      acc += (nch + DCB_PAR_RUN - 1) / DCB_PAR_RUN;
+      acc += (nch + par_run_len[n] - 1) / par_run_len[n];
     }
     if (acc > 0xFFFFFFF0ull) return DCB_ERR_UNSUPPORTED;
     par_runs[n].push_back((uint32_t)acc);
@@ -1482,8 +1499,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         }
       }
       uint32_t *d_runs = sh.d_order + par_aux_off[n];
-      CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, d_runs, np, par_runs[n][np], d_runs + np + 1,
-                                   num_sms, n, dump, next_epoch(sh), A, st));
+      CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, d_runs, np, par_runs[n][np], par_run_len[n],
+                                   par_claim[n], d_runs + np + 1, num_sms, n, dump, next_epoch(sh), A, st));
       stats.n_launches += 1;
       if (par_delta[n]) {
         // streams whose corrections break the modular-sum condition fall back to the exact serial recurrence

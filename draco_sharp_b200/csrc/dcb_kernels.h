@@ -7,7 +7,6 @@
 
 #define DCB_TAG_CHUNK 256u   // points per bit-offset checkpoint of a Tagged stream = one warp-chunk of par_post2_kernel
 #define DCB_PAR_WARPS 8u     // par_post2_kernel: independent persistent warps per CTA
-#define DCB_PAR_RUN 8u       // par_post2_kernel: consecutive chunks a warp carries its running value through (one look-back per run)
 #define DCB_RING_BYTES 128u   // per-lane shared-memory ring of compressed bytes (rANS kernels)
 // chain / consumer warp pairs (dcb_rans_pc.cu): shared memory of one pair beyond its lanes' tables
 #define DCB_PC_STAGES 4u       // queue depth in groups
@@ -46,12 +45,15 @@ cudaError_t dcb_launch_resolve(const DevArenas &a, BufWalk *d_walks, const uint3
 cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t dump,
                                    uint32_t only_irregular, const DevArenas &a, cudaStream_t st);
 // point-parallel path behind Tagged / uncompressed sources (recon none or delta + wrap; corrections of parallelogram /
-// octahedral streams go to the int32 scratch).  Persistent warps pull runs of DCB_PAR_RUN chunks from *d_ticket;
+// octahedral streams go to the int32 scratch).  Persistent warps pull runs of `run_len` chunks from *d_ticket;
 // d_run_prefix[i] = runs in front of stream d_order[i] (n + 1 values).
 uint32_t dcb_par_post_smem_bytes(int ncp);
+// run length (chunks) and runs per ticket for a launch: whole streams when there are enough of them, else single chunks
+void dcb_par_post_plan(uint32_t n_streams, uint64_t total_chunks, uint32_t max_chunks, bool any_delta, uint32_t num_sms, int ncp,
+                       uint32_t *run_len, uint32_t *claim);
 cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, const uint32_t *d_run_prefix, uint32_t n,
-                                uint32_t total_runs, unsigned int *d_ticket, uint32_t num_sms, int ncp, uint32_t dump,
-                                uint32_t epoch, const DevArenas &a, cudaStream_t st);
+                                uint32_t total_runs, uint32_t run_len, uint32_t claim, unsigned int *d_ticket, uint32_t num_sms,
+                                int ncp, uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
                             uint32_t dump, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_oct_chain(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t dump,

@@ -9,9 +9,12 @@
 //
 // Shape of the kernel (round 2; the round-1 kernel was one CTA per 1,024 points with five __syncthreads around a
 // synchronous staging loop, 26 % of the HBM peak):
-//   * persistent WARPS, no CTA-level synchronisation at all.  A warp claims runs of kRun consecutive 256-point chunks
-//     with an atomic ticket (so the predecessor of every claimed run belongs to a warp that is running), 8 points per
-//     lane, and carries the running delta value through its run in registers.
+//   * persistent WARPS, no CTA-level synchronisation at all.  A warp claims runs of consecutive 256-point chunks with an
+//     atomic ticket (so the predecessor of every claimed run belongs to a warp that is running), 8 points per lane, and
+//     carries the running delta value through its run in registers.  The run length is a launch parameter with two
+//     useful values (dcb_par_post_plan): a WHOLE STREAM when the batch has enough streams to fill the machine (no
+//     look-back at all), else ONE chunk (every chunk publishes its aggregate before it looks back).  Anything in
+//     between serialises a stream: a run's later chunks cannot publish before the run's look-back has returned.
 //   * the chunk's tags and bit fields arrive by 1-D TMA: cp.async.bulk global -> shared with an mbarrier transaction
 //     count, issued by lane 0 one chunk ahead (two stages per warp), so the loads of chunk k+1 are in flight while
 //     chunk k is scanned and extracted.  Full chunks leave the same way: the decoded entries are staged in shared
@@ -33,8 +36,6 @@ using namespace dcb;
 namespace {
 
 constexpr uint32_t kWarps = DCB_PAR_WARPS;       // independent warps per CTA
-constexpr uint32_t kRun = DCB_PAR_RUN;           // chunks per run (one look-back per run)
-constexpr uint32_t kClaim = 4;                   // runs per ticket
 constexpr uint32_t kPts = DCB_TAG_CHUNK / 32u;   // consecutive points per lane (8)
 static_assert(kPts == 8, "a lane owns 8 consecutive points (two tag words)");
 
@@ -139,8 +140,8 @@ template <int NCP, bool DUMP>
 __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                                 const uint32_t *__restrict__ order,
                                                                 const uint32_t *__restrict__ run_prefix, uint32_t n_streams,
-                                                                uint32_t total_runs, unsigned int *ticket,
-                                                                uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
+                                                                uint32_t total_runs, uint32_t kRun, uint32_t kClaim,
+                                                                unsigned int *ticket, uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
                                                                 uint8_t *__restrict__ aux, uint32_t dump, uint32_t epoch) {
   extern __shared__ __align__(128) uint8_t smem[];
   typedef Geo<NCP> G;
@@ -167,8 +168,11 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
     if (lane == 0) t = atomicAdd(ticket, kClaim);
     return __shfl_sync(0xffffffffu, t, 0);
   };
+  // chunk-sized runs look back at their predecessors: a claim held in reserve would keep its successors waiting for as
+  // long as the claim in front of it takes, so the next ticket is only prefetched when runs are whole streams
+  const bool prefetch_ticket = kRun > 1u;
   claim_base = fetch_ticket();
-  claim_next = fetch_ticket();
+  if (prefetch_ticket) claim_next = fetch_ticket();
   uint32_t claim_pos = 0;  // run inside the claim
 
   uint32_t slot_hint = 0;
@@ -208,8 +212,12 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
     } else {
       for (;;) {
         if (claim_pos >= kClaim) {
-          claim_base = claim_next;
-          claim_next = fetch_ticket();
+          if (prefetch_ticket) {
+            claim_base = claim_next;
+            claim_next = fetch_ticket();
+          } else {
+            claim_base = fetch_ticket();
+          }
           claim_pos = 0;
         }
         const uint32_t run = claim_base + claim_pos;
@@ -526,6 +534,24 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
 
 }  // namespace
 
+void dcb_par_post_plan(uint32_t n_streams, uint64_t total_chunks, uint32_t max_chunks, bool any_delta, uint32_t num_sms, int ncp,
+                       uint32_t *run_len, uint32_t *claim) {
+  const uint32_t smem = dcb_par_post_smem_bytes(ncp);
+  const uint64_t warps = (uint64_t)num_sms * std::max<uint32_t>(1u, (227u * 1024u) / (smem + 1024u)) * kWarps;
+  // whole-stream runs: the longest stream must be a small part of one warp's share of the batch
+  const bool whole = (uint64_t)max_chunks * warps * 2ull <= total_chunks && n_streams >= 2ull * warps;
+  if (whole) {
+    *run_len = std::max(1u, max_chunks);
+    *claim = 1u;
+  } else if (any_delta) {
+    *run_len = 1u;
+    *claim = 4u;
+  } else {
+    *run_len = 8u;  // no scan: runs only keep a warp on one stream's descriptor for a while
+    *claim = 2u;
+  }
+}
+
 uint32_t dcb_par_post_smem_bytes(int ncp) {
   switch (ncp) {
     case 1: return Geo<1>::kWarpBytes * kWarps;
@@ -537,8 +563,8 @@ uint32_t dcb_par_post_smem_bytes(int ncp) {
 
 template <int NCP>
 static cudaError_t launch_par_post_n(StreamDesc *d_streams, const uint32_t *d_order, const uint32_t *d_run_prefix, uint32_t n,
-                                     uint32_t total_runs, unsigned int *d_ticket, uint32_t num_sms, uint32_t dump, uint32_t epoch,
-                                     const DevArenas &a, cudaStream_t st) {
+                                     uint32_t total_runs, uint32_t run_len, uint32_t claim, unsigned int *d_ticket, uint32_t num_sms,
+                                     uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
   const uint32_t smem = Geo<NCP>::kWarpBytes * kWarps;
   auto k0 = par_post2_kernel<NCP, false>;
   auto k1 = par_post2_kernel<NCP, true>;
@@ -550,27 +576,29 @@ static cudaError_t launch_par_post_n(StreamDesc *d_streams, const uint32_t *d_or
   cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   // persistent: as many CTAs as fit the machine, never more than there are claims
   const uint32_t per_sm = std::max<uint32_t>(1u, (227u * 1024u) / (smem + 1024u));
-  const uint32_t claims = (total_runs + kClaim - 1u) / kClaim;
+  const uint32_t claims = (total_runs + claim - 1u) / claim;
   uint32_t grid = std::min<uint32_t>(num_sms * per_sm, (claims + kWarps - 1u) / kWarps);
   grid = std::max<uint32_t>(grid, 1u);
   e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   if (dump)
-    k1<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
+    k1<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
   else
-    k0<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
+    k0<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
   return cudaGetLastError();
 }
 
 cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, const uint32_t *d_run_prefix, uint32_t n,
-                                uint32_t total_runs, unsigned int *d_ticket, uint32_t num_sms, int ncp, uint32_t dump,
-                                uint32_t epoch, const DevArenas &a, cudaStream_t st) {
+                                uint32_t total_runs, uint32_t run_len, uint32_t claim, unsigned int *d_ticket, uint32_t num_sms,
+                                int ncp, uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
   if (n == 0 || total_runs == 0) return cudaSuccess;
+  run_len = std::max(1u, run_len);
+  claim = std::max(1u, claim);
   switch (ncp) {
-    case 1: return launch_par_post_n<1>(d_streams, d_order, d_run_prefix, n, total_runs, d_ticket, num_sms, dump, epoch, a, st);
-    case 2: return launch_par_post_n<2>(d_streams, d_order, d_run_prefix, n, total_runs, d_ticket, num_sms, dump, epoch, a, st);
-    case 3: return launch_par_post_n<3>(d_streams, d_order, d_run_prefix, n, total_runs, d_ticket, num_sms, dump, epoch, a, st);
-    case 4: return launch_par_post_n<4>(d_streams, d_order, d_run_prefix, n, total_runs, d_ticket, num_sms, dump, epoch, a, st);
+    case 1: return launch_par_post_n<1>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
+    case 2: return launch_par_post_n<2>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
+    case 3: return launch_par_post_n<3>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
+    case 4: return launch_par_post_n<4>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
     default: return cudaErrorInvalidValue;
   }
 }
