@@ -47,7 +47,8 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 // experiment / test switches, read once per process (never per stream or per decode)
 struct EnvFlags {
   bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_pc, no_direct, no_fast_tagged, no_threads;
-  int ctas_per_sm, pairs, par_run;
+  int ctas_per_sm, pairs, par_run, rec_ka;
+  bool no_rec;
   EnvFlags() {
     no_par_post = getenv("DCB_NO_PAR_POST") != nullptr;
     no_fanout = getenv("DCB_NO_FANOUT") != nullptr;
@@ -61,6 +62,8 @@ struct EnvFlags {
     ctas_per_sm = getenv("DCB_CTAS_PER_SM") ? atoi(getenv("DCB_CTAS_PER_SM")) : 0;
     pairs = getenv("DCB_PAIRS") ? atoi(getenv("DCB_PAIRS")) : 0;
     par_run = getenv("DCB_PAR_RUN") ? atoi(getenv("DCB_PAR_RUN")) : 0;  // run length of par_post2_kernel, in chunks
+    no_rec = getenv("DCB_NO_REC") != nullptr;                            // never plan the bucket-record kernels
+    rec_ka = getenv("DCB_REC_KA") ? atoi(getenv("DCB_REC_KA")) : 0;     // force their wide-region bucket size (experiments)
   }
 };
 const EnvFlags &env_flags() {
@@ -127,11 +130,17 @@ struct Group {            // one kernel launch (or a few, for global tables)
   // earliest / latest 128-slot block (over the group's streams) holding the first entry narrower than 2^k slots
   uint32_t nb_min[8], nb_max[8];
   bool nb_any;
+  // bucket-record kernels (dcb_rans_rec.cu): largest table need over the group's streams per candidate bucket size
+  // (8-byte units, 0xFFFF = some stream's table does not have the shape), value slots over ALL streams, and the plan
+  uint32_t rec_max[4], exc_all;
+  uint32_t rec_ka, rec_bytes;  // rec_ka != 0: the group runs on the bucket-record kernels
   void note_table(const StreamDesc &s) {
     for (int k = 1; k <= 7; ++k) {
       nb_min[k] = nb_any ? std::min<uint32_t>(nb_min[k], s.narrow_blk[k]) : s.narrow_blk[k];
       nb_max[k] = nb_any ? std::max<uint32_t>(nb_max[k], s.narrow_blk[k]) : s.narrow_blk[k];
     }
+    for (int j = 0; j < 4; ++j) rec_max[j] = nb_any ? std::max<uint32_t>(rec_max[j], s.rec_need[j]) : s.rec_need[j];
+    exc_all = std::max(exc_all, s.n_active - std::min(s.n_active, s.dense_prefix));
     nb_any = true;
   }
 };
@@ -874,6 +883,36 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
         continue;
       }
     }
+    // ---- bucket-record tables (dcb_rans_rec.cu): one dependent shared-memory access per symbol, warp pairs, one CTA of
+    // up to four pairs per SM.  Taken whenever every stream of the group has the table shape and is resident that way.
+    g.rec_ka = 0;
+    if (!g.wide && g.prec_bits <= 15 && g.nb_any && !env_flags().no_rec && !env_flags().rans_pc && want == per_sm[i] && want <= 128) {
+      const uint32_t pairs = std::min<uint32_t>(std::max<uint32_t>(1u, 4u / share), want), lanes = (want + pairs - 1) / pairs;
+      uint32_t best_j = 4, best_bytes = 0xFFFFFFFFu;
+      for (uint32_t j = 0; j < 4; ++j) {
+        if (g.rec_max[j] >= 0xFFFFu || DCB_REC_KA0 + j >= g.prec_bits) continue;
+        if (env_flags().rec_ka > 0 && (uint32_t)env_flags().rec_ka != DCB_REC_KA0 + j) continue;
+        const uint32_t bytes = 8u * g.rec_max[j] + (uint32_t)align_up(2ull * g.exc_all, 8);
+        if (bytes < best_bytes) { best_bytes = bytes; best_j = j; }
+      }
+      if (best_j < 4 && lanes <= 32) {
+        RansLaunch L{};
+        L.lanes_per_warp = lanes;
+        L.prec_bits = g.prec_bits;
+        L.pairs = pairs;
+        L.rec_ka = DCB_REC_KA0 + best_j;
+        L.rec_bytes = best_bytes;
+        if ((uint64_t)dcb_rans_rec_smem_bytes(L, ksym) + kSmemPerCtaReserve <= sm_cap) {
+          g.rec_ka = L.rec_ka;
+          g.rec_bytes = best_bytes;
+          g.pairs = pairs;
+          g.lanes = lanes;
+          g.ctas_per_sm = 1;
+          g.lutb_bytes = 0;
+          continue;
+        }
+      }
+    }
     if (!g.wide && env_flags().rans_pc) {
       // ---- chain / consumer warp pairs with the two-level tables (experiment: measured slower than one warp per
       // sub-partition when the SM is full of streams -- the two warps of a pair compete for the same issue port) ----
@@ -1173,7 +1212,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     L.pairs = g.pairs;
     L.direct = g.direct;
-    CUDA_TRY(g.pairs ? dcb_launch_rans_tag_pc(L, A, st) : dcb_launch_rans_tag(L, A, st));
+    L.rec_ka = g.rec_ka;
+    L.rec_bytes = g.rec_bytes;
+    L.cap_exc = g.rec_ka ? g.exc_all : g.exc;
+    CUDA_TRY(g.rec_ka ? dcb_launch_rans_tag_rec(L, A, st) : g.pairs ? dcb_launch_rans_tag_pc(L, A, st) : dcb_launch_rans_tag(L, A, st));
     if (time_tag) {
       CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
       ctx->ev_tag = true;
@@ -1405,10 +1447,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     if (env_flags().debug_plan)
       fprintf(stderr, "[dcb plan] raw group ncp=%d wide=%d compact=%u prec=%u entries=%u mode=%u zig=%u: %u streams, %llu symbols, "
-                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u pairs=%u direct=%u global=%d\n",
+                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u pairs=%u direct=%u global=%d rec_ka=%u rec=%uB (need x8: %u %u %u %u, exc %u)\n",
               g->ncp, (int)g->wide, g->compact, g->prec_bits, g->entries, g->mode, g->zig, n,
               (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->lanes, g->pairs,
-              g->direct, (int)g->table_global);
+              g->direct, (int)g->table_global, g->rec_ka, g->rec_bytes, g->rec_max[0], g->rec_max[1], g->rec_max[2], g->rec_max[3], g->exc_all);
     if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (g->table_global) {
       const uint64_t slot_bytes = (uint64_t)g->lut_bytes + g->ent_bytes;
@@ -1435,7 +1477,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       tl_begin(g->mode == 1 ? "rans mode1" : g->mode == 2 ? "rans mode2" : g->mode == 3 ? "rans mode3" : g->mode == 4 ? "rans mode4" : "rans mode0", st);
       L.pairs = g->pairs;
       L.direct = g->direct;
-      CUDA_TRY(g->pairs ? dcb_launch_rans_raw_pc(L, g->ncp, A, st) : dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
+      L.rec_ka = g->rec_ka;
+      L.rec_bytes = g->rec_bytes;
+      if (g->rec_ka) L.cap_exc = g->exc_all;
+      CUDA_TRY(g->rec_ka ? dcb_launch_rans_raw_rec(L, g->ncp, A, st)
+               : g->pairs ? dcb_launch_rans_raw_pc(L, g->ncp, A, st) : dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));
       tl_end(st);
       stats.n_launches++;
     }
@@ -1459,10 +1505,16 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       stats.lanes_per_warp = (int32_t)g->lanes;
       stats.smem_per_stream = (uint64_t)g->lut_bytes + g->lutb_bytes + g->ent_bytes + DCB_RING_BYTES;
       RansLaunch Ls{nullptr, nullptr, n, g->lanes, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->entries, g->exc, g->lut_shift, g->prec_bits, 0, g->compact, g->zig, g->mode, g->pairs, g->direct};
-      const uint32_t cta_smem = (g->pairs ? dcb_rans_pc_smem_bytes(Ls, 4u * (uint32_t)g->ncp) : dcb_rans_smem_bytes(Ls, g->table_global)) + kSmemPerCtaReserve;
+      Ls.rec_ka = g->rec_ka;
+      Ls.rec_bytes = g->rec_bytes;
+      const uint32_t cta_smem = (g->rec_ka ? dcb_rans_rec_smem_bytes(Ls, 4u * (uint32_t)g->ncp)
+                                 : g->pairs ? dcb_rans_pc_smem_bytes(Ls, 4u * (uint32_t)g->ncp) : dcb_rans_smem_bytes(Ls, g->table_global)) + kSmemPerCtaReserve;
       const uint64_t per_wave = (uint64_t)num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(32u, (kSmemPerSM + 1024u) / cta_smem)) * g->lanes * std::max(1u, g->pairs);
       stats.n_waves = g->table_global ? 1 : (int32_t)((n + per_wave - 1) / per_wave);
-      if (g->pairs)
+      if (g->rec_ka)
+        snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_rec<ncp=%d,u16,smem,mode=%u,bucket records 2^%u|16|1,%ux%u lanes,%uB>", g->ncp,
+                 g->mode, g->rec_ka, g->pairs, g->lanes, g->rec_bytes);
+      else if (g->pairs)
         snprintf(ctx->raw_name, sizeof ctx->raw_name, "rans_raw_pc<ncp=%d,u16,smem,mode=%u,%s,%s,%ux%u lanes>", g->ncp, g->mode,
                  g->direct ? "direct slot LUT" : "two-level LUT", g->compact ? "compact" : "dense", g->pairs, g->lanes);
       else

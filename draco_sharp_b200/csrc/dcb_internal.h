@@ -96,6 +96,9 @@ struct StreamDesc {
   // narrow_blk[k] (k = 1..7): 128-slot block holding the first table entry narrower than 2^k slots (2^prec >> 7 when
   // there is none) -- what the launch planner needs to size the narrow region of the two-region LUT
   uint16_t narrow_blk[8];
+  // bucket-record kernels (dcb_rans_rec.cu): 8-byte units of table memory a lane needs, per candidate bucket size of the
+  // wide region (2^(DCB_REC_KA0 + j) slots); 0xFFFF = the table does not have the shape (see walk_rans_table)
+  uint16_t rec_need[4];
 };
 
 // Resumable container walk of one buffer (runs on the host; continues on the device behind Tagged
@@ -127,6 +130,77 @@ DCB_HD int dcb_rans_precision(int max_bit_length) {
   return p < 12 ? 12 : (p > 20 ? 20 : p);
 }
 
+// ---- bucket-record tables (dcb_rans_rec.cu) ----
+// The slot axis [0, 2^prec) of a table is cut at ta <= tb <= tc:
+//   [0, ta)        one 8-byte record per 2^ka slots     every such bucket meets at most two table entries below ta
+//   [ta, tb)       one record per 16 slots              likewise below tb
+//   [tb, tc)       one record per 8 slots               likewise below tc
+//   [tc, 2^prec)   one byte per slot                    every entry reaching into it is at most 16 slots wide, and
+//                                                       starts at or behind tc
+// then a bitmap of entry starts over the byte region (u32 words) with a u16 running count per word.  The value map of
+// the table follows (planned separately).  A bucket meets at most two entries iff at most one entry boundary lies
+// strictly inside it; RecShape finds, while the table streams by, for every bucket size the second boundary of the
+// first bucket that breaks the rule (records of that size are good for all slots in front of it) and the end of the
+// last entry wider than 16 slots, and from them the cuts.  Host (container walk -> launch planner) and device (table
+// build) run the same code on the same bytes.
+#define DCB_REC_KA0 5
+struct RecLayout {
+  uint32_t n_a, n_b, n_b2, n_c;                     // records / records / records / bytes
+  uint32_t off_b, off_b2, off_c, off_bm, off_cnt;   // byte offsets inside the lane's area (records first: 8-byte aligned)
+  uint32_t bytes;                                   // multiple of 8
+};
+DCB_HD RecLayout dcb_rec_layout(uint32_t ta, uint32_t tb, uint32_t tc, uint32_t prec, uint32_t ka) {
+  RecLayout l;
+  l.n_a = (ta + (1u << ka) - 1u) >> ka;
+  l.n_b = tb > ta ? ((tb + 15u) >> 4) - (ta >> 4) : 0u;
+  l.n_b2 = tc > tb ? ((tc + 7u) >> 3) - (tb >> 3) : 0u;
+  l.n_c = prec - tc;
+  l.off_b = 8u * l.n_a;
+  l.off_b2 = l.off_b + 8u * l.n_b;
+  l.off_c = l.off_b2 + 8u * l.n_b2;
+  l.off_bm = (l.off_c + l.n_c + 3u) & ~3u;
+  const uint32_t words = (l.n_c + 31u) >> 5;
+  l.off_cnt = l.off_bm + 4u * words;
+  l.bytes = (l.off_cnt + 2u * words + 7u) & ~7u;
+  return l;
+}
+struct RecShape {
+  // bucket sizes 2^3, 2^4, 2^DCB_REC_KA0 .. 2^(DCB_REC_KA0 + 3)
+  uint32_t bad_at[6];      // second boundary inside the first bucket holding two (0xFFFFFFFF: none)
+  uint32_t prev_bucket[6]; // bucket of the last boundary seen that lies strictly inside one
+  uint32_t end_wide;       // end of the last entry wider than 16 slots
+  DCB_HD static uint32_t scale(int j) { return j < 2 ? 3u + (uint32_t)j : (uint32_t)(DCB_REC_KA0 + j - 2); }
+  DCB_HD void begin() {
+    for (int j = 0; j < 6; ++j) {
+      bad_at[j] = 0xFFFFFFFFu;
+      prev_bucket[j] = 0xFFFFFFFFu;
+    }
+    end_wide = 0;
+  }
+  // entries in table order: [start, start + width), width > 0
+  DCB_HD void entry(uint32_t start, uint32_t width) {
+    if (width > 16u) end_wide = start + width;
+    if (start == 0) return;
+    for (int j = 0; j < 6; ++j) {
+      const uint32_t k = scale(j);
+      if ((start & ((1u << k) - 1u)) == 0) continue;  // on a bucket edge: inside none
+      const uint32_t bucket = start >> k;
+      if (bucket == prev_bucket[j] && bad_at[j] == 0xFFFFFFFFu) bad_at[j] = start;
+      prev_bucket[j] = bucket;
+    }
+  }
+  // the cuts for wide-region buckets of 2^ka slots; false: the table does not have the shape
+  DCB_HD bool cuts(uint32_t prec, uint32_t ka, uint32_t &ta, uint32_t &tb, uint32_t &tc) const {
+    // 8-slot records cost what the byte region costs per slot, without its bitmap: they reach as far as they are good
+    tc = bad_at[0] < prec ? bad_at[0] : prec;
+    if (tc < end_wide) return false;
+    tb = bad_at[1] < tc ? bad_at[1] : tc;
+    const uint32_t fa = bad_at[ka - DCB_REC_KA0 + 2];
+    ta = fa < tb ? fa : tb;
+    return true;
+  }
+};
+
 // ---- launch plan for the lane-per-stream rANS kernels ----
 struct RansLaunch {
   StreamDesc *d_streams;          // device array of all streams of the shard
@@ -146,4 +220,6 @@ struct RansLaunch {
   uint32_t mode;                  // 0 generic post-processing, 1..4 specialised (dcb_device.cuh)
   uint32_t pairs;                 // chain/consumer warp pairs per CTA (dcb_rans_pc.cu); 0 = the single-warp kernels
   uint32_t direct;                // 1: direct slot LUT (lut_bytes = 6 << prec_bits per lane; warp-pair kernels only)
+  uint32_t rec_ka;                // bucket-record kernels: log2(slots per record) of the wide region (0 = not that path)
+  uint32_t rec_bytes;             // bucket-record kernels: table area per lane (records + byte region + bitmap + value map)
 };

@@ -13,6 +13,10 @@
 #define DCB_PC_ROW_BYTES 64u   // one queue row: symbol j of all 32 lanes, 2 bytes each
 #define DCB_PC_CTL_BYTES 112u  // mbarriers full[4] empty[4] setup handoff filled + flag[4]
 #define DCB_PC_HAND_BYTES 48u  // per-lane hand-over record
+// bucket-record kernels (dcb_rans_rec.cu)
+#define DCB_REC_HAND_BYTES 56u // per-lane hand-over record
+#define DCB_REC_STAGES 2u      // queue depth in groups: the tables need the shared memory more than the queue does
+#define DCB_REC_CTL_BYTES 64u  // mbarriers full[2] empty[2] setup handoff + flag[2]
 struct PcGeom {
   uint32_t tab_bytes;    // table part of a pair's slice (worst-case alignment slack included)
   uint32_t slice_bytes;  // whole slice
@@ -38,6 +42,10 @@ PcGeom dcb_pc_geom(const RansLaunch &p, uint32_t syms_per_group);
 uint32_t dcb_rans_pc_smem_bytes(const RansLaunch &p, uint32_t syms_per_group);
 cudaError_t dcb_launch_rans_raw_pc(const RansLaunch &p, int ncp, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_rans_tag_pc(const RansLaunch &p, const DevArenas &a, cudaStream_t st);
+// bucket-record tables (dcb_rans_rec.cu): one dependent shared-memory access per symbol; warp pairs; RansLaunch::rec_ka / rec_bytes
+uint32_t dcb_rans_rec_smem_bytes(const RansLaunch &p, uint32_t syms_per_group);
+cudaError_t dcb_launch_rans_raw_rec(const RansLaunch &p, int ncp, const DevArenas &a, cudaStream_t st);
+cudaError_t dcb_launch_rans_tag_rec(const RansLaunch &p, const DevArenas &a, cudaStream_t st);
 // tag stream of Tagged attributes; one stream per lane
 cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_resolve(const DevArenas &a, BufWalk *d_walks, const uint32_t *d_list, uint32_t n,

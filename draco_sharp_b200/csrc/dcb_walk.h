@@ -65,12 +65,17 @@ DCB_HD uint64_t wr_varint(WalkRd &r) {
 }
 
 // RANS_TABLE: validates it and advances past it.  Entropy/RAnsSymbolDecoder.cs:12-51 + RAnsDecoder.cs:69-88
+// rec_need[j] (j = 0..3, kA = DCB_REC_KA0 + j): 8-byte units a lane of the bucket-record kernels (dcb_rans_rec.cu) needs
+// for this table (RecShape below), or 0xFFFF when the table does not have the shape.
 DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint32_t &n_active, uint32_t &dense_prefix,
-                           uint16_t *narrow_blk) {
+                           uint16_t *narrow_blk, uint16_t *rec_need) {
   num_symbols = 0;
   n_active = 0;
   dense_prefix = 0;  // number of leading symbols that all have non-zero probability
   bool gap = false;
+  RecShape shape;
+  shape.begin();
+  for (int j = 0; j < 4; ++j) rec_need[j] = 0xFFFFu;
   const uint32_t none_blk = (uint32_t)((1ull << prec_bits) >> 7) > 0xFFFFu ? 0xFFFFu : (uint32_t)((1ull << prec_bits) >> 7);
   for (int k = 0; k < 8; ++k) narrow_blk[k] = (uint16_t)none_blk;
   const uint64_t ns = wr_varint(r);
@@ -97,6 +102,7 @@ DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint
         if (!gap) ++dense_prefix;
         for (int k = 1; k <= 7; ++k)
           if (prob < (1u << k) && narrow_blk[k] == (uint16_t)none_blk && (sum >> 7) < none_blk) narrow_blk[k] = (uint16_t)(sum >> 7);
+        if (sum + prob <= (1ull << prec_bits)) shape.entry((uint32_t)sum, prob);
       } else {
         gap = true;
       }
@@ -104,6 +110,22 @@ DCB_HD int walk_rans_table(WalkRd &r, int prec_bits, uint32_t &num_symbols, uint
     }
   }
   if (sum != (1ull << prec_bits)) return DCB_ERR_TABLE;  // RAnsDecoder.cs:80,87
+#if !defined(__CUDA_ARCH__) && defined(DCB_DEBUG_SHAPE)
+  fprintf(stderr, "[shape] prec=%d ns=%u active=%u end_wide=%u bad_at: s3=%u s4=%u s5=%u s6=%u s7=%u s8=%u\n", prec_bits, num_symbols, n_active,
+          shape.end_wide, shape.bad_at[0], shape.bad_at[1], shape.bad_at[2], shape.bad_at[3], shape.bad_at[4], shape.bad_at[5]);
+#endif
+  if (prec_bits <= 15) {
+    const uint32_t prec = 1u << prec_bits;
+    for (int j = 0; j < 4; ++j) {
+      uint32_t ta, tb, tc;
+      if (!shape.cuts(prec, (uint32_t)(DCB_REC_KA0 + j), ta, tb, tc)) continue;
+      const uint32_t units = dcb_rec_layout(ta, tb, tc, prec, (uint32_t)(DCB_REC_KA0 + j)).bytes >> 3;
+#if !defined(__CUDA_ARCH__) && defined(DCB_DEBUG_SHAPE)
+      fprintf(stderr, "[shape]   ka=%d ta=%u tb=%u tc=%u bytes=%u\n", DCB_REC_KA0 + j, ta, tb, tc, units * 8);
+#endif
+      rec_need[j] = units < 0xFFFFu ? (uint16_t)units : (uint16_t)0xFFFFu;
+    }
+  }
   return DCB_OK;
 }
 
@@ -235,7 +257,7 @@ DCB_HD int walk_portable(WalkRd &r, const BufWalk &w, StreamDesc &s, int *st) {
         return 0;
       }
       s.table_off = r.pos;
-      e = walk_rans_table(r, s.prec_bits, s.num_symbols, s.n_active, s.dense_prefix, s.narrow_blk);
+      e = walk_rans_table(r, s.prec_bits, s.num_symbols, s.n_active, s.dense_prefix, s.narrow_blk, s.rec_need);
       if (!e && s.num_symbols == 0) e = DCB_ERR_NUM_SYMBOLS;
       if (!e) e = walk_rans_payload(r, s.prec_bits, s.payload_off, s.payload_len);
       if (e) { *st = e; return 0; }
