@@ -48,7 +48,7 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 struct EnvFlags {
   bool no_par_post, no_fanout, debug_plan, debug_timing, lutb_full, rans_pc, no_direct, no_fast_tagged, no_threads;
   int ctas_per_sm, pairs, par_run, rec_ka;
-  bool no_rec;
+  bool no_rec, split;
   EnvFlags() {
     no_par_post = getenv("DCB_NO_PAR_POST") != nullptr;
     no_fanout = getenv("DCB_NO_FANOUT") != nullptr;
@@ -62,7 +62,9 @@ struct EnvFlags {
     ctas_per_sm = getenv("DCB_CTAS_PER_SM") ? atoi(getenv("DCB_CTAS_PER_SM")) : 0;
     pairs = getenv("DCB_PAIRS") ? atoi(getenv("DCB_PAIRS")) : 0;
     par_run = getenv("DCB_PAR_RUN") ? atoi(getenv("DCB_PAR_RUN")) : 0;  // run length of par_post2_kernel, in chunks
-    no_rec = getenv("DCB_NO_REC") != nullptr;                            // never plan the bucket-record kernels
+    no_rec = getenv("DCB_REC") == nullptr;                               // the bucket-record kernels are opt-in (DCB_REC=1): measured
+                                                                         // slower than the fused kernel at full residency
+    split = getenv("DCB_SPLIT") != nullptr;                              // warp-pair kernels: consumers on their own sub-partition
     rec_ka = getenv("DCB_REC_KA") ? atoi(getenv("DCB_REC_KA")) : 0;     // force their wide-region bucket size (experiments)
   }
 };
@@ -134,6 +136,7 @@ struct Group {            // one kernel launch (or a few, for global tables)
   // (8-byte units, 0xFFFF = some stream's table does not have the shape), value slots over ALL streams, and the plan
   uint32_t rec_max[4], exc_all;
   uint32_t rec_ka, rec_bytes;  // rec_ka != 0: the group runs on the bucket-record kernels
+  uint32_t split;              // warp-pair kernels: chain warps on sub-partitions 0..2, consumers on sub-partition 3
   void note_table(const StreamDesc &s) {
     for (int k = 1; k <= 7; ++k) {
       nb_min[k] = nb_any ? std::min<uint32_t>(nb_min[k], s.narrow_blk[k]) : s.narrow_blk[k];
@@ -886,8 +889,10 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
     // ---- bucket-record tables (dcb_rans_rec.cu): one dependent shared-memory access per symbol, warp pairs, one CTA of
     // up to four pairs per SM.  Taken whenever every stream of the group has the table shape and is resident that way.
     g.rec_ka = 0;
+    g.split = 0;
     if (!g.wide && g.prec_bits <= 15 && g.nb_any && !env_flags().no_rec && !env_flags().rans_pc && want == per_sm[i] && want <= 128) {
-      const uint32_t pairs = std::min<uint32_t>(std::max<uint32_t>(1u, 4u / share), want), lanes = (want + pairs - 1) / pairs;
+      const bool split = env_flags().split && share == 1;
+      const uint32_t pairs = std::min<uint32_t>(split ? 3u : std::max<uint32_t>(1u, 4u / share), want), lanes = (want + pairs - 1) / pairs;
       uint32_t best_j = 4, best_bytes = 0xFFFFFFFFu;
       for (uint32_t j = 0; j < 4; ++j) {
         if (g.rec_max[j] >= 0xFFFFu || DCB_REC_KA0 + j >= g.prec_bits) continue;
@@ -905,6 +910,7 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
         if ((uint64_t)dcb_rans_rec_smem_bytes(L, ksym) + kSmemPerCtaReserve <= sm_cap) {
           g.rec_ka = L.rec_ka;
           g.rec_bytes = best_bytes;
+          g.split = split ? 1u : 0u;
           g.pairs = pairs;
           g.lanes = lanes;
           g.ctas_per_sm = 1;
@@ -920,6 +926,26 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
       if (env_flags().pairs > 0) target = (uint32_t)env_flags().pairs;
       const uint32_t lutb_min = g.compact ? 16u : 0u;
       uint32_t pairs = 1, lanes = 1, ctas = 1;
+      if (env_flags().split && share == 1 && (want + 2) / 3 <= 32) {
+        // split layout: one CTA per SM, three chain warps with a sub-partition each, their consumers on the fourth
+        const uint32_t lutb_min0 = g.compact ? 16u : 0u;
+        const uint32_t p3 = std::min<uint32_t>(3u, want), l3 = (want + p3 - 1) / p3;
+        if ((uint64_t)l3 * g.ent_bytes <= 65535 && pc_cta_bytes(p3, l3, g.lut_bytes, lutb_min0, 0) <= sm_cap) {
+          g.split = 1;
+          g.lanes = l3;
+          g.pairs = p3;
+          g.ctas_per_sm = 1;
+          g.lutb_bytes = 0;
+          if (g.compact) {
+            const uint64_t base = pc_cta_bytes(p3, l3, g.lut_bytes, lutb_min0, 0);
+            const uint64_t spare = sm_cap > base ? (sm_cap - base) / ((uint64_t)p3 * (l3 + 1)) : 0;
+            g.lutb_bytes = (uint32_t)std::min<uint64_t>((1u << g.prec_bits) >> 1, lutb_min0 + spare / 16 * 16);
+            const uint32_t need = lutb_need();
+            if (need != 0xFFFFFFFFu && !env_flags().lutb_full) g.lutb_bytes = std::min(g.lutb_bytes, need);
+          }
+          continue;
+        }
+      }
       for (;; --want) {
         uint32_t nw = std::max<uint32_t>((want + 31) / 32, std::min<uint32_t>(target, want));
         while ((uint64_t)((want + nw - 1) / nw) * g.ent_bytes > 65535) ++nw;  // 16-bit entry offsets inside a pair
@@ -1214,6 +1240,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     L.direct = g.direct;
     L.rec_ka = g.rec_ka;
     L.rec_bytes = g.rec_bytes;
+    L.split = g.split;
     L.cap_exc = g.rec_ka ? g.exc_all : g.exc;
     CUDA_TRY(g.rec_ka ? dcb_launch_rans_tag_rec(L, A, st) : g.pairs ? dcb_launch_rans_tag_pc(L, A, st) : dcb_launch_rans_tag(L, A, st));
     if (time_tag) {
@@ -1447,9 +1474,9 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     if (env_flags().debug_plan)
       fprintf(stderr, "[dcb plan] raw group ncp=%d wide=%d compact=%u prec=%u entries=%u mode=%u zig=%u: %u streams, %llu symbols, "
-                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u pairs=%u direct=%u global=%d rec_ka=%u rec=%uB (need x8: %u %u %u %u, exc %u)\n",
+                      "k=%u lut=%uB lutb=%uB ent=%uB lanes=%u pairs=%u split=%u direct=%u global=%d rec_ka=%u rec=%uB (need x8: %u %u %u %u, exc %u)\n",
               g->ncp, (int)g->wide, g->compact, g->prec_bits, g->entries, g->mode, g->zig, n,
-              (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->lanes, g->pairs,
+              (unsigned long long)g->total_symbols, g->lut_shift, g->lut_bytes, g->lutb_bytes, g->ent_bytes, g->lanes, g->pairs, g->split,
               g->direct, (int)g->table_global, g->rec_ka, g->rec_bytes, g->rec_max[0], g->rec_max[1], g->rec_max[2], g->rec_max[3], g->exc_all);
     if (is_dom) CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (g->table_global) {
@@ -1479,6 +1506,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       L.direct = g->direct;
       L.rec_ka = g->rec_ka;
       L.rec_bytes = g->rec_bytes;
+      L.split = g->split;
       if (g->rec_ka) L.cap_exc = g->exc_all;
       CUDA_TRY(g->rec_ka ? dcb_launch_rans_raw_rec(L, g->ncp, A, st)
                : g->pairs ? dcb_launch_rans_raw_pc(L, g->ncp, A, st) : dcb_launch_rans_raw(L, g->ncp, g->wide, false, A, st));

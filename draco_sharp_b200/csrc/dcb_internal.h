@@ -222,4 +222,5 @@ struct RansLaunch {
   uint32_t direct;                // 1: direct slot LUT (lut_bytes = 6 << prec_bits per lane; warp-pair kernels only)
   uint32_t rec_ka;                // bucket-record kernels: log2(slots per record) of the wide region (0 = not that path)
   uint32_t rec_bytes;             // bucket-record kernels: table area per lane (records + byte region + bitmap + value map)
+  uint32_t split;                 // warp-pair kernels: chain warps on sub-partitions 0..2, all consumers on sub-partition 3
 };

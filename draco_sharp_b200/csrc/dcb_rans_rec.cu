@@ -449,6 +449,31 @@ struct RecMap {
   }
 };
 
+// Which pair a warp belongs to and on which side.  Packed layout: warps 0..pairs-1 are chain warps, the next `pairs`
+// their consumers (a pair shares a sub-partition when pairs == 4).  Split layout (bit 31 of `pairs`, at most 3 pairs,
+// 4 * pairs warps): chain warps 0..pairs-1 have a sub-partition each to themselves (warp id mod 4), ALL consumers sit
+// on sub-partition 3 (warps 3, 7, 11), the warps in between leave at once.  The ALU and FMA pipes of a sub-partition
+// take one warp instruction every two cycles each, so a consumer next to its chain warp takes issue slots from it.
+__device__ __forceinline__ void warp_role(uint32_t warp, uint32_t &pairs, uint32_t &pair, uint32_t &role) {
+  const bool split = (pairs >> 31) != 0u, chain_low = ((pairs >> 30) & 1u) != 0u;
+  pairs &= 0x3FFFFFFFu;
+  if (!split) {
+    // the sub-partition's arbiter prefers the warp with the higher id: the chain warps take the upper half, so that
+    // the consumer only gets the issue slots the chain leaves
+    pair = warp % pairs;
+    role = chain_low ? warp / pairs : 1u - warp / pairs;
+  } else if (warp < pairs) {
+    pair = warp;
+    role = 0;
+  } else if ((warp & 3u) == 3u) {
+    pair = warp >> 2;
+    role = 1;
+  } else {
+    pair = 0;
+    role = 2;
+  }
+}
+
 // The chain warp's main loop.  NSYM symbols per group and lane; returns the number of groups queued.
 template <int NSYM>
 __device__ __forceinline__ uint32_t produce(RecChain &rc, bool active, uint32_t g_min, uint32_t q_addr, const PairCtl &ctl,
@@ -554,7 +579,7 @@ __device__ __forceinline__ bool chain_setup(const uint8_t *arena, StreamDesc *dp
 // Raw scheme (SymbolDecoding.cs:52-67) fused with inverse prediction + transform + store
 // ---------------------------------------------------------------------------------------------
 template <int NCP, bool DUMP, int MODE>
-__global__ void __launch_bounds__(256) rans_raw_rec_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+__global__ void __launch_bounds__(384) rans_raw_rec_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                            const uint32_t *__restrict__ order, uint32_t n_streams,
                                                            uint32_t lanes, uint32_t pairs, RecGeom geom,
                                                            uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
@@ -562,7 +587,8 @@ __global__ void __launch_bounds__(256) rans_raw_rec_kernel(const uint8_t *__rest
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int kSym = 4 * NCP;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t pair = warp % pairs, role = warp / pairs;
+  uint32_t pair, role;
+  warp_role(warp, pairs, pair, role);
   uint8_t *slice = smem + (size_t)pair * geom.slice_bytes;
   const uint32_t slice_addr = smem_u32(slice);
   const uint32_t q_addr = slice_addr + geom.q_off;
@@ -572,6 +598,7 @@ __global__ void __launch_bounds__(256) rans_raw_rec_kernel(const uint8_t *__rest
     for (uint32_t i = 0; i < kNumBarriers; ++i) mbar_init(ctl.base + 8u * i, 1u);
   }
   __syncthreads();
+  if (role == 2u) return;
   const uint32_t slot = (blockIdx.x * pairs + pair) * lanes + lane;
   const bool have = lane < lanes && slot < n_streams;
   StreamDesc *dp = have ? &streams[order[slot]] : nullptr;
@@ -689,14 +716,15 @@ __global__ void __launch_bounds__(256) rans_raw_rec_kernel(const uint8_t *__rest
 // values.  16 tags per group; the consumer writes one byte per point, the running bit offset at every DCB_TAG_CHUNK
 // points and validates (tag <= 32, DecoderBuffer.cs:141; bit area inside the buffer).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rans_tag_rec_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+__global__ void __launch_bounds__(384) rans_tag_rec_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                            const uint32_t *__restrict__ order, uint32_t n_streams,
                                                            uint32_t lanes, uint32_t pairs, RecGeom geom,
                                                            uint8_t *__restrict__ aux) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int kSym = 16;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t pair = warp % pairs, role = warp / pairs;
+  uint32_t pair, role;
+  warp_role(warp, pairs, pair, role);
   uint8_t *slice = smem + (size_t)pair * geom.slice_bytes;
   const uint32_t slice_addr = smem_u32(slice);
   const uint32_t q_addr = slice_addr + geom.q_off;
@@ -706,6 +734,7 @@ __global__ void __launch_bounds__(256) rans_tag_rec_kernel(const uint8_t *__rest
     for (uint32_t i = 0; i < kNumBarriers; ++i) mbar_init(ctl.base + 8u * i, 1u);
   }
   __syncthreads();
+  if (role == 2u) return;
   const uint32_t slot = (blockIdx.x * pairs + pair) * lanes + lane;
   const bool have = lane < lanes && slot < n_streams;
   StreamDesc *dp = have ? &streams[order[slot]] : nullptr;
@@ -832,6 +861,10 @@ __global__ void __launch_bounds__(256) rans_tag_rec_kernel(const uint8_t *__rest
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static uint32_t chain_low_bit() {  // DCB_CHAIN_LOW=1: chain warps in the lower half of the CTA (experiments)
+  static const uint32_t bit = getenv("DCB_CHAIN_LOW") ? 0x40000000u : 0u;
+  return bit;
+}
 // a pair's slice: lanes x area | rings | queue | control block | hand-over records
 static RecGeom rec_geom(const RansLaunch &p, uint32_t syms_per_group) {
   RecGeom g{};
@@ -874,7 +907,7 @@ static cudaError_t launch_raw_rec_t(const RansLaunch &p, const DevArenas &a, cud
   cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   const uint32_t per_cta = p.lanes_per_warp * pairs;
   const uint32_t grid = (p.n_streams + per_cta - 1) / per_cta;
-  k<<<grid, 64 * pairs, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, pairs, g, a.out, a.dbg,
+  k<<<grid, (p.split ? 128 : 64) * pairs, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, pairs | (p.split ? 0x80000000u : 0u) | chain_low_bit(), g, a.out, a.dbg,
                                           a.aux, p.dump);
   return cudaGetLastError();
 }
@@ -917,7 +950,7 @@ cudaError_t dcb_launch_rans_tag_rec(const RansLaunch &p, const DevArenas &a, cud
   cudaFuncSetAttribute(rans_tag_rec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   const uint32_t per_cta = p.lanes_per_warp * pairs;
   const uint32_t grid = (p.n_streams + per_cta - 1) / per_cta;
-  rans_tag_rec_kernel<<<grid, 64 * pairs, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, pairs,
+  rans_tag_rec_kernel<<<grid, (p.split ? 128 : 64) * pairs, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, pairs | (p.split ? 0x80000000u : 0u) | chain_low_bit(),
                                                              g, a.aux);
   return cudaGetLastError();
 }

@@ -194,3 +194,15 @@ def test_two_level_tables_warp_pair_kernels_are_bit_exact():
     """DCB_RANS_PC=1 + DCB_NO_DIRECT=1: chain / consumer warp pairs over the two-level tables (kept as an experiment
     path: measured slower than one warp per sub-partition when the SM is full of streams)."""
     _rerun_in_child({"DCB_NO_DIRECT": "1", "DCB_RANS_PC": "1"}, _PATH_CASES)
+
+
+def test_bucket_record_kernels_are_bit_exact():
+    """DCB_REC=1 + DCB_NO_DIRECT=1: the bucket-record tables of dcb_rans_rec.cu (one dependent shared-memory access per
+    symbol; taken for every group whose tables have the shape, the others keep the two-level kernels)."""
+    _rerun_in_child({"DCB_NO_DIRECT": "1", "DCB_REC": "1"}, _PATH_CASES)
+
+
+def test_split_layout_of_the_warp_pair_kernels_is_bit_exact():
+    """DCB_SPLIT=1: chain warps on sub-partitions 0..2, every consumer warp on sub-partition 3 (both pair kernels)."""
+    _rerun_in_child({"DCB_NO_DIRECT": "1", "DCB_REC": "1", "DCB_SPLIT": "1"}, "positions_small_sizes or positions_normals_colors or ragged_batch or crafted_streams")
+    _rerun_in_child({"DCB_NO_DIRECT": "1", "DCB_RANS_PC": "1", "DCB_SPLIT": "1"}, "positions_small_sizes or positions_normals_colors or ragged_batch or crafted_streams")
