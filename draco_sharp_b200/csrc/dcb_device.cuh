@@ -34,6 +34,18 @@ __device__ __forceinline__ int32_t wrap_original(int32_t pred, int32_t corr, int
   return o;
 }
 
+// wrap_original for a REGULAR stream: the prediction is known to lie in [mn, mx] (every correction the stream's table can
+// produce is smaller than max_diff in magnitude, so one +-max_diff always re-enters the range and the clamp of
+// ClampPredictedValue, PredictionSchemeWrapTransformBase.cs, is the identity).  Same operations in the same order.
+__device__ __forceinline__ int32_t wrap_regular(int32_t pred, int32_t corr, int32_t mn, int32_t mx, int32_t max_diff) {
+  int32_t o = (int32_t)((uint32_t)pred + (uint32_t)corr);
+  if (o > mx)
+    o = (int32_t)((uint32_t)o - (uint32_t)max_diff);
+  else if (o < mn)
+    o = (int32_t)((uint32_t)o + (uint32_t)max_diff);
+  return o;
+}
+
 struct OctBox {
   int32_t max_q, max_value, center;
   __device__ __forceinline__ void set(int bits) {
@@ -317,6 +329,7 @@ struct RansLane {
   uint32_t cum_addr;    // smem address of the lane's cum[0]
   uint32_t n_entries_tab;  // entries built (ne)
   bool split_ok;        // the two-region LUT fits this lane's LUT capacity
+  uint32_t max_abs_val; // largest magnitude a zig-zag decoded symbol of this table can have (lean main loop: regular streams)
   // direct slot LUT (low-residency launches): shared-memory addresses of the lane's freq[], offset[] and entry[] arrays
   // (u16 per slot).  One dependent LDS per symbol instead of two: x' = q * freq[r] + offset[r] (RAnsDecoder.cs:90-99
   // with lut[] / prob[] / cum[] folded per slot, which is what BuildLookupTable :69-88 itself materialises).
@@ -459,6 +472,64 @@ struct RansLane {
     return r;
   }
 
+  // ---- lean main loop (u16 tables in shared memory, two-region LUT) ----
+  // Byte window: the 8 payload bytes below the read position, newest byte in the top bits of w_hi.  Three symbols of a
+  // u16 table consume at most 6 bytes, so the window is opened once per three symbols (three aligned ring words, two
+  // funnel shifts) instead of two ring words + shift bookkeeping per symbol.
+  uint32_t w_hi, w_lo, w_cb;
+  __device__ __forceinline__ void window_open() {
+    const uint32_t W0 = lds_u32(ring | (p1 & (DCB_RING_BYTES - 4u)));
+    const uint32_t W1 = lds_u32(ring | ((p1 + DCB_RING_BYTES - 4u) & (DCB_RING_BYTES - 4u)));
+    const uint32_t W2 = lds_u32(ring | ((p1 + DCB_RING_BYTES - 8u) & (DCB_RING_BYTES - 4u)));
+    const uint32_t sh = (p1 & 3u) * 8u + 8u;
+    w_hi = __funnelshift_rc(W1, W0, sh);
+    w_lo = __funnelshift_rc(W2, W1, sh);
+    w_cb = 0;
+  }
+  __device__ __forceinline__ void window_close() { p1 -= w_cb >> 3; }
+  // One RAnsDecoder.Read() inside an open window; the caller has checked that the bytes cannot run out.  Same probe as
+  // step<false, 1>; the renormalisation is two predicated funnel shifts (RAnsDecoder.cs:58-61, at most two bytes for
+  // precision <= 15).  Returns the shared-memory ADDRESS of cum[entry].
+  template <bool FIRST>
+  __device__ __forceinline__ uint32_t step_lean() {
+    const uint32_t v = FIRST ? w_hi : __funnelshift_lc(w_lo, w_hi, w_cb);
+    const bool one = x < L, two = x < L8;
+    uint32_t xr = x;
+    if (one) xr = __funnelshift_l(v, x, 8);
+    if (two) xr = __funnelshift_l(v, x, 16);
+    if (FIRST) w_cb = one ? 8u : 0u;
+    else if (one) w_cb += 8u;
+    if (two) w_cb += 8u;
+    const uint32_t r = xr & mask;
+    const uint32_t q = xr >> prec_bits;
+    const uint32_t a_a = ((xr >> a_sh) & a_mask) | lut_base;
+    const uint32_t a_b = (r >> 1) + b_base;
+    const uint32_t a = r >= t_split ? a_b : a_a;
+    const uint32_t a_k = ((xr >> 5) & blk_mask) | blk_addr;
+    uint32_t dl, bb, c0, c1, c2;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(dl) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(bb) : "r"(a_k));
+    const uint32_t ca = dl * 2u + bb;
+    asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(c0) : "r"(ca));
+    asm volatile("ld.shared.u16 %0, [%1+2];\n" : "=r"(c1) : "r"(ca));
+    asm volatile("ld.shared.u16 %0, [%1+4];\n" : "=r"(c2) : "r"(ca));
+    const bool second = r >= c1;
+    const uint32_t xa = q * (c1 - c0) + (r - c0);
+    const uint32_t xb = q * (c2 - c1) + (r - c1);
+    x = second ? xb : xa;
+    return ca + (second ? 2u : 0u);
+  }
+  // value of the entry whose cum lives at shared-memory address ca (compact u16 tables, zig-zag decoded value slots)
+  __device__ __forceinline__ int32_t value_at(uint32_t ca) const {
+    const uint32_t rank2 = ca - cum_addr;  // 2 * rank
+    if (rank2 >= 2u * dprefix) {
+      int32_t v;
+      asm volatile("ld.shared.s16 %0, [%1];\n" : "=r"(v) : "r"(ca + val_delta));
+      return v;
+    }
+    return zigzag_dec(rank2 >> 1);
+  }
+
   // table entry -> symbol value.  dense: the entry index is the symbol id.  compact: entries below the dense
   // prefix are their own symbol ids, the others carry a value slot (zig-zag decoded when zig).
   __device__ __forceinline__ int32_t value(uint32_t o, bool compact, bool zig) const {
@@ -533,6 +604,7 @@ struct RansLane {
     uint64_t c = 0;
     uint32_t ne = 0;
     bool overflow = false;
+    uint32_t last_sym = 0;  // largest symbol id with a non-zero probability
     for (uint32_t i = 0; i < ns; ++i) {
       if (pos >= bend) return DCB_ERR_EOF;
       const uint32_t pd = arena_[pos++];
@@ -549,6 +621,7 @@ struct RansLane {
           if (pos >= bend) return DCB_ERR_EOF;
           prob |= (uint32_t)arena_[pos++] << (8 * (b + 1) - 2);
         }
+        if (prob) last_sym = i;
         if (g.compact) {
           if (prob) {
             if (c + prob > prec || ne >= g.cap_entries) overflow = true;
@@ -577,6 +650,7 @@ struct RansLane {
     cum[ne] = (T)prec;
     cum[ne + 1] = (T)prec;  // pad: the two-candidate probe reads cum[i + 2]
     n_entries_tab = ne;
+    max_abs_val = (last_sym + 1u) >> 1;  // |zigzag_dec(i)| = (i + 1) / 2
     val_delta = (g.cap_entries + 2u - (g.compact ? dprefix : 0u)) * (uint32_t)sizeof(T);
     // ---- two-region LUT: pick the bucket size 2^kA of the wide region that needs the fewest LUT bytes ----
     // Dense tables may hold zero-width entries between two owners of one bucket (the two-candidate probe would

@@ -39,6 +39,10 @@ namespace {
 // TABLE_GLOBAL: the lane tables live in a global scratch arena instead of shared memory (alphabets
 // too large for smem: precision 16..20).
 // ---------------------------------------------------------------------------------------------
+template <int NCP, typename T, bool DUMP, bool TG, int MODE, int TAB, bool SPLIT>
+__device__ __forceinline__ void run_tail(RansLane<T, TG> &rl, const TableGeom &geom, const PostParams &pp, uint8_t *optr,
+                                         int32_t *dptr, uint32_t dump, uint32_t n_entries, uint32_t g, int32_t *prev);
+
 // One stream, start to end: main loop over groups of 4 entries, then the careful per-entry tail.
 template <int NCP, typename T, bool DUMP, bool TG, int MODE, int TAB, bool SPLIT>
 __device__ __forceinline__ void run_stream(RansLane<T, TG> &rl, const TableGeom &geom, const PostParams &pp, uint8_t *optr,
@@ -60,7 +64,14 @@ __device__ __forceinline__ void run_stream(RansLane<T, TG> &rl, const TableGeom 
     rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
     cp_async_wait<1>();
   }
-  // ---- per-lane tail: exact `off > 0` handling ----
+  run_tail<NCP, T, DUMP, TG, MODE, TAB, SPLIT>(rl, geom, pp, optr, dptr, dump, n_entries, g, prev);
+}
+
+// per-lane tail of a stream: exact `off > 0` handling, one entry at a time
+template <int NCP, typename T, bool DUMP, bool TG, int MODE, int TAB, bool SPLIT>
+__device__ __forceinline__ void run_tail(RansLane<T, TG> &rl, const TableGeom &geom, const PostParams &pp, uint8_t *optr,
+                                         int32_t *dptr, uint32_t dump, uint32_t n_entries, uint32_t g, int32_t *prev) {
+  const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp);
   for (uint32_t e = g * 4u; e < n_entries; ++e) {
     int32_t v[NCP];
     decode_entry<NCP, T, TG, DUMP, MODE, TAB, true, SPLIT>(rl, geom, pp, prev, v, dptr, dump, e);
@@ -68,6 +79,43 @@ __device__ __forceinline__ void run_stream(RansLane<T, TG> &rl, const TableGeom 
     rl.template top_up<(3 * NCP + 15) / 16 + 1>();
     cp_async_wait<0>();
   }
+}
+
+// LEAN main loop for the hot shape: compact u16 tables in shared memory behind the two-region LUT, delta + wrap on a
+// REGULAR stream (see wrap_regular), no debug dumps.  Same group structure as run_stream; per symbol it issues ~1/4
+// fewer instructions: the byte supply is one window per three symbols, the renormalisation two predicated funnel
+// shifts, the wrap has no clamp.  A warp whose lanes all qualify takes it (vote in the kernel); streams end in the same
+// careful tail.
+template <int NCP, int MODE>
+__device__ __forceinline__ void run_stream_lean(RansLane<uint16_t, false> &rl, const TableGeom &geom, const PostParams &pp,
+                                                uint8_t *optr, uint32_t n_entries, uint32_t g_min) {
+  const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp);
+  int32_t prev[NCP];
+  const int32_t p0 = 0 > pp.mx ? pp.mx : (0 < pp.mn ? pp.mn : 0);  // the clamp the first prediction (zero) would get
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) prev[c] = p0;
+  constexpr uint32_t kGroupBytes = 4u * NCP * 3u;
+  constexpr int kSyms = 4 * NCP;
+  uint32_t g = 0;
+  for (; g < g_min; ++g) {
+    if (rl.bytes_left() < kGroupBytes) break;
+    int32_t v[4][NCP];
+#pragma unroll
+    for (int s = 0; s < kSyms; ++s) {
+      if (s % 3 == 0) rl.window_open();
+      const uint32_t ca = (s % 3 == 0) ? rl.template step_lean<true>() : rl.template step_lean<false>();
+      if (s % 3 == 2 || s == kSyms - 1) rl.window_close();
+      const int32_t corr = rl.value_at(ca);
+      const int c = s % NCP;
+      prev[c] = wrap_regular(prev[c], corr, pp.mn, pp.mx, pp.max_diff);
+      v[s / NCP][c] = prev[c];
+    }
+    store_group4<NCP>(pp, store, dsize, optr, (uint64_t)g * 4, v);
+    rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
+    cp_async_wait<1>();
+  }
+  rl.prefetch();  // the careful tail reads through the two-word peek
+  run_tail<NCP, uint16_t, false, false, MODE, 2, true>(rl, geom, pp, optr, nullptr, 0u, n_entries, g, prev);
 }
 
 template <int NCP, typename T, bool DUMP, bool TABLE_GLOBAL, int MODE, int TAB>
@@ -90,6 +138,7 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   uint8_t *lutb = nullptr;
   uint32_t *blk = nullptr;
   bool split_ok = true;  // idle lanes do not veto
+  bool lean_ok = true;
   if (have) {
     const StreamDesc &d = *dp;
     n_entries = d.n_entries;
@@ -121,6 +170,12 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
       status = rl.build(arena, d, geom, ent, ent_off);
       if (status == DCB_OK) status = rl.init_state(arena, d);
       if (status == DCB_OK) split_ok = rl.split_ok && !(dump & 0x80000000u);
+      if (status == DCB_OK) {
+        // regular delta + wrap stream (wrap_regular): no correction of the table reaches max_diff, bounds far from int32
+        const int64_t md = 1ll + (int64_t)d.xf_b - (int64_t)d.xf_a;
+        lean_ok = split_ok && geom.zig != 0 && !(dump & 0x40000000u) && (int64_t)rl.max_abs_val < md &&
+                  d.xf_a >= -(1 << 29) && d.xf_b <= (1 << 29);
+      }
     }
     if (status != DCB_OK) {
       dp->status = status;
@@ -129,6 +184,7 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   }
   // the branch-free two-region LUT is used when every stream of the warp can have one
   const bool use_split = __all_sync(0xffffffffu, split_ok);
+  const bool use_lean = __all_sync(0xffffffffu, lean_ok);
   // groups of 4 entries every active lane of the warp can run without per-lane bounds checks
   uint32_t g_min = n_entries ? (n_entries >> 2) : 0xFFFFFFFFu;
 #pragma unroll
@@ -150,6 +206,13 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
     }
     pp.store = STORE_NARROW;
     pp.dsize = 4;
+  }
+  if constexpr (sizeof(T) == 2 && !TABLE_GLOBAL && !DUMP && (MODE == 1 || MODE == 2) && TAB == 2) {
+    // lean main loop: every active lane of the warp decodes a regular delta + wrap stream through the two-region LUT
+    if (use_lean) {
+      run_stream_lean<NCP, MODE>(rl, geom, pp, optr, n_entries, g_min);
+      return;
+    }
   }
   if (use_split)
     run_stream<NCP, T, DUMP, TABLE_GLOBAL, MODE, TAB, true>(rl, geom, pp, optr, dptr, dump, n_entries, g_min);
@@ -725,9 +788,10 @@ uint32_t dcb_rans_smem_bytes(const RansLaunch &p, bool table_global) {
   return b;
 }
 
-// DCB_NO_SPLIT=1 forces the uniform-LUT probe (tests of the fallback path); bit 31 of the kernel's `dump` word
+// DCB_NO_SPLIT=1 forces the uniform-LUT probe (tests of the fallback path): bit 31 of the kernel's `dump` word;
+// DCB_NO_LEAN=1 keeps regular streams on the general main loop (A/B measurements, tests): bit 30
 static uint32_t no_split_bit() {
-  static const uint32_t bit = getenv("DCB_NO_SPLIT") ? 0x80000000u : 0u;
+  static const uint32_t bit = (getenv("DCB_NO_SPLIT") ? 0x80000000u : 0u) | (getenv("DCB_NO_LEAN") ? 0x40000000u : 0u);
   return bit;
 }
 
