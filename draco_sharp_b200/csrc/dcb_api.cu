@@ -440,6 +440,13 @@ void parse_attr_section(BufRec &b, Shard &sh, int buf_index, const dcb_batch *ba
   w.pos = b.arena_off + r.pos;
   w.stream_count = (int32_t)sh.streams.size() - w.stream_first;
   w.phase = w.stream_count > 0 ? 0 : 2;
+  {  // parent of the tex-coord predictor: PointCloud.GetNamedAttributeId(Position) = the buffer's first position
+     // attribute (SequentialAttributeDecoder.InitPredictionScheme :58-72)
+    int32_t pos_stream = -1;
+    for (int i = 0; i < w.stream_count && pos_stream < 0; ++i)
+      if (sh.streams[(size_t)w.stream_first + i].att_type == 0) pos_stream = w.stream_first + i;
+    for (int i = 0; i < w.stream_count; ++i) sh.streams[(size_t)w.stream_first + i].parent = pos_stream;
+  }
   // host part of the payload walk (stops at the first Tagged bit area)
   if (w.stream_count > 0) walk_continue(b.src - b.arena_off, w, sh.streams.data());
   finish(w.status);
@@ -589,8 +596,11 @@ void layout_shard(Shard &sh) {
         aux = align_up(aux + align_up(s.n_entries, 16) + 8ull * (nch + 1) + 32ull * nch, 16);
       }
       if (s.seq_type != SEQ_GENERIC && s.has_maps && (s.recon == RECON_PARA_WRAP || s.state < ST_READY)) {
+        // corrections int32[nv] | quantized ints int32[nv] | parallelogram: deps int32[3 n]; tex coords (two components):
+        // TexRec[n] (32 bytes each) + orientation flags u8[<= 2n + 1]
         s.aux_off = aux;
-        aux = align_up(aux + (2ull * nv + 3ull * s.n_entries) * 4, 16);
+        const uint64_t tail = s.ncp == 2 ? 34ull * s.n_entries + 16ull : 12ull * s.n_entries;
+        aux = align_up(aux + 2ull * nv * 4 + tail, 16);
       } else if (s.seq_type == SEQ_NORMALS) {
         s.aux_off = aux;  // quantized octahedral (s, t) pairs between the serial kernels and oct_unit_kernel
         aux = align_up(aux + 8ull * s.n_entries, 16);
@@ -1291,9 +1301,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
 
   // ---- classify ----
   std::map<RawKey, Group> raw;
-  Group post[5], para[5], par[5], copy{}, octs{}, octc{};
+  Group post[5], para[5], par[5], copy{}, octs{}, octc{}, tex{};
   octs.kind = 6;
   octc.kind = 6;
+  tex.kind = 7;
   bool par_delta[5] = {false, false, false, false, false};
   for (int n = 1; n <= 4; ++n) {
     post[n] = Group{}; post[n].kind = 2; post[n].ncp = n;
@@ -1359,7 +1370,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       } else {
         post[s.ncp].order.push_back(si);
       }
-      if (s.recon == RECON_PARA_WRAP) {
+      if (s.recon == RECON_PARA_WRAP && s.pred_method == PRED_TEX_COORDS_PORTABLE) {
+        tex.order.push_back(si);
+        tex.max_entries = std::max(tex.max_entries, s.n_entries);
+        has_para = true;
+      } else if (s.recon == RECON_PARA_WRAP) {
         para[s.ncp].order.push_back(si);
         para[s.ncp].max_entries = std::max(para[s.ncp].max_entries, s.n_entries);
         has_para = true;
@@ -1390,6 +1405,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   add(copy);
   add(octs);
   add(octc);
+  add(tex);
   // par_post2_kernel: per group the run prefix of its streams (runs of par_run_len chunks) and one ticket word
   std::vector<uint32_t> par_runs[5];
   uint64_t par_aux_off[5] = {0, 0, 0, 0, 0};
@@ -1406,7 +1422,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       max_chunks = std::max(max_chunks, nch);
     }
     dcb_par_post_plan((uint32_t)par[n].order.size(), total_chunks, (uint32_t)std::min<uint64_t>(max_chunks, 0xFFFFFFFFull),
-                      par_delta[n], num_sms, n, &par_run_len[n], &par_claim[n]);
+                      par_delta[n], num_sms, n, (uint32_t)sh.share, &par_run_len[n], &par_claim[n]);
     if (env_flags().par_run > 0) {  // experiments
       par_run_len[n] = (uint32_t)env_flags().par_run;
       par_claim[n] = 1;
@@ -1445,6 +1461,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     all.insert(all.end(), copy.order.begin(), copy.order.end());
     all.insert(all.end(), octs.order.begin(), octs.order.end());
     all.insert(all.end(), octc.order.begin(), octc.order.end());
+    all.insert(all.end(), tex.order.begin(), tex.order.end());
     for (int n = 1; n <= 4; ++n) all.insert(all.end(), par_runs[n].begin(), par_runs[n].end());
 
     CUDA_TRY(cudaMemcpyAsync(sh.d_order, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st));
@@ -1617,6 +1634,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         ctx->ev_para = true;
       }
     }
+  if (!tex.order.empty()) {  // behind the parallelogram kernels: the predictor reads the decoded positions of its parent
+    CUDA_TRY(dcb_launch_tex(sh.d_streams, sh.d_order + tex.order_off, (uint32_t)tex.order.size(), tex.max_entries, dump, A, st));
+    stats.n_launches += 2;
+  }
   if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
   if (has_para || deferred_descs) {
     // parallelogram kernels validate the caller's maps on the device, resumed walks parse and validate on the device:

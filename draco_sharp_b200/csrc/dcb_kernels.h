@@ -58,12 +58,17 @@ cudaError_t dcb_launch_serial_post(StreamDesc *d_streams, const uint32_t *d_orde
 uint32_t dcb_par_post_smem_bytes(int ncp);
 // run length (chunks) and runs per ticket for a launch: whole streams when there are enough of them, else single chunks
 void dcb_par_post_plan(uint32_t n_streams, uint64_t total_chunks, uint32_t max_chunks, bool any_delta, uint32_t num_sms, int ncp,
+                       uint32_t share,
                        uint32_t *run_len, uint32_t *claim);
 cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, const uint32_t *d_run_prefix, uint32_t n,
                                 uint32_t total_runs, uint32_t run_len, uint32_t claim, unsigned int *d_ticket, uint32_t num_sms,
                                 int ncp, uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
                             uint32_t dump, const DevArenas &a, cudaStream_t st);
+// MeshPredictionSchemeTexCoordsPortableDecoder (dcb_texcoord.cu): tex_prep_kernel (point-parallel) + tex_chain_kernel
+// (one warp per stream); the parent position streams must have been through dcb_launch_para on the same stream
+cudaError_t dcb_launch_tex(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries, uint32_t dump,
+                           const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_oct_chain(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t dump,
                                  const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_oct_unit(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries,

@@ -535,9 +535,11 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
 }  // namespace
 
 void dcb_par_post_plan(uint32_t n_streams, uint64_t total_chunks, uint32_t max_chunks, bool any_delta, uint32_t num_sms, int ncp,
-                       uint32_t *run_len, uint32_t *claim) {
+                       uint32_t share, uint32_t *run_len, uint32_t *claim) {
   const uint32_t smem = dcb_par_post_smem_bytes(ncp);
-  const uint64_t warps = (uint64_t)num_sms * std::max<uint32_t>(1u, (227u * 1024u) / (smem + 1024u)) * kWarps;
+  // `share` pipeline slices decode on this device at the same time: each one fills its part of the machine
+  const uint64_t warps = std::max<uint64_t>(
+      kWarps, (uint64_t)num_sms * std::max<uint32_t>(1u, (227u * 1024u) / (smem + 1024u)) * kWarps / std::max(1u, share));
   // whole-stream runs: the longest stream must be a small part of one warp's share of the batch
   const bool whole = (uint64_t)max_chunks * warps * 2ull <= total_chunks && n_streams >= 2ull * warps;
   if (whole) {

@@ -156,6 +156,30 @@ DCB_HD int walk_pred_data(WalkRd &r, StreamDesc &s, bool has_scheme, bool mesh_s
     return DCB_OK;
   }
   if (s.transform == XF_WRAP) {
+    if (mesh_scheme && s.pred_method == PRED_TEX_COORDS_PORTABLE) {
+      // MeshPredictionSchemeTexCoordsPortableDecoder.DecodePredictionData (:68-84): i32 count, then the rABS-coded flags
+      // (RAnsBitDecoder.StartDecoding, BitCoders/RAnsBitDecoder.cs:12-24: u8 prob_zero, varint size, data), in front of
+      // the transform data.  Located and validated here; tex_chain_kernel decodes them.
+      const int32_t no = (int32_t)wr_u32(r);
+      if (r.err) return r.err;
+      if (no < 0 || (uint64_t)(uint32_t)no > (uint64_t)s.n_entries * s.ncp + 1ull) return DCB_ERR_PRED;  // one flag per entry at most
+      s.n_orient = (uint32_t)no;
+      s.orient_off = r.pos;
+      wr_u8(r);
+      const uint64_t nb = wr_varint(r);
+      if (r.err) return r.err;
+      if (!wr_need(r, nb)) return r.err;
+      if (nb < 1) return DCB_ERR_CONNECTIVITY;                   // AnsDecoder.ReadInit (the oracle's rabs_start)
+      const uint8_t *tail = r.p + r.pos + nb;
+      const uint32_t x = (uint32_t)tail[-1] >> 6;
+      uint32_t st;
+      if (x == 0) st = tail[-1] & 0x3Fu;
+      else if (x == 1) { if (nb < 2) return DCB_ERR_CONNECTIVITY; st = ((uint32_t)tail[-2] | ((uint32_t)tail[-1] << 8)) & 0x3FFFu; }
+      else if (x == 2) { if (nb < 3) return DCB_ERR_CONNECTIVITY; st = ((uint32_t)tail[-3] | ((uint32_t)tail[-2] << 8) | ((uint32_t)tail[-1] << 16)) & 0x3FFFFFu; }
+      else return DCB_ERR_CONNECTIVITY;
+      if (st + 4096u >= 4096u * 256u) return DCB_ERR_CONNECTIVITY;
+      r.pos += nb;
+    }
     s.xf_a = (int32_t)wr_u32(r);
     s.xf_b = (int32_t)wr_u32(r);
     if (r.err) return r.err;
@@ -164,6 +188,7 @@ DCB_HD int walk_pred_data(WalkRd &r, StreamDesc &s, bool has_scheme, bool mesh_s
     if ((int32_t)diff < 0 || diff >= 2147483647ll) return DCB_ERR_WRAP;
     if (mesh_scheme) {
       if ((uint64_t)s.n_entries * s.ncp > 0 && !s.has_maps) return DCB_ERR_MAPS;
+      if (s.pred_method == PRED_TEX_COORDS_PORTABLE && s.ncp != 2) return DCB_ERR_PRED;  // ...TexCoordsPortableDecoder.cs:51
       s.recon = RECON_PARA_WRAP;
     } else {
       s.recon = RECON_DELTA_WRAP;
@@ -195,10 +220,10 @@ DCB_HD void walk_scheme_kind(const BufWalk &w, const StreamDesc &s, bool &has_sc
       has_scheme = (s.transform == XF_WRAP);
   }
   if (has_scheme && w.geom_type == 1 && w.method == 1) {  // PredictionSchemeDecoderFactory.cs:9-75
-    if (s.pred_method == PRED_PARALLELOGRAM)
+    if (s.pred_method == PRED_PARALLELOGRAM || s.pred_method == PRED_TEX_COORDS_PORTABLE)
       mesh_scheme = true;
     else if (s.pred_method != PRED_DIFFERENCE)
-      err = DCB_ERR_UNSUPPORTED;  // multi-/constrained-multi-parallelogram, tex coords, geometric normal
+      err = DCB_ERR_UNSUPPORTED;  // multi-/constrained-multi-parallelogram, deprecated tex coords, geometric normal
   }
 }
 

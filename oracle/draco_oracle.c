@@ -827,9 +827,12 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
     if (nv > 0) {
       if (mesh_scheme == 5) {
         if (!maps || a->decoder_id >= n_maps) { free(orient); return ORC_ERR_MAPS; }
-        const orc_attr *pos = NULL; /* parent attribute: the (already decoded) position attribute, portable form */
-        for (int i = 0; i < res->n_attrs && &res->attrs[i] != a; ++i)
-          if (res->attrs[i].att_type == 0 && res->attrs[i].nc_portable == 3 && res->attrs[i].qints) pos = &res->attrs[i];
+        /* parent attribute: PointCloud.GetNamedAttributeId(Position) = the FIRST position attribute, in its portable
+         * form (SequentialAttributeDecoder.InitPredictionScheme :58-72); it must have been decoded already */
+        const orc_attr *pos = NULL;
+        for (int i = 0; i < res->n_attrs && &res->attrs[i] != a && !pos; ++i)
+          if (res->attrs[i].att_type == 0) pos = &res->attrs[i];
+        if (pos && (pos->nc_portable != 3 || !pos->qints)) pos = NULL;
         if (!pos || pos->decoder_id >= n_maps) { free(orient); return ORC_ERR_PRED; }
         int st = orc_texcoords_portable_wrap(a->corr, n, a->xf_a, a->xf_b, &maps[a->decoder_id], pos->qints, pos->n_entries,
                                              &maps[pos->decoder_id], orient, n_or, a->qints);

@@ -144,6 +144,48 @@ def test_house_mesh_end_to_end_through_product_host_helper(gpu_decoder):
     assert dist.max() < 0.49094
 
 
+def test_house_whole_sample_on_gpu(gpu_decoder):
+    """The reference's sample asset, bytes verbatim and whole: positions (parallelogram), texture coordinates
+    (TexCoordsPortable predictor, SURVEY 8f-3: rABS orientation flags, 64-bit projection, IntSqrt) and the generic uint8
+    attribute (parallelogram -> narrowing store) through the CUDA kernels; connectivity from the product's host helper.
+    Quantized ints and output bytes against the oracle and the SHA-256 goldens pinned in test_oracle_kats.py."""
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    assert o.status == 0
+    for flags in (0, N.DCB_DUMP_QINTS):
+        batch = gpu_decoder.index([b])
+        batch.host_connectivity(0)
+        batch.finish()
+        out, dbg = gpu_decoder.decode(batch, flags=flags)
+        assert batch.status(0) == 0
+        assert batch.buffer_info(0).n_attrs == 3
+        for k in range(3):
+            ai = batch.attr_info(0, k)
+            got = out[ai.out_off: ai.out_off + ai.out_bytes]
+            assert np.array_equal(got, o.attrs[k].out.view(np.uint8).ravel()), k
+            if flags:
+                nv = ai.n_entries * o.attrs[k].nc_portable
+                ints = dbg[ai.dbg_off: ai.dbg_off + 4 * nv].view(np.int32)
+                assert np.array_equal(ints, o.attrs[k].qints.ravel()), k
+        ai = batch.attr_info(0, 1)
+        assert (ai.pred_method, ai.n_entries) == (5, 3220)
+        assert sha(out[ai.out_off: ai.out_off + ai.out_bytes]) == "26bd6cc9ae35d081caba5b2061dd9d6d049a66c9050f7c5b9cfdc345c3c8449a"
+        if flags:
+            assert sha(dbg[ai.dbg_off: ai.dbg_off + 4 * 6440]) == "a243b8cf61c7145d3f75eda19721098918e735e925822b6a211ae6686a6d2990"
+        ai = batch.attr_info(0, 0)
+        assert sha(out[ai.out_off: ai.out_off + ai.out_bytes]) == "028840c055ebfbc5b9a3a04b28d2fc5d0f9cae9c12821f030a815a0826bdcb37"
+        batch.free()
+    # and through the reference-shaped host mirror: Draco / PointAttribute objects
+    (d,) = gpu_decoder.decode_batch([b])
+    assert d.ok and d.points_count == 3220
+    uv = d.get_named_attribute(3)
+    assert uv is not None and uv.unique_entries_count == 3220
+    vts = np.load(os.path.join(GOLD, "house_04_obj_texcoords.npy"))
+    half_step = float(o.attrs[1].qrange) / ((1 << o.attrs[1].qbits) - 1) / 2
+    dist = np.abs(uv.values.astype(np.float64)[:, None, :] - vts[None, :, :]).max(axis=2).min(axis=1)
+    assert dist.max() < half_step
+
+
 def test_mixed_batch_meshes_and_clouds(gpu_decoder):
     """Meshes (host connectivity) and point clouds in one batch; a mesh with broken connectivity fails alone."""
     from draco_sharp_b200 import synth_gen as G

@@ -35,9 +35,10 @@ def test_house_connectivity_matches_oracle_and_goldens():
     # SHA-256 of the position decoder's data_to_corner map (uint32 LE)
     assert hashlib.sha256(bt.mesh_map(0, 0, 2).tobytes()).hexdigest().startswith("742b5197")
     assert [bt.attr_info(0, a).n_entries for a in range(3)] == [1775, 3220, 1775]
-    # the sample's tex-coord attribute uses the TexCoordsPortable predictor: decoded by the oracle,
-    # reported as unsupported by the CUDA path's indexer
-    assert bi.status == -3 and o.status == 0
+    # the sample's tex-coord attribute uses the TexCoordsPortable predictor: the indexer locates its
+    # orientation flags and hands the stream to the tex-coord kernels
+    assert bi.status == 0 and o.status == 0
+    assert (bt.attr_info(0, 1).pred_method, bt.attr_info(0, 1).transform) == (5, 1)
     bt.free()
 
 

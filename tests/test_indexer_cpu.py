@@ -108,9 +108,11 @@ def test_mesh_buffers_need_connectivity_from_the_host():
         bt.set_mesh_maps(0, d, m["opposite"], m["corner_to_vertex"], m["data_to_corner"], m["vertex_to_data"])
     bt.finish()
     bi = bt.buffer_info(0)
-    # attribute 1 uses the TexCoordsPortable predictor: the oracle decodes it, the CUDA path's indexer
-    # reports the buffer as unsupported
-    assert bi.status == -3 and o.status == 0
+    # attribute 1 uses the TexCoordsPortable predictor: indexed like the parallelogram streams
+    assert bi.status == 0 and o.status == 0
+    at = bt.attr_info(0, 1)
+    assert (at.pred_method, at.transform, at.n_entries) == (5, 1, 3220)
+    assert (at.xf_a, at.xf_b) == (o.attrs[1].xf_a, o.attrs[1].xf_b)
     ai = bt.attr_info(0, 0)
     assert (ai.pred_method, ai.transform, ai.scheme, ai.precision_bits, ai.n_entries) == (1, 1, 1, 13, 1775)
     assert (ai.xf_a, ai.xf_b) == (0, 2047)
