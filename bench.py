@@ -524,7 +524,7 @@ def run_sweep(args, rank, local_rank):
     dec.set_stream(0, stream.cuda_stream)
     peak, _ = measured_peak()
     cells = [("points_per_buffer", n, max(1, 200_000_000 // n)) for n in (1000, 10_000, 100_000, 1_000_000, 10_000_000)]
-    cells += [("batch_size", 100_000, b) for b in (1, 16, 256, 4096, 16384)]
+    cells += [("batch_size", 100_000, b) for b in (1, 16, 256, 4096, 16384, 65536)]
     for scheme, sname in ((1, "raw"), (0, "tagged")):
         for axis, n, b in cells:
             uniq = min(b, max(1, 20_000_000 // n))
@@ -557,7 +557,8 @@ def run_sweep(args, rank, local_rank):
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / steps
             st = dec.stats()
-            print(json.dumps({"sweep": axis, "scheme": sname, "points_per_buffer": n, "buffers": b, "ms_per_step": ms,
+            print(json.dumps({"sweep": axis, "scheme": sname, "rank": rank, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+                              "points_per_buffer": n, "buffers": b, "ms_per_step": ms,
                               "points_per_s": batch.points / (ms * 1e-3), "algorithmic_GBps": batch.algo_bytes / (ms * 1e-3) / 1e9,
                               "frac_of_hbm_peak": batch.algo_bytes / (ms * 1e-3) / 1e9 / peak, "parity_ok": bool(ok),
                               "launches": st.n_launches, "stage_ms": {"raw": st.ms_raw, "tag": st.ms_tag, "par": st.ms_par}}), flush=True)
@@ -578,6 +579,7 @@ def main():
     ap.add_argument("--e2e-slices", type=int, default=8, help="pipeline slices of the e2e leg (dcb_create with the device listed K times)")
     ap.add_argument("--meshes", type=int, default=0, help="mesh workloads: meshes per GPU (0 = the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-copy-ceiling", action="store_true", help="skip the bare pinned-copy leg (e2e.host_ceiling_*)")
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: points-per-buffer and batch-size sweep (one JSON line per cell)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -706,6 +708,31 @@ def main():
         dec_e2e.close()
     e2e_value = total_points / (e2e_t * 1e-3)
 
+    # ---- what the host side of this box can do at all: the e2e leg's bytes as BARE pinned copies, all ranks at once
+    # (H2D and D2H on a stream each, overlapping as in the decode pipeline; no kernels, no indexing).  e2e time over
+    # this time says how much of the leg is the link / the host's memory system and how much is ours.
+    ceil_ms = float("nan")
+    if args.e2e_steps > 0 and not args.no_copy_ceiling:
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        d_in = torch.empty(in_bytes, dtype=torch.uint8, device="cuda")
+        h_in_t = pinned["in"][:in_bytes] if len(pinned["in"]) >= in_bytes else None
+        ts = []
+        for i in range(3):
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_in):
+                if h_in_t is not None:
+                    d_in.copy_(h_in_t, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            if i > 0:
+                ts.append((time.perf_counter() - t0) * 1e3)
+        del d_in
+        ceil_ms, _ = reduce_over_ranks(dist, "cuda", float(np.mean(ts)), [0.0])
+
     if rank == 0:
         peak, peak_src = measured_peak()
         dom = float(np.mean(dom_ms)) if dom_ms else 0.0
@@ -725,6 +752,12 @@ def main():
             "output_GBps": total_out / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": profile_traffic(args.workload),
+                         "frac_of_8TBps": achieved / 8000.0,
+                         "chain_bound": {"symbols_per_stream": WORKLOADS[args.workload][1] * 3,
+                                         "cycles_per_symbol": (dom * 1e-3 * clocks.get("sm_mhz", 0) * 1e6 / (WORKLOADS[args.workload][1] * 3))
+                                         if dom > 0 and clocks.get("sm_mhz") else None,
+                                         "what": "serial-chain bound of BASELINE.md 3.4: symbols_per_stream x cycles/symbol / clock = kernel_ms "
+                                                 "while every stream is resident; more streams per launch do not lengthen it"},
                          "peak_source": peak_src, "kernel": stats.dominant_name.decode(), "kernel_ms": dom,
                          "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_bytes_per_step": algo_bytes,
                          "stage_ms": {"raw_fused": stats.ms_raw, "tag_rans": stats.ms_tag, "par_post": stats.ms_par,
@@ -735,7 +768,13 @@ def main():
                     "ms_per_step": e2e_t, "steps": args.e2e_steps, "pipeline_slices": args.e2e_slices,
                     "ms_each": [round(x, 1) for x in e2e_ms],
                     "host_buffers_pinned": bool(out_pinned and pinned.get("in_ok", False)),
+                    "host_ceiling_ms": ceil_ms,
+                    "host_ceiling_GBps": (world * (in_bytes + out_bytes) / (ceil_ms * 1e-3) / 1e9) if ceil_ms == ceil_ms else None,
+                    "frac_of_host_ceiling": (ceil_ms / e2e_t) if ceil_ms == ceil_ms and e2e_t == e2e_t else None,
+                    "host_ceiling_what": "the same bytes as bare pinned cudaMemcpyAsync (H2D and D2H on a stream each), all ranks at "
+                                         "once: the link and the host memory system alone, max over ranks",
                     "what": "dcb_index_arena + dcb_decode: host indexing, H2D from pinned memory, kernels, D2H to pinned memory"},
+            "reference_csharp": "not runnable: no .NET SDK in image (BASELINE.md 3.1); the reference arm is the C oracle port",
             "gpu_launches": total_launches,
             "clocks": clocks,
         }

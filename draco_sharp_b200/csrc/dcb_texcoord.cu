@@ -275,14 +275,15 @@ __global__ void __launch_bounds__(32) tex_chain_kernel(const uint8_t *__restrict
         if (lane < take) s_flag[lane] = flags[left - take + lane];
       }
       __syncwarp();
-      // ---- chain: lane 0 ----
+      // ---- chain: lanes 0 and 1, one component each (they meet in shared memory after every entry) ----
       uint32_t used = 0;
-      if (lane == 0) {
+      if (lane < 2) {
         const uint32_t take = min(left, kTexBlock);
+        const uint32_t pair = 0x3u;
         for (uint32_t j = 0; j < cnt; ++j) {
           const uint32_t p = e0 + j;
           const TexRec r = s_rec[j];
-          int64_t pred0 = 0, pred1 = 0;
+          int64_t pred = 0;
           bool have = false;
           auto value_of = [&](int32_t e, const int2 &staged) -> int2 {
             return (uint32_t)e >= e0 ? s_out[(uint32_t)e - e0] : staged;
@@ -290,36 +291,35 @@ __global__ void __launch_bounds__(32) tex_chain_kernel(const uint8_t *__restrict
           if (r.pd < (int32_t)p && r.nd < (int32_t)p) {
             const int2 nuv = value_of(r.nd, s_nuv[j]), puv = value_of(r.pd, s_puv[j]);
             if (puv.x == nuv.x && puv.y == nuv.y) {  // :66-71
-              pred0 = puv.x;
-              pred1 = puv.y;
+              pred = lane ? puv.y : puv.x;
               have = true;
             } else if (r.flag == 1) {
               status = DCB_ERR_MAPS;
-              break;
             } else if ((int64_t)r.pn2 != 0) {  // :78
-              const int64_t pn2 = (int64_t)r.pn2;
+              const uint64_t pn2 = r.pn2;
               const int64_t n0 = nuv.x, n1 = nuv.y;
               const int64_t d0 = (int64_t)puv.x - n0, d1 = (int64_t)puv.y - n1;
               const uint64_t amax = max(abs64(n0), abs64(n1)), bmax = max(abs64(d0), abs64(d1));
-              if ((int64_t)amax > kI64Max / pn2 || r.cdp > kI64Max / (int64_t)bmax || r.flag == 2) {  // :85, :87, :90
+              // a > INT64_MAX / b  <=>  a * b > INT64_MAX  (a, b > 0): the guards :85, :87 without a division
+              const bool g85 = (int64_t)pn2 < 0 ? (int64_t)amax > kI64Max / (int64_t)pn2  // wrapped edge length: as written
+                                                : (__umul64hi(amax, pn2) != 0 || amax * pn2 > (uint64_t)kI64Max);
+              const bool g87 = r.cdp > 0 && (__umul64hi((uint64_t)r.cdp, bmax) != 0 || (uint64_t)r.cdp * bmax > (uint64_t)kI64Max);
+              if (g85 || g87 || r.flag == 2) {  // :85, :87, :90
                 status = DCB_ERR_PRED;
-                break;
-              }
-              const int64_t x0 = (int64_t)((uint64_t)n0 * (uint64_t)pn2 + (uint64_t)r.cdp * (uint64_t)d0);
-              const int64_t x1 = (int64_t)((uint64_t)n1 * (uint64_t)pn2 + (uint64_t)r.cdp * (uint64_t)d1);
-              const int64_t c0 = (int64_t)((uint64_t)d1 * (uint64_t)r.nrm);
-              const int64_t c1 = (int64_t)(0ull - (uint64_t)d0 * (uint64_t)r.nrm);
-              if (used >= take) {  // no flag left (:125)
+              } else if (used >= take) {  // no flag left (:125)
                 status = DCB_ERR_PRED;
-                break;
+              } else {
+                const int64_t nc = lane ? n1 : n0, dc = lane ? d1 : d0;
+                const int64_t x = (int64_t)((uint64_t)nc * pn2 + (uint64_t)r.cdp * (uint64_t)dc);
+                const int64_t cx = lane ? (int64_t)(0ull - (uint64_t)d0 * (uint64_t)r.nrm) : (int64_t)((uint64_t)d1 * (uint64_t)r.nrm);
+                const bool o = s_flag[take - 1 - used] != 0;  // Last() + PopBack()
+                ++used;
+                pred = (o ? (int64_t)((uint64_t)x + (uint64_t)cx) : (int64_t)((uint64_t)x - (uint64_t)cx)) / (int64_t)pn2;  // :128
+                have = true;
               }
-              const bool o = s_flag[take - 1 - used] != 0;  // Last() + PopBack()
-              ++used;
-              pred0 = (o ? (int64_t)((uint64_t)x0 + (uint64_t)c0) : (int64_t)((uint64_t)x0 - (uint64_t)c0)) / pn2;  // :128
-              pred1 = (o ? (int64_t)((uint64_t)x1 + (uint64_t)c1) : (int64_t)((uint64_t)x1 - (uint64_t)c1)) / pn2;
-              have = true;
             }
           }
+          if (status != DCB_OK) break;  // both lanes see the same operands: the same verdict
           if (!have) {  // :135-160
             int64_t off = -1;
             bool any = true;
@@ -333,15 +333,13 @@ __global__ void __launch_bounds__(32) tex_chain_kernel(const uint8_t *__restrict
                 break;
               }
               const int2 f = (uint64_t)off >= e0 ? s_out[(uint32_t)off - e0] : s_fb[j];
-              pred0 = f.x;
-              pred1 = f.y;
+              pred = lane ? f.y : f.x;
             }
           }
           const int2 co = s_cor[j];
-          int2 o;
-          o.x = wrap_original((int32_t)pred0, co.x, pp.mn, pp.mx, pp.max_diff);
-          o.y = wrap_original((int32_t)pred1, co.y, pp.mn, pp.mx, pp.max_diff);
-          s_out[j] = o;
+          const int32_t o = wrap_original((int32_t)pred, lane ? co.y : co.x, pp.mn, pp.mx, pp.max_diff);
+          reinterpret_cast<int32_t *>(&s_out[j])[lane] = o;
+          __syncwarp(pair);
         }
       }
       status = __shfl_sync(0xffffffffu, status, 0);

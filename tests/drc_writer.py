@@ -166,6 +166,43 @@ def portable_int(corr, nc, pred_method=0, transform=1, scheme="raw", pred_data=b
     return bytes(out)
 
 
+def rabs_block(bits, prob_zero=None):
+    """A bit sequence as RAnsBitEncoder leaves it (Draco ans.h rabs_desc_write / ans_write_end): u8 prob_zero | varint
+    size | rABS bytes.  A RAnsBitDecoder reads the bits back in the order given (BitCoders/RAnsBitDecoder.cs:12-35)."""
+    bits = [1 if b else 0 for b in bits]
+    if prob_zero is None:
+        zeros = len(bits) - sum(bits)
+        prob_zero = min(255, max(1, int(256.0 * zeros / max(1, len(bits)) + 0.5)))
+    p0, p1 = prob_zero, 256 - prob_zero
+    state, data = 4096, bytearray()
+    for b in reversed(bits):
+        ls = p1 if b else p0
+        if state >= 4096 * ls:
+            data.append(state & 0xFF)
+            state >>= 8
+        quot, rem = divmod(state, ls)
+        state = quot * 256 + rem + (0 if b else p1)
+    state -= 4096
+    if state < (1 << 6):
+        data.append(state)
+    elif state < (1 << 14):
+        data += int((1 << 14) + state).to_bytes(2, "little")
+    else:
+        assert state < (1 << 22)
+        data += int((2 << 22) + state).to_bytes(3, "little")
+    return bytes([prob_zero]) + varint(len(data)) + bytes(data)
+
+
+def tex_coords_data(flags, mn, mx, prob_zero=None):
+    """PRED_DATA of MeshPredictionSchemeTexCoordsPortableDecoder (:68-84): i32 count, rABS flags where a 0 bit FLIPS the
+    running orientation (starting from true), then the wrap transform's bounds."""
+    bits, last = [], True
+    for f in flags:
+        bits.append(1 if bool(f) == last else 0)
+        last = bool(f)
+    return struct.pack("<i", len(bits)) + rabs_block(bits, prob_zero) + wrap_data(mn, mx)
+
+
 def wrap_data(mn, mx):
     return struct.pack("<ii", mn, mx)
 

@@ -101,6 +101,44 @@ def test_parallelogram_random_corrections(gpu_decoder, scheme):
     batch.free()
 
 
+@pytest.mark.parametrize("scheme,n_flags,uv_bits", [("raw", 3300, 10), ("tagged", 3300, 12), ("uncompressed", 3300, 10),
+                                                     ("raw", 700, 10), ("raw", 0, 10), ("uncompressed", 3300, 30)])
+def test_texcoords_portable_random_corrections(gpu_decoder, scheme, n_flags, uv_bits):
+    """TexCoordsPortable predictor over the sample's real connectivity with random corrections and random
+    orientation flags, every symbol source; too few flags must fail the buffer exactly where the oracle fails it
+    (:125), and 30-bit coordinates exercise the 64-bit overflow guards (:85-:90)."""
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    rng = np.random.default_rng(17 + n_flags + uv_bits)
+    n0, n1 = o.maps[0]["data_to_corner"].size, o.maps[1]["data_to_corner"].size
+    big = uv_bits >= 30          # 30-bit positions and coordinates: |prev - next|^2 * |uv| leaves int64 (:85)
+    pos_hi = (1 << 30) - 1 if big else 4095
+    c_pos = rng.integers(-(1 << 28), 1 << 28, size=n0 * 3) if big else rng.integers(-30, 31, size=n0 * 3)
+    hi = (1 << uv_bits) - 1
+    c_uv = rng.integers(-(1 << 28), 1 << 28, size=n1 * 2) if big else rng.integers(-9, 10, size=n1 * 2)
+    flags = rng.integers(0, 2, size=n_flags)
+    sec = bytearray([2, 0xFF, 0, 0, 0, 1, 0])
+    sec += W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
+    sec += W.varint(1) + bytes([3, 9, 2, 0]) + W.varint(1) + bytes([2])
+    sec += W.portable_int(c_pos, 3, 1, 1, scheme, W.wrap_data(0, pos_hi), num_bytes=4)
+    sec += W.quant_params([1.0, 2.0, 3.0], 10.0, 30 if big else 12)
+    sec += W.portable_int(c_uv, 2, 5, 1, scheme, W.tex_coords_data(flags, 0, hi), num_bytes=4)
+    sec += W.quant_params([0.0, 0.0], 1.0, uv_bits)
+    buf, attr_off = _mesh_buffer(bytes(sec))
+    maps = [o.maps[0], o.maps[1]]
+    ref = O.decode(np.frombuffer(buf, dtype=np.uint8), maps, attr_off, o.n_points)
+    batch, out, dbg = _decode_mesh(gpu_decoder, buf, attr_off, o.n_points, maps, N.DCB_DUMP_QINTS)
+    assert batch.status(0) == ref.status
+    assert (ref.status == 0) == (n_flags >= 3300 and not big)
+    if ref.status == 0:
+        for k, ra in enumerate(ref.attrs):
+            ai = batch.attr_info(0, k)
+            assert ai.n_entries == ra.n_entries
+            assert np.array_equal(dbg[ai.dbg_off: ai.dbg_off + 4 * ra.qints.size].view(np.int32), ra.qints), k
+            assert np.array_equal(out[ai.out_off: ai.out_off + ai.out_bytes], ra.out), k
+    batch.free()
+
+
 def test_mesh_without_maps_fails_cleanly(gpu_decoder):
     sec = bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
     sec += W.portable_int(np.zeros(30, dtype=np.int64), 3, 1, 1, "raw", W.wrap_data(0, 7)) + W.quant_params([0, 0, 0], 1.0, 3)
