@@ -1409,7 +1409,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   // par_post2_kernel: per group the run prefix of its streams (runs of par_run_len chunks) and one ticket word
   std::vector<uint32_t> par_runs[5];
   uint64_t par_aux_off[5] = {0, 0, 0, 0, 0};
-  uint32_t par_run_len[5] = {1, 1, 1, 1, 1}, par_claim[5] = {1, 1, 1, 1, 1};
+  uint32_t par_run_len[5] = {1, 1, 1, 1, 1}, par_claim[5] = {1, 1, 1, 1, 1}, par_rounds[5] = {0, 0, 0, 0, 0};
   for (int n = 1; n <= 4; ++n) {
     if (par[n].order.empty()) continue;
     // longest streams first: whole-stream runs are handed out by ticket, longest-processing-time first
@@ -1427,16 +1427,42 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       par_run_len[n] = (uint32_t)env_flags().par_run;
       par_claim[n] = 1;
     }
-    par_runs[n].reserve(par[n].order.size() + 2);
-    uint64_t acc = 0;
-    for (uint32_t si : par[n].order) {
+    // Chunk-sized runs that look back (delta streams) are ticketed ROUND by round -- chunk r of every stream that has
+    // one, then chunk r + 1 -- so that the chunks a warp claims together, and the chunks of neighbouring claims, belong
+    // to different streams: in stream-major order a claim's look-back waits for the previous claim's LAST chunk, which
+    // waits for that claim's first look-back, and a stream decodes chunk after chunk (measured: 195 ms instead of ~8
+    // for 2,000 streams of 100,000 points).  The prefix then runs over rounds: the streams are sorted by length, so
+    // round r holds the first count(r) of them.
+    par_rounds[n] = 0;
+    if (par_run_len[n] == 1 && par_delta[n] && !getenv("DCB_PAR_STREAM_MAJOR") && max_chunks <= (1ull << 24)) {
+      par_rounds[n] = (uint32_t)max_chunks;
+      par_runs[n].assign((size_t)max_chunks + 2, 0u);
+      // count(r) = streams with more than r chunks; par_runs[r + 1] - par_runs[r] = count(r)
+      for (uint32_t si : par[n].order) {
+        const uint64_t nch = ((uint64_t)sh.streams[si].n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
+        if (nch > 0) par_runs[n][(size_t)nch] += 1;  // streams that END after round nch - 1
+      }
+      if (total_chunks > 0xFFFFFFF0ull) return DCB_ERR_UNSUPPORTED;
+      uint64_t alive = par[n].order.size(), acc = 0;
+      for (uint64_t r = 0; r <= max_chunks; ++r) {
+        const uint32_t ending = par_runs[n][(size_t)r];  // streams with exactly r chunks: gone from round r on
+        alive -= ending;
+        par_runs[n][(size_t)r] = (uint32_t)acc;
+        acc += alive;
+      }
+      par_runs[n][(size_t)max_chunks + 1] = 0u;  // the ticket
+    } else {
+      par_runs[n].reserve(par[n].order.size() + 2);
+      uint64_t acc = 0;
+      for (uint32_t si : par[n].order) {
+        par_runs[n].push_back((uint32_t)acc);
+        const uint64_t nch = ((uint64_t)sh.streams[si].n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
+        acc += (nch + par_run_len[n] - 1) / par_run_len[n];
+      }
+      if (acc > 0xFFFFFFF0ull) return DCB_ERR_UNSUPPORTED;
       par_runs[n].push_back((uint32_t)acc);
-      const uint64_t nch = ((uint64_t)sh.streams[si].n_entries + DCB_TAG_CHUNK - 1) / DCB_TAG_CHUNK;
-      acc += (nch + par_run_len[n] - 1) / par_run_len[n];
+      par_runs[n].push_back(0u);  // the ticket
     }
-    if (acc > 0xFFFFFFF0ull) return DCB_ERR_UNSUPPORTED;
-    par_runs[n].push_back((uint32_t)acc);
-    par_runs[n].push_back(0u);  // the ticket
     par_aux_off[n] = n_order;
     n_order += par_runs[n].size();
   }
@@ -1596,8 +1622,9 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         }
       }
       uint32_t *d_runs = sh.d_order + par_aux_off[n];
-      CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, d_runs, np, par_runs[n][np], par_run_len[n],
-                                   par_claim[n], d_runs + np + 1, num_sms, n, dump, next_epoch(sh), A, st));
+      const uint32_t n_prefix = par_rounds[n] ? par_rounds[n] : np;  // entries of the run prefix (rounds or streams)
+      CUDA_TRY(dcb_launch_par_post(sh.d_streams, sh.d_order + par[n].order_off, d_runs, np, par_runs[n][n_prefix], par_run_len[n],
+                                   par_claim[n], par_rounds[n], d_runs + n_prefix + 1, num_sms, n, dump, next_epoch(sh), A, st));
       stats.n_launches += 1;
       if (par_delta[n]) {
         // streams whose corrections break the modular-sum condition fall back to the exact serial recurrence
@@ -2173,8 +2200,24 @@ int dcb_host_connectivity(dcb_batch *b, int buf) {
     BufRec &r = b->bufs[buf];
     if (!r.info.needs_connectivity) return DCB_ERR_STATE;
     if (r.info.status != DCB_OK) return DCB_OK;
-    if (!r.is_eb) {  // sequential mesh connectivity (MeshSequentialDecoder.cs:8-118): SURVEY 8f-4, not built yet
-      r.info.status = DCB_ERR_UNSUPPORTED;
+    if (!r.is_eb) {  // sequential mesh connectivity (MeshSequentialDecoder.cs:8-118): indices on the host,
+                     // attributes through the sequential (point-cloud) kernels -- no maps
+      uint64_t attr_off = 0;
+      uint32_t n_points = 0;
+      int st;
+      try {
+        st = dcb_host_sequential(r.src, r.len, r.conn_off, &attr_off, &n_points, &r.faces);
+      } catch (const std::bad_alloc &) {
+        st = DCB_ERR_OOM;
+      } catch (...) {
+        st = DCB_ERR_CONNECTIVITY;
+      }
+      if (st != DCB_OK) {
+        r.info.status = st;
+        return DCB_OK;
+      }
+      r.info.attr_section_off = attr_off;
+      r.info.n_points = n_points;
       return DCB_OK;
     }
     std::vector<DcbHostMaps> maps;

@@ -60,8 +60,9 @@ uint32_t dcb_par_post_smem_bytes(int ncp);
 void dcb_par_post_plan(uint32_t n_streams, uint64_t total_chunks, uint32_t max_chunks, bool any_delta, uint32_t num_sms, int ncp,
                        uint32_t share,
                        uint32_t *run_len, uint32_t *claim);
+// n_rounds != 0: chunk-sized runs ticketed round by round; d_run_prefix then has n_rounds + 1 entries (runs in front of round r)
 cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, const uint32_t *d_run_prefix, uint32_t n,
-                                uint32_t total_runs, uint32_t run_len, uint32_t claim, unsigned int *d_ticket, uint32_t num_sms,
+                                uint32_t total_runs, uint32_t run_len, uint32_t claim, uint32_t n_rounds, unsigned int *d_ticket, uint32_t num_sms,
                                 int ncp, uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
                             uint32_t dump, const DevArenas &a, cudaStream_t st);

@@ -706,3 +706,59 @@ int dcb_host_edgebreaker(const uint8_t *buf, uint64_t len, uint64_t conn_off, ui
   if (faces) faces->swap(eb.faces);
   return DCB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Sequential mesh connectivity (MeshSequentialDecoder.cs:8-118), v2.2: varint faces, varint points, u8 method, then
+// either entropy-coded index differences (method 0, the symbol streams of SymbolDecoding.cs) or plain indices whose
+// width follows the point count (method 1).  Host work like the Edgebreaker connectivity: the attributes behind it
+// are sequential (LinearSequencer) and decode through the point-cloud kernels, no maps needed.
+// Index differences: symbol >> 1 with the sign in bit 0, ODD = negative -- the bitstream's rule; the C# tests the
+// bit the other way round (:97) and cannot decode an ordinary mesh.  Its range checks are kept:
+// an index may neither drop below zero (:99) nor pass int.MaxValue (:107).
+int dcb_host_sequential(const uint8_t *buf, uint64_t len, uint64_t conn_off, uint64_t *attr_section_off, uint32_t *n_points,
+                        std::vector<uint32_t> *faces) {
+  Reader r{buf, len, conn_off};
+  const uint64_t n_faces = r.varint();
+  const uint64_t points = r.varint();
+  const uint32_t method = r.u8();
+  if (r.err) return r.err;
+  if (n_faces > (1u << 28) || points > 0xFFFFFFFFull) return DCB_ERR_CONNECTIVITY;
+  const uint64_t n_idx = 3 * n_faces;
+  // counts the data cannot back fail this buffer before they size anything (as for the Edgebreaker counts)
+  if (n_idx > 65536 + 4096 * (len - r.pos)) return DCB_ERR_CONNECTIVITY;
+  std::vector<uint32_t> idx;
+  if (method == 0) {
+    const int st = host_symbols(r, (uint32_t)n_idx, idx);
+    if (st) return st;
+    int64_t cur = 0;
+    for (uint64_t i = 0; i < n_idx; ++i) {
+      const int64_t step = (int64_t)(idx[i] >> 1);
+      cur += (idx[i] & 1u) ? -step : step;
+      if (cur < 0 || cur > 0x7FFFFFFFll) return DCB_ERR_CONNECTIVITY;
+      idx[i] = (uint32_t)cur;
+    }
+  } else if (method == 1) {
+    // bytes per index: 1, 2, varint (0) or 4
+    const int width = points < 256 ? 1 : points < 65536 ? 2 : points < (1u << 21) ? 0 : 4;
+    if (width && (len - r.pos) / (uint64_t)width < n_idx) return DCB_ERR_EOF;
+    if (!width && len - r.pos < n_idx) return DCB_ERR_EOF;  // a varint is at least one byte
+    idx.resize((size_t)n_idx);
+    for (uint64_t i = 0; i < n_idx; ++i) {
+      if (width == 0) {
+        idx[i] = (uint32_t)r.varint();
+      } else {
+        uint32_t v = 0;
+        for (int k = 0; k < width; ++k) v |= (uint32_t)buf[r.pos + k] << (8 * k);
+        r.pos += (uint64_t)width;
+        idx[i] = v;
+      }
+    }
+    if (r.err) return r.err;
+  } else {
+    return DCB_ERR_CONNECTIVITY;  // :81
+  }
+  *attr_section_off = r.pos;
+  *n_points = (uint32_t)points;
+  if (faces) faces->swap(idx);
+  return DCB_OK;
+}

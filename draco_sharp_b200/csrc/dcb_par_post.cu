@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
                                                                 const uint32_t *__restrict__ order,
                                                                 const uint32_t *__restrict__ run_prefix, uint32_t n_streams,
                                                                 uint32_t total_runs, uint32_t kRun, uint32_t kClaim,
-                                                                unsigned int *ticket, uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
+                                                                uint32_t n_rounds, unsigned int *ticket, uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
                                                                 uint8_t *__restrict__ aux, uint32_t dump, uint32_t epoch) {
   extern __shared__ __align__(128) uint8_t smem[];
   typedef Geo<NCP> G;
@@ -176,19 +176,21 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
   uint32_t claim_pos = 0;  // run inside the claim
 
   uint32_t slot_hint = 0;
-  // run -> slot: run_prefix[slot] <= run < run_prefix[slot + 1]; tickets only grow, so the search gallops forward
+  // run -> item: run_prefix[item] <= run < run_prefix[item + 1]; tickets only grow, so the search gallops forward.
+  // Items are streams (stream-major runs) or rounds (n_rounds != 0: chunk r of every stream that has one, see the host).
+  const uint32_t n_items = n_rounds ? n_rounds : n_streams;
   auto slot_of_run = [&](uint32_t run) -> uint32_t {
     uint32_t lo = slot_hint;
     if (run < run_prefix[lo + 1]) return lo;
     uint32_t step = 1, hi = lo + 1;
-    while (hi < n_streams && run >= run_prefix[hi + 1 > n_streams ? n_streams : hi + 1]) {
+    while (hi < n_items && run >= run_prefix[hi + 1 > n_items ? n_items : hi + 1]) {
       lo = hi;
-      hi = hi + step > n_streams ? n_streams : hi + step;
+      hi = hi + step > n_items ? n_items : hi + step;
       step <<= 1;
-      if (hi == n_streams) break;
+      if (hi == n_items) break;
     }
-    // invariant: run_prefix[lo] <= run; answer in [lo, min(hi, n_streams - 1)]
-    uint32_t a = lo, b = hi >= n_streams ? n_streams - 1u : hi;
+    // invariant: run_prefix[lo] <= run; answer in [lo, min(hi, n_items - 1)]
+    uint32_t a = lo, b = hi >= n_items ? n_items - 1u : hi;
     while (a < b) {
       const uint32_t mid = (a + b + 1u) >> 1;
       if (run_prefix[mid] <= run) a = mid;
@@ -227,14 +229,15 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
           o.cnt = 0;
           return;
         }
-        const uint32_t slot = slot_of_run(run);
-        slot_hint = slot;
+        const uint32_t item = slot_of_run(run);
+        slot_hint = item;
+        const uint32_t slot = n_rounds ? run - run_prefix[item] : item;
         if (slot != vj.slot || !vj.ok) vo = view_of(streams, order, slot, aux);
         else vo = vj;
         if (!vo.ok) continue;  // failed or empty stream: its runs are skipped
         o.run = run;
         o.k = 0;
-        o.chunk = (run - run_prefix[slot]) * kRun;
+        o.chunk = n_rounds ? item : (run - run_prefix[item]) * kRun;
         if (o.chunk >= vo.n_chunks) continue;
         break;
       }
@@ -565,8 +568,8 @@ uint32_t dcb_par_post_smem_bytes(int ncp) {
 
 template <int NCP>
 static cudaError_t launch_par_post_n(StreamDesc *d_streams, const uint32_t *d_order, const uint32_t *d_run_prefix, uint32_t n,
-                                     uint32_t total_runs, uint32_t run_len, uint32_t claim, unsigned int *d_ticket, uint32_t num_sms,
-                                     uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
+                                     uint32_t total_runs, uint32_t run_len, uint32_t claim, uint32_t n_rounds, unsigned int *d_ticket,
+                                     uint32_t num_sms, uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
   const uint32_t smem = Geo<NCP>::kWarpBytes * kWarps;
   auto k0 = par_post2_kernel<NCP, false>;
   auto k1 = par_post2_kernel<NCP, true>;
@@ -584,23 +587,23 @@ static cudaError_t launch_par_post_n(StreamDesc *d_streams, const uint32_t *d_or
   e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   if (dump)
-    k1<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
+    k1<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, n_rounds, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
   else
-    k0<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
+    k0<<<grid, kWarps * 32, smem, st>>>(a.in, d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, n_rounds, d_ticket, a.out, a.dbg, a.aux, dump, epoch);
   return cudaGetLastError();
 }
 
 cudaError_t dcb_launch_par_post(StreamDesc *d_streams, const uint32_t *d_order, const uint32_t *d_run_prefix, uint32_t n,
-                                uint32_t total_runs, uint32_t run_len, uint32_t claim, unsigned int *d_ticket, uint32_t num_sms,
-                                int ncp, uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
+                                uint32_t total_runs, uint32_t run_len, uint32_t claim, uint32_t n_rounds, unsigned int *d_ticket,
+                                uint32_t num_sms, int ncp, uint32_t dump, uint32_t epoch, const DevArenas &a, cudaStream_t st) {
   if (n == 0 || total_runs == 0) return cudaSuccess;
   run_len = std::max(1u, run_len);
   claim = std::max(1u, claim);
   switch (ncp) {
-    case 1: return launch_par_post_n<1>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
-    case 2: return launch_par_post_n<2>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
-    case 3: return launch_par_post_n<3>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
-    case 4: return launch_par_post_n<4>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, d_ticket, num_sms, dump, epoch, a, st);
+    case 1: return launch_par_post_n<1>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, n_rounds, d_ticket, num_sms, dump, epoch, a, st);
+    case 2: return launch_par_post_n<2>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, n_rounds, d_ticket, num_sms, dump, epoch, a, st);
+    case 3: return launch_par_post_n<3>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, n_rounds, d_ticket, num_sms, dump, epoch, a, st);
+    case 4: return launch_par_post_n<4>(d_streams, d_order, d_run_prefix, n, total_runs, run_len, claim, n_rounds, d_ticket, num_sms, dump, epoch, a, st);
     default: return cudaErrorInvalidValue;
   }
 }

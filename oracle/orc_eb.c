@@ -753,7 +753,62 @@ int orc_eb_build_maps(orc_result *res, const uint8_t *dec_ids, int n_dec) {
 }
 
 /* Sequential mesh connectivity (MeshSequentialDecoder.cs:8-118): SURVEY 8f-4, not restated yet. */
+/* MeshSequentialDecoder.DecodeConnectivity (D/IO/Mesh/MeshSequentialDecoder.cs:8-83) and DecodeAndDecompressIndices
+ * (:85-118), v2.2 container.  Two sites follow the bitstream the C# ports instead of the C# (SURVEY Appendix B):
+ * the point count is recorded (the C# never sets it, :23/:122, so its LinearSequencer would cover zero points), and
+ * an ODD symbol is a negative index difference (:97 tests `== 0`, the inverse of the encoder it ports; with that test
+ * the second index of any ordinary mesh throws).  The range checks keep the C#'s meaning. */
 int orc_seq_mesh_connectivity(const uint8_t *buf, uint64_t len, uint64_t *pos, orc_result *res) {
-  (void)buf; (void)len; (void)pos; (void)res;
-  return ORC_ERR_UNSUPPORTED;
+  rd_t r = {buf, len, *pos, 0};
+  uint64_t nf = e_varint(&r), np = e_varint(&r);
+  uint8_t method = e_u8(&r);
+  if (r.err) return r.err;
+  if (nf > (1u << 28) || np > 0xFFFFFFFFull) return ORC_ERR_CONNECTIVITY;
+  uint32_t *faces = (uint32_t *)malloc((size_t)(nf ? nf : 1) * 12);
+  if (!faces) return ORC_ERR_CONNECTIVITY;
+  int st = ORC_OK;
+  if (method == 0) { /* compressed indices */
+    uint32_t *sym = (uint32_t *)malloc((size_t)(nf ? nf : 1) * 12);
+    st = orc_decode_symbols(buf, len, &r.pos, (uint32_t)(nf * 3), 1, sym, NULL);
+    int32_t last = 0;
+    for (uint64_t i = 0; i < nf * 3 && !st; ++i) {
+      int32_t diff = (int32_t)(sym[i] >> 1);
+      if (sym[i] & 1u) {
+        if (diff > last) st = ORC_ERR_CONNECTIVITY; /* :99 would go negative */
+        diff = -diff;
+      } else if (diff > 0x7FFFFFFF - last) {
+        st = ORC_ERR_CONNECTIVITY; /* :107 would overflow */
+      }
+      last += diff;
+      faces[i] = (uint32_t)last;
+    }
+    free(sym);
+  } else if (method == 1) { /* uncompressed indices, width by point count :27-79 */
+    for (uint64_t i = 0; i < nf * 3 && !st; ++i) {
+      uint64_t v = 0;
+      if (np < 256) {
+        v = e_u8(&r);
+      } else if (np < (1u << 16)) {
+        v = e_u8(&r);
+        v |= (uint64_t)e_u8(&r) << 8;
+      } else if (np < (1u << 21)) {
+        v = e_varint(&r);
+      } else {
+        for (int k = 0; k < 4; ++k) v |= (uint64_t)e_u8(&r) << (8 * k);
+      }
+      if (r.err) st = r.err;
+      faces[i] = (uint32_t)v;
+    }
+  } else {
+    st = ORC_ERR_CONNECTIVITY; /* :81 */
+  }
+  if (st) {
+    free(faces);
+    return st;
+  }
+  res->n_points = (uint32_t)np;
+  res->n_faces = (uint32_t)nf;
+  res->faces = faces;
+  *pos = r.pos;
+  return ORC_OK;
 }
