@@ -116,7 +116,9 @@ def reduce_over_ranks(dist, device, ms, sums):
 
 
 def rank_seed(rank):
-    """Every rank decodes its own, distinct batch (work shards by buffer: weak scaling, no collective on the data path)."""
+    """Every rank decodes its own, distinct batch (work shards by buffer: weak scaling, no collective on the data path).
+    DCB_BENCH_DATA_RANK=r: a one-GPU run decodes the batch rank r of a multi-GPU run would get."""
+    rank = int(os.environ.get("DCB_BENCH_DATA_RANK", rank))
     return 0xD5AC0000 + (rank << 20)
 
 

@@ -137,6 +137,7 @@ struct Group {            // one kernel launch (or a few, for global tables)
   uint32_t rec_max[4], exc_all;
   uint32_t rec_ka, rec_bytes;  // rec_ka != 0: the group runs on the bucket-record kernels
   uint32_t split;              // warp-pair kernels: chain warps on sub-partitions 0..2, consumers on sub-partition 3
+  bool no_direct;              // a machine-filling group runs in the same step: keep this one's shared memory small
   void note_table(const StreamDesc &s) {
     for (int k = 1; k <= 7; ++k) {
       nb_min[k] = nb_any ? std::min<uint32_t>(nb_min[k], s.narrow_blk[k]) : s.narrow_blk[k];
@@ -883,7 +884,7 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
     // access per symbol (slot -> {freq, offset}, 6 bytes per slot) instead of two, and a chain warp that carries
     // nothing but the chain; its consumer warp sits on another sub-partition (two pairs per CTA: warps 0,1 are
     // chain warps, 2,3 their consumers).  Taken whenever every stream of the group is resident that way.
-    if (!g.wide && g.prec_bits <= 15 && !env_flags().no_direct && per_sm[i] <= 64 && want == per_sm[i]) {
+    if (!g.wide && g.prec_bits <= 15 && !env_flags().no_direct && !g.no_direct && per_sm[i] <= 64 && want == per_sm[i]) {
       const uint32_t pairs = std::min<uint32_t>(2u, want), lanes = (want + pairs - 1) / pairs;
       const uint32_t dlut = 6u << g.prec_bits;
       if ((uint64_t)lanes * g.ent_bytes <= 65535 && pc_cta_bytes(pairs, lanes, dlut, 0, 1) <= sm_cap) {
@@ -1387,6 +1388,12 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   bool side_followers = false;
   for (Group *g : rgs) side_followers = side_followers || (g->mode == 3 && rgs.size() > 1);
   for (Group *g : rgs) {
+    // A handful of outlier streams next to a machine-filling group (one cloud of a batch whose table came out dense)
+    // must stay small: the direct slot LUT wants ~50 KB per stream, finds no room beside the big group's CTAs and would
+    // run BEHIND it (measured: +17 ms on a 27 ms step); with the two-level tables it runs beside it, on a side stream.
+    g->no_direct = false;
+    for (Group *o : rgs)
+      if (o != g && o->order.size() >= (size_t)num_sms * 8) g->no_direct = true;
     std::vector<Group *> one{g};
     plan_rans_groups(one, num_sms, (uint32_t)sh.share, side_followers ? 6u * 1024u : 0u);
   }

@@ -232,3 +232,33 @@ def point_cloud(n_points, attrs, version=(2, 2), geom_type=0, method=0, flags=0,
         for i in dec:
             out += attrs[i].get("xform", b"")
     return bytes(out)
+
+
+def sequential_mesh(faces, n_points, attrs, method=0, scheme="raw", decoders=None):
+    """A v2.2 sequential mesh (MeshSequentialDecoder.cs:8-118): header, varint faces / points, u8 method, indices
+    (method 0: index differences as symbols, magnitude << 1 with bit 0 set for negative ones; method 1: plain indices,
+    width by point count), then the ATTRIBUTES section of point_cloud()."""
+    faces = [int(v) for f in faces for v in f]
+    out = bytearray(b"DRACO" + bytes([2, 2, 1, 0]) + struct.pack("<H", 0))
+    out += varint(len(faces) // 3) + varint(n_points)
+    out.append(method)
+    if method == 0:
+        syms, last = [], 0
+        for v in faces:
+            d = v - last
+            syms.append((abs(d) << 1) | (1 if d < 0 else 0))
+            last = v
+        if syms:
+            out += symbols_raw(syms) if scheme == "raw" else symbols_tagged(syms, 1)
+    else:
+        for v in faces:
+            if n_points < 256:
+                out.append(v)
+            elif n_points < (1 << 16):
+                out += struct.pack("<H", v)
+            elif n_points < (1 << 21):
+                out += varint(v)
+            else:
+                out += struct.pack("<I", v)
+    body = point_cloud(n_points, attrs, decoders=decoders)
+    return bytes(out) + body[15:]  # point_cloud(): 11-byte header + int32 point count, then the ATTRIBUTES section

@@ -224,6 +224,33 @@ def test_house_whole_sample_on_gpu(gpu_decoder):
     assert dist.max() < half_step
 
 
+@pytest.mark.parametrize("w,h,method,scheme", [(20, 17, 0, "raw"), (20, 17, 0, "tagged"), (300, 300, 1, "raw"), (300, 300, 0, "tagged")])
+def test_sequential_meshes_decode_through_the_product(gpu_decoder, w, h, method, scheme):
+    """Sequential meshes (MeshSequentialDecoder.cs:8-118): indices by the product's host helper, attributes
+    (delta + wrap positions, octahedral normals, 8-bit colours) through the sequential CUDA kernels; next to a point
+    cloud and an Edgebreaker mesh in one batch."""
+    rng = np.random.default_rng(w + h + method)
+    n = w * h
+    faces = [(y * w + x, y * w + x + 1, (y + 1) * w + x) for y in range(h - 1) for x in range(w - 1)]
+    attrs = [dict(att_type=0, data_type=9, nc=3, seq_type=2,
+                  portable=W.portable_int(rng.integers(-20, 21, size=n * 3), 3, 0, 1, scheme, W.wrap_data(0, 4095), num_bytes=2),
+                  xform=W.quant_params([0.0, 1.0, 2.0], 8.0, 12)),
+             dict(att_type=2, data_type=2, nc=3, seq_type=1,
+                  portable=W.portable_int(rng.integers(-3, 4, size=n * 3), 3, 0, 1, "raw", W.wrap_data(0, 255)))]
+    mesh = np.frombuffer(W.sequential_mesh(faces, n, attrs, method, scheme), dtype=np.uint8)
+    cloud = np.frombuffer(W.point_cloud(n, attrs), dtype=np.uint8)
+    house = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    refs = [O.decode(b) for b in (mesh, cloud, house)]
+    assert all(r.status == 0 for r in refs)
+    got = gpu_decoder.decode_batch([mesh, cloud, house])
+    for d, r in zip(got, refs):
+        assert d.ok and d.points_count == r.n_points and len(d.attributes) == len(r.attrs)
+        for a, ra in zip(d.attributes, r.attrs):
+            assert np.array_equal(np.asarray(a.buffer).view(np.uint8).ravel(), ra.out.view(np.uint8).ravel())
+    assert np.array_equal(got[0].faces, refs[0].faces) and np.array_equal(got[0].faces, np.asarray(faces, dtype=np.uint32))
+    assert got[1].faces is None and np.array_equal(got[2].faces, refs[2].faces)
+
+
 def test_mixed_batch_meshes_and_clouds(gpu_decoder):
     """Meshes (host connectivity) and point clouds in one batch; a mesh with broken connectivity fails alone."""
     from draco_sharp_b200 import synth_gen as G

@@ -149,6 +149,42 @@ def test_pipeline_slices_match_single_shard(gpu_decoder, scheme, slices):
         one.free()
 
 
+def test_library_shards_a_batch_across_distinct_devices(gpu_decoder):
+    """dcb_create with DISTINCT device ids: the library's own sharding -- longest-processing-time-first by
+    compressed bytes, one host thread per physical device, no collective -- against the single-device decode.  Needs a
+    box with at least two GPUs (`gpurun --gpus 2`); skipped on the one-GPU boxes of the round-end run."""
+    import draco_sharp_b200 as D
+    from draco_sharp_b200 import _native as Nn
+    n_dev = Nn.lib().dcb_device_count()
+    if n_dev < 2:
+        pytest.skip("one device")
+    for scheme in (-1, 0):
+        sp = G.make_spec(30000, seed=0xD5AC0200 + scheme, scheme=scheme, normal_bits=10, colors=1)
+        arena, offs, lens, sums, schemes, used = G.synth_batch(sp, 61)
+        arena = arena.copy()
+        arena[int(offs[7]) + 40] ^= 0x55
+        one = gpu_decoder.index_arena(arena, offs, lens)
+        ref, _ = gpu_decoder.decode(one)
+        dec = D.DracoBatchDecoder(list(range(n_dev)))
+        try:
+            many = dec.index_arena(arena, offs, lens)
+            out, _ = dec.decode(many)
+            devs = set()
+            for k in range(61):
+                assert many.status(k) == one.status(k)
+                devs.add(many.buffer_info(k).device)
+                if one.status(k):
+                    continue
+                for a in range(3):
+                    x, y = one.attr_info(k, a), many.attr_info(k, a)
+                    assert np.array_equal(ref[x.out_off: x.out_off + x.out_bytes], out[y.out_off: y.out_off + y.out_bytes]), (k, a)
+            assert len(devs) == n_dev
+            many.free()
+        finally:
+            dec.close()
+            one.free()
+
+
 def test_uniform_lut_fallback_path_is_bit_exact_too():
     """DCB_NO_SPLIT=1 forces every Raw stream through the uniform-LUT probe (the path tables take when they cannot
     satisfy the two-region LUT); the switch is read once per process, so the parity cases re-run in a child."""
