@@ -755,6 +755,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": profile_traffic(args.workload),
                          "frac_of_8TBps": achieved / 8000.0,
+                         "whole_step": {"achieved": algo_bytes / (ms_per_step * 1e-3) / 1e9, "frac": algo_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                                        "what": "algorithmic bytes of the whole step / step time: the figure to compare across workloads "
+                                                "(the dominant kernel may share the SMs with the step's other kernels)"},
                          "chain_bound": {"symbols_per_stream": WORKLOADS[args.workload][1] * 3,
                                          "cycles_per_symbol": (dom * 1e-3 * clocks.get("sm_mhz", 0) * 1e6 / (WORKLOADS[args.workload][1] * 3))
                                          if dom > 0 and clocks.get("sm_mhz") else None,

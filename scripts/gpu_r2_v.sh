@@ -1,0 +1,37 @@
+#!/bin/bash
+# round 2, call V: final state -- GPU tests, smoke, bench lines of every workload (e2e + bare-copy ceiling + cpu baseline),
+# outlier batches (data ranks 1, 6), launch lists, ncu --set full of the dominant kernel (after the plain run of the same command)
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/v_gpu.txt 2>&1
+echo "== smoke" ; timeout 300 python __graft_entry__.py --smoke > gpurun_out/v_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/v_smoke.log
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/v_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/v_pytest.log
+summ() { python - "$1" <<'PY'
+import json,sys
+try:
+    l=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    e=l.get("e2e",{})
+    print(" ms_per_step", round(l["ms_per_step"],3), "e2e_ms", e.get("ms_per_step"), "ceiling_ms", e.get("host_ceiling_ms"), "stages", (l.get("roofline") or {}).get("stage_ms"))
+    if "cpu_baseline" in l: print(" cpu", l["cpu_baseline"]["value"], "gpu value", l["value"], "e2e value", e.get("value"))
+except Exception as ex:
+    print(" no line", ex)
+PY
+}
+for r in 1 6; do
+  echo "== c2 data rank $r"
+  DCB_BENCH_DATA_RANK=$r DCB_DEBUG_PLAN=1 timeout 600 python bench.py --steps 5 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/v_c2_r$r.json 2> gpurun_out/v_c2_r$r.err; echo " rc=$?"; summ gpurun_out/v_c2_r$r.json
+  grep "dcb plan" gpurun_out/v_c2_r$r.err | sort | uniq -c | grep -v "125[0-9] streams\|124[0-9] streams" | head -3
+done
+for w in c2 c2tagged c3 c4 c4tagged c1; do
+  echo "== $w"
+  timeout 900 python bench.py --workload $w --steps 10 --warmup 3 > gpurun_out/v_bench_$w.json 2> gpurun_out/v_bench_$w.err
+  echo " rc=$?"; summ gpurun_out/v_bench_$w.json
+done
+echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/v_bench_reference.json 2> gpurun_out/v_bench_reference.err; echo " rc=$?"; tail -c 600 gpurun_out/v_bench_reference.json
+B="python bench.py --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline"
+for w in c2 c2tagged c3 c4tagged; do
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/v_launches_$w.csv $B --workload $w > gpurun_out/v_ncu_l_$w.log 2>&1; echo "launches $w rc=$?"
+done
+$B --workload c2 > gpurun_out/v_plain_c2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:rans_raw_fused -s 3 -c 1 -f -o gpurun_out/prof_r2_final_raw_c2 $B --workload c2 > gpurun_out/v_ncu_raw.log 2>&1; echo "ncu raw rc=$?"
+$B --workload c1 > gpurun_out/v_plain_c1.log 2>&1; ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/v_launches_c1.csv python bench.py --workload c1 --steps 1 > gpurun_out/v_ncu_l_c1.log 2>&1; echo "launches c1 rc=$?"
+ls -la gpurun_out/prof_r2_final_raw_c2.ncu-rep
