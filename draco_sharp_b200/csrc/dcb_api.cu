@@ -138,6 +138,7 @@ struct Group {            // one kernel launch (or a few, for global tables)
   uint32_t rec_ka, rec_bytes;  // rec_ka != 0: the group runs on the bucket-record kernels
   uint32_t split;              // warp-pair kernels: chain warps on sub-partitions 0..2, consumers on sub-partition 3
   bool no_direct;              // a machine-filling group runs in the same step: keep this one's shared memory small
+  bool force_single_warp;      // wide attributes: only the fused single-warp kernel knows to decode n * nc symbols
   void note_table(const StreamDesc &s) {
     for (int k = 1; k <= 7; ++k) {
       nb_min[k] = nb_any ? std::min<uint32_t>(nb_min[k], s.narrow_blk[k]) : s.narrow_blk[k];
@@ -413,8 +414,9 @@ void parse_attr_section(BufRec &b, Shard &sh, int buf_index, const dcb_batch *ba
       if (s.seq_type == SEQ_NORMALS && (s.data_type != DT_FLOAT32 || s.nc != 3)) status = DCB_ERR_ATTR;
       s.ncp = (s.seq_type == SEQ_NORMALS) ? 2 : s.nc;  // AttributeOctahedronTransform.cs:23-26, B-8
       if (s.nc > 4 && s.seq_type == SEQ_QUANTIZATION) status = DCB_ERR_UNSUPPORTED;
-      // kernels are specialised for 1..4 portable components
-      if (!status && s.seq_type != SEQ_GENERIC && s.ncp > 4) status = DCB_ERR_UNSUPPORTED;
+      // the fast kernels are specialised for 1..4 portable components; integer attributes with more (the reference loops
+      // over any nc, SequentialIntegerAttributeDecoder.cs:144-152) take the generic wide path (wide_post_kernel)
+      if (!status && s.seq_type != SEQ_GENERIC && s.seq_type != SEQ_INTEGER && s.ncp > 4) status = DCB_ERR_UNSUPPORTED;
     }
     if (status) return finish(status);
     // entry count of this decoder: LinearSequencer.cs:7-13 (B-2) / traversal observer for Edgebreaker
@@ -605,6 +607,9 @@ void layout_shard(Shard &sh) {
       } else if (s.seq_type == SEQ_NORMALS) {
         s.aux_off = aux;  // quantized octahedral (s, t) pairs between the serial kernels and oct_unit_kernel
         aux = align_up(aux + 8ull * s.n_entries, 16);
+      } else if (s.seq_type == SEQ_INTEGER && s.ncp > 4) {
+        s.aux_off = aux;  // wide attributes: zig-zag decoded symbols of a Raw source, int32[n * nc]
+        aux = align_up(aux + 4ull * nv, 16);
       }
     }
   }
@@ -901,7 +906,7 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
     // up to four pairs per SM.  Taken whenever every stream of the group has the table shape and is resident that way.
     g.rec_ka = 0;
     g.split = 0;
-    if (!g.wide && g.prec_bits <= 15 && g.nb_any && !env_flags().no_rec && !env_flags().rans_pc && want == per_sm[i] && want <= 128) {
+    if (!g.wide && g.prec_bits <= 15 && g.nb_any && !env_flags().no_rec && !env_flags().rans_pc && !g.force_single_warp && want == per_sm[i] && want <= 128) {
       const bool split = env_flags().split && share == 1;
       const uint32_t pairs = std::min<uint32_t>(split ? 3u : std::max<uint32_t>(1u, 4u / share), want), lanes = (want + pairs - 1) / pairs;
       uint32_t best_j = 4, best_bytes = 0xFFFFFFFFu;
@@ -930,7 +935,7 @@ void plan_rans_groups(std::vector<Group *> &gs, uint32_t num_sms, uint32_t share
         }
       }
     }
-    if (!g.wide && env_flags().rans_pc) {
+    if (!g.wide && env_flags().rans_pc && !g.force_single_warp) {
       // ---- chain / consumer warp pairs with the two-level tables (experiment: measured slower than one warp per
       // sub-partition when the SM is full of streams -- the two warps of a pair compete for the same issue port) ----
       uint32_t target = std::max<uint32_t>(1u, 4u / share);
@@ -1332,7 +1337,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
   }
   std::map<RawKey, Group> raw;
-  Group post[5], para[5], par[5], copy{}, octs{}, octc{}, tex{};
+  Group post[5], para[5], par[5], copy{}, octs{}, octc{}, tex{}, wide{};
+  wide.kind = 8;
   octs.kind = 6;
   octc.kind = 6;
   tex.kind = 7;
@@ -1357,6 +1363,35 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         continue;
       }
       if (s.n_entries == 0) continue;
+      if (s.ncp > 4) {
+        // wide integer attribute: a Raw source decodes as n * nc one-component symbols into the scratch (the fused
+        // kernel's generic instantiation), then -- as for Tagged and uncompressed sources -- wide_post_kernel
+        // reconstructs and stores entry by entry with a run-time component count
+        if ((uint64_t)s.n_entries * s.ncp > 0xFFFFFFF0ull || (s.recon != RECON_NONE && s.recon != RECON_DELTA_WRAP)) {
+          sh.streams[si].status = DCB_ERR_UNSUPPORTED;
+          continue;
+        }
+        if (s.scheme == SCHEME_RAW) {
+          RawKey key = raw_key_of(s, false, -1);
+          key.ncp = 1;
+          key.mode = 5;
+          const uint32_t entries = key.compact ? s.n_active : s.num_symbols;
+          Group &g = raw[key];
+          if (g.order.empty()) {
+            g.kind = 0; g.ncp = 1; g.wide = key.wide != 0; g.compact = (uint32_t)key.compact; g.prec_bits = (uint32_t)key.prec;
+            g.zig = (uint32_t)key.zig; g.mode = 0;
+          }
+          g.entries = std::max(g.entries, entries);
+          if (key.compact) g.exc = std::max(g.exc, s.n_active - std::min(s.n_active, s.dense_prefix));
+          g.total_symbols += (uint64_t)s.n_entries * s.ncp;
+          g.max_entries = std::max(g.max_entries, s.n_entries);
+          g.note_table(s);
+          g.order.push_back(si);
+          g.force_single_warp = true;
+        }
+        wide.order.push_back(si);
+        continue;
+      }
       // normals behind a Raw stream: the rANS kernel leaves corrections, oct_chain + oct_unit follow on its stream
       const bool raw_normals = s.scheme == SCHEME_RAW && s.ncp == 2 && s.store == STORE_OCT_UNIT &&
                                (s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON);
@@ -1418,7 +1453,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     // A handful of outlier streams next to a machine-filling group (one cloud of a batch whose table came out dense)
     // must stay small: the direct slot LUT wants ~50 KB per stream, finds no room beside the big group's CTAs and would
     // run BEHIND it (measured: +17 ms on a 27 ms step); with the two-level tables it runs beside it, on a side stream.
-    g->no_direct = false;
+    g->no_direct = g->force_single_warp;
     for (Group *o : rgs)
       if (o != g && o->order.size() >= (size_t)num_sms * 8) g->no_direct = true;
     std::vector<Group *> one{g};
@@ -1440,6 +1475,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   add(octs);
   add(octc);
   add(tex);
+  add(wide);
   // par_post2_kernel: per group the run prefix of its streams (runs of par_run_len chunks) and one ticket word
   std::vector<uint32_t> par_runs[5];
   uint64_t par_aux_off[5] = {0, 0, 0, 0, 0};
@@ -1522,6 +1558,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     all.insert(all.end(), octs.order.begin(), octs.order.end());
     all.insert(all.end(), octc.order.begin(), octc.order.end());
     all.insert(all.end(), tex.order.begin(), tex.order.end());
+    all.insert(all.end(), wide.order.begin(), wide.order.end());
     for (int n = 1; n <= 4; ++n) all.insert(all.end(), par_runs[n].begin(), par_runs[n].end());
 
     CUDA_TRY(cudaMemcpyAsync(sh.d_order, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st));
@@ -1638,6 +1675,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       CUDA_TRY(cudaEventRecord(ctx->join_ev[dev_index][k], ctx->side[dev_index][k]));
       CUDA_TRY(cudaStreamWaitEvent(st, ctx->join_ev[dev_index][k], 0));
     }
+  if (!wide.order.empty()) {
+    CUDA_TRY(dcb_launch_wide_post(sh.d_streams, sh.d_order + wide.order_off, (uint32_t)wide.order.size(), dump, A, st));
+    stats.n_launches++;
+  }
   for (int n = 1; n <= 4; ++n) {
     if (!post[n].order.empty()) {
       CUDA_TRY(dcb_launch_serial_post(sh.d_streams, sh.d_order + post[n].order_off, (uint32_t)post[n].order.size(), n, dump, 0, A, st));

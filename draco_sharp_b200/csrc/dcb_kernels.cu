@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   if (have) {
     const StreamDesc &d = *dp;
     n_entries = d.n_entries;
+    // wide integer attribute (more than 4 components): its n * nc symbols as one-component entries
+    if (NCP == 1 && MODE == 0 && d.ncp > 4) n_entries *= d.ncp;
     int status = DCB_OK;
     if (n_entries > 0) {
       uint32_t ent_off;
@@ -197,8 +199,13 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   pp.load(*dp);
   uint8_t *optr = out + dp->out_off;
   int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + dp->dbg_off) : nullptr;
-  if (MODE == 3 || MODE == 4 || (MODE == 0 && (pp.recon == RECON_PARA_WRAP || pp.store == STORE_OCT_UNIT))) {
-    // int32 scratch: corrections for the parallelogram kernel / for oct_chain_kernel
+  const bool wide_nc = NCP == 1 && MODE == 0 && dp->ncp > 4;
+  if (wide_nc) {  // wide_post_kernel reconstructs and dumps the quantized ints
+    pp.recon = RECON_NONE;
+    dump &= ~(uint32_t)DCB_DUMP_QINTS;
+  }
+  if (MODE == 3 || MODE == 4 || (MODE == 0 && (pp.recon == RECON_PARA_WRAP || pp.store == STORE_OCT_UNIT || wide_nc))) {
+    // int32 scratch: corrections for the parallelogram kernel / for oct_chain_kernel / for wide_post_kernel
     optr = aux + dp->aux_off;
     if (NCP == 2 && pp.store == STORE_OCT_UNIT) {  // normals: the recurrence and its quantized-int dump run in oct_chain_kernel
       pp.recon = RECON_NONE;
@@ -437,6 +444,67 @@ __global__ void __launch_bounds__(32) serial_post_kernel(const uint8_t *__restri
       for (int c = 0; c < NCP; ++c) dptr[(size_t)e * NCP + c] = v[c];
     }
     store_entry<NCP>(pp, pp.store, pp.dsize, optr, e, v);
+  }
+}
+
+// wide_post_kernel: integer attributes with MORE THAN 4 components (the reference loops over any nc:
+// SequentialIntegerAttributeDecoder.cs:53-101 for the values, :142-160 for the narrowing store).  One stream per lane,
+// run-time component count, running values of the delta decoder in local memory.  Sources: the zig-zag decoded symbols
+// a Raw stream left in the scratch (fused kernel, one-component instantiation), tags + bit fields, or uncompressed
+// values.  Rare shapes (joint indices / weights beyond 4, custom vectors): correctness, not speed.
+template <bool DUMP>
+__global__ void __launch_bounds__(32) wide_post_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
+                                                       const uint32_t *__restrict__ order, uint32_t n_streams,
+                                                       uint8_t *__restrict__ out, uint8_t *__restrict__ dbg,
+                                                       uint8_t *__restrict__ aux, uint32_t dump) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_streams) return;
+  StreamDesc &d = streams[order[slot]];
+  if (d.status != DCB_OK) return;
+  const uint32_t n_entries = d.n_entries, nc = d.ncp;
+  PostParams pp;
+  pp.load(d);
+  uint8_t *optr = out + d.out_off;
+  int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
+  const uint8_t scheme = d.scheme;
+  const int32_t *corr = reinterpret_cast<const int32_t *>(aux + d.aux_off);
+  const uint8_t *tags = aux + d.tag_off;
+  const uint8_t *bits = arena + d.bits_off;
+  const uint8_t *raw = arena + d.raw_off;
+  const uint32_t nb = d.raw_num_bytes;
+  const int dsize = dcb_dtype_len(d.data_type);
+  uint64_t bitpos = 0;
+  int32_t prev[256];
+  for (uint32_t c = 0; c < nc; ++c) prev[c] = 0;
+  for (uint32_t e = 0; e < n_entries; ++e) {
+    uint32_t tag = 0;
+    if (scheme == SCHEME_TAGGED) tag = tags[e];
+    for (uint32_t c = 0; c < nc; ++c) {
+      const uint64_t i = (uint64_t)e * nc + c;
+      int32_t v;
+      if (scheme == SCHEME_RAW) {
+        v = corr[i];  // value map of the fused kernel: zig-zag decoded already (or the plain symbol when !zig)
+      } else {
+        uint32_t sym = 0;
+        if (scheme == SCHEME_TAGGED) {
+          sym = read_bits_lsb(bits, bitpos, tag);
+          bitpos += tag;
+        } else if (scheme == SCHEME_UNCOMPRESSED) {
+          const uint8_t *q = raw + i * nb;
+          for (uint32_t k = 0; k < nb; ++k) sym |= (uint32_t)q[k] << (8u * k);
+        }
+        if (DUMP && (dump & DCB_DUMP_SYMBOLS)) dptr[i] = (int32_t)sym;
+        v = pp.zig ? zigzag_dec(sym) : (int32_t)sym;
+      }
+      if (pp.recon == RECON_DELTA_WRAP) {
+        prev[c] = wrap_original(prev[c], v, pp.mn, pp.mx, pp.max_diff);
+        v = prev[c];
+      }
+      if (DUMP && (dump & DCB_DUMP_QINTS)) dptr[i] = v;
+      if (dsize == 1) optr[i] = (uint8_t)v;
+      else if (dsize == 2) reinterpret_cast<uint16_t *>(optr)[i] = (uint16_t)v;
+      else reinterpret_cast<int32_t *>(optr)[i] = v;
+    }
   }
 }
 
@@ -862,6 +930,17 @@ cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, cudaStr
   const uint32_t grid = (p.n_streams + p.lanes_per_warp - 1) / p.lanes_per_warp;
   rans_tag_kernel<<<grid, 32, smem_bytes, st>>>(a.in, p.d_streams, p.d_order, p.n_streams, p.lanes_per_warp, geom_of(p),
                                                 a.aux);
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_wide_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t dump, const DevArenas &a,
+                                 cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const uint32_t grid = (n + 31) / 32;
+  if (dump)
+    wide_post_kernel<true><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump);
+  else
+    wide_post_kernel<false><<<grid, 32, 0, st>>>(a.in, d_streams, d_order, n, a.out, a.dbg, a.aux, dump);
   return cudaGetLastError();
 }
 

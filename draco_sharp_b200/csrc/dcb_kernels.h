@@ -70,6 +70,9 @@ cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint
 // (one warp per stream); the parent position streams must have been through dcb_launch_para on the same stream
 cudaError_t dcb_launch_tex(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries, uint32_t dump,
                            const DevArenas &a, cudaStream_t st);
+// integer attributes with more than 4 components (run-time component count): reconstruction + narrowing store, one lane per stream
+cudaError_t dcb_launch_wide_post(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t dump, const DevArenas &a,
+                                 cudaStream_t st);
 cudaError_t dcb_launch_oct_chain(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t dump,
                                  const DevArenas &a, cudaStream_t st);
 cudaError_t dcb_launch_oct_unit(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries,

@@ -187,6 +187,7 @@ DCB_HD int walk_pred_data(WalkRd &r, StreamDesc &s, bool has_scheme, bool mesh_s
     const int64_t diff = (int64_t)s.xf_b - (int64_t)s.xf_a;      // WrapTransform.cs:90-91
     if ((int32_t)diff < 0 || diff >= 2147483647ll) return DCB_ERR_WRAP;
     if (mesh_scheme) {
+      if (s.ncp > 4) return DCB_ERR_UNSUPPORTED;  // the mesh chain kernels are built for 1..4 components
       if ((uint64_t)s.n_entries * s.ncp > 0 && !s.has_maps) return DCB_ERR_MAPS;
       if (s.pred_method == PRED_TEX_COORDS_PORTABLE && s.ncp != 2) return DCB_ERR_PRED;  // ...TexCoordsPortableDecoder.cs:51
       s.recon = RECON_PARA_WRAP;

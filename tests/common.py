@@ -46,9 +46,6 @@ def compare_with_oracle(gpu, buffers, maps=None, check_ints=True):
     n_ok = 0
     for k, (g, buf) in enumerate(zip(gpu, buffers)):
         o = O.decode(buf, maps[k] if maps else None)
-        if o.status == 0 and any(a.seq_type != 0 and a.nc_portable > 4 for a in o.attrs):
-            assert g["status"] == -3  # documented limit: more than 4 components per int-like attribute
-            continue
         assert g["status"] == o.status, "buffer %d: gpu status %d oracle %d" % (k, g["status"], o.status)
         if o.status != 0:
             continue

@@ -72,6 +72,23 @@ def crafted_buffers():
     bad = bytearray(W.point_cloud(10, [_attr(0, 9, 3, 2, W.portable_int(np.zeros(30), 3, 0, 1, "raw", W.wrap_data(0, 4)), W.quant_params([0, 0, 0], 1, 8))]))
     bad[11 + 1 + 1 + 5 + 1 + 3] = 7  # scheme byte
     bufs.append(bytes(bad))
+    # integer attributes with MORE than 4 components (the reference loops over any nc,
+    # SequentialIntegerAttributeDecoder.cs:144-152): Raw / Tagged / uncompressed sources, every store width, with and
+    # without a prediction scheme, clamping corrections, 255 components
+    m = 700
+    for nc, dt, scheme, nb, lo, hi, pm in ((5, 2, "raw", None, 0, 255, 0), (8, 4, "tagged", None, 0, 65535, 0),
+                                           (7, 5, "uncompressed", 2, -2000, 2000, 0), (6, 6, "raw", None, 0, 0, -2),
+                                           (16, 1, "raw", None, -128, 127, 0), (255, 3, "tagged", None, -500, 500, 0)):
+        k = rng.integers(-9, 10, size=m * nc)
+        if nc == 16:
+            k[rng.integers(0, m * nc, size=60)] = rng.integers(-700, 700, size=60)  # the clamp fires
+        if pm == -2:
+            port = W.portable_int(np.abs(k) * 37, nc, -2, -1, scheme)
+        else:
+            port = W.portable_int(k, nc, 0, 1, scheme, W.wrap_data(lo, hi), num_bytes=nb)
+        bufs.append(W.point_cloud(m, [_attr(4, dt, nc, 1, port),
+                                      _attr(0, 9, 3, 2, W.portable_int(rng.integers(-4, 5, size=m * 3), 3, 0, 1, "raw",
+                                                                       W.wrap_data(0, 1023)), W.quant_params([0, 0, 0], 1.0, 10), 1)]))
     return bufs
 
 
@@ -80,3 +97,4 @@ def test_crafted_streams(gpu_decoder):
     gpu = gpu_decode_all(gpu_decoder, bufs)
     n_ok = compare_with_oracle(gpu, bufs)
     assert n_ok == len(bufs) - 4  # four of the buffers are invalid on purpose
+    assert len(bufs) >= 39

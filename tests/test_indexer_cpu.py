@@ -17,10 +17,6 @@ def _check(bufs, expect_resolved=True):
     for k, b in enumerate(bufs):
         o = O.decode(b)
         bi = bt.buffer_info(k)
-        if o.status == 0 and any(a.seq_type != 0 and a.nc_portable > 4 for a in o.attrs):
-            # documented limit of the CUDA path: int-like attributes with more than 4 components
-            assert bi.status == -3
-            continue
         blocked = bi.status == 0 and any(not bt.attr_info(k, a).resolved for a in range(bi.n_attrs))
         if expect_resolved or not blocked:
             # everything the oracle rejects is rejected by the walker with the same code (unless the walk is
