@@ -490,8 +490,12 @@ struct RansLane {
   // One RAnsDecoder.Read() inside an open window; the caller has checked that the bytes cannot run out.  Same probe as
   // step<false, 1>; the renormalisation is two predicated funnel shifts (RAnsDecoder.cs:58-61, at most two bytes for
   // precision <= 15).  Returns the shared-memory ADDRESS of cum[entry].
-  template <bool FIRST>
-  __device__ __forceinline__ uint32_t step_lean() {
+  // GATED: the rank-byte load is predicated on (gate & zero) == 0 with `zero` a register the compiler cannot see through
+  // (always true at run time).  It ties the load to the instructions that produce `gate` -- the post-processing of an
+  // EARLIER symbol -- so that ptxas has to place that work before this step's table probe instead of clumping it at the
+  // end of the unrolled group (software-pipelined main loop, run_stream_lean_sp).
+  template <bool FIRST, bool GATED = false>
+  __device__ __forceinline__ uint32_t step_lean(uint32_t gate = 0u, uint32_t zero = 0u) {
     const uint32_t v = FIRST ? w_hi : __funnelshift_lc(w_lo, w_hi, w_cb);
     const bool one = x < L, two = x < L8;
     uint32_t xr = x;
@@ -507,7 +511,11 @@ struct RansLane {
     const uint32_t a = r >= t_split ? a_b : a_a;
     const uint32_t a_k = ((xr >> 5) & blk_mask) | blk_addr;
     uint32_t dl, bb, c0, c1, c2;
-    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(dl) : "r"(a));
+    if (GATED)
+      asm volatile("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %2, %3;\n setp.eq.u32 p, t, 0;\n @p ld.shared.u8 %0, [%1];\n}\n"
+                   : "=r"(dl) : "r"(a), "r"(gate), "r"(zero));
+    else
+      asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(dl) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(bb) : "r"(a_k));
     const uint32_t ca = dl * 2u + bb;
     asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(c0) : "r"(ca));

@@ -118,6 +118,66 @@ __device__ __forceinline__ void run_stream_lean(RansLane<uint16_t, false> &rl, c
   run_tail<NCP, uint16_t, false, false, MODE, 2, true>(rl, geom, pp, optr, nullptr, 0u, n_entries, g, prev);
 }
 
+// SOFTWARE-PIPELINED lean main loop (MODE 1: delta + wrap -> float).  The chain runs ONE SYMBOL AHEAD of the
+// post-processing: while the table probe of symbol j is in flight (two dependent LDS, ~60 cycles in which a single
+// in-order warp has nothing else to issue), the value map / wrap / dequantisation of symbol j-1 is executed.  ptxas
+// left to itself clumps that independent work (profiles/r2_rans_raw_fused_c2_step_cycles.txt); the gate of
+// step_lean<.., true> pins the post-processing of symbol j-1 in front of the probe of symbol j+1.
+template <int NCP, int MODE, bool LAST>
+__device__ __forceinline__ void lean_sp_group(RansLane<uint16_t, false> &rl, const PostParams &pp, uint8_t *optr, uint32_t g,
+                                              int32_t *prev, uint32_t &ca_prev, uint32_t &gate, uint32_t zero) {
+  constexpr int kSyms = 4 * NCP;
+  float f[kSyms];
+#pragma unroll
+  for (int s = 1; s <= kSyms; ++s) {
+    uint32_t ca = 0;
+    if (!(LAST && s == kSyms)) {
+      if (s % 3 == 0) rl.window_open();
+      ca = (s % 3 == 0) ? rl.template step_lean<true, true>(gate, zero) : rl.template step_lean<false, true>(gate, zero);
+      if (s % 3 == 2) rl.window_close();
+    }
+    const int c = (s - 1) % NCP;
+    prev[c] = wrap_regular(prev[c], rl.value_at(ca_prev), pp.mn, pp.mx, pp.max_diff);
+    f[s - 1] = pp.dequant(prev[c], c);
+    gate = __float_as_uint(f[s - 1]);
+    ca_prev = ca;
+  }
+  float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(optr) + (uint64_t)g * kSyms);
+#pragma unroll
+  for (int k = 0; k < NCP; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+}
+
+template <int NCP, int MODE>
+__device__ __forceinline__ void run_stream_lean_sp(RansLane<uint16_t, false> &rl, const TableGeom &geom, const PostParams &pp,
+                                                   uint8_t *optr, uint32_t n_entries, uint32_t g_min, uint32_t zero) {
+  int32_t prev[NCP];
+  const int32_t p0 = 0 > pp.mx ? pp.mx : (0 < pp.mn ? pp.mn : 0);  // the clamp the first prediction (zero) would get
+#pragma unroll
+  for (int c = 0; c < NCP; ++c) prev[c] = p0;
+  constexpr uint32_t kGroupBytes = 4u * NCP * 3u;
+  uint32_t g = 0;
+  if (g_min > 0 && rl.bytes_left() >= kGroupBytes) {
+    // prologue: symbol 0 of group 0 (the window stays open: symbols 1 and 2 follow in the loop)
+    rl.window_open();
+    uint32_t ca_prev = rl.template step_lean<true>();
+    uint32_t gate = 0;
+    // a group in the middle decodes symbols 1..12 past its base (one ahead) and needs the bytes of the next group's
+    // first symbol: 2 more than kGroupBytes, and p1 lags the open window by at most 2
+    while (g + 1 < g_min && rl.bytes_left() >= 2u * kGroupBytes + 4u) {
+      lean_sp_group<NCP, MODE, false>(rl, pp, optr, g, prev, ca_prev, gate, zero);
+      ++g;
+      rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
+      cp_async_wait<1>();
+    }
+    lean_sp_group<NCP, MODE, true>(rl, pp, optr, g, prev, ca_prev, gate, zero);
+    ++g;
+    rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
+    cp_async_wait<1>();
+  }
+  rl.prefetch();  // the careful tail reads through the two-word peek
+  run_tail<NCP, uint16_t, false, false, MODE, 2, true>(rl, geom, pp, optr, nullptr, 0u, n_entries, g, prev);
+}
+
 template <int NCP, typename T, bool DUMP, bool TABLE_GLOBAL, int MODE, int TAB>
 __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                             const uint32_t *__restrict__ order, uint32_t n_streams,
@@ -217,6 +277,12 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
   if constexpr (sizeof(T) == 2 && !TABLE_GLOBAL && !DUMP && (MODE == 1 || MODE == 2) && TAB == 2) {
     // lean main loop: every active lane of the warp decodes a regular delta + wrap stream through the two-region LUT
     if (use_lean) {
+#ifndef DCB_NO_LEAN_SP
+      if constexpr (MODE == 1) {
+        run_stream_lean_sp<NCP, MODE>(rl, geom, pp, optr, n_entries, g_min, blockIdx.y);  // blockIdx.y: an opaque zero
+        return;
+      }
+#endif
       run_stream_lean<NCP, MODE>(rl, geom, pp, optr, n_entries, g_min);
       return;
     }

@@ -1,0 +1,21 @@
+#!/bin/bash
+# round 2, call X: software-pipelined lean loop vs the plain lean loop (A/B on c2 and c3), parity first
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/x_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/x_pytest.log
+summ() { python - "$1" <<'PY'
+import json,sys
+try:
+    l=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(" ms_per_step", round(l["ms_per_step"],3), "stages", (l.get("roofline") or {}).get("stage_ms"))
+except Exception as ex:
+    print(" no line", ex)
+PY
+}
+for w in c2 c3; do
+  for v in sp nosp; do
+    echo "== $w $v"
+    L=""; [ $v = nosp ] && L="$GRAFT_REPO_ROOT/draco_sharp_b200/libdracob200_nosp.so"
+    DCB_LIB=$L timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/x_${w}_$v.json 2> gpurun_out/x_${w}_$v.err; echo " rc=$?"; summ gpurun_out/x_${w}_$v.json
+  done
+done
