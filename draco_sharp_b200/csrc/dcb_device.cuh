@@ -518,14 +518,37 @@ struct RansLane {
       asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(dl) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(bb) : "r"(a_k));
     const uint32_t ca = dl * 2u + bb;
-    asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(c0) : "r"(ca));
-    asm volatile("ld.shared.u16 %0, [%1+2];\n" : "=r"(c1) : "r"(ca));
-    asm volatile("ld.shared.u16 %0, [%1+4];\n" : "=r"(c2) : "r"(ca));
+    // one block: ptxas has been seen to issue the third load only after the first two came back (a third LDS latency)
+    asm volatile("ld.shared.u16 %1, [%3+2];\n ld.shared.u16 %2, [%3+4];\n ld.shared.u16 %0, [%3];\n"
+                 : "=r"(c0), "=r"(c1), "=r"(c2) : "r"(ca));
     const bool second = r >= c1;
     const uint32_t xa = q * (c1 - c0) + (r - c0);
     const uint32_t xb = q * (c2 - c1) + (r - c1);
     x = second ? xb : xa;
     return ca + (second ? 2u : 0u);
+  }
+  // The same inside the direct slot LUT (low-residency launches): ONE dependent access per symbol.  Returns the
+  // shared-memory address of cum[entry] like step_lean (the entry[] load is off the chain: only the value map wants it).
+  template <bool FIRST>
+  __device__ __forceinline__ uint32_t step_lean_direct(uint32_t gate, uint32_t zero) {
+    const uint32_t v = FIRST ? w_hi : __funnelshift_lc(w_lo, w_hi, w_cb);
+    const bool one = x < L, two = x < L8;
+    uint32_t xr = x;
+    if (one) xr = __funnelshift_l(v, x, 8);
+    if (two) xr = __funnelshift_l(v, x, 16);
+    if (FIRST) w_cb = one ? 8u : 0u;
+    else if (one) w_cb += 8u;
+    if (two) w_cb += 8u;
+    const uint32_t r2 = (xr & mask) << 1;
+    const uint32_t q = xr >> prec_bits;
+    uint32_t f, off, o;
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %6, %7;\n setp.eq.u32 p, t, 0;\n"
+        " @p ld.shared.u16 %0, [%3];\n @p ld.shared.u16 %1, [%4];\n @p ld.shared.u16 %2, [%5];\n}\n"
+        : "=r"(f), "=r"(off), "=r"(o)
+        : "r"(d_freq + r2), "r"(d_off + r2), "r"(d_ent + r2), "r"(gate), "r"(zero));
+    x = q * f + off;
+    return o + (cum_addr - ent_off);
   }
   // value of the entry whose cum lives at shared-memory address ca (compact u16 tables, zig-zag decoded value slots)
   __device__ __forceinline__ int32_t value_at(uint32_t ca) const {
@@ -536,6 +559,17 @@ struct RansLane {
       return v;
     }
     return zigzag_dec(rank2 >> 1);
+  }
+
+  // the same for symbols that are not zig-zag coded (tags): the value slots of a compact table hold symbol ids
+  __device__ __forceinline__ uint32_t value_at_plain(uint32_t ca, bool compact) const {
+    const uint32_t rank2 = ca - cum_addr;  // 2 * rank
+    if (compact && rank2 >= 2u * dprefix) {
+      uint32_t v;
+      asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(v) : "r"(ca + val_delta));
+      return v;
+    }
+    return rank2 >> 1;
   }
 
   // table entry -> symbol value.  dense: the entry index is the symbol id.  compact: entries below the dense
@@ -825,5 +859,48 @@ __device__ __forceinline__ void decode_entry(RansLane<T, TG> &rl, const TableGeo
   }
 }
 
+// SOFTWARE-PIPELINED lean main loop (zig-zag coded corrections, MODE 1..4).  The chain runs ONE SYMBOL AHEAD of the
+// post-processing: while the table probe of symbol j is in flight (two dependent LDS, ~60 cycles in which a single
+// in-order warp has nothing else to issue), the value map / wrap / dequantisation of symbol j-1 is executed.  ptxas
+// left to itself clumps that independent work (profiles/r2_rans_raw_fused_c2_step_cycles.txt); the gate of
+// step_lean<.., true> pins the post-processing of symbol j-1 in front of the probe of symbol j+1.
+// PROBE: 1 two-region LUT (step_lean), 2 direct slot LUT (step_lean_direct).  COMPACT: the table has a value map.
+template <int NCP, int MODE, bool LAST, int PROBE, bool COMPACT>
+__device__ __forceinline__ void lean_sp_group(RansLane<uint16_t, false> &rl, const PostParams &pp, uint8_t *optr, uint32_t g,
+                                              int32_t *prev, uint32_t &ca_prev, uint32_t &gate, uint32_t zero) {
+  constexpr int kSyms = 4 * NCP;
+  float f[kSyms];
+  int32_t v[4][NCP];
+#pragma unroll
+  for (int s = 1; s <= kSyms; ++s) {
+    uint32_t ca = 0;
+    if (!(LAST && s == kSyms)) {
+      const int sp = s % kSyms;  // position inside its own group: the windows restart with every group (as run_stream_lean)
+      if (sp % 3 == 0) rl.window_open();
+      if (PROBE == 2) ca = (sp % 3 == 0) ? rl.template step_lean_direct<true>(gate, zero) : rl.template step_lean_direct<false>(gate, zero);
+      else ca = (sp % 3 == 0) ? rl.template step_lean<true, true>(gate, zero) : rl.template step_lean<false, true>(gate, zero);
+      if (sp % 3 == 2 || sp == kSyms - 1) rl.window_close();
+    }
+    const int c = (s - 1) % NCP;
+    const int32_t corr = COMPACT ? rl.value_at(ca_prev) : zigzag_dec((ca_prev - rl.cum_addr) >> 1);
+    if (MODE == 3 || MODE == 4) prev[c] = corr;  // corrections for oct_chain / the parallelogram kernels
+    else prev[c] = wrap_regular(prev[c], corr, pp.mn, pp.mx, pp.max_diff);
+    if (MODE == 1) {
+      f[s - 1] = pp.dequant(prev[c], c);
+      gate = __float_as_uint(f[s - 1]);
+    } else {
+      v[(s - 1) / NCP][c] = prev[c];
+      gate = (uint32_t)corr;  // the value map's load: the integer wrap behind it is three ALU levels
+    }
+    ca_prev = ca;
+  }
+  if (MODE == 1) {
+    float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(optr) + (uint64_t)g * kSyms);
+#pragma unroll
+    for (int k = 0; k < NCP; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+  } else {
+    store_group4<NCP>(pp, store_of<MODE>(pp), dsize_of<MODE>(pp), optr, (uint64_t)g * 4, v);
+  }
+}
 
 }  // namespace dcb

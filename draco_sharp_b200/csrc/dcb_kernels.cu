@@ -118,35 +118,7 @@ __device__ __forceinline__ void run_stream_lean(RansLane<uint16_t, false> &rl, c
   run_tail<NCP, uint16_t, false, false, MODE, 2, true>(rl, geom, pp, optr, nullptr, 0u, n_entries, g, prev);
 }
 
-// SOFTWARE-PIPELINED lean main loop (MODE 1: delta + wrap -> float).  The chain runs ONE SYMBOL AHEAD of the
-// post-processing: while the table probe of symbol j is in flight (two dependent LDS, ~60 cycles in which a single
-// in-order warp has nothing else to issue), the value map / wrap / dequantisation of symbol j-1 is executed.  ptxas
-// left to itself clumps that independent work (profiles/r2_rans_raw_fused_c2_step_cycles.txt); the gate of
-// step_lean<.., true> pins the post-processing of symbol j-1 in front of the probe of symbol j+1.
-template <int NCP, int MODE, bool LAST>
-__device__ __forceinline__ void lean_sp_group(RansLane<uint16_t, false> &rl, const PostParams &pp, uint8_t *optr, uint32_t g,
-                                              int32_t *prev, uint32_t &ca_prev, uint32_t &gate, uint32_t zero) {
-  constexpr int kSyms = 4 * NCP;
-  float f[kSyms];
-#pragma unroll
-  for (int s = 1; s <= kSyms; ++s) {
-    uint32_t ca = 0;
-    if (!(LAST && s == kSyms)) {
-      if (s % 3 == 0) rl.window_open();
-      ca = (s % 3 == 0) ? rl.template step_lean<true, true>(gate, zero) : rl.template step_lean<false, true>(gate, zero);
-      if (s % 3 == 2) rl.window_close();
-    }
-    const int c = (s - 1) % NCP;
-    prev[c] = wrap_regular(prev[c], rl.value_at(ca_prev), pp.mn, pp.mx, pp.max_diff);
-    f[s - 1] = pp.dequant(prev[c], c);
-    gate = __float_as_uint(f[s - 1]);
-    ca_prev = ca;
-  }
-  float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(optr) + (uint64_t)g * kSyms);
-#pragma unroll
-  for (int k = 0; k < NCP; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-}
-
+// Software-pipelined lean main loop (lean_sp_group, dcb_device.cuh) around the two-region LUT.
 template <int NCP, int MODE>
 __device__ __forceinline__ void run_stream_lean_sp(RansLane<uint16_t, false> &rl, const TableGeom &geom, const PostParams &pp,
                                                    uint8_t *optr, uint32_t n_entries, uint32_t g_min, uint32_t zero) {
@@ -164,12 +136,12 @@ __device__ __forceinline__ void run_stream_lean_sp(RansLane<uint16_t, false> &rl
     // a group in the middle decodes symbols 1..12 past its base (one ahead) and needs the bytes of the next group's
     // first symbol: 2 more than kGroupBytes, and p1 lags the open window by at most 2
     while (g + 1 < g_min && rl.bytes_left() >= 2u * kGroupBytes + 4u) {
-      lean_sp_group<NCP, MODE, false>(rl, pp, optr, g, prev, ca_prev, gate, zero);
+      lean_sp_group<NCP, MODE, false, 1, true>(rl, pp, optr, g, prev, ca_prev, gate, zero);
       ++g;
       rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
       cp_async_wait<1>();
     }
-    lean_sp_group<NCP, MODE, true>(rl, pp, optr, g, prev, ca_prev, gate, zero);
+    lean_sp_group<NCP, MODE, true, 1, true>(rl, pp, optr, g, prev, ca_prev, gate, zero);
     ++g;
     rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
     cp_async_wait<1>();
@@ -235,8 +207,9 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
       if (status == DCB_OK) {
         // regular delta + wrap stream (wrap_regular): no correction of the table reaches max_diff, bounds far from int32
         const int64_t md = 1ll + (int64_t)d.xf_b - (int64_t)d.xf_a;
-        lean_ok = split_ok && geom.zig != 0 && !(dump & 0x40000000u) && (int64_t)rl.max_abs_val < md &&
-                  d.xf_a >= -(1 << 29) && d.xf_b <= (1 << 29);
+        lean_ok = split_ok && geom.zig != 0 && !(dump & 0x40000000u) &&
+                  (MODE == 3 || MODE == 4 ||  // corrections go to the scratch as they are: no wrap to be regular about
+                   ((int64_t)rl.max_abs_val < md && d.xf_a >= -(1 << 29) && d.xf_b <= (1 << 29)));
       }
     }
     if (status != DCB_OK) {
@@ -274,17 +247,17 @@ __global__ void __launch_bounds__(32) rans_raw_fused_kernel(const uint8_t *__res
     pp.store = STORE_NARROW;
     pp.dsize = 4;
   }
-  if constexpr (sizeof(T) == 2 && !TABLE_GLOBAL && !DUMP && (MODE == 1 || MODE == 2) && TAB == 2) {
+  if constexpr (sizeof(T) == 2 && !TABLE_GLOBAL && !DUMP && MODE >= 1 && MODE <= 4 && TAB == 2) {
     // lean main loop: every active lane of the warp decodes a regular delta + wrap stream through the two-region LUT
     if (use_lean) {
 #ifndef DCB_NO_LEAN_SP
-      if constexpr (MODE == 1) {
-        run_stream_lean_sp<NCP, MODE>(rl, geom, pp, optr, n_entries, g_min, blockIdx.y);  // blockIdx.y: an opaque zero
+      run_stream_lean_sp<NCP, MODE>(rl, geom, pp, optr, n_entries, g_min, blockIdx.y);  // blockIdx.y: an opaque zero
+      return;
+#endif
+      if constexpr (MODE == 1 || MODE == 2) {
+        run_stream_lean<NCP, MODE>(rl, geom, pp, optr, n_entries, g_min);
         return;
       }
-#endif
-      run_stream_lean<NCP, MODE>(rl, geom, pp, optr, n_entries, g_min);
-      return;
     }
   }
   if (use_split)
@@ -368,6 +341,104 @@ __device__ __forceinline__ void run_tags(RansLane<uint16_t, false> &rl, const Ta
   if (status != DCB_OK) dp->status = status;
 }
 
+// Software-pipelined tag loop (see run_stream_lean_sp): the lean chain step -- one byte window per three symbols, two-region
+// LUT -- runs one tag ahead; the previous tag's value map sits in the probe's latency shadow (gate).  LAST: the group that
+// does not look ahead (the careful tail continues from a clean state).
+template <bool LAST>
+__device__ __forceinline__ void tag_sp_group(RansLane<uint16_t, false> &rl, bool compact, uint32_t *t, uint32_t &ca_prev,
+                                             uint32_t &gate, uint32_t zero) {
+#pragma unroll
+  for (int s = 1; s <= 16; ++s) {
+    uint32_t ca = 0;
+    if (!(LAST && s == 16)) {
+      const int sp = s % 16;
+      if (sp % 3 == 0) rl.window_open();
+      ca = (sp % 3 == 0) ? rl.template step_lean<true, true>(gate, zero) : rl.template step_lean<false, true>(gate, zero);
+      if (sp % 3 == 2 || sp == 15) rl.window_close();
+    }
+    t[s - 1] = rl.value_at_plain(ca_prev, compact) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
+    gate = t[s - 1];
+    ca_prev = ca;
+  }
+}
+
+__device__ __forceinline__ void run_tags_sp(RansLane<uint16_t, false> &rl, const TableGeom &geom, StreamDesc *dp, uint8_t *aux,
+                                            uint32_t zero) {
+  const StreamDesc &d = *dp;
+  const uint32_t n_entries = d.n_entries;
+  const uint32_t ncp = d.ncp;
+  const uint64_t avail_bits = (d.buf_end - d.bits_off) * 8ull;
+  uint8_t *tags = aux + d.tag_off;
+  uint64_t *chunk_bits = reinterpret_cast<uint64_t *>(aux + d.tag_off + (((uint64_t)n_entries + 15ull) & ~15ull));
+  const bool compact = geom.compact != 0;
+  int status = DCB_OK;
+  uint64_t bits = 0;
+  uint32_t e = 0;
+  // ---- groups of 16 tags (at most 32 bytes), no per-symbol branches; errors are sorted out when the group is left ----
+  if (n_entries >= 16u && rl.bytes_left() >= 48u) {
+    rl.window_open();
+    uint32_t ca_prev = rl.template step_lean<true>();
+    uint32_t gate = 0;
+    for (;;) {
+      // a group in the middle looks one tag ahead and leaves enough bytes for the group behind it
+      const bool last = !(e + 32u <= n_entries && rl.bytes_left() >= 96u);
+      if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
+      uint32_t t[16];
+      if (last) tag_sp_group<true>(rl, compact, t, ca_prev, gate, zero);
+      else tag_sp_group<false>(rl, compact, t, ca_prev, gate, zero);
+      uint32_t tmax = 0, tsum = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        tmax = max(tmax, t[j]);
+        tsum += t[j];
+      }
+      const uint64_t nbits = bits + (uint64_t)tsum * ncp;
+      if (tmax > 32u || nbits > avail_bits) {
+        // first failing point decides the status, as in the sequential reference loop
+        for (int j = 0; j < 16 && status == DCB_OK; ++j) {
+          if (t[j] > 32u) status = DCB_ERR_TAG;
+          else {
+            bits += (uint64_t)t[j] * ncp;
+            if (bits > avail_bits) status = DCB_ERR_EOF;
+          }
+        }
+        break;
+      }
+      uint4 pk;
+      pk.x = t[0] | (t[1] << 8) | (t[2] << 16) | (t[3] << 24);
+      pk.y = t[4] | (t[5] << 8) | (t[6] << 16) | (t[7] << 24);
+      pk.z = t[8] | (t[9] << 8) | (t[10] << 16) | (t[11] << 24);
+      pk.w = t[12] | (t[13] << 8) | (t[14] << 16) | (t[15] << 24);
+      *reinterpret_cast<uint4 *>(tags + e) = pk;
+      bits = nbits;
+      e += 16u;
+      rl.template top_up<4>();
+      cp_async_wait<1>();
+      if (last) break;
+    }
+    rl.prefetch();  // the careful tail reads through the two-word peek
+  }
+  // ---- careful tail (exact `off > 0` handling, per-point checks) ----
+  for (; status == DCB_OK && e < n_entries; ++e) {
+    if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
+    const uint32_t tag = (uint32_t)rl.value(rl.template step<true, true>(), compact, false) & 0xFFu;
+    if (tag > 32u) {
+      status = DCB_ERR_TAG;
+      break;
+    }
+    bits += (uint64_t)tag * ncp;
+    if (bits > avail_bits) {
+      status = DCB_ERR_EOF;
+      break;
+    }
+    tags[e] = (uint8_t)tag;
+    rl.top_up<1>();
+    cp_async_wait<0>();
+  }
+  dp->bits_total = bits;
+  if (status != DCB_OK) dp->status = status;
+}
+
 __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                       const uint32_t *__restrict__ order, uint32_t n_streams,
                                                       uint32_t lanes, TableGeom geom, uint8_t *__restrict__ aux) {
@@ -405,6 +476,10 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
               smem + lay.lutb0 + (size_t)lane * geom.lutb_bytes,
               reinterpret_cast<uint32_t *>(smem + lay.blk0 + (size_t)lane * geom.blk_bytes), ent, use_split);
   rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
+#ifndef DCB_NO_LEAN_SP
+  if (use_split) run_tags_sp(rl, geom, dp, aux, blockIdx.y);  // blockIdx.y: an opaque zero
+  else
+#endif
   if (use_split) run_tags<true>(rl, geom, dp, aux);
   else run_tags<false>(rl, geom, dp, aux);
 }
@@ -956,6 +1031,9 @@ static cudaError_t launch_raw_n(const RansLaunch &p, bool table_global, const De
 
 cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool table_global, const DevArenas &a,
                                 cudaStream_t st) {
+#ifdef DCB_DEV_ONLY_C2  // development builds (SASS inspection of the headline instantiation alone): never shipped
+  return launch_raw_t<3, uint16_t, false, false, 1, 2>(p, a, st);
+#else
   // specialised hot shapes (u16 tables in shared memory, no debug dump)
   if (!wide && !table_global && !p.dump) {
 #define DCB_SPEC(M, N)                                                                           \
@@ -984,6 +1062,7 @@ cudaError_t dcb_launch_rans_raw(const RansLaunch &p, int ncp, bool wide, bool ta
       return cudaErrorInvalidValue;
   }
 #undef DCB_CASE
+#endif
 }
 
 cudaError_t dcb_launch_rans_tag(const RansLaunch &p, const DevArenas &a, cudaStream_t st) {

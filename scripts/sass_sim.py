@@ -63,8 +63,7 @@ def parse(line):
         for o in ops[k:]:
             src += regs(o, 2 if ".64" in o else 1)
     if pred:
-        src.append(pred)
-        src += dst  # predicated write keeps the old value
+        src.append(pred)  # (a predicated write keeps the old value without reading it: WAW order only)
     src = [r for r in src if r not in ("PT", "UPT", "RZ", "URZ")]
     pipe = "lsu" if base in LSU_OPS else ("fma" if base in FMA_OPS else ("none" if base in ("BRA", "NOP") else "alu"))
     return dict(op=op, base=base, dst=dst, src=src, pipe=pipe, text=s)
