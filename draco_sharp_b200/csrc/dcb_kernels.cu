@@ -341,104 +341,6 @@ __device__ __forceinline__ void run_tags(RansLane<uint16_t, false> &rl, const Ta
   if (status != DCB_OK) dp->status = status;
 }
 
-// Software-pipelined tag loop (see run_stream_lean_sp): the lean chain step -- one byte window per three symbols, two-region
-// LUT -- runs one tag ahead; the previous tag's value map sits in the probe's latency shadow (gate).  LAST: the group that
-// does not look ahead (the careful tail continues from a clean state).
-template <bool LAST>
-__device__ __forceinline__ void tag_sp_group(RansLane<uint16_t, false> &rl, bool compact, uint32_t *t, uint32_t &ca_prev,
-                                             uint32_t &gate, uint32_t zero) {
-#pragma unroll
-  for (int s = 1; s <= 16; ++s) {
-    uint32_t ca = 0;
-    if (!(LAST && s == 16)) {
-      const int sp = s % 16;
-      if (sp % 3 == 0) rl.window_open();
-      ca = (sp % 3 == 0) ? rl.template step_lean<true, true>(gate, zero) : rl.template step_lean<false, true>(gate, zero);
-      if (sp % 3 == 2 || sp == 15) rl.window_close();
-    }
-    t[s - 1] = rl.value_at_plain(ca_prev, compact) & 0xFFu;  // (byte) cast, SymbolDecoding.cs:41
-    gate = t[s - 1];
-    ca_prev = ca;
-  }
-}
-
-__device__ __forceinline__ void run_tags_sp(RansLane<uint16_t, false> &rl, const TableGeom &geom, StreamDesc *dp, uint8_t *aux,
-                                            uint32_t zero) {
-  const StreamDesc &d = *dp;
-  const uint32_t n_entries = d.n_entries;
-  const uint32_t ncp = d.ncp;
-  const uint64_t avail_bits = (d.buf_end - d.bits_off) * 8ull;
-  uint8_t *tags = aux + d.tag_off;
-  uint64_t *chunk_bits = reinterpret_cast<uint64_t *>(aux + d.tag_off + (((uint64_t)n_entries + 15ull) & ~15ull));
-  const bool compact = geom.compact != 0;
-  int status = DCB_OK;
-  uint64_t bits = 0;
-  uint32_t e = 0;
-  // ---- groups of 16 tags (at most 32 bytes), no per-symbol branches; errors are sorted out when the group is left ----
-  if (n_entries >= 16u && rl.bytes_left() >= 48u) {
-    rl.window_open();
-    uint32_t ca_prev = rl.template step_lean<true>();
-    uint32_t gate = 0;
-    for (;;) {
-      // a group in the middle looks one tag ahead and leaves enough bytes for the group behind it
-      const bool last = !(e + 32u <= n_entries && rl.bytes_left() >= 96u);
-      if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-      uint32_t t[16];
-      if (last) tag_sp_group<true>(rl, compact, t, ca_prev, gate, zero);
-      else tag_sp_group<false>(rl, compact, t, ca_prev, gate, zero);
-      uint32_t tmax = 0, tsum = 0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        tmax = max(tmax, t[j]);
-        tsum += t[j];
-      }
-      const uint64_t nbits = bits + (uint64_t)tsum * ncp;
-      if (tmax > 32u || nbits > avail_bits) {
-        // first failing point decides the status, as in the sequential reference loop
-        for (int j = 0; j < 16 && status == DCB_OK; ++j) {
-          if (t[j] > 32u) status = DCB_ERR_TAG;
-          else {
-            bits += (uint64_t)t[j] * ncp;
-            if (bits > avail_bits) status = DCB_ERR_EOF;
-          }
-        }
-        break;
-      }
-      uint4 pk;
-      pk.x = t[0] | (t[1] << 8) | (t[2] << 16) | (t[3] << 24);
-      pk.y = t[4] | (t[5] << 8) | (t[6] << 16) | (t[7] << 24);
-      pk.z = t[8] | (t[9] << 8) | (t[10] << 16) | (t[11] << 24);
-      pk.w = t[12] | (t[13] << 8) | (t[14] << 16) | (t[15] << 24);
-      *reinterpret_cast<uint4 *>(tags + e) = pk;
-      bits = nbits;
-      e += 16u;
-      rl.template top_up<4>();
-      cp_async_wait<1>();
-      if (last) break;
-    }
-    rl.prefetch();  // the careful tail reads through the two-word peek
-  }
-  // ---- careful tail (exact `off > 0` handling, per-point checks) ----
-  for (; status == DCB_OK && e < n_entries; ++e) {
-    if ((e & (DCB_TAG_CHUNK - 1u)) == 0) chunk_bits[e / DCB_TAG_CHUNK] = bits;
-    const uint32_t tag = (uint32_t)rl.value(rl.template step<true, true>(), compact, false) & 0xFFu;
-    if (tag > 32u) {
-      status = DCB_ERR_TAG;
-      break;
-    }
-    bits += (uint64_t)tag * ncp;
-    if (bits > avail_bits) {
-      status = DCB_ERR_EOF;
-      break;
-    }
-    tags[e] = (uint8_t)tag;
-    rl.top_up<1>();
-    cp_async_wait<0>();
-  }
-  dp->bits_total = bits;
-  if (status != DCB_OK) dp->status = status;
-}
-
 __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                       const uint32_t *__restrict__ order, uint32_t n_streams,
                                                       uint32_t lanes, TableGeom geom, uint8_t *__restrict__ aux) {
@@ -477,7 +379,7 @@ __global__ void __launch_bounds__(32) rans_tag_kernel(const uint8_t *__restrict_
               reinterpret_cast<uint32_t *>(smem + lay.blk0 + (size_t)lane * geom.blk_bytes), ent, use_split);
   rl.init_ring(smem_base + lay.ring0 + lane * DCB_RING_BYTES);
 #ifndef DCB_NO_LEAN_SP
-  if (use_split) run_tags_sp(rl, geom, dp, aux, blockIdx.y);  // blockIdx.y: an opaque zero
+  if (use_split) run_tags_sp<1>(rl, geom, dp, aux, blockIdx.y);  // blockIdx.y: an opaque zero
   else
 #endif
   if (use_split) run_tags<true>(rl, geom, dp, aux);

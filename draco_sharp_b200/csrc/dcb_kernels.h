@@ -21,6 +21,7 @@ struct PcGeom {
   uint32_t tab_bytes;    // table part of a pair's slice (worst-case alignment slack included)
   uint32_t slice_bytes;  // whole slice
   uint32_t q_off, ctl_off, hand_off;  // offsets inside the slice
+  uint32_t fuse;         // raw kernel, direct slot LUT: the chain warp may keep the post-processing (fused_direct_loop)
 };
 
 // device arenas of one shard

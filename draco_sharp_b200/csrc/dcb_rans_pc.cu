@@ -50,7 +50,7 @@ struct LaneHand {
   int32_t status;       // tags: consumer -> chain
   uint32_t e;           // tags: consumer -> chain: first tag the careful tail has to decode
   uint32_t ne;          // chain -> both: table entries built (direct slot LUT fill)
-  uint32_t pad_;
+  uint32_t fused;       // chain -> consumer (first record of the slice): the chain warp runs the fused main loop, leave
   uint64_t bits;        // tags: consumer -> chain: bits consumed in the bit area so far
 };
 static_assert(sizeof(LaneHand) == DCB_PC_HAND_BYTES, "LaneHand size is part of the shared-memory plan");
@@ -266,6 +266,34 @@ __device__ __forceinline__ void redirect_post(PostParams &pp, uint32_t &dump, ui
 // ---------------------------------------------------------------------------------------------
 // Raw scheme (SymbolDecoding.cs:52-67) fused with inverse prediction + transform + store
 // ---------------------------------------------------------------------------------------------
+// FUSED main loop on the direct slot LUT: the chain warp keeps the post-processing and runs the software-pipelined lean
+// loop of dcb_device.cuh (lean_sp_group, one dependent LDS per symbol, the previous symbol's value map / wrap / store
+// in its latency shadow).  With a handful of lanes per warp the queue push costs the chain about what the
+// post-processing does, and the consumer warp shares the sub-partition's issue port.  Returns the groups decoded.
+template <int NCP, int MODE, bool COMPACT>
+__device__ __forceinline__ uint32_t fused_direct_loop(RansLane<uint16_t, false> &rl, const PostParams &pp, uint8_t *optr,
+                                                      uint32_t g_min, int32_t *prev, uint32_t zero) {
+  constexpr uint32_t kGroupBytes = 4u * NCP * 3u;
+  uint32_t g = 0;
+  if (g_min != 0xFFFFFFFFu && g_min > 0 && rl.bytes_left() >= kGroupBytes) {
+    rl.window_open();  // prologue: symbol 0 of group 0
+    uint32_t ca_prev = rl.template step_lean_direct<true>(0u, zero);
+    uint32_t gate = 0;
+    while (g + 1 < g_min && rl.bytes_left() >= 2u * kGroupBytes + 4u) {
+      lean_sp_group<NCP, MODE, false, 2, COMPACT>(rl, pp, optr, g, prev, ca_prev, gate, zero);
+      ++g;
+      rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
+      cp_async_wait<1>();
+    }
+    lean_sp_group<NCP, MODE, true, 2, COMPACT>(rl, pp, optr, g, prev, ca_prev, gate, zero);
+    ++g;
+    rl.template top_up<(kGroupBytes + 15) / 16 + 1>();
+    cp_async_wait<1>();
+  }
+  rl.prefetch();  // the careful tail reads through the two-word peek
+  return g;
+}
+
 template <int NCP, bool DUMP, int MODE, int TAB>
 __global__ void __launch_bounds__(384) rans_raw_pc_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                           const uint32_t *__restrict__ order, uint32_t n_streams,
@@ -349,6 +377,16 @@ __global__ void __launch_bounds__(384) rans_raw_pc_kernel(const uint8_t *__restr
       hand->active = active ? 1 : 0;
       hand->ne = active ? rl.n_entries_tab : 0u;
     }
+    // fused main loop (fused_direct_loop): direct slot LUT, zig-zag coded corrections of a specialised mode, no dumps;
+    // delta + wrap modes only on regular streams (wrap_regular, as the lean loop of rans_raw_fused_kernel)
+    bool fuse_ok = true;
+    constexpr bool kFusable = !DUMP && MODE >= 1 && MODE <= 4 && TAB != 0;
+    if (kFusable && active && (MODE == 1 || MODE == 2)) {
+      const int64_t md = 1ll + (int64_t)dp->xf_b - (int64_t)dp->xf_a;
+      fuse_ok = (int64_t)rl.max_abs_val < md && dp->xf_a >= -(1 << 29) && dp->xf_b <= (1 << 29);
+    }
+    const bool fuse = kFusable && zig && geom.zig != 0u && geom.direct && pc.fuse != 0u && __all_sync(0xffffffffu, fuse_ok);
+    if (lane == 0) reinterpret_cast<LaneHand *>(slice + pc.hand_off)->fused = fuse ? 1u : 0u;
     __syncwarp();
     if (lane == 0) mbar_arrive(ctl.setup());
     const int probe = geom.direct ? 2 : (use_split ? 1 : 0);
@@ -356,21 +394,34 @@ __global__ void __launch_bounds__(384) rans_raw_pc_kernel(const uint8_t *__restr
       mbar_wait(ctl.setup(), 0u);
       fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, lane, ctl);
     }
-    const uint32_t groups = probe == 2 ? produce<kSym, 2>(rl, active, g_min, q_addr, ctl, lane)
-                          : probe == 1 ? produce<kSym, 1>(rl, active, g_min, q_addr, ctl, lane)
-                                       : produce<kSym, 0>(rl, active, g_min, q_addr, ctl, lane);
-    mbar_wait(ctl.handoff(), 0u);
-    if (!active) return;
-    // ---- per-lane tail: exact `off > 0` handling, as RAnsDecoder.Read does it byte by byte ----
     PostParams pp;
-    pp.load(*dp);
-    uint8_t *optr = out + dp->out_off;
-    int32_t *dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + dp->dbg_off) : nullptr;
-    redirect_post<NCP, MODE>(pp, dump, optr, aux, *dp);
-    const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp);
+    uint8_t *optr = nullptr;
+    int32_t *dptr = nullptr;
+    if (active) {
+      pp.load(*dp);
+      optr = out + dp->out_off;
+      dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + dp->dbg_off) : nullptr;
+      redirect_post<NCP, MODE>(pp, dump, optr, aux, *dp);
+    }
     int32_t prev[NCP];
+    uint32_t groups = 0;
+    if (fuse) {
+      if (!active) return;
+      const int32_t p0 = (MODE == 1 || MODE == 2) ? (0 > pp.mx ? pp.mx : (0 < pp.mn ? pp.mn : 0)) : 0;
 #pragma unroll
-    for (int c = 0; c < NCP; ++c) prev[c] = hand->prev[c];
+      for (int c = 0; c < NCP; ++c) prev[c] = p0;
+      if constexpr (kFusable) groups = fused_direct_loop<NCP, MODE, TAB == 2>(rl, pp, optr, g_min, prev, blockIdx.y);
+    } else {
+      groups = probe == 2 ? produce<kSym, 2>(rl, active, g_min, q_addr, ctl, lane)
+             : probe == 1 ? produce<kSym, 1>(rl, active, g_min, q_addr, ctl, lane)
+                          : produce<kSym, 0>(rl, active, g_min, q_addr, ctl, lane);
+      mbar_wait(ctl.handoff(), 0u);
+      if (!active) return;
+#pragma unroll
+      for (int c = 0; c < NCP; ++c) prev[c] = hand->prev[c];
+    }
+    // ---- per-lane tail: exact `off > 0` handling, as RAnsDecoder.Read does it byte by byte ----
+    const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp);
     for (uint32_t e = groups * 4u; e < n_entries; ++e) {
       int32_t v[NCP];
       if (probe == 2) decode_entry<NCP, T, false, DUMP, MODE, TAB, true, 2>(rl, geom, pp, prev, v, dptr, dump, e);
@@ -394,6 +445,7 @@ __global__ void __launch_bounds__(384) rans_raw_pc_kernel(const uint8_t *__restr
     const int store = store_of<MODE>(pp), dsize = dsize_of<MODE>(pp), recon = recon_of<MODE>(pp);
     mbar_wait(ctl.setup(), 0u);
     if (geom.direct) fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, 32u + lane, ctl);
+    if (reinterpret_cast<const volatile LaneHand *>(slice + pc.hand_off)->fused != 0u) return;  // the chain warp does it all
     const uint32_t d_ent = slice_addr + lay.lut0 + lane * geom.lut_bytes + (4u << geom.direct_prec);  // direct LUT: entry[] of this lane
     bool active = false;
     ValMap vm{slice + lay.ent0, lane * geom.ent_bytes, 0u, 0u};
@@ -534,12 +586,19 @@ __global__ void __launch_bounds__(384) rans_tag_pc_kernel(const uint8_t *__restr
       hand->active = active ? 1 : 0;
       hand->ne = active ? rl.n_entries_tab : 0u;
     }
+    // fused: the chain warp keeps the (small) post-processing of the tags -- run_tags_sp on the direct slot LUT
+    const bool fuse = geom.direct && pc.fuse != 0u;
+    if (lane == 0) reinterpret_cast<LaneHand *>(slice + pc.hand_off)->fused = fuse ? 1u : 0u;
     __syncwarp();
     if (lane == 0) mbar_arrive(ctl.setup());
     const int probe = geom.direct ? 2 : (use_split ? 1 : 0);
     if (geom.direct) {
       mbar_wait(ctl.setup(), 0u);
       fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, lane, ctl);
+    }
+    if (fuse) {
+      if (active) run_tags_sp<2>(rl, geom, dp, aux, blockIdx.y);  // blockIdx.y: an opaque zero
+      return;
     }
     if (probe == 2) produce<kSym, 2>(rl, active, g_min, q_addr, ctl, lane);
     else if (probe == 1) produce<kSym, 1>(rl, active, g_min, q_addr, ctl, lane);
@@ -588,6 +647,7 @@ __global__ void __launch_bounds__(384) rans_tag_pc_kernel(const uint8_t *__restr
     }
     mbar_wait(ctl.setup(), 0u);
     if (geom.direct) fill_direct_all(slice, lay, geom, lanes, pc.hand_off, geom.direct_prec, 32u + lane, ctl);
+    if (reinterpret_cast<const volatile LaneHand *>(slice + pc.hand_off)->fused != 0u) return;  // the chain warp does it all
     const uint32_t d_ent = slice_addr + lay.lut0 + lane * geom.lut_bytes + (4u << geom.direct_prec);
     bool active = false;
     ValMap vm{slice + lay.ent0, lane * geom.ent_bytes, 0u, 0u};
@@ -688,6 +748,8 @@ PcGeom dcb_pc_geom(const RansLaunch &p, uint32_t syms_per_group) {
   g.ctl_off = g.q_off + DCB_PC_STAGES * syms_per_group * DCB_PC_ROW_BYTES;
   g.hand_off = g.ctl_off + DCB_PC_CTL_BYTES;
   g.slice_bytes = (g.hand_off + p.lanes_per_warp * DCB_PC_HAND_BYTES + 15u) & ~15u;
+  static const bool no_fuse = getenv("DCB_NO_PC_FUSED") != nullptr;  // A/B measurements, tests of the queue path
+  g.fuse = no_fuse ? 0u : 1u;
   return g;
 }
 

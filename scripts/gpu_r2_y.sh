@@ -12,7 +12,7 @@ except Exception as ex:
     print(" no line", ex)
 PY
 }
-for w in c2 c3 c2tagged c4; do
+for w in c4 c4tagged c1 c2tagged; do
     echo "== $w"
     timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/y_${w}.json 2> gpurun_out/y_${w}.err; echo " rc=$?"; summ gpurun_out/y_${w}.json
 done

@@ -4,7 +4,7 @@ Usage: sass_loops.py obj.o <mangled-name-substring> [min_instr] [syms]"""
 import re, subprocess, sys, os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import sass_sim as S
-S.LAT_LDS, S.LDS_ISSUE = 34, 6
+S.LAT_LDS, S.LDS_ISSUE = int(os.environ.get('LAT_LDS', 34)), int(os.environ.get('LDS_ISSUE', 6))
 obj, pat = sys.argv[1], sys.argv[2]
 min_ins = int(sys.argv[3]) if len(sys.argv) > 3 else 300
 syms = int(sys.argv[4]) if len(sys.argv) > 4 else 12

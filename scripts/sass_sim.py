@@ -52,6 +52,8 @@ def parse(line):
         dst += regs(ops[0]) + regs(ops[1])
         for o in ops[2:]:
             src += regs(o)
+    elif not ops:
+        pass
     else:
         dst += regs(ops[0], w if base in ("LDS", "LDG", "IMAD") else 1)
         k = 1
