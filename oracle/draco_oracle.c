@@ -416,6 +416,94 @@ int orc_parallelogram_wrap(const int32_t *corr, uint32_t n, int nc, int32_t mn, 
   return ORC_OK;
 }
 
+/* One parallelogram of entry p at `corner`: MeshPredictionSchemeParallelogramDecoder.TryComputeParallelogramPrediction
+ * (:62-89) without the arithmetic -- the three operand entries, or 0 when the corner has no usable parallelogram. */
+static int para_entries(const orc_mesh_maps *m, uint32_t p, uint32_t corner, int32_t e[3], int *bad) {
+  if (corner >= m->n_corners) { *bad = 1; return 0; }
+  uint32_t oc = m->opposite[corner]; /* :66 */
+  if (oc == 0xFFFFFFFFu) return 0;
+  if (oc >= m->n_corners) { *bad = 1; return 0; }
+  uint32_t nx = (oc % 3u == 2u) ? oc - 2u : oc + 1u;
+  uint32_t pv = (oc % 3u == 0u) ? oc + 2u : oc - 1u;
+  uint32_t v_o = m->corner_to_vertex[oc], v_n = m->corner_to_vertex[nx], v_p = m->corner_to_vertex[pv];
+  if (v_o >= m->n_vertices || v_n >= m->n_vertices || v_p >= m->n_vertices) { *bad = 1; return 0; }
+  e[0] = m->vertex_to_data[v_o]; e[1] = m->vertex_to_data[v_n]; e[2] = m->vertex_to_data[v_p]; /* :56-59 */
+  if (e[0] < (int32_t)p && e[1] < (int32_t)p && e[2] < (int32_t)p) {                            /* :75 */
+    if (e[0] < 0 || e[1] < 0 || e[2] < 0) { *bad = 1; return 0; }
+    return 1;
+  }
+  return 0;
+}
+static uint32_t m_next(uint32_t c) { return c == 0xFFFFFFFFu ? c : ((c % 3u == 2u) ? c - 2u : c + 1u); }
+static uint32_t m_prev(uint32_t c) { return c == 0xFFFFFFFFu ? c : ((c % 3u == 0u) ? c + 2u : c - 1u); }
+static uint32_t m_opp(const orc_mesh_maps *m, uint32_t c, int *bad) {
+  if (c == 0xFFFFFFFFu) return c;
+  if (c >= m->n_corners) { *bad = 1; return 0xFFFFFFFFu; }
+  return m->opposite[c];
+}
+
+/* MeshPredictionSchemeConstrainedMultiParallelogramDecoder.ComputeOriginalValues (:32-116) with the wrap transform, in
+ * the bitstream's semantics where the C# is defective (`predictedValues[j][j]` is never filled,
+ * the crease flags are never decoded): every parallelogram found while swinging left, then right, around the entry's
+ * vertex (at most four, :60-80) keeps its own prediction; the flags of context (count - 1) say which of them are
+ * crease edges (:89-101); the prediction is the truncated integer mean of the others (:112), or entry p-1 when none
+ * is left (:105-108).  crease[c] / n_crease[c]: the decoded flag sequence of context c (DecodeTransformData :125-139). */
+int orc_cmp_wrap(const int32_t *corr, uint32_t n, int nc, int32_t mn, int32_t mx, const orc_mesh_maps *m,
+                 uint8_t *const crease[4], const uint32_t n_crease[4], int32_t *out) {
+  int32_t max_diff = (int32_t)(1u + (uint32_t)mx - (uint32_t)mn);
+  if (n == 0) return ORC_OK;
+  if (!m || m->n_entries < n) return ORC_ERR_MAPS;
+  if (nc > 16) return ORC_ERR_UNSUPPORTED;
+  uint32_t pos[4] = {0, 0, 0, 0};
+  for (int c = 0; c < nc; ++c) out[c] = wrap_original(0, corr[c], mn, mx, max_diff); /* :43 */
+  for (uint32_t p = 1; p < n; ++p) {                                                 /* :45 */
+    const uint32_t start = m->data_to_corner[p];
+    uint32_t corner = start;
+    int32_t pe[4][3];
+    int np = 0, first_pass = 1, bad = 0;
+    uint64_t guard = 0;
+    while (corner != 0xFFFFFFFFu) { /* :52-80 */
+      if (++guard > (uint64_t)m->n_corners + 2) return ORC_ERR_MAPS; /* not a corner table: the swing never closes */
+      if (para_entries(m, p, corner, pe[np], &bad)) {
+        if (++np == 4) break; /* Constants.ConstrainedMultiParallelogramMaxNumParallelograms */
+      }
+      if (bad) return ORC_ERR_MAPS;
+      corner = first_pass ? m_next(m_opp(m, m_next(corner), &bad)) : m_prev(m_opp(m, m_prev(corner), &bad)); /* SwingLeft / SwingRight */
+      if (bad) return ORC_ERR_MAPS;
+      if (corner == start) break;
+      if (corner == 0xFFFFFFFFu && first_pass) {
+        first_pass = 0;
+        corner = m_prev(m_opp(m, m_prev(start), &bad));
+        if (bad) return ORC_ERR_MAPS;
+      }
+    }
+    int32_t sum[16];
+    int used = 0;
+    for (int c = 0; c < nc; ++c) sum[c] = 0;
+    for (int i = 0; i < np; ++i) { /* :89-101 */
+      const int ctx = np - 1;
+      const uint32_t at = pos[ctx]++;
+      if (at >= n_crease[ctx]) return ORC_ERR_PRED; /* :93 */
+      if (!crease[ctx][at]) {
+        ++used;
+        for (int c = 0; c < nc; ++c) {
+          int32_t pred = (int32_t)((uint32_t)out[(uint64_t)pe[i][1] * nc + c] + (uint32_t)out[(uint64_t)pe[i][2] * nc + c] -
+                                   (uint32_t)out[(uint64_t)pe[i][0] * nc + c]); /* ParallelogramDecoder :84 */
+          sum[c] = (int32_t)((uint32_t)sum[c] + (uint32_t)pred);          /* AddAsUnsigned :98 */
+        }
+      }
+    }
+    uint64_t dst = (uint64_t)p * nc;
+    if (used == 0) {
+      uint64_t src = (uint64_t)(p - 1) * nc; /* :105-108 */
+      for (int c = 0; c < nc; ++c) out[dst + c] = wrap_original(out[src + c], corr[dst + c], mn, mx, max_diff);
+    } else {
+      for (int c = 0; c < nc; ++c) out[dst + c] = wrap_original(sum[c] / used, corr[dst + c], mn, mx, max_diff); /* :112-114 */
+    }
+  }
+  return ORC_OK;
+}
+
 /* MeshPredictionSchemeTexCoordsPortableDecoder.ComputeOriginalValues (:49-66) over
  * MeshPredictionSchemeTexCoordsPortablePredictor.ComputePredictedValue (:52-150) and the wrap transform.
  * uv: maps of the attribute's own decoder; pos_q / pm: quantized positions (portable parent attribute) and the maps of
@@ -766,9 +854,11 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
     if (a->pred_method == 1)
       mesh_scheme = 1;
     else if (a->pred_method == 5 && a->nc_portable == 2 && a->transform == 1)
-      mesh_scheme = 5; /* TexCoordsPortable: oracle only so far, the CUDA path reports UNSUPPORTED */
+      mesh_scheme = 5; /* TexCoordsPortable */
+    else if (a->pred_method == 4 && a->transform == 1)
+      mesh_scheme = 4; /* ConstrainedMultiParallelogram */
     else if (a->pred_method != 0)
-      return ORC_ERR_UNSUPPORTED; /* multi-/constrained-parallelogram, deprecated texcoords, geometric normal: SURVEY 8f-3 */
+      return ORC_ERR_UNSUPPORTED; /* multi-parallelogram, deprecated texcoords, geometric normal: SURVEY 8f-3 */
   }
   int ncp = a->nc_portable;
   uint64_t nv = (uint64_t)n * ncp;
@@ -816,12 +906,29 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
       orient[i] = (uint8_t)last;
     }
   }
+  uint8_t *crease[4] = {NULL, NULL, NULL, NULL};
+  uint32_t n_crease[4] = {0, 0, 0, 0};
+  if (mesh_scheme == 4) { /* ...ConstrainedMultiParallelogramDecoder.DecodeTransformData :119-141 (v2.2: no mode byte) */
+    int st = ORC_OK;
+    for (int i = 0; i < 4 && !st; ++i) {
+      uint64_t nf = rd_varint(r);
+      if (r->err) { st = r->err; break; }
+      if (nf > 4ull * (uint64_t)n + 4ull) { st = ORC_ERR_PRED; break; } /* an entry consumes at most four flags */
+      n_crease[i] = (uint32_t)nf;
+      if (nf > 0) {
+        crease[i] = (uint8_t *)malloc((size_t)nf);
+        st = orc_rabs_bits(r->p, r->len, &r->pos, n_crease[i], crease[i]);
+      }
+    }
+    if (st) { for (int i = 0; i < 4; ++i) free(crease[i]); return st; }
+  }
   if (a->transform == 1) { /* PredictionSchemeWrapDecodingTransform.cs:69-75 */
     a->xf_a = rd_i32(r);
     a->xf_b = rd_i32(r);
     int64_t diff = (int64_t)a->xf_b - (int64_t)a->xf_a; /* WrapTransform.cs:90-91 (int overflow -> negative) */
     if (r->err || a->xf_a > a->xf_b || (int32_t)diff < 0 || diff >= 2147483647ll) {
       free(orient);
+      for (int i = 0; i < 4; ++i) free(crease[i]);
       return r->err ? r->err : ORC_ERR_WRAP;
     }
     if (nv > 0) {
@@ -839,6 +946,11 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
         free(orient);
         orient = NULL;
         if (st) return st;
+      } else if (mesh_scheme == 4) {
+        int st = (!maps || a->decoder_id >= n_maps) ? ORC_ERR_MAPS
+                 : orc_cmp_wrap(a->corr, n, ncp, a->xf_a, a->xf_b, &maps[a->decoder_id], crease, n_crease, a->qints);
+        for (int i = 0; i < 4; ++i) { free(crease[i]); crease[i] = NULL; }
+        if (st) return st;
       } else if (mesh_scheme) {
         if (!maps || a->decoder_id >= n_maps) return ORC_ERR_MAPS;
         int st = orc_parallelogram_wrap(a->corr, n, ncp, a->xf_a, a->xf_b, &maps[a->decoder_id], a->qints);
@@ -848,6 +960,7 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
       }
     }
     free(orient);
+    for (int i = 0; i < 4; ++i) free(crease[i]);
   } else { /* octahedron transforms */
     a->xf_a = rd_i32(r); /* max_quantized_value */
     if (a->transform == 3) a->xf_b = rd_i32(r); /* center_value (ignored) ...CanonicalizedDecodingTransform.cs:80-84 */

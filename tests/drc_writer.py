@@ -203,6 +203,88 @@ def tex_coords_data(flags, mn, mx, prob_zero=None):
     return struct.pack("<i", len(bits)) + rabs_block(bits, prob_zero) + wrap_data(mn, mx)
 
 
+def cmp_data(crease, mn, mx):
+    """PRED_DATA of MeshPredictionSchemeConstrainedMultiParallelogramDecoder (DecodeTransformData :119-141, v2.2: no mode
+    byte): per context (1..4 parallelograms) a varint flag count and, when it is not zero, the rABS-coded crease flags;
+    then the wrap transform's bounds."""
+    out = bytearray()
+    for ctx in range(4):
+        bits = list(crease[ctx]) if ctx < len(crease) else []
+        out += varint(len(bits))
+        if bits:
+            out += rabs_block(bits)
+    return bytes(out) + wrap_data(mn, mx)
+
+
+def cmp_encode(values, nc, maps, mn, mx, rng, p_crease=0.3, max_par=4):
+    """Encoder side of the constrained multi-parallelogram scheme, written from the Draco bitstream specification
+    (independent of oracle/ and of the CUDA path): for every entry, the parallelograms found swinging left then right
+    around its corner, random crease flags, the truncated mean of the kept predictions, and the wrapped correction.
+    Returns (corrections, [flags of context 0..3])."""
+    INV = 0xFFFFFFFF
+    opp, c2v = maps["opposite"], maps["corner_to_vertex"]
+    d2c, v2d = maps["data_to_corner"], maps["vertex_to_data"]
+    n = len(values) // nc
+    vals = [int(v) for v in values]
+    nxt = lambda c: INV if c == INV else (c - 2 if c % 3 == 2 else c + 1)
+    prv = lambda c: INV if c == INV else (c + 2 if c % 3 == 0 else c - 1)
+    op = lambda c: INV if c == INV else int(opp[c])
+    max_diff = 1 + mx - mn
+    max_corr = max_diff // 2
+    min_corr = -max_corr
+    if max_diff % 2 == 0:
+        max_corr -= 1
+    trunc_div = lambda a, b: abs(a) // b * (1 if a >= 0 else -1)
+    to_i32 = lambda v: ((v + (1 << 31)) & 0xFFFFFFFF) - (1 << 31)
+    corr, crease = [], [[], [], [], []]
+
+    def emit(p, pred):
+        for c in range(nc):
+            q = min(max(pred[c], mn), mx)
+            d = vals[p * nc + c] - q
+            if d < min_corr:
+                d += max_diff
+            elif d > max_corr:
+                d -= max_diff
+            corr.append(d)
+
+    emit(0, [0] * nc)
+    for p in range(1, n):
+        start = int(d2c[p])
+        corner, first, found = start, True, []
+        while corner != INV:
+            oc = op(corner)
+            if oc != INV:
+                e = [int(v2d[int(c2v[x])]) for x in (oc, nxt(oc), prv(oc))]
+                if all(x < p for x in e):
+                    found.append(e)
+                    if len(found) == max_par:
+                        break
+            corner = nxt(op(nxt(corner))) if first else prv(op(prv(corner)))
+            if corner == start:
+                break
+            if corner == INV and first:
+                first = False
+                corner = prv(op(prv(start)))
+        kept = []
+        for e in found:
+            f = bool(rng.random() < p_crease)
+            crease[len(found) - 1].append(1 if f else 0)
+            if not f:
+                kept.append(e)
+        if not kept:
+            emit(p, vals[(p - 1) * nc: p * nc])
+        else:
+            pred = []
+            for c in range(nc):
+                sm = 0
+                for (eo, en, ep) in kept:
+                    sm = to_i32(sm + to_i32(vals[en * nc + c] + vals[ep * nc + c] - vals[eo * nc + c]))
+                pred.append(trunc_div(sm, len(kept)))
+            emit(p, pred)
+    return corr, crease
+
+
 def wrap_data(mn, mx):
     return struct.pack("<ii", mn, mx)
 
