@@ -601,8 +601,15 @@ void layout_shard(Shard &sh) {
       if (s.seq_type != SEQ_GENERIC && s.has_maps && (s.recon == RECON_PARA_WRAP || s.state < ST_READY)) {
         // corrections int32[nv] | quantized ints int32[nv] | parallelogram: deps int32[3 n]; tex coords (two components):
         // TexRec[n] (32 bytes each) + orientation flags u8[<= 2n + 1]
+        // constrained multi-parallelogram: deps int32[12 n] | count u8[n] | crease flags u8[10 n] (CmpScratch, dcb_cmp.cu).
+        // A stream the host walk has not reached yet (behind a Tagged bit area) may turn out to be any of them.
         s.aux_off = aux;
-        const uint64_t tail = s.ncp == 2 ? 34ull * s.n_entries + 16ull : 12ull * s.n_entries;
+        const uint64_t n = s.n_entries;
+        const uint64_t t_para = 12ull * n, t_tex = 34ull * n + 16ull, t_cmp = 59ull * n + 48ull;
+        uint64_t tail;
+        if (s.state == ST_UNPARSED) tail = std::max(t_cmp, s.ncp == 2 ? t_tex : t_para);
+        else if (s.pred_method == PRED_CONSTRAINED_MULTI) tail = t_cmp;
+        else tail = s.ncp == 2 ? t_tex : t_para;
         aux = align_up(aux + 2ull * nv * 4 + tail, 16);
       } else if (s.seq_type == SEQ_NORMALS) {
         s.aux_off = aux;  // quantized octahedral (s, t) pairs between the serial kernels and oct_unit_kernel
@@ -1337,7 +1344,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
   }
   std::map<RawKey, Group> raw;
-  Group post[5], para[5], par[5], copy{}, octs{}, octc{}, tex{}, wide{};
+  Group post[5], para[5], cmp[5], par[5], copy{}, octs{}, octc{}, tex{}, wide{};
   wide.kind = 8;
   octs.kind = 6;
   octc.kind = 6;
@@ -1437,6 +1444,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         tex.order.push_back(si);
         tex.max_entries = std::max(tex.max_entries, s.n_entries);
         has_para = true;
+      } else if (s.recon == RECON_PARA_WRAP && s.pred_method == PRED_CONSTRAINED_MULTI) {
+        cmp[s.ncp].order.push_back(si);
+        cmp[s.ncp].max_entries = std::max(cmp[s.ncp].max_entries, s.n_entries);
+        has_para = true;
       } else if (s.recon == RECON_PARA_WRAP) {
         para[s.ncp].order.push_back(si);
         para[s.ncp].max_entries = std::max(para[s.ncp].max_entries, s.n_entries);
@@ -1470,7 +1481,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
                      [&](uint32_t x, uint32_t y) { return sh.streams[x].n_entries > sh.streams[y].n_entries; });
     add(*g);
   }
-  for (int n = 1; n <= 4; ++n) { add(post[n]); add(para[n]); add(par[n]); }
+  for (int n = 1; n <= 4; ++n) { add(post[n]); add(para[n]); add(cmp[n]); add(par[n]); }
   add(copy);
   add(octs);
   add(octc);
@@ -1552,6 +1563,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     for (int n = 1; n <= 4; ++n) {
       all.insert(all.end(), post[n].order.begin(), post[n].order.end());
       all.insert(all.end(), para[n].order.begin(), para[n].order.end());
+      all.insert(all.end(), cmp[n].order.begin(), cmp[n].order.end());
       all.insert(all.end(), par[n].order.begin(), par[n].order.end());
     }
     all.insert(all.end(), copy.order.begin(), copy.order.end());
@@ -1735,6 +1747,12 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         CUDA_TRY(cudaEventRecord(ctx->ev[9], st));
         ctx->ev_para = true;
       }
+    }
+  for (int n = 1; n <= 4; ++n)
+    if (!cmp[n].order.empty()) {  // constrained multi-parallelogram: dependencies, crease flags, chain
+      CUDA_TRY(dcb_launch_cmp(sh.d_streams, sh.d_order + cmp[n].order_off, (uint32_t)cmp[n].order.size(), n, cmp[n].max_entries,
+                              dump, A, st));
+      stats.n_launches += 3;
     }
   if (!tex.order.empty()) {  // behind the parallelogram kernels: the predictor reads the decoded positions of its parent
     CUDA_TRY(dcb_launch_tex(sh.d_streams, sh.d_order + tex.order_off, (uint32_t)tex.order.size(), tex.max_entries, dump, A, st));

@@ -17,7 +17,9 @@ enum : int32_t {
   DT_INT64 = 7, DT_UINT64 = 8, DT_FLOAT32 = 9, DT_FLOAT64 = 10, DT_BOOL = 11, DT_COUNT = 12
 };
 enum : int32_t { SEQ_GENERIC = 0, SEQ_INTEGER = 1, SEQ_QUANTIZATION = 2, SEQ_NORMALS = 3 };
-enum : int32_t { PRED_NONE = -2, PRED_DIFFERENCE = 0, PRED_PARALLELOGRAM = 1, PRED_TEX_COORDS_PORTABLE = 5, PRED_COUNT = 7 };
+enum : int32_t {
+  PRED_NONE = -2, PRED_DIFFERENCE = 0, PRED_PARALLELOGRAM = 1, PRED_CONSTRAINED_MULTI = 4, PRED_TEX_COORDS_PORTABLE = 5, PRED_COUNT = 7
+};
 enum : int32_t { XF_NONE = -1, XF_DELTA = 0, XF_WRAP = 1, XF_OCT = 2, XF_OCT_CANON = 3, XF_COUNT = 4 };
 // symbol source of a stream
 enum : uint8_t {
@@ -36,7 +38,8 @@ enum : uint8_t {
   RECON_DELTA_OCT_CANON = 3,
   RECON_PARA_WRAP = 4      // a mesh prediction scheme + wrap transform: the symbol kernels leave the corrections in the stream's
                            // scratch and a chain kernel follows -- MeshPredictionSchemeParallelogramDecoder (pred_method
-                           // PRED_PARALLELOGRAM) or MeshPredictionSchemeTexCoordsPortableDecoder (PRED_TEX_COORDS_PORTABLE)
+                           // PRED_PARALLELOGRAM), MeshPredictionSchemeConstrainedMultiParallelogramDecoder (PRED_CONSTRAINED_MULTI)
+                           // or MeshPredictionSchemeTexCoordsPortableDecoder (PRED_TEX_COORDS_PORTABLE)
 };
 // how portable integers become attribute bytes
 enum : uint8_t {
@@ -70,6 +73,9 @@ struct StreamDesc {
   uint64_t map_off[4];           // parallelogram: opposite, corner_to_vertex, data_to_corner, vertex_to_data
   uint64_t bits_total;           // device-written: bits consumed in the Tagged bit area
   uint64_t orient_off;           // tex coords: first byte (prob_zero) of the rABS-coded orientation flags
+  uint64_t crease_off[4];        // constrained multi-parallelogram: first byte (prob_zero) of the rABS-coded crease flags of
+                                 // context c (entries with c + 1 parallelograms); meaningless when n_crease[c] == 0
+  uint32_t n_crease[4];          // ... and their number
   uint32_t n_orient;             // tex coords: number of orientation flags
   int32_t parent;                // tex coords: shard-wide stream index of the buffer's position attribute, or -1
   uint32_t n_corners, n_vertices;

@@ -66,7 +66,7 @@ __global__ void tex_prep_kernel(StreamDesc *streams, const uint32_t *__restrict_
       continue;
     }
     const StreamDesc &pa = streams[d.parent];
-    if (pa.status != DCB_OK || pa.ncp != 3 || pa.recon != RECON_PARA_WRAP || pa.pred_method != PRED_PARALLELOGRAM ||
+    if (pa.status != DCB_OK || pa.ncp != 3 || pa.recon != RECON_PARA_WRAP || (pa.pred_method != PRED_PARALLELOGRAM && pa.pred_method != PRED_CONSTRAINED_MULTI) ||
         pa.attr_index >= d.attr_index || !pa.has_maps) {
       if (blockIdx.x == 0 && threadIdx.x == 0) d.status = pa.status != DCB_OK ? pa.status : DCB_ERR_UNSUPPORTED;
       continue;

@@ -150,6 +150,26 @@ DCB_HD int walk_rans_payload(WalkRd &r, int prec_bits, uint64_t &off, uint64_t &
 }
 
 // PRED_DATA of an attribute whose symbols have been located.  Returns status.
+// u8 prob_zero | varint size | data of one RAnsBitDecoder block (BitCoders/RAnsBitDecoder.cs:12-24) with the checks of
+// AnsDecoder.ReadInit; r.pos ends behind the block.
+DCB_HD int walk_rabs_block(WalkRd &r) {
+  wr_u8(r);
+  const uint64_t nb = wr_varint(r);
+  if (r.err) return r.err;
+  if (!wr_need(r, nb)) return r.err;
+  if (nb < 1) return DCB_ERR_CONNECTIVITY;
+  const uint8_t *tail = r.p + r.pos + nb;
+  const uint32_t x = (uint32_t)tail[-1] >> 6;
+  uint32_t st;
+  if (x == 0) st = tail[-1] & 0x3Fu;
+  else if (x == 1) { if (nb < 2) return DCB_ERR_CONNECTIVITY; st = ((uint32_t)tail[-2] | ((uint32_t)tail[-1] << 8)) & 0x3FFFu; }
+  else if (x == 2) { if (nb < 3) return DCB_ERR_CONNECTIVITY; st = ((uint32_t)tail[-3] | ((uint32_t)tail[-2] << 8) | ((uint32_t)tail[-1] << 16)) & 0x3FFFFFu; }
+  else return DCB_ERR_CONNECTIVITY;
+  if (st + 4096u >= 4096u * 256u) return DCB_ERR_CONNECTIVITY;
+  r.pos += nb;
+  return DCB_OK;
+}
+
 DCB_HD int walk_pred_data(WalkRd &r, StreamDesc &s, bool has_scheme, bool mesh_scheme) {
   if (!has_scheme) {
     s.recon = RECON_NONE;
@@ -165,20 +185,24 @@ DCB_HD int walk_pred_data(WalkRd &r, StreamDesc &s, bool has_scheme, bool mesh_s
       if (no < 0 || (uint64_t)(uint32_t)no > (uint64_t)s.n_entries * s.ncp + 1ull) return DCB_ERR_PRED;  // one flag per entry at most
       s.n_orient = (uint32_t)no;
       s.orient_off = r.pos;
-      wr_u8(r);
-      const uint64_t nb = wr_varint(r);
-      if (r.err) return r.err;
-      if (!wr_need(r, nb)) return r.err;
-      if (nb < 1) return DCB_ERR_CONNECTIVITY;                   // AnsDecoder.ReadInit (the oracle's rabs_start)
-      const uint8_t *tail = r.p + r.pos + nb;
-      const uint32_t x = (uint32_t)tail[-1] >> 6;
-      uint32_t st;
-      if (x == 0) st = tail[-1] & 0x3Fu;
-      else if (x == 1) { if (nb < 2) return DCB_ERR_CONNECTIVITY; st = ((uint32_t)tail[-2] | ((uint32_t)tail[-1] << 8)) & 0x3FFFu; }
-      else if (x == 2) { if (nb < 3) return DCB_ERR_CONNECTIVITY; st = ((uint32_t)tail[-3] | ((uint32_t)tail[-2] << 8) | ((uint32_t)tail[-1] << 16)) & 0x3FFFFFu; }
-      else return DCB_ERR_CONNECTIVITY;
-      if (st + 4096u >= 4096u * 256u) return DCB_ERR_CONNECTIVITY;
-      r.pos += nb;
+      const int rc = walk_rabs_block(r);
+      if (rc) return rc;
+    }
+    if (mesh_scheme && s.pred_method == PRED_CONSTRAINED_MULTI) {
+      // MeshPredictionSchemeConstrainedMultiParallelogramDecoder.DecodeTransformData (:119-141; v2.2: no mode byte): per
+      // context a varint flag count and, when it is not zero, one rABS block.  Located and validated here;
+      // cmp_flags_kernel decodes them.
+      for (int c = 0; c < 4; ++c) {
+        const uint64_t nf = wr_varint(r);
+        if (r.err) return r.err;
+        if (nf > 4ull * (uint64_t)s.n_entries + 4ull) return DCB_ERR_PRED;  // an entry consumes at most four flags
+        s.n_crease[c] = (uint32_t)nf;
+        s.crease_off[c] = r.pos;
+        if (nf > 0) {
+          const int rc = walk_rabs_block(r);
+          if (rc) return rc;
+        }
+      }
     }
     s.xf_a = (int32_t)wr_u32(r);
     s.xf_b = (int32_t)wr_u32(r);
@@ -221,10 +245,11 @@ DCB_HD void walk_scheme_kind(const BufWalk &w, const StreamDesc &s, bool &has_sc
       has_scheme = (s.transform == XF_WRAP);
   }
   if (has_scheme && w.geom_type == 1 && w.method == 1) {  // PredictionSchemeDecoderFactory.cs:9-75
-    if (s.pred_method == PRED_PARALLELOGRAM || s.pred_method == PRED_TEX_COORDS_PORTABLE)
+    if (s.pred_method == PRED_PARALLELOGRAM || s.pred_method == PRED_TEX_COORDS_PORTABLE ||
+        (s.pred_method == PRED_CONSTRAINED_MULTI && s.transform == XF_WRAP))
       mesh_scheme = true;
     else if (s.pred_method != PRED_DIFFERENCE)
-      err = DCB_ERR_UNSUPPORTED;  // multi-/constrained-multi-parallelogram, deprecated tex coords, geometric normal
+      err = DCB_ERR_UNSUPPORTED;  // multi-parallelogram (pre-2.2 streams), deprecated tex coords, geometric normal
   }
 }
 

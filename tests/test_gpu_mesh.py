@@ -139,6 +139,108 @@ def test_texcoords_portable_random_corrections(gpu_decoder, scheme, n_flags, uv_
     batch.free()
 
 
+def _cmp_attr(values, nc, maps, bits, rng, scheme, p_crease=0.3, drop_flags=0):
+    hi = (1 << bits) - 1
+    corr, crease = W.cmp_encode(values, nc, maps, 0, hi, rng, p_crease)
+    if drop_flags:
+        k = max(range(4), key=lambda i: len(crease[i]))
+        crease[k] = crease[k][:-drop_flags]
+    return W.portable_int(corr, nc, 4, 1, scheme, W.cmp_data(crease, 0, hi), num_bytes=4)
+
+
+@pytest.mark.parametrize("scheme,p_crease,drop", [("raw", 0.3, 0), ("tagged", 0.3, 0), ("uncompressed", 0.5, 0), ("raw", 0.0, 0),
+                                                  ("raw", 1.0, 0), ("raw", 0.3, 1)])
+def test_constrained_multi_parallelogram_round_trip(gpu_decoder, scheme, p_crease, drop):
+    """ConstrainedMultiParallelogram predictor over the sample's real connectivity: three attributes in two
+    decoders (3, 1 and 2 components; the second decoder's maps carry attribute seams), values chosen by the test, encoded
+    by the bitstream-specification encoder in tests/drc_writer.py.  The CUDA path must return exactly those values, equal
+    the oracle in every output byte, and fail the buffer like the oracle when a flag sequence is one flag short (:93)."""
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    rng = np.random.default_rng(31 + int(p_crease * 10) + drop)
+    n0, n1 = o.maps[0]["data_to_corner"].size, o.maps[1]["data_to_corner"].size
+    v_pos = rng.integers(0, 4096, size=n0 * 3)
+    v_gen = (np.cumsum(rng.integers(-2, 3, size=n0)) + 128).clip(0, 255)
+    v_uv = rng.integers(0, 1024, size=n1 * 2)
+    sec = bytearray([2, 0xFF, 0, 0, 0, 1, 0])
+    sec += W.varint(2) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([4, 2, 1, 0]) + W.varint(1) + bytes([2, 1])
+    sec += W.varint(1) + bytes([3, 9, 2, 0]) + W.varint(2) + bytes([2])
+    sec += _cmp_attr(v_pos, 3, o.maps[0], 12, rng, scheme, p_crease, drop)
+    sec += _cmp_attr(v_gen, 1, o.maps[0], 8, rng, scheme, p_crease)
+    sec += W.quant_params([1.0, 2.0, 3.0], 10.0, 12)
+    sec += _cmp_attr(v_uv, 2, o.maps[1], 10, rng, scheme, p_crease)
+    sec += W.quant_params([0.0, 0.0], 1.0, 10)
+    buf, attr_off = _mesh_buffer(bytes(sec))
+    maps = [o.maps[0], o.maps[1]]
+    ref = O.decode(np.frombuffer(buf, dtype=np.uint8), maps, attr_off, o.n_points)
+    batch, out, dbg = _decode_mesh(gpu_decoder, buf, attr_off, o.n_points, maps, N.DCB_DUMP_QINTS)
+    assert batch.status(0) == ref.status
+    assert (ref.status == 0) == (drop == 0)
+    if ref.status == 0:
+        for k, (ra, want) in enumerate(zip(ref.attrs, (v_pos, v_gen, v_uv))):
+            ai = batch.attr_info(0, k)
+            assert ai.n_entries == ra.n_entries and ai.pred_method == 4
+            q = dbg[ai.dbg_off: ai.dbg_off + 4 * ra.qints.size].view(np.int32)
+            assert np.array_equal(q, want.astype(np.int32)), k
+            assert np.array_equal(q, ra.qints), k
+            assert np.array_equal(out[ai.out_off: ai.out_off + ai.out_bytes], ra.out), k
+    batch.free()
+
+
+def test_constrained_multi_parallelogram_with_texcoords_and_grid(gpu_decoder):
+    """(1) Positions by ConstrainedMultiParallelogram feeding the TexCoordsPortable predictor of the same buffer (what
+    upstream encoders emit at their slowest speeds); (2) a 300 x 300 grid surface whose parallelogram operands lie ~300
+    entries back (gathered from the scratch, not the history ring), next to a plain-parallelogram mesh in one batch."""
+    from draco_sharp_b200 import synth_gen as G
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    rng = np.random.default_rng(77)
+    n0, n1 = o.maps[0]["data_to_corner"].size, o.maps[1]["data_to_corner"].size
+    v_pos = (np.cumsum(rng.integers(-9, 10, size=(n0, 3)), axis=0) + 2000).clip(0, 4095).ravel()
+    c_uv = rng.integers(-9, 10, size=n1 * 2)
+    flags = rng.integers(0, 2, size=3300)
+    sec = bytearray([2, 0xFF, 0, 0, 0, 1, 0])
+    sec += W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
+    sec += W.varint(1) + bytes([3, 9, 2, 0]) + W.varint(1) + bytes([2])
+    sec += _cmp_attr(v_pos, 3, o.maps[0], 12, rng, "raw") + W.quant_params([1.0, 2.0, 3.0], 10.0, 12)
+    sec += W.portable_int(c_uv, 2, 5, 1, "raw", W.tex_coords_data(flags, 0, 1023), num_bytes=4) + W.quant_params([0.0, 0.0], 1.0, 10)
+    house, house_off = _mesh_buffer(bytes(sec))
+    w = h = 300
+    topo = G.grid_topology(w, h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    surf = np.stack([xx * 50, yy * 50, (2000 + 1500 * np.sin(xx / 17.0) * np.cos(yy / 23.0)).astype(np.int64)], axis=-1).reshape(-1, 3)
+    v_grid = np.zeros_like(surf)
+    v_grid[topo["vertex_to_data"]] = surf          # entry order
+    v_grid = v_grid.ravel()
+    gsec = bytearray([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
+    gsec += _cmp_attr(v_grid, 3, topo, 14, rng, "tagged", 0.2) + W.quant_params([-1.0, -1.0, -1.0], 2.0, 14)
+    grid, grid_off = _mesh_buffer(bytes(gsec))
+    plain = G.grid_mesh(w, h, topo, seed=5, want_q=True)
+    batch = gpu_decoder.index([house, grid, plain[0]])
+    batch.set_attr_section(0, house_off, o.n_points)
+    for dd in (0, 1):
+        m = o.maps[dd]
+        batch.set_mesh_maps(0, dd, m["opposite"], m["corner_to_vertex"], m["data_to_corner"], m["vertex_to_data"])
+    batch.set_attr_section(1, grid_off, w * h)
+    batch.set_attr_section(2, plain[1], w * h)
+    for k in (1, 2):
+        batch.set_mesh_maps(k, 0, topo["opposite"], topo["corner_to_vertex"], topo["data_to_corner"], topo["vertex_to_data"])
+    batch.finish()
+    out, dbg = gpu_decoder.decode(batch, flags=N.DCB_DUMP_QINTS)
+    refs = [O.decode(np.frombuffer(house, dtype=np.uint8), [o.maps[0], o.maps[1]], house_off, o.n_points),
+            O.decode(np.frombuffer(grid, dtype=np.uint8), [topo], grid_off, w * h),
+            O.decode(plain[0], [topo], plain[1], w * h)]
+    for k, ref in enumerate(refs):
+        assert batch.status(k) == ref.status == 0, (k, batch.status(k), ref.status)
+        for a, ra in enumerate(ref.attrs):
+            ai = batch.attr_info(k, a)
+            assert np.array_equal(dbg[ai.dbg_off: ai.dbg_off + 4 * ra.qints.size].view(np.int32), ra.qints), (k, a)
+            assert np.array_equal(out[ai.out_off: ai.out_off + ai.out_bytes], ra.out), (k, a)
+    assert np.array_equal(refs[0].attrs[0].qints, v_pos.astype(np.int32))
+    assert np.array_equal(refs[1].attrs[0].qints, v_grid.astype(np.int32))
+    batch.free()
+
+
 def test_mesh_without_maps_fails_cleanly(gpu_decoder):
     sec = bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
     sec += W.portable_int(np.zeros(30, dtype=np.int64), 3, 1, 1, "raw", W.wrap_data(0, 7)) + W.quant_params([0, 0, 0], 1.0, 3)
