@@ -703,6 +703,131 @@ void orc_delta_oct(const int32_t *corr, uint32_t n, int32_t max_q, int canonical
   for (uint32_t i = 1; i < n; ++i) oct_original(&t, canonical, out + 2 * (uint64_t)(i - 1), corr + 2 * (uint64_t)i, out + 2 * (uint64_t)i);
 }
 
+/* OctahedronToolBox.CanonicalizeIntegerVector (:121-137), 64-bit products as the bitstream defines them (the C#
+ * multiplies in int, which overflows for 30-bit centres). */
+static void oct_canonicalize_vector(const octbox_t *t, int32_t v[3]) {
+  const int64_t abs_sum = (int64_t)iabs32(v[0]) + (int64_t)iabs32(v[1]) + (int64_t)iabs32(v[2]);
+  if (abs_sum == 0) {
+    v[0] = t->center;
+  } else {
+    v[0] = (int32_t)(((int64_t)v[0] * (int64_t)t->center) / abs_sum);
+    v[1] = (int32_t)(((int64_t)v[1] * (int64_t)t->center) / abs_sum);
+    const int32_t rest = t->center - iabs32(v[0]) - iabs32(v[1]);
+    v[2] = v[2] >= 0 ? rest : -rest;
+  }
+}
+/* OctahedronToolBox.IntegerVectorToQuantizedOctahedralCoords (:61-77) + CanonicalizeOctahedralCoords (:28-54) */
+static void oct_vector_to_coords(const octbox_t *t, const int32_t v[3], int32_t *os, int32_t *ot) {
+  int32_t s, tt;
+  if (v[0] >= 0) {
+    s = v[1] + t->center;
+    tt = v[2] + t->center;
+  } else {
+    s = v[1] < 0 ? iabs32(v[2]) : t->max_value - iabs32(v[2]);
+    tt = v[2] < 0 ? iabs32(v[1]) : t->max_value - iabs32(v[1]);
+  }
+  const int32_t mv = t->max_value, ce = t->center;
+  if ((s == 0 && tt == 0) || (s == 0 && tt == mv) || (s == mv && tt == 0)) { s = mv; tt = mv; }
+  else if (s == 0 && tt > ce) tt = ce - (tt - ce);
+  else if (s == mv && tt < ce) tt = ce + (ce - tt);
+  else if (tt == mv && s < ce) s = ce + (ce - s);
+  else if (tt == 0 && s > ce) s = ce - (s - ce);
+  *os = s;
+  *ot = tt;
+}
+/* Vector<long>.AbsSum (D/IO/Core/Vector.cs:211-226) with the absolute values the C# forgets: saturates at INT64_MAX */
+static int64_t abs_sum3_sat(const int64_t v[3]) {
+  int64_t r = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (v[i] == INT64_MIN) return INT64_MAX;
+    const int64_t a = v[i] < 0 ? -v[i] : v[i];
+    if (r > INT64_MAX - a) return INT64_MAX;
+    r += a;
+  }
+  return r;
+}
+
+/* MeshPredictionSchemeGeometricNormalDecoder.ComputeOriginalValues (:44-69) over
+ * MeshPredictionSchemeGeometricNormalPredictorArea.ComputePredictedValue (:11-60, TriangleArea mode) and the octahedron
+ * transform, in the bitstream's semantics where the C# is defective (the corner iterator skips
+ * its first corner, AbsSum takes no absolute values, the result is returned as (n0, n1, n0)).  The predicted normal of
+ * an entry is the sum of the cross products of the triangles around the entry's vertex in POSITION space -- no
+ * dependence on other normals: the scheme is point-parallel -- scaled below 2^29, canonicalised to |n|_1 = centre,
+ * negated when the entry's rABS-coded flip bit is set, and mapped to octahedral coordinates.
+ * m: maps of the normal attribute's decoder; pm / pos_q / n_pos: maps and decoded portable values of the position
+ * attribute (parent).  The position of a corner is the position entry of that corner's vertex in pm (the same
+ * lookup GetPositionForCorner :27-32 performs through the entry-to-point map). */
+int orc_geometric_normal_oct(const int32_t *corr, uint32_t n, int32_t max_q, int canonical, const orc_mesh_maps *m,
+                             const int32_t *pos_q, uint32_t n_pos, const orc_mesh_maps *pm, const uint8_t *flip,
+                             int32_t *out) {
+  octbox_t t;
+  int msb = -1;
+  for (uint32_t v = (uint32_t)max_q; v; v >>= 1) ++msb;
+  octbox_set(&t, msb + 1);
+  if (n == 0) return ORC_OK;
+  if (!m || !pm || m->n_entries < n) return ORC_ERR_MAPS;
+  int bad = 0;
+#define POS_OF(corner, dst)                                                                   \
+  do {                                                                                        \
+    uint32_t c_ = (corner);                                                                   \
+    if (c_ >= pm->n_corners) return ORC_ERR_MAPS;                                             \
+    uint32_t v_ = pm->corner_to_vertex[c_];                                                   \
+    if (v_ >= pm->n_vertices) return ORC_ERR_MAPS;                                            \
+    int32_t e_ = pm->vertex_to_data[v_];                                                      \
+    if (e_ < 0 || (uint32_t)e_ >= n_pos) return ORC_ERR_MAPS;                                 \
+    for (int k_ = 0; k_ < 3; ++k_) (dst)[k_] = pos_q[3ull * (uint32_t)e_ + k_];               \
+  } while (0)
+  for (uint32_t p = 0; p < n; ++p) {
+    const uint32_t start = m->data_to_corner[p];
+    if (start >= m->n_corners) return ORC_ERR_MAPS;
+    int64_t cent[3], nx[3], pv[3];
+    uint64_t nrm[3] = {0, 0, 0};
+    POS_OF(start, cent);
+    uint32_t corner = start;
+    int left = 1;
+    uint64_t guard = 0;
+    while (corner != 0xFFFFFFFFu) { /* VertexCornersIterator (D/IO/Mesh/VertexCornersIterator.cs:19-44), start included */
+      if (++guard > (uint64_t)m->n_corners + 2) return ORC_ERR_MAPS;
+      POS_OF(m_next(corner), nx);
+      POS_OF(m_prev(corner), pv);
+      int64_t dn[3], dp[3];
+      for (int k = 0; k < 3; ++k) { dn[k] = nx[k] - cent[k]; dp[k] = pv[k] - cent[k]; }
+      nrm[0] += (uint64_t)dn[1] * (uint64_t)dp[2] - (uint64_t)dn[2] * (uint64_t)dp[1]; /* CrossProduct, summed as unsigned :33-36 */
+      nrm[1] += (uint64_t)dn[2] * (uint64_t)dp[0] - (uint64_t)dn[0] * (uint64_t)dp[2];
+      nrm[2] += (uint64_t)dn[0] * (uint64_t)dp[1] - (uint64_t)dn[1] * (uint64_t)dp[0];
+      if (left) {
+        corner = m_next(m_opp(m, m_next(corner), &bad)); /* SwingLeft */
+        if (bad) return ORC_ERR_MAPS;
+        if (corner == 0xFFFFFFFFu) {
+          corner = m_prev(m_opp(m, m_prev(start), &bad)); /* SwingRight(start) */
+          left = 0;
+        } else if (corner == start) {
+          corner = 0xFFFFFFFFu;
+        }
+      } else {
+        corner = m_prev(m_opp(m, m_prev(corner), &bad));
+      }
+      if (bad) return ORC_ERR_MAPS;
+    }
+    int64_t nv[3] = {(int64_t)nrm[0], (int64_t)nrm[1], (int64_t)nrm[2]};
+    const int64_t upper = 1ll << 29; /* :38 */
+    const int64_t abs_sum = abs_sum3_sat(nv);
+    if (abs_sum > upper) {           /* :49-53 */
+      const int64_t q = abs_sum / upper;
+      for (int k = 0; k < 3; ++k) nv[k] /= q;
+    }
+    int32_t v3[3] = {(int32_t)nv[0], (int32_t)nv[1], (int32_t)nv[2]};
+    oct_canonicalize_vector(&t, v3); /* ...GeometricNormalDecoder.cs:55 */
+    if (flip[p])                     /* :58-61 */
+      for (int k = 0; k < 3; ++k) v3[k] = (int32_t)(0u - (uint32_t)v3[k]);
+    int32_t pred[2];
+    oct_vector_to_coords(&t, v3, &pred[0], &pred[1]);
+    oct_original(&t, canonical, pred, corr + 2ull * p, out + 2ull * p); /* :65 */
+  }
+#undef POS_OF
+  return ORC_OK;
+}
+
 /* D/IO/Attributes/AttributeQuantizationTransform.cs:179-199 + D/IO/Core/Dequantizer.cs:14-23.
  * delta = range / (float)max_q : one rounded binary32 division;
  * out = (float)q * delta + min : two separately rounded binary32 operations. */
@@ -857,6 +982,8 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
       mesh_scheme = 5; /* TexCoordsPortable */
     else if (a->pred_method == 4 && a->transform == 1)
       mesh_scheme = 4; /* ConstrainedMultiParallelogram */
+    else if (a->pred_method == 6 && a->seq_type == 3)
+      mesh_scheme = 6; /* GeometricNormal */
     else if (a->pred_method != 0)
       return ORC_ERR_UNSUPPORTED; /* multi-parallelogram, deprecated texcoords, geometric normal: SURVEY 8f-3 */
   }
@@ -969,6 +1096,22 @@ static int decode_portable(rd_t *r, orc_result *res, orc_attr *a, const orc_mesh
     int msb = -1;
     for (uint32_t v = (uint32_t)a->xf_a; v; v >>= 1) ++msb;
     if (msb + 1 < 2 || msb + 1 > 30) return ORC_ERR_QUANT; /* OctahedronToolBox.cs:15 */
+    if (mesh_scheme == 6) { /* MeshPredictionSchemeGeometricNormalDecoder.DecodePredictionData :72-82: transform data, then the flip bits */
+      uint8_t *flip = (uint8_t *)malloc(n ? n : 1);
+      int st = orc_rabs_bits(r->p, r->len, &r->pos, n, flip);
+      if (!st && nv > 0) {
+        const orc_attr *pos = NULL;
+        for (int i = 0; i < res->n_attrs && &res->attrs[i] != a && !pos; ++i)
+          if (res->attrs[i].att_type == 0) pos = &res->attrs[i];
+        if (pos && (pos->nc_portable != 3 || !pos->qints)) pos = NULL;
+        if (!maps || a->decoder_id >= n_maps) st = ORC_ERR_MAPS;
+        else if (!pos || pos->decoder_id >= n_maps) st = ORC_ERR_PRED;
+        else st = orc_geometric_normal_oct(a->corr, n, a->xf_a, a->transform == 3, &maps[a->decoder_id], pos->qints,
+                                           pos->n_entries, &maps[pos->decoder_id], flip, a->qints);
+      }
+      free(flip);
+      return st;
+    }
     if (mesh_scheme) return ORC_ERR_UNSUPPORTED;           /* parallelogram on normals: not a Draco combination */
     if (nv > 0) orc_delta_oct(a->corr, n, a->xf_a, a->transform == 3, a->qints);
   }

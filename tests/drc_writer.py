@@ -285,6 +285,93 @@ def cmp_encode(values, nc, maps, mn, mx, rng, p_crease=0.3, max_par=4):
     return corr, crease
 
 
+def geometric_normal_data(flips, bits, canonical=True):
+    """PRED_DATA of MeshPredictionSchemeGeometricNormalDecoder (DecodePredictionData :72-82, v2.2: no mode byte): the
+    octahedron transform's data (i32 max_quantized_value [, i32 center_value]) and then the rABS-coded flip bits."""
+    max_q = (1 << bits) - 1
+    out = struct.pack("<i", max_q)
+    if canonical:
+        out += struct.pack("<i", (max_q - 1) // 2)
+    return out + rabs_block(flips)
+
+
+def geometric_normal_predictions(maps, pos_maps, pos_values, bits, flips):
+    """Predicted octahedral coordinates of every entry under the geometric-normal scheme, written from the Draco bitstream
+    specification (independent of oracle/ and of the CUDA path): area-weighted normal of the triangles around the
+    entry's vertex in position space, scaled below 2^29, canonicalised to an L1 norm of the centre value, flipped, then
+    mapped to canonical octahedral coordinates.  Python integers emulate the int64 / int32 wrapping."""
+    INV = 0xFFFFFFFF
+    opp, d2c = maps["opposite"], maps["data_to_corner"]
+    p_c2v, p_v2d = pos_maps["corner_to_vertex"], pos_maps["vertex_to_data"]
+    nxt = lambda c: INV if c == INV else (c - 2 if c % 3 == 2 else c + 1)
+    prv = lambda c: INV if c == INV else (c + 2 if c % 3 == 0 else c - 1)
+    op = lambda c: INV if c == INV else int(opp[c])
+    wrap64 = lambda v: ((v + (1 << 63)) & ((1 << 64) - 1)) - (1 << 63)
+    wrap32 = lambda v: ((v + (1 << 31)) & 0xFFFFFFFF) - (1 << 31)
+    tdiv = lambda a, b: abs(a) // abs(b) * (1 if (a >= 0) == (b >= 0) else -1)
+    max_q = (1 << bits) - 1
+    max_value = max_q - 1
+    center = max_value // 2
+
+    def pos_of(c):
+        e = int(p_v2d[int(p_c2v[c])])
+        return [int(x) for x in pos_values[3 * e: 3 * e + 3]]
+
+    preds = []
+    for p in range(len(d2c)):
+        start = int(d2c[p])
+        cent = pos_of(start)
+        corners, c = [], start
+        while c != INV:                      # all corners around the vertex: swing left, then right from the start
+            corners.append(c)
+            c = nxt(op(nxt(c)))
+            if c == start:
+                c = INV
+        if nxt(op(nxt(corners[-1]))) == INV:  # open fan: continue on the right-hand side
+            c = prv(op(prv(start)))
+            while c != INV:
+                corners.append(c)
+                c = prv(op(prv(c)))
+        nrm = [0, 0, 0]
+        for c in corners:
+            a = [x - y for x, y in zip(pos_of(nxt(c)), cent)]
+            b = [x - y for x, y in zip(pos_of(prv(c)), cent)]
+            cr = [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+            nrm = [wrap64(x + y) for x, y in zip(nrm, cr)]
+        abs_sum = min(sum(abs(x) for x in nrm), (1 << 63) - 1)
+        if abs_sum > (1 << 29):
+            q = abs_sum // (1 << 29)
+            nrm = [tdiv(x, q) for x in nrm]
+        v = [wrap32(x) for x in nrm]
+        l1 = abs(v[0]) + abs(v[1]) + abs(v[2])
+        if l1 == 0:
+            v[0] = center
+        else:
+            v[0] = tdiv(v[0] * center, l1)
+            v[1] = tdiv(v[1] * center, l1)
+            rest = center - abs(v[0]) - abs(v[1])
+            v[2] = rest if v[2] >= 0 else -rest
+        if flips[p]:
+            v = [-x for x in v]
+        if v[0] >= 0:
+            s_, t_ = v[1] + center, v[2] + center
+        else:
+            s_ = abs(v[2]) if v[1] < 0 else max_value - abs(v[2])
+            t_ = abs(v[1]) if v[2] < 0 else max_value - abs(v[1])
+        if (s_, t_) in ((0, 0), (0, max_value), (max_value, 0)):
+            s_, t_ = max_value, max_value
+        elif s_ == 0 and t_ > center:
+            t_ = center - (t_ - center)
+        elif s_ == max_value and t_ < center:
+            t_ = center + (center - t_)
+        elif t_ == max_value and s_ < center:
+            s_ = center + (center - s_)
+        elif t_ == 0 and s_ > center:
+            s_ = center - (s_ - center)
+        preds += [s_, t_]
+    return preds
+
+
 def wrap_data(mn, mx):
     return struct.pack("<ii", mn, mx)
 
