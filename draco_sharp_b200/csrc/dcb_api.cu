@@ -613,7 +613,8 @@ void layout_shard(Shard &sh) {
         aux = align_up(aux + 2ull * nv * 4 + tail, 16);
       } else if (s.seq_type == SEQ_NORMALS) {
         s.aux_off = aux;  // quantized octahedral (s, t) pairs between the serial kernels and oct_unit_kernel
-        aux = align_up(aux + 8ull * s.n_entries, 16);
+        // (+ geometric normal: flip bits u8[n] behind the pairs)
+        aux = align_up(aux + 9ull * s.n_entries + 16ull, 16);
       } else if (s.seq_type == SEQ_INTEGER && s.ncp > 4) {
         s.aux_off = aux;  // wide attributes: zig-zag decoded symbols of a Raw source, int32[n * nc]
         aux = align_up(aux + 4ull * nv, 16);
@@ -1294,7 +1295,8 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
             walk_scheme_kind(w, s, has_scheme, mesh_scheme, e);
             s.recon = !has_scheme ? (uint8_t)RECON_NONE
                       : s.transform == XF_WRAP ? (uint8_t)(mesh_scheme ? RECON_PARA_WRAP : RECON_DELTA_WRAP)
-                      : s.transform == XF_OCT_CANON ? (uint8_t)RECON_DELTA_OCT_CANON : (uint8_t)RECON_DELTA_OCT;
+                      : s.transform == XF_OCT_CANON ? (uint8_t)(mesh_scheme ? RECON_GEO_OCT_CANON : RECON_DELTA_OCT_CANON)
+                                                    : (uint8_t)(mesh_scheme ? RECON_GEO_OCT : RECON_DELTA_OCT);
           }
           if (s.seq_type == SEQ_QUANTIZATION) s.store = STORE_DEQUANT;
           else if (s.seq_type == SEQ_NORMALS) s.store = STORE_OCT_UNIT;
@@ -1344,7 +1346,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
   }
   std::map<RawKey, Group> raw;
-  Group post[5], para[5], cmp[5], par[5], copy{}, octs{}, octc{}, tex{}, wide{};
+  Group post[5], para[5], cmp[5], par[5], copy{}, octs{}, octc{}, tex{}, geo{}, wide{};
   wide.kind = 8;
   octs.kind = 6;
   octc.kind = 6;
@@ -1402,7 +1404,12 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       // normals behind a Raw stream: the rANS kernel leaves corrections, oct_chain + oct_unit follow on its stream
       const bool raw_normals = s.scheme == SCHEME_RAW && s.ncp == 2 && s.store == STORE_OCT_UNIT &&
                                (s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON);
-      if (s.store == STORE_OCT_UNIT && !raw_normals) {
+      const bool geo_normals = s.recon == RECON_GEO_OCT || s.recon == RECON_GEO_OCT_CANON;
+      if (geo_normals) {  // geo_normal_kernel finishes the attribute behind the parallelogram kernels of its parent
+        geo.order.push_back(si);
+        geo.max_entries = std::max(geo.max_entries, s.n_entries);
+        has_para = true;
+      } else if (s.store == STORE_OCT_UNIT && !raw_normals) {
         octs.order.push_back(si);
         octs.max_entries = std::max(octs.max_entries, s.n_entries);
       }
@@ -1428,7 +1435,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         g.max_entries = std::max(g.max_entries, s.n_entries);
         g.note_table(s);
         g.order.push_back(si);
-      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP ||
+      } else if ((s.recon == RECON_NONE || s.recon == RECON_DELTA_WRAP || s.recon == RECON_PARA_WRAP || (geo_normals && s.ncp == 2) ||
                   ((s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON) && s.ncp == 2 && s.store == STORE_OCT_UNIT)) &&
                  !env_flags().no_par_post) {
         // Tagged / uncompressed source: point-parallel extraction; scan-able reconstructions finish there, octahedral
@@ -1486,6 +1493,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   add(octs);
   add(octc);
   add(tex);
+  add(geo);
   add(wide);
   // par_post2_kernel: per group the run prefix of its streams (runs of par_run_len chunks) and one ticket word
   std::vector<uint32_t> par_runs[5];
@@ -1570,6 +1578,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     all.insert(all.end(), octs.order.begin(), octs.order.end());
     all.insert(all.end(), octc.order.begin(), octc.order.end());
     all.insert(all.end(), tex.order.begin(), tex.order.end());
+    all.insert(all.end(), geo.order.begin(), geo.order.end());
     all.insert(all.end(), wide.order.begin(), wide.order.end());
     for (int n = 1; n <= 4; ++n) all.insert(all.end(), par_runs[n].begin(), par_runs[n].end());
 
@@ -1756,6 +1765,10 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
   if (!tex.order.empty()) {  // behind the parallelogram kernels: the predictor reads the decoded positions of its parent
     CUDA_TRY(dcb_launch_tex(sh.d_streams, sh.d_order + tex.order_off, (uint32_t)tex.order.size(), tex.max_entries, dump, A, st));
+    stats.n_launches += 2;
+  }
+  if (!geo.order.empty()) {  // behind the parallelogram kernels: the predictor reads the decoded positions of its parent
+    CUDA_TRY(dcb_launch_geo_normal(sh.d_streams, sh.d_order + geo.order_off, (uint32_t)geo.order.size(), geo.max_entries, dump, A, st));
     stats.n_launches += 2;
   }
   if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));

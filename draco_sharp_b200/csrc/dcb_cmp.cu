@@ -26,6 +26,7 @@
 #include "dcb_device.cuh"
 #include "dcb_internal.h"
 #include "dcb_kernels.h"
+#include "dcb_rabs.cuh"
 
 using namespace dcb;
 
@@ -123,15 +124,12 @@ __global__ void cmp_deps_kernel(StreamDesc *streams, const uint32_t *__restrict_
   }
 }
 
-// One warp per (stream, context): lane 0 runs the rABS chain over a 256-byte shared-memory window the warp refills and
-// leaves up to 256 flags per round in shared memory; the warp writes them out coalesced.
-constexpr uint32_t kWin = 256;
-
+// One warp per (stream, context): rabs_decode_block (dcb_rabs.cuh).
 __global__ void __launch_bounds__(128) cmp_flags_kernel(const uint8_t *__restrict__ arena, StreamDesc *streams,
                                                         const uint32_t *__restrict__ order, uint32_t n_streams,
                                                         uint8_t *__restrict__ aux) {
-  __shared__ uint8_t s_win[4][kWin];
-  __shared__ uint8_t s_bits[4][kWin];
+  __shared__ uint8_t s_win[4][kRabsWin];
+  __shared__ uint8_t s_bits[4][kRabsWin];
   const uint32_t ctx = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   for (uint32_t si = blockIdx.x; si < n_streams; si += gridDim.x) {
     const StreamDesc &d = streams[order[si]];
@@ -140,50 +138,7 @@ __global__ void __launch_bounds__(128) cmp_flags_kernel(const uint8_t *__restric
     const uint32_t want = (uint32_t)(got < cap ? got : cap);  // more flags than that are never consumed
     if (want == 0) continue;
     CmpScratch sc(aux, d);
-    uint8_t *dst = sc.flags[ctx];
-    const uint8_t *blk = arena + d.crease_off[ctx];
-    const uint32_t prob_zero = blk[0];
-    uint64_t pos = 1, nb = 0;
-    for (int i = 0, shift = 0; i < 10; ++i, shift += 7) {  // varint size (validated by the container walk)
-      const uint32_t b = blk[pos++];
-      nb |= (uint64_t)(b & 0x7Fu) << shift;
-      if (!(b & 0x80u)) break;
-    }
-    const uint8_t *data = blk + pos;
-    const uint32_t p1 = (256u - prob_zero) & 0xFFu;
-    const uint32_t x = (uint32_t)data[nb - 1] >> 6;
-    int64_t off = (int64_t)nb - 1 - x;
-    uint32_t state = 0;
-    for (uint32_t i = 0; i <= x; ++i) state |= (uint32_t)data[nb - 1 - x + i] << (8 * i);
-    state &= (x == 0) ? 0x3Fu : (x == 1) ? 0x3FFFu : 0x3FFFFFu;
-    state += 4096u;
-    uint32_t done = 0;
-    while (done < want) {  // uniform over the warp
-      const int64_t lo = off > (int64_t)kWin ? off - (int64_t)kWin : 0;
-      for (uint32_t i = lane; i < (uint32_t)(off - lo); i += 32) s_win[ctx][i] = data[lo + i];
-      __syncwarp();
-      uint32_t made = 0;
-      if (lane == 0) {
-        const uint32_t room = min(kWin, want - done);
-        while (made < room) {
-          if (state < 4096u && off > 0) {
-            if (off <= lo) break;  // refill
-            state = state * 256u + s_win[ctx][--off - lo];
-          }
-          const uint32_t quot = state >> 8, rem = state & 255u, xn = quot * p1;
-          const bool val = rem < p1;
-          state = val ? xn + rem : state - xn - p1;
-          s_bits[ctx][made++] = val ? 1 : 0;
-        }
-      }
-      made = __shfl_sync(0xffffffffu, made, 0);
-      off = __shfl_sync(0xffffffffu, off, 0);
-      state = __shfl_sync(0xffffffffu, state, 0);
-      __syncwarp();
-      for (uint32_t i = lane; i < made; i += 32) dst[done + i] = s_bits[ctx][i];
-      done += made;
-      __syncwarp();
-    }
+    rabs_decode_block(arena + d.crease_off[ctx], want, sc.flags[ctx], s_win[ctx], s_bits[ctx], lane);
   }
 }
 

@@ -18,7 +18,8 @@ enum : int32_t {
 };
 enum : int32_t { SEQ_GENERIC = 0, SEQ_INTEGER = 1, SEQ_QUANTIZATION = 2, SEQ_NORMALS = 3 };
 enum : int32_t {
-  PRED_NONE = -2, PRED_DIFFERENCE = 0, PRED_PARALLELOGRAM = 1, PRED_CONSTRAINED_MULTI = 4, PRED_TEX_COORDS_PORTABLE = 5, PRED_COUNT = 7
+  PRED_NONE = -2, PRED_DIFFERENCE = 0, PRED_PARALLELOGRAM = 1, PRED_CONSTRAINED_MULTI = 4, PRED_TEX_COORDS_PORTABLE = 5,
+  PRED_GEOMETRIC_NORMAL = 6, PRED_COUNT = 7
 };
 enum : int32_t { XF_NONE = -1, XF_DELTA = 0, XF_WRAP = 1, XF_OCT = 2, XF_OCT_CANON = 3, XF_COUNT = 4 };
 // symbol source of a stream
@@ -40,6 +41,9 @@ enum : uint8_t {
                            // scratch and a chain kernel follows -- MeshPredictionSchemeParallelogramDecoder (pred_method
                            // PRED_PARALLELOGRAM), MeshPredictionSchemeConstrainedMultiParallelogramDecoder (PRED_CONSTRAINED_MULTI)
                            // or MeshPredictionSchemeTexCoordsPortableDecoder (PRED_TEX_COORDS_PORTABLE)
+  ,
+  RECON_GEO_OCT = 5,       // MeshPredictionSchemeGeometricNormalDecoder + octahedron transform: the symbol kernels leave the
+  RECON_GEO_OCT_CANON = 6  // corrections in the stream's scratch, geo_normal_kernel (point-parallel) finishes the attribute
 };
 // how portable integers become attribute bytes
 enum : uint8_t {
@@ -72,11 +76,11 @@ struct StreamDesc {
   uint64_t tag_off;              // scratch arena offset (tags u8[n] then u32 chunk sums), 16-byte aligned
   uint64_t map_off[4];           // parallelogram: opposite, corner_to_vertex, data_to_corner, vertex_to_data
   uint64_t bits_total;           // device-written: bits consumed in the Tagged bit area
-  uint64_t orient_off;           // tex coords: first byte (prob_zero) of the rABS-coded orientation flags
+  uint64_t orient_off;           // tex coords: first byte (prob_zero) of the rABS-coded orientation flags; geometric normal: of the flip bits
   uint64_t crease_off[4];        // constrained multi-parallelogram: first byte (prob_zero) of the rABS-coded crease flags of
                                  // context c (entries with c + 1 parallelograms); meaningless when n_crease[c] == 0
   uint32_t n_crease[4];          // ... and their number
-  uint32_t n_orient;             // tex coords: number of orientation flags
+  uint32_t n_orient;             // tex coords: number of orientation flags; geometric normal: number of flip bits (= entries)
   int32_t parent;                // tex coords: shard-wide stream index of the buffer's position attribute, or -1
   uint32_t n_corners, n_vertices;
   uint32_t n_entries;

@@ -71,6 +71,10 @@ cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint
 // (rABS crease flags, one warp per context) + cmp_chain_kernel (one warp per stream)
 cudaError_t dcb_launch_cmp(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
                            uint32_t dump, const DevArenas &a, cudaStream_t st);
+// MeshPredictionSchemeGeometricNormalDecoder (dcb_geonormal.cu): geo_flips_kernel (rABS flip bits, one warp per stream) +
+// geo_normal_kernel (point-parallel: prediction from the parent's decoded positions, octahedron transform, unit vectors)
+cudaError_t dcb_launch_geo_normal(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries, uint32_t dump,
+                                  const DevArenas &a, cudaStream_t st);
 // MeshPredictionSchemeTexCoordsPortableDecoder (dcb_texcoord.cu): tex_prep_kernel (point-parallel) + tex_chain_kernel
 // (one warp per stream); the parent position streams must have been through dcb_launch_para on the same stream
 cudaError_t dcb_launch_tex(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries, uint32_t dump,

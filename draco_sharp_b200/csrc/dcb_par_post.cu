@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(kWarps * 32) par_post2_kernel(const uint8_t *_
       dptr = DUMP ? reinterpret_cast<int32_t *>(dbg + d.dbg_off) : nullptr;
       // parallelogram corrections and octahedral corrections go to the stream's int32 scratch: para_chain_kernel /
       // oct_chain_kernel run the recurrences that are not scans
-      chain_follows = recon == RECON_PARA_WRAP || recon == RECON_DELTA_OCT || recon == RECON_DELTA_OCT_CANON;
+      chain_follows = recon == RECON_PARA_WRAP || recon == RECON_DELTA_OCT || recon == RECON_DELTA_OCT_CANON ||
+                      recon == RECON_GEO_OCT || recon == RECON_GEO_OCT_CANON;
       to_scratch = chain_follows || pp.store == STORE_OCT_UNIT;  // oct_unit_kernel reads (s, t) pairs from the scratch
       if (to_scratch) {
         pp.store = STORE_NARROW;

@@ -226,7 +226,18 @@ DCB_HD int walk_pred_data(WalkRd &r, StreamDesc &s, bool has_scheme, bool mesh_s
     int msb = -1;
     for (uint32_t v = (uint32_t)s.xf_a; v; v >>= 1) ++msb;
     if (msb + 1 < 2 || msb + 1 > 30) return DCB_ERR_QUANT;        // OctahedronToolBox.cs:15
-    if (mesh_scheme) return DCB_ERR_UNSUPPORTED;
+    if (mesh_scheme) {
+      if (s.pred_method != PRED_GEOMETRIC_NORMAL) return DCB_ERR_UNSUPPORTED;  // parallelogram on normals: not a Draco combination
+      // MeshPredictionSchemeGeometricNormalDecoder.DecodePredictionData (:72-82; v2.2: no mode byte): behind the
+      // transform data, one rABS block with a flip bit per entry.  Located and validated here; geo_flips_kernel decodes it.
+      s.orient_off = r.pos;
+      s.n_orient = s.n_entries;
+      const int rc = walk_rabs_block(r);
+      if (rc) return rc;
+      if (s.n_entries > 0 && !s.has_maps) return DCB_ERR_MAPS;
+      s.recon = (s.transform == XF_OCT_CANON) ? RECON_GEO_OCT_CANON : RECON_GEO_OCT;
+      return DCB_OK;
+    }
     s.recon = (s.transform == XF_OCT_CANON) ? RECON_DELTA_OCT_CANON : RECON_DELTA_OCT;
   }
   return DCB_OK;
@@ -246,10 +257,11 @@ DCB_HD void walk_scheme_kind(const BufWalk &w, const StreamDesc &s, bool &has_sc
   }
   if (has_scheme && w.geom_type == 1 && w.method == 1) {  // PredictionSchemeDecoderFactory.cs:9-75
     if (s.pred_method == PRED_PARALLELOGRAM || s.pred_method == PRED_TEX_COORDS_PORTABLE ||
-        (s.pred_method == PRED_CONSTRAINED_MULTI && s.transform == XF_WRAP))
+        (s.pred_method == PRED_CONSTRAINED_MULTI && s.transform == XF_WRAP) ||
+        (s.pred_method == PRED_GEOMETRIC_NORMAL && s.seq_type == SEQ_NORMALS))
       mesh_scheme = true;
     else if (s.pred_method != PRED_DIFFERENCE)
-      err = DCB_ERR_UNSUPPORTED;  // multi-parallelogram (pre-2.2 streams), deprecated tex coords, geometric normal
+      err = DCB_ERR_UNSUPPORTED;  // multi-parallelogram and deprecated tex coords (pre-2.2 streams)
   }
 }
 

@@ -241,6 +241,93 @@ def test_constrained_multi_parallelogram_with_texcoords_and_grid(gpu_decoder):
     batch.free()
 
 
+@pytest.mark.parametrize("dec,nbits,pos_bits,canonical,scheme", [(0, 10, 12, True, "raw"), (1, 8, 12, True, "tagged"),
+                                                                 (1, 30, 30, True, "uncompressed"), (1, 2, 12, True, "raw"),
+                                                                 (0, 12, 14, False, "tagged"), (1, 10, 12, True, "uncompressed")])
+def test_geometric_normal_predictor(gpu_decoder, dec, nbits, pos_bits, canonical, scheme):
+    """GeometricNormal predictor over the sample's real connectivity, normals in the positions' decoder or
+    in the second one (attribute seams), every symbol source.  With all-zero corrections the decoded octahedral
+    coordinates must equal the predictions computed by the bitstream-specification restatement in tests/drc_writer.py;
+    with random corrections every quantized int and output byte must equal the oracle's (30-bit positions exercise the
+    wrapping 64-bit sums and the scaling below 2^29)."""
+    from test_geometric_normal_cpu import normals_section
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    rng = np.random.default_rng(dec * 7 + nbits)
+    n0 = o.maps[0]["data_to_corner"].size
+    m = o.maps[dec]
+    n = m["data_to_corner"].size
+    big = pos_bits >= 30
+    c_pos = rng.integers(-(1 << 28), 1 << 28, size=n0 * 3) if big else rng.integers(-40, 41, size=n0 * 3)
+    flips = rng.integers(0, 2, size=n)
+    pos_scheme = "uncompressed" if big else "raw"
+    maps = [o.maps[0], o.maps[1]]
+    for zero in (True, False):
+        corr = np.zeros(n * 2, dtype=np.int64) if zero else rng.integers(0, 1 << nbits, size=n * 2)
+        sec = normals_section(c_pos, corr, flips, nbits, pos_bits, dec, scheme, canonical, pos_scheme)
+        buf, attr_off = _mesh_buffer(sec)
+        ref = O.decode(np.frombuffer(buf, dtype=np.uint8), maps, attr_off, o.n_points)
+        assert ref.status == 0
+        batch, out, dbg = _decode_mesh(gpu_decoder, buf, attr_off, o.n_points, maps, N.DCB_DUMP_QINTS)
+        assert batch.status(0) == 0
+        for k, ra in enumerate(ref.attrs):
+            ai = batch.attr_info(0, k)
+            q = dbg[ai.dbg_off: ai.dbg_off + 4 * ra.qints.size].view(np.int32)
+            assert np.array_equal(q, ra.qints), (zero, k)
+            assert np.array_equal(out[ai.out_off: ai.out_off + ai.out_bytes], ra.out), (zero, k)
+            if k == 1 and zero:
+                assert ai.pred_method == 6
+                want = W.geometric_normal_predictions(m, o.maps[0], ref.attrs[0].qints, nbits, flips)
+                assert np.array_equal(q, np.asarray(want, dtype=np.int32))
+        batch.free()
+        # and without the dump flag (the template instantiation a plain decode uses)
+        batch, out2, _ = _decode_mesh(gpu_decoder, buf, attr_off, o.n_points, maps, 0)
+        ai = batch.attr_info(0, 1)
+        assert np.array_equal(out2[ai.out_off: ai.out_off + ai.out_bytes], ref.attrs[1].out)
+        batch.free()
+
+
+def test_geometric_normal_behind_cmp_positions_on_a_grid(gpu_decoder):
+    """A 200 x 200 grid surface the way upstream encoders write meshes at their slowest speeds: positions by
+    ConstrainedMultiParallelogram, normals by GeometricNormal in the same decoder; next to a cloud in one batch."""
+    from draco_sharp_b200 import synth_gen as G
+    w = h = 200
+    topo = G.grid_topology(w, h)
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:h, 0:w]
+    surf = np.stack([xx * 80, yy * 80, (8000 + 6000 * np.sin(xx / 13.0) * np.cos(yy / 19.0)).astype(np.int64)], axis=-1).reshape(-1, 3)
+    v_pos = np.zeros_like(surf)
+    v_pos[topo["vertex_to_data"]] = surf
+    v_pos = v_pos.ravel()
+    n = w * h
+    flips = rng.integers(0, 2, size=n)
+    corr_n = rng.integers(0, 40, size=n * 2)
+    sec = bytearray([1, 0xFF, 0, 0])
+    sec += W.varint(2) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([1, 9, 3, 0]) + W.varint(1) + bytes([2, 3])
+    sec += _cmp_attr(v_pos, 3, topo, 14, rng, "raw", 0.2)
+    sec += W.portable_int(corr_n, 2, 6, 3, "raw", W.geometric_normal_data(flips, 10), zig=False)
+    sec += W.quant_params([-1.0, -1.0, -1.0], 2.0, 14) + bytes([10])
+    mesh, aoff = _mesh_buffer(bytes(sec))
+    cloud = G.synth_cloud(G.make_spec(4000, seed=8, normal_bits=10, colors=1))[0]
+    batch = gpu_decoder.index([cloud, mesh])
+    batch.set_attr_section(1, aoff, n)
+    batch.set_mesh_maps(1, 0, topo["opposite"], topo["corner_to_vertex"], topo["data_to_corner"], topo["vertex_to_data"])
+    batch.finish()
+    out, dbg = gpu_decoder.decode(batch, flags=N.DCB_DUMP_QINTS)
+    refs = [O.decode(cloud), O.decode(np.frombuffer(mesh, dtype=np.uint8), [topo], aoff, n)]
+    for k, ref in enumerate(refs):
+        assert batch.status(k) == ref.status == 0, (k, batch.status(k), ref.status)
+        for a, ra in enumerate(ref.attrs):
+            ai = batch.attr_info(k, a)
+            assert np.array_equal(out[ai.out_off: ai.out_off + ai.out_bytes], ra.out), (k, a)
+            if ra.seq_type != 0:
+                assert np.array_equal(dbg[ai.dbg_off: ai.dbg_off + 4 * ra.qints.size].view(np.int32), ra.qints), (k, a)
+    assert np.array_equal(refs[1].attrs[0].qints, v_pos.astype(np.int32))
+    nrm = refs[1].attrs[1].out.view(np.float32).reshape(-1, 3)
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
+    batch.free()
+
+
 def test_mesh_without_maps_fails_cleanly(gpu_decoder):
     sec = bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
     sec += W.portable_int(np.zeros(30, dtype=np.int64), 3, 1, 1, "raw", W.wrap_data(0, 7)) + W.quant_params([0, 0, 0], 1.0, 3)
