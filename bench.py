@@ -52,6 +52,11 @@ MESH_WORKLOADS = {
                      "from the host, 14-bit positions, parallelogram + wrap, rANS (upstream scheme rule)", -1),
     "c4tagged": (64, 1000, "configs[3] with the Tagged scheme forced", 0),
     "c4s": (8, 300, "configs[3] at CI size: 8 meshes of 300 x 300 vertices", -1),
+    # SURVEY 8f-3 predictors at configs[3] size: what upstream encoders write at their slowest speeds
+    "c4cmp": (64, 1000, "configs[3] shape with the 8f-3 predictors: positions by ConstrainedMultiParallelogram + wrap, normals by "
+                        "GeometricNormal + canonicalized octahedron transform (10 bits), Raw rANS; ONE 1,000 x 1,000 mesh written by "
+                        "the test suite's bitstream writer (tests/drc_writer.py), repeated 64 times", 1),
+    "c4cmps": (8, 300, "c4cmp at CI size: 8 meshes of 300 x 300 vertices", 1),
 }
 METRIC = "decoded points/sec"
 UNIT = "points/s"
@@ -289,12 +294,55 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def make_cmp_mesh(side, topo):
+    """One grid mesh with CMP positions and geometric normals, written by tests/drc_writer.py; cached under
+    bench_cache/ (git-ignored, travels with the snapshot) because the pure-Python writer needs about a minute per million
+    vertices.  Returns (buffer, attr_section_off, checksum of the expected position floats, 1, None)."""
+    import struct
+    from draco_sharp_b200 import synth_gen as G
+    cache = os.path.join(ROOT, "bench_cache", "c4cmp_%d.npz" % side)
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z["buf"], int(z["aoff"]), int(z["sum"]), 1, None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import drc_writer as W
+    rng = np.random.default_rng(0xC4C)
+    n, bits = side * side, 14
+    yy, xx = np.mgrid[0:side, 0:side]
+    z = 8000 + 6000 * np.sin(xx / 37.0) * np.cos(yy / 53.0) + rng.normal(0.0, 6.0, size=xx.shape)
+    step = ((1 << bits) - 200) // side
+    surf = np.stack([xx * step + rng.integers(0, 3, size=xx.shape), yy * step + rng.integers(0, 3, size=xx.shape),
+                     z.astype(np.int64)], axis=-1).reshape(-1, 3)
+    q = np.zeros_like(surf)
+    q[topo["vertex_to_data"]] = surf   # entry order
+    q = q.ravel()
+    hi = (1 << bits) - 1
+    corr, crease = W.cmp_encode(q, 3, topo, 0, hi, rng, 0.15)
+    sec = bytearray([1, 0xFF, 0, 0])
+    sec += W.varint(2) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([1, 9, 3, 0]) + W.varint(1) + bytes([2, 3])
+    sec += W.portable_int(corr, 3, 4, 1, "raw", W.cmp_data(crease, 0, hi))
+    sec += W.portable_int(rng.integers(0, 24, size=n * 2), 2, 6, 3, "raw", W.geometric_normal_data(rng.integers(0, 2, size=n) < 1, 10), zig=False)
+    pos_min, rng_f = np.float32(-1.0), np.float32(2.0)
+    sec += W.quant_params([-1.0, -1.0, -1.0], 2.0, bits) + bytes([10])
+    head = b"DRACO" + bytes([2, 2, 1, 1]) + struct.pack("<H", 0) + bytes([0]) + b"\xEB" * 15  # connectivity: the host's business
+    buf = np.frombuffer(head + bytes(sec), dtype=np.uint8).copy()
+    delta = np.float32(rng_f / np.float32(hi))
+    fl = (q.astype(np.float32) * delta).astype(np.float32) + pos_min   # two separately rounded binary32 operations
+    sm = G.word_checksum(fl.astype(np.float32))
+    os.makedirs(os.path.dirname(cache), exist_ok=True)
+    np.savez(cache, buf=buf, aoff=len(head), sum=np.uint64(sm))
+    return buf, len(head), int(sm), 1, None
+
+
 def make_meshes(name, rank, n_meshes=None):
     from concurrent.futures import ThreadPoolExecutor
     from draco_sharp_b200 import synth_gen as G
     m, side, _, scheme = MESH_WORKLOADS[name]
     m = n_meshes or m
     topo = G.grid_topology(side, side)
+    if name.startswith("c4cmp"):
+        one = make_cmp_mesh(side, topo)
+        return topo, [one] * m, side * side
     with ThreadPoolExecutor(max_workers=host_cores()) as ex:
         meshes = list(ex.map(lambda k: G.grid_mesh(side, side, topo, seed=rank_seed(rank) + 0x4000 + k, scheme=scheme), range(m)))
     return topo, meshes, side * side

@@ -1334,7 +1334,9 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     return key;
   };
   auto is_raw_normals = [](const StreamDesc &s) {
-    return s.scheme == SCHEME_RAW && s.ncp == 2 && s.store == STORE_OCT_UNIT && (s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON);
+    // (geometric normals too: the rANS kernel leaves corrections either way; oct_chain / oct_unit skip those streams)
+    return s.scheme == SCHEME_RAW && s.ncp == 2 && s.store == STORE_OCT_UNIT &&
+           (s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON || s.recon == RECON_GEO_OCT || s.recon == RECON_GEO_OCT_CANON);
   };
   std::map<RawKey, size_t> raw_count;  // streams per natural key
   for (size_t bi = 0; bi < sh.walks.size(); ++bi) {
@@ -1402,8 +1404,7 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
         continue;
       }
       // normals behind a Raw stream: the rANS kernel leaves corrections, oct_chain + oct_unit follow on its stream
-      const bool raw_normals = s.scheme == SCHEME_RAW && s.ncp == 2 && s.store == STORE_OCT_UNIT &&
-                               (s.recon == RECON_DELTA_OCT || s.recon == RECON_DELTA_OCT_CANON);
+      const bool raw_normals = is_raw_normals(s);
       const bool geo_normals = s.recon == RECON_GEO_OCT || s.recon == RECON_GEO_OCT_CANON;
       if (geo_normals) {  // geo_normal_kernel finishes the attribute behind the parallelogram kernels of its parent
         geo.order.push_back(si);
@@ -1591,7 +1592,12 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   // ---- launches ----
   // independent smem-table groups go to side streams so that their chains overlap (c3: positions, normals, colours)
   const bool fan_out = rgs.size() > 1 && !env_flags().no_fanout;
-  if (fan_out) {
+  // crease flags / flip bits of the 8f-3 predictors depend on the bitstream only: their (serial, small) rABS kernels run on
+  // a side stream next to the rANS kernels -- unless descriptors are still being resolved on the device behind Tagged bit areas
+  bool flag_kernels = !geo.order.empty();
+  for (int n = 1; n <= 4; ++n) flag_kernels = flag_kernels || !cmp[n].order.empty();
+  const bool flags_early = flag_kernels && !deferred_descs && !env_flags().no_fanout;
+  if (fan_out || flags_early) {
     CUDA_TRY(cudaEventRecord(ctx->fork_ev[dev_index], st));
     for (cudaStream_t ss : ctx->side[dev_index]) CUDA_TRY(cudaStreamWaitEvent(ss, ctx->fork_ev[dev_index], 0));
   }
@@ -1687,6 +1693,23 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     stats.n_streams += (int32_t)n;
   }
+  auto launch_flag_kernels = [&](cudaStream_t fs) -> int {
+    for (int n = 1; n <= 4; ++n)
+      if (!cmp[n].order.empty()) {
+        CUDA_TRY(dcb_launch_cmp_flags(sh.d_streams, sh.d_order + cmp[n].order_off, (uint32_t)cmp[n].order.size(), A, fs));
+        stats.n_launches++;
+      }
+    if (!geo.order.empty()) {
+      CUDA_TRY(dcb_launch_geo_flips(sh.d_streams, sh.d_order + geo.order_off, (uint32_t)geo.order.size(), A, fs));
+      stats.n_launches++;
+    }
+    return DCB_OK;
+  };
+  if (flags_early) {  // issued behind the rANS launches so that those get their SMs first
+    int rcf = launch_flag_kernels(ctx->side[dev_index][2]);
+    if (rcf) return rcf;
+    side_used[2] = true;
+  }
   {  // mesh maps: behind the rANS launches (their chains hide the copy), in front of the parallelogram kernels
     int rcm = issue_maps_copy(ctx, b, sh, dev_index);
     if (rcm) return rcm;
@@ -1745,23 +1768,27 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     CUDA_TRY(dcb_launch_copy(sh.d_streams, sh.d_order + copy.order_off, (uint32_t)copy.order.size(), copy.max_bytes, A, st));
     stats.n_launches++;
   }
+  // mesh prediction stage (ms_para of the stats): parallelogram, constrained multi-parallelogram, tex-coord and
+  // geometric-normal kernels, timed as one span
+  bool any_mesh_stage = !tex.order.empty() || !geo.order.empty();
+  for (int n = 1; n <= 4; ++n) any_mesh_stage = any_mesh_stage || !para[n].order.empty() || !cmp[n].order.empty();
+  const bool time_para = timed && dev_index == 0 && !ctx->ev_para && any_mesh_stage;
+  if (time_para) CUDA_TRY(cudaEventRecord(ctx->ev[8], st));
   for (int n = 1; n <= 4; ++n)
     if (!para[n].order.empty()) {
-      const bool time_para = timed && dev_index == 0 && !ctx->ev_para;
-      if (time_para) CUDA_TRY(cudaEventRecord(ctx->ev[8], st));
       CUDA_TRY(dcb_launch_para(sh.d_streams, sh.d_order + para[n].order_off, (uint32_t)para[n].order.size(), n,
                                para[n].max_entries, dump, A, st));
       stats.n_launches += 2;
-      if (time_para) {
-        CUDA_TRY(cudaEventRecord(ctx->ev[9], st));
-        ctx->ev_para = true;
-      }
     }
+  if (flag_kernels && !flags_early) {
+    int rcf = launch_flag_kernels(st);
+    if (rcf) return rcf;
+  }
   for (int n = 1; n <= 4; ++n)
-    if (!cmp[n].order.empty()) {  // constrained multi-parallelogram: dependencies, crease flags, chain
+    if (!cmp[n].order.empty()) {  // constrained multi-parallelogram: dependencies, chain
       CUDA_TRY(dcb_launch_cmp(sh.d_streams, sh.d_order + cmp[n].order_off, (uint32_t)cmp[n].order.size(), n, cmp[n].max_entries,
                               dump, A, st));
-      stats.n_launches += 3;
+      stats.n_launches += 2;
     }
   if (!tex.order.empty()) {  // behind the parallelogram kernels: the predictor reads the decoded positions of its parent
     CUDA_TRY(dcb_launch_tex(sh.d_streams, sh.d_order + tex.order_off, (uint32_t)tex.order.size(), tex.max_entries, dump, A, st));
@@ -1769,7 +1796,11 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
   }
   if (!geo.order.empty()) {  // behind the parallelogram kernels: the predictor reads the decoded positions of its parent
     CUDA_TRY(dcb_launch_geo_normal(sh.d_streams, sh.d_order + geo.order_off, (uint32_t)geo.order.size(), geo.max_entries, dump, A, st));
-    stats.n_launches += 2;
+    stats.n_launches++;
+  }
+  if (time_para) {
+    CUDA_TRY(cudaEventRecord(ctx->ev[9], st));
+    ctx->ev_para = true;
   }
   if (timed && dev_index == 0) CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
   if (has_para || deferred_descs) {

@@ -13,11 +13,13 @@
 //   cmp_deps_kernel   the operand entries of every parallelogram of every entry: connectivity only, point-parallel
 //   cmp_flags_kernel  the four rABS-coded flag sequences of a stream, one warp per context (RAnsBitDecoder.cs:26-30)
 //   cmp_chain_kernel  the recurrence, one warp per stream over blocks of 32 entries.  All lanes build the block's
-//                     records (flag positions by ballot, kept parallelograms, operand ADDRESSES: the 64-entry history
-//                     ring in shared memory, or operands gathered from the quantized-int scratch when older); lanes
-//                     0..NCP-1 then walk the chain, one component each, branch-free: 12 operand loads (unused slots
-//                     point at a zero word), + k * value(p - 1) for operands that ARE entry p - 1 so that value never
-//                     leaves its register, division by 1..4 by select, wrap.
+//                     records: flag positions by ballot, kept parallelograms, and -- because every entry before the
+//                     block is final by then (previous block in a shared-memory ring, older ones in the quantized-int
+//                     scratch) -- the SUM of all operands from outside the block, per component.  Lanes 0..NCP-1 then
+//                     walk the chain, one component each: pre-summed base + k * value(p - 1) (operands that ARE entry
+//                     p - 1 never leave the register) + the few operands inside the block, division by 1..4 by
+//                     select, wrap.  (First version: 12 operand loads per entry, 164 ms per million entries; this
+//                     one: see profiles/.)
 // Product code: nothing here touches oracle/.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -147,9 +149,9 @@ __device__ __forceinline__ int32_t lds32(uint32_t a) {
   asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ void sts32(uint32_t a, int32_t v) {
@@ -164,28 +166,23 @@ __device__ __forceinline__ int32_t div_small(int32_t s, uint32_t used) {
   return used == 1u ? s : used == 2u ? d2 : used == 3u ? d3 : d4;
 }
 
-struct Operands {
-  int32_t v[12];
-};
-
 template <int NCP, bool DUMP>
 __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
                                                        uint32_t n_streams, uint8_t *__restrict__ out,
                                                        uint8_t *__restrict__ dbg, uint8_t *__restrict__ aux, uint32_t dump) {
-  __shared__ __align__(16) uint32_t s_addr[kBlk * 12];  // operand addresses of component 0; slot i: opp, next, prev
-  __shared__ uint32_t s_meta[kBlk];                     // (k & 0xFF) | used << 8
+  // per entry of the block: {meta, first four in-block operands}, eight more in-block operands, per component the
+  // pre-summed operands from outside the block and the correction
+  __shared__ __align__(8) uint2 s_meta[kBlk];   // x: (k & 0xFF) | used << 8 | n_in << 16   y: in-block operands 0..3
+  __shared__ __align__(8) uint2 s_more[kBlk];   // in-block operands 4..11 (one byte each: index in block | 0x80 = subtract)
+  __shared__ int32_t s_base[kBlk * NCP];
   __shared__ int32_t s_cor[kBlk * NCP];
-  __shared__ int32_t s_far[kBlk * 12 * NCP];            // operands older than the ring
   __shared__ int32_t s_ring[kRing * NCP];
-  __shared__ int32_t s_zero[4];
   const uint32_t lane = threadIdx.x;
   const uint32_t a_ring = (uint32_t)__cvta_generic_to_shared(s_ring);
-  const uint32_t a_far = (uint32_t)__cvta_generic_to_shared(s_far);
-  const uint32_t a_zero = (uint32_t)__cvta_generic_to_shared(s_zero);
-  const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(s_addr);
   const uint32_t a_meta = (uint32_t)__cvta_generic_to_shared(s_meta);
+  const uint32_t a_more = (uint32_t)__cvta_generic_to_shared(s_more);
+  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(s_base);
   const uint32_t a_cor = (uint32_t)__cvta_generic_to_shared(s_cor);
-  if (lane < 4) s_zero[lane] = 0;
   for (uint32_t si = blockIdx.x; si < n_streams; si += gridDim.x) {
     StreamDesc &d = streams[order[si]];
     if (d.status != DCB_OK) continue;
@@ -227,7 +224,9 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
         for (int c = 0; c < NCP; ++c) ncor[c] = corr[(uint64_t)p * NCP + c];
       }
     };
-    // records of block blk from the fetched registers; every entry before block blk - 1 is in the scratch by now
+    // Records of block blk from the fetched registers.  Every entry before the block is final by now: the previous
+    // block sits in the ring, older ones in the quantized-int scratch -- so every operand from outside the block is
+    // summed HERE, by 32 lanes at once, and the serial chain is left with the operands inside the block only.
     auto build = [&](uint32_t blk) {
       const uint32_t e0 = blk * kBlk, p = e0 + lane;
       const bool live = p < n;
@@ -253,12 +252,13 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
       }
       if (__any_sync(0xffffffffu, short_of_flags)) status = DCB_ERR_PRED;
       const int32_t dep[12] = {nd0.x, nd0.y, nd0.z, nd0.w, nd1.x, nd1.y, nd1.z, nd1.w, nd2.x, nd2.y, nd2.z, nd2.w};
-      const uint32_t far_limit = e0 >= kBlk ? e0 - kBlk : 0u;  // entries below it have left the ring
+      const uint32_t ring_limit = e0 >= kBlk ? e0 - kBlk : 0u;  // entries below it have left the ring
       int32_t k = 0;
-      uint32_t used = 0, slot = 0;
-      uint32_t addr[12];
+      uint32_t used = 0, n_in = 0;
+      uint32_t base[NCP];
 #pragma unroll
-      for (int i = 0; i < 12; ++i) addr[i] = a_zero;
+      for (int c = 0; c < NCP; ++c) base[c] = 0;
+      uint32_t w[3] = {0, 0, 0};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (keep & (1u << i)) {
@@ -266,44 +266,36 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
             const uint32_t e = (uint32_t)dep[3 * i + o];
-            uint32_t a;
+            const bool neg = o == 0;  // next + prev - opp (...ParallelogramDecoder.cs:84)
             if (e + 1u == p) {
-              k += (o == 0) ? -1 : 1;
-              a = a_zero;
-            } else if (e < far_limit) {
-              const uint32_t idx = (lane * 12u + slot * 3u + (uint32_t)o) * NCP;
+              k += neg ? -1 : 1;  // entry p - 1 rides in the chain lane's register
+            } else if (e >= e0) {
+              const uint32_t byte = (e - e0) | (neg ? 0x80u : 0u);
 #pragma unroll
-              for (int c = 0; c < NCP; ++c) s_far[idx + c] = qints[(uint64_t)e * NCP + c];
-              a = a_far + idx * 4u;
+              for (uint32_t s = 0; s < 3; ++s)
+                if ((n_in >> 2) == s) w[s] |= byte << (8u * (n_in & 3u));
+              ++n_in;
             } else {
-              a = a_ring + ((e & (kRing - 1u)) * NCP) * 4u;
-            }
-            // kept parallelograms are packed into the leading slots (written through selects: addr[] stays in registers)
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-              if ((uint32_t)s == slot) addr[3 * s + o] = a;
+              for (int c = 0; c < NCP; ++c) {
+                const uint32_t v = (uint32_t)(e >= ring_limit ? s_ring[(e & (kRing - 1u)) * NCP + c] : qints[(uint64_t)e * NCP + c]);
+                base[c] += neg ? 0u - v : v;
+              }
+            }
           }
-          ++slot;
         }
       }
       if (used == 0) {  // no parallelogram left: entry p - 1 (:105-108); entry 0 is predicted from zero (:43)
         used = 1;
         k = p > 0 ? 1 : 0;
       }
-      uint4 *ra = reinterpret_cast<uint4 *>(&s_addr[lane * 12u]);
-      ra[0] = make_uint4(addr[0], addr[1], addr[2], addr[3]);
-      ra[1] = make_uint4(addr[4], addr[5], addr[6], addr[7]);
-      ra[2] = make_uint4(addr[8], addr[9], addr[10], addr[11]);
-      s_meta[lane] = ((uint32_t)k & 0xFFu) | (used << 8);
+      s_meta[lane] = make_uint2(((uint32_t)k & 0xFFu) | (used << 8) | (n_in << 16), w[0]);
+      s_more[lane] = make_uint2(w[1], w[2]);
 #pragma unroll
-      for (int c = 0; c < NCP; ++c) s_cor[lane * NCP + c] = ncor[c];
-    };
-    auto load_ops = [&](uint32_t j, Operands &o) {  // the twelve operands of the block's entry j, this lane's component
-      const uint4 r0 = lds128(a_addr + j * 48u), r1 = lds128(a_addr + j * 48u + 16u), r2 = lds128(a_addr + j * 48u + 32u);
-      const uint32_t co = 4u * lane;
-      o.v[0] = lds32(r0.x + co); o.v[1] = lds32(r0.y + co); o.v[2] = lds32(r0.z + co); o.v[3] = lds32(r0.w + co);
-      o.v[4] = lds32(r1.x + co); o.v[5] = lds32(r1.y + co); o.v[6] = lds32(r1.z + co); o.v[7] = lds32(r1.w + co);
-      o.v[8] = lds32(r2.x + co); o.v[9] = lds32(r2.y + co); o.v[10] = lds32(r2.z + co); o.v[11] = lds32(r2.w + co);
+      for (int c = 0; c < NCP; ++c) {
+        s_base[lane * NCP + c] = (int32_t)base[c];
+        s_cor[lane * NCP + c] = ncor[c];
+      }
     };
 
     __syncwarp();
@@ -315,32 +307,37 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
       const uint32_t e0 = blk * kBlk, cnt = min(kBlk, n - e0);
       fetch(blk + 1);  // in flight while the chain runs
       if (lane < NCP) {
-        const uint32_t a_st = a_ring + ((e0 & (kRing - 1u)) * NCP + lane) * 4u;  // a block never wraps the ring
-        Operands cur, nxt;
-        load_ops(0, cur);
-        uint32_t meta = (uint32_t)lds32(a_meta);
-        int32_t co = lds32(a_cor + lane * 4u);
+        const uint32_t a_blk = a_ring + ((e0 & (kRing - 1u)) * NCP + lane) * 4u;  // this block in the ring (a block never wraps it)
+        uint2 meta = lds64(a_meta);
+        int32_t bs = lds32(a_base + lane * 4u), co = lds32(a_cor + lane * 4u);
         for (uint32_t j = 0; j < cnt; ++j) {
-          // operands of entry j + 1: everything up to entry j - 1 is in shared memory, entry j itself rides in k
-          const uint32_t j1 = j + 1 < cnt ? j + 1 : j;
-          load_ops(j1, nxt);
-          const uint32_t nmeta = (uint32_t)lds32(a_meta + 4u * j1);
-          const int32_t nco = lds32(a_cor + (j1 * NCP + lane) * 4u);
-          uint32_t sum = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sum += (uint32_t)cur.v[3 * i + 1] + (uint32_t)cur.v[3 * i + 2] - (uint32_t)cur.v[3 * i];
-          const int32_t kk = (int32_t)(int8_t)(meta & 0xFFu);
-          sum += (uint32_t)kk * (uint32_t)prev;
-          const int32_t pred = div_small((int32_t)sum, meta >> 8);
+          const uint32_t j1 = j + 1 < cnt ? j + 1 : j;  // record of the next entry: independent of the chain
+          const uint2 nmeta = lds64(a_meta + 8u * j1);
+          const int32_t nbs = lds32(a_base + (j1 * NCP + lane) * 4u), nco = lds32(a_cor + (j1 * NCP + lane) * 4u);
+          uint32_t sum = (uint32_t)bs + (uint32_t)(int32_t)(int8_t)(meta.x & 0xFFu) * (uint32_t)prev;
+          uint32_t n_in = (meta.x >> 16) & 15u;
+          if (n_in) {  // operands decoded earlier in this block (never entry j - 1: that one is in k)
+            uint32_t wv = meta.y;
+            const uint2 more = n_in > 4u ? lds64(a_more + 8u * j) : make_uint2(0u, 0u);
+            for (uint32_t i = 0; i < n_in; ++i) {
+              if (i == 4u) wv = more.x;
+              if (i == 8u) wv = more.y;
+              const uint32_t b = wv & 0xFFu;
+              wv >>= 8;
+              const uint32_t v = (uint32_t)lds32(a_blk + (b & 31u) * (4u * NCP));
+              sum += (b & 0x80u) ? 0u - v : v;
+            }
+          }
+          const int32_t pred = div_small((int32_t)sum, (meta.x >> 8) & 7u);
           prev = wrap_original(pred, co, pp.mn, pp.mx, pp.max_diff);
-          sts32(a_st + j * (4u * NCP), prev);
-          cur = nxt;
+          sts32(a_blk + j * (4u * NCP), prev);
           meta = nmeta;
+          bs = nbs;
           co = nco;
         }
       }
       __syncwarp();
-      // finished block -> quantized-int scratch (later gathers and the tex-coord predictor read it), dump, typed output
+      // finished block -> quantized-int scratch (later blocks and the tex-coord / normal predictors read it), dump, output
       if (lane < cnt) {
         const uint32_t p = e0 + lane;
         int32_t v[NCP];
@@ -365,15 +362,18 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
 
 }  // namespace
 
+cudaError_t dcb_launch_cmp_flags(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, const DevArenas &a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  cmp_flags_kernel<<<n, 128, 0, st>>>(a.in, d_streams, d_order, n, a.aux);
+  return cudaGetLastError();
+}
+
 cudaError_t dcb_launch_cmp(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
                            uint32_t dump, const DevArenas &a, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)max_entries + 127) / 128, 1u << 20));
   cmp_deps_kernel<<<dim3(gx, n > 65535u ? 65535u : n), 128, 0, st>>>(d_streams, d_order, n, a.maps, a.aux);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  cmp_flags_kernel<<<n, 128, 0, st>>>(a.in, d_streams, d_order, n, a.aux);
-  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
 #define DCB_CMP_LAUNCH(N)                                                                                  \
   case N:                                                                                                  \

@@ -207,12 +207,15 @@ __global__ void geo_normal_kernel(StreamDesc *streams, const uint32_t *__restric
 
 }  // namespace
 
+cudaError_t dcb_launch_geo_flips(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, const DevArenas &a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  geo_flips_kernel<<<n, 32, 0, st>>>(a.in, d_streams, d_order, n, a.aux);
+  return cudaGetLastError();
+}
+
 cudaError_t dcb_launch_geo_normal(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries, uint32_t dump,
                                   const DevArenas &a, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  geo_flips_kernel<<<n, 32, 0, st>>>(a.in, d_streams, d_order, n, a.aux);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
   const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)max_entries + 127) / 128, 1u << 20));
   const dim3 grid(gx, n > 65535u ? 65535u : n);
   if (dump)

@@ -793,6 +793,7 @@ __global__ void __launch_bounds__(32) oct_chain_kernel(StreamDesc *streams, cons
   if (slot >= n_streams) return;
   const StreamDesc &d = streams[order[slot]];
   if (d.status != DCB_OK) return;
+  if (d.recon != RECON_DELTA_OCT && d.recon != RECON_DELTA_OCT_CANON) return;  // geometric normals: geo_normal_kernel
   const uint32_t n = d.n_entries;
   PostParams pp;
   pp.load(d);
@@ -840,6 +841,7 @@ __global__ void oct_unit_kernel(StreamDesc *streams, const uint32_t *__restrict_
   for (uint32_t si = blockIdx.y; si < n_streams; si += gridDim.y) {
     const StreamDesc &d = streams[order[si]];
     if (d.status != DCB_OK) continue;
+    if (d.recon == RECON_GEO_OCT || d.recon == RECON_GEO_OCT_CANON) continue;  // geo_normal_kernel stores the unit vectors itself
     const int32_t max_value = (int32_t)((1u << d.q_bits) - 2u);
     const float scale = __fdiv_rn(2.0f, __int2float_rn(max_value));  // OctahedronToolBox.cs:19
     const int2 *st = reinterpret_cast<const int2 *>(aux + d.aux_off);
