@@ -239,50 +239,60 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
         if (np == c + 1u) my_pos = fpos[c] + (c + 1u) * (uint32_t)__popc(m & ((1u << lane) - 1u));
         fpos[c] += (c + 1u) * (uint32_t)__popc(m);
       }
-      bool short_of_flags = false;
-      uint32_t keep = 0;  // bit i: parallelogram i is not a crease edge
-      if (np) {
-        if (my_pos + np > have[np - 1u]) {
-          short_of_flags = true;  // :93
-        } else {
-          const uint8_t *f = sc.flags[np - 1u] + my_pos;
-          for (uint32_t i = 0; i < np; ++i)
-            if (f[i] == 0) keep |= 1u << i;
+      const int32_t dep[12] = {nd0.x, nd0.y, nd0.z, nd0.w, nd1.x, nd1.y, nd1.z, nd1.w, nd2.x, nd2.y, nd2.z, nd2.w};
+      const uint32_t ring_limit = e0 >= kBlk ? e0 - kBlk : 0u;  // entries below it have left the ring
+      // Every load of the block is issued before anything waits on one: the crease flags (their position needs the
+      // ballots only) and, per operand, one read of the scratch and one of the ring -- at a harmless address when the
+      // operand lives elsewhere -- so that a block costs one global-memory latency, not one per operand.
+      const uint32_t ctx = np ? np - 1u : 0u;
+      const bool short_of_flags = np && my_pos + np > have[ctx];  // :93
+      const uint8_t *f = sc.flags[0] + (uint64_t)n * (ctx * (ctx + 1u) / 2u) + my_pos;
+      uint32_t fl[4];
+#pragma unroll
+      for (uint32_t i = 0; i < 4; ++i) fl[i] = f[(np && !short_of_flags) ? min(i, np - 1u) : 0u];
+      uint32_t kind[12];  // 0 unused | 1 entry p - 1 | 2 inside the block | 3 ring | 4 scratch
+      uint32_t far_v[12][NCP], ring_v[12][NCP];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const uint32_t e = (uint32_t)dep[i];
+        const bool valid = (uint32_t)(i / 3) < np;
+        kind[i] = !valid ? 0u : (e + 1u == p) ? 1u : (e >= e0) ? 2u : (e >= ring_limit) ? 3u : 4u;
+        const uint64_t g = kind[i] == 4u ? (uint64_t)e * NCP : 0ull;
+        const uint32_t r = kind[i] == 3u ? (e & (kRing - 1u)) * NCP : 0u;
+#pragma unroll
+        for (int c = 0; c < NCP; ++c) {
+          far_v[i][c] = (uint32_t)__ldcg(qints + g + c);
+          ring_v[i][c] = (uint32_t)s_ring[r + c];
         }
       }
       if (__any_sync(0xffffffffu, short_of_flags)) status = DCB_ERR_PRED;
-      const int32_t dep[12] = {nd0.x, nd0.y, nd0.z, nd0.w, nd1.x, nd1.y, nd1.z, nd1.w, nd2.x, nd2.y, nd2.z, nd2.w};
-      const uint32_t ring_limit = e0 >= kBlk ? e0 - kBlk : 0u;  // entries below it have left the ring
+      uint32_t keep = 0;  // bit i: parallelogram i is not a crease edge
+#pragma unroll
+      for (uint32_t i = 0; i < 4; ++i)
+        if (i < np && !short_of_flags && fl[i] == 0) keep |= 1u << i;
       int32_t k = 0;
-      uint32_t used = 0, n_in = 0;
+      uint32_t used = (uint32_t)__popc(keep), n_in = 0;
       uint32_t base[NCP];
 #pragma unroll
       for (int c = 0; c < NCP; ++c) base[c] = 0;
       uint32_t w[3] = {0, 0, 0};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (keep & (1u << i)) {
-          ++used;
+      for (int i = 0; i < 12; ++i) {
+        const bool on = (keep >> (i / 3)) & 1u;
+        const bool neg = (i % 3) == 0;  // next + prev - opp (...ParallelogramDecoder.cs:84)
+        const uint32_t kd = on ? kind[i] : 0u;
+        if (kd == 1u) k += neg ? -1 : 1;  // entry p - 1 rides in the chain lane's register
+        if (kd == 2u) {
+          const uint32_t byte = ((uint32_t)dep[i] - e0) | (neg ? 0x80u : 0u);
 #pragma unroll
-          for (int o = 0; o < 3; ++o) {
-            const uint32_t e = (uint32_t)dep[3 * i + o];
-            const bool neg = o == 0;  // next + prev - opp (...ParallelogramDecoder.cs:84)
-            if (e + 1u == p) {
-              k += neg ? -1 : 1;  // entry p - 1 rides in the chain lane's register
-            } else if (e >= e0) {
-              const uint32_t byte = (e - e0) | (neg ? 0x80u : 0u);
+          for (uint32_t sl = 0; sl < 3; ++sl)
+            if ((n_in >> 2) == sl) w[sl] |= byte << (8u * (n_in & 3u));
+          ++n_in;
+        }
 #pragma unroll
-              for (uint32_t s = 0; s < 3; ++s)
-                if ((n_in >> 2) == s) w[s] |= byte << (8u * (n_in & 3u));
-              ++n_in;
-            } else {
-#pragma unroll
-              for (int c = 0; c < NCP; ++c) {
-                const uint32_t v = (uint32_t)(e >= ring_limit ? s_ring[(e & (kRing - 1u)) * NCP + c] : qints[(uint64_t)e * NCP + c]);
-                base[c] += neg ? 0u - v : v;
-              }
-            }
-          }
+        for (int c = 0; c < NCP; ++c) {
+          const uint32_t v = kd == 4u ? far_v[i][c] : kd == 3u ? ring_v[i][c] : 0u;
+          base[c] += neg ? 0u - v : v;
         }
       }
       if (used == 0) {  // no parallelogram left: entry p - 1 (:105-108); entry 0 is predicted from zero (:43)
