@@ -12,14 +12,13 @@
 //
 //   cmp_deps_kernel   the operand entries of every parallelogram of every entry: connectivity only, point-parallel
 //   cmp_flags_kernel  the four rABS-coded flag sequences of a stream, one warp per context (RAnsBitDecoder.cs:26-30)
-//   cmp_chain_kernel  the recurrence, one warp per stream over blocks of 32 entries.  All lanes build the block's
-//                     records: flag positions by ballot, kept parallelograms, and -- because every entry before the
-//                     block is final by then (previous block in a shared-memory ring, older ones in the quantized-int
-//                     scratch) -- the SUM of all operands from outside the block, per component.  Lanes 0..NCP-1 then
-//                     walk the chain, one component each: pre-summed base + k * value(p - 1) (operands that ARE entry
-//                     p - 1 never leave the register) + the few operands inside the block, division by 1..4 by
-//                     select, wrap.  (First version: 12 operand loads per entry, 164 ms per million entries; this
-//                     one: see profiles/.)
+//   cmp_chain_kernel  the recurrence, two warps per stream over blocks of 32 entries.  The helper warp builds the next
+//                     block's records while the chain warp decodes the current one: flag positions by ballot, kept
+//                     parallelograms, and the SUM of all operands that are final by then (two blocks back in a
+//                     shared-memory ring, older ones in the quantized-int scratch), per component; it also stores the
+//                     finished block.  Lanes 0..NCP-1 of the chain warp walk the chain, one component each: pre-summed
+//                     base + k * value(p - 1) (operands that ARE entry p - 1 never leave the register) + the near
+//                     operands out of the ring, division by 1..4 by shift / multiply-high, wrap.
 // Product code: nothing here touches oracle/.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -158,34 +157,39 @@ __device__ __forceinline__ void sts32(uint32_t a, int32_t v) {
   asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory");
 }
 
-// truncating signed division by 1..4 (:112): by select, no divide
-__device__ __forceinline__ int32_t div_small(int32_t s, uint32_t used) {
-  const int32_t d2 = (s + (int32_t)((uint32_t)s >> 31)) >> 1;
-  const int32_t d4 = (s + ((s >> 31) & 3)) >> 2;
-  const int32_t d3 = s / 3;
-  return used == 1u ? s : used == 2u ? d2 : used == 3u ? d3 : d4;
+// truncating signed division by 1..4 (:112) without a divide or a branch: powers of two by a biased shift (mask and
+// shift come with the entry's record), 3 by a multiply-high
+__device__ __forceinline__ int32_t div_small(int32_t s, uint32_t mask, uint32_t shift, bool by3) {
+  const int32_t sign = s >> 31;
+  const int32_t qp = (s + (sign & (int32_t)mask)) >> shift;
+  const int32_t q3 = __mulhi(s, 0x55555556) - sign;  // floor(s / 3) + (s < 0)
+  int32_t q;
+  asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.s32 %0, %1, %2, p; }" : "=r"(q) : "r"(q3), "r"(qp), "r"((int)by3));
+  return q;
 }
 
+// Two warps per stream, in lock step over blocks of 32 entries (one __syncthreads per block):
+//   warp 0  the chain of block b (lanes 0..NCP-1, one component each)
+//   warp 1  stores the finished block b - 1, builds the records of block b + 1, fetches the dependencies of block b + 2
+// Operands of an entry of block b + 1, by age: entry p - 1 -> coefficient k (the value never leaves the chain lane's
+// register); blocks b and b + 1 -> "near" list, read from the 64-entry ring by the chain; block b - 1 (final, still in
+// the ring) and older ones (final, in the quantized-int scratch) -> summed per component by the builder.
 template <int NCP, bool DUMP>
-__global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
+__global__ void __launch_bounds__(64) cmp_chain_kernel(StreamDesc *streams, const uint32_t *__restrict__ order,
                                                        uint32_t n_streams, uint8_t *__restrict__ out,
                                                        uint8_t *__restrict__ dbg, uint8_t *__restrict__ aux, uint32_t dump) {
-  // per entry of the block: {meta, first four in-block operands}, eight more in-block operands, per component the
-  // pre-summed operands from outside the block and the correction
-  __shared__ __align__(8) uint2 s_meta[kBlk];   // x: (k & 0xFF) | used << 8 | n_in << 16   y: in-block operands 0..3
-  __shared__ __align__(8) uint2 s_more[kBlk];   // in-block operands 4..11 (one byte each: index in block | 0x80 = subtract)
-  __shared__ int32_t s_base[kBlk * NCP];
-  __shared__ int32_t s_cor[kBlk * NCP];
+  // x: (k & 0xFF) | bias mask << 8 | shift << 12 | by3 << 14 | n_near << 16   y: near operands 0..3
+  __shared__ __align__(8) uint2 s_meta[2][kBlk];
+  __shared__ __align__(8) uint2 s_more[2][kBlk];  // near operands 4..11 (one byte each: ring index | 0x80 = subtract)
+  __shared__ int32_t s_base[2][kBlk * NCP];
+  __shared__ int32_t s_cor[2][kBlk * NCP];
   __shared__ int32_t s_ring[kRing * NCP];
-  const uint32_t lane = threadIdx.x;
+  __shared__ int s_status[2];  // written by the helper while it builds in iteration i: word i & 1; read by all at the top of i + 1
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t a_ring = (uint32_t)__cvta_generic_to_shared(s_ring);
-  const uint32_t a_meta = (uint32_t)__cvta_generic_to_shared(s_meta);
-  const uint32_t a_more = (uint32_t)__cvta_generic_to_shared(s_more);
-  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(s_base);
-  const uint32_t a_cor = (uint32_t)__cvta_generic_to_shared(s_cor);
   for (uint32_t si = blockIdx.x; si < n_streams; si += gridDim.x) {
     StreamDesc &d = streams[order[si]];
-    if (d.status != DCB_OK) continue;
+    if (d.status != DCB_OK) continue;  // uniform over the CTA
     const uint32_t n = d.n_entries;
     if (n == 0) continue;
     PostParams pp;
@@ -196,15 +200,14 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
     int32_t *qints = reinterpret_cast<int32_t *>(aux + d.aux_off) + (uint64_t)n * NCP;
     const CmpScratch sc(aux, d);
     const uint32_t n_blocks = (n + kBlk - 1) / kBlk;
-    uint32_t fpos[4] = {0, 0, 0, 0};  // flags consumed per context (uniform)
+    uint32_t fpos[4] = {0, 0, 0, 0};  // flags consumed per context (uniform over the helper warp)
     uint32_t have[4];  // flags decoded per context (cmp_flags_kernel stops at the most an attribute can consume)
 #pragma unroll
     for (uint32_t c = 0; c < 4; ++c) {
       const unsigned long long cap = (unsigned long long)(c + 1u) * n, got = d.n_crease[c];
       have[c] = (uint32_t)(got < cap ? got : cap);
     }
-    int status = DCB_OK;
-    // registers holding the next block's dependencies (issued before the chain of the current block runs)
+    // helper warp: registers holding a block's dependencies between its fetch and its build
     int4 nd0, nd1, nd2;
     uint32_t ncnt = 0;
     int32_t ncor[NCP];
@@ -224,11 +227,8 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
         for (int c = 0; c < NCP; ++c) ncor[c] = corr[(uint64_t)p * NCP + c];
       }
     };
-    // Records of block blk from the fetched registers.  Every entry before the block is final by now: the previous
-    // block sits in the ring, older ones in the quantized-int scratch -- so every operand from outside the block is
-    // summed HERE, by 32 lanes at once, and the serial chain is left with the operands inside the block only.
-    auto build = [&](uint32_t blk) {
-      const uint32_t e0 = blk * kBlk, p = e0 + lane;
+    auto build = [&](uint32_t blk, uint32_t iter) {  // helper warp, while the chain warp decodes block blk - 1
+      const uint32_t e0 = blk * kBlk, p = e0 + lane, buf = blk & 1u;
       const bool live = p < n;
       const uint32_t np = live ? ncnt : 0u;
       // flag positions: entries with np parallelograms draw np flags from context np - 1, in entry order (:89-92)
@@ -240,114 +240,81 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
         fpos[c] += (c + 1u) * (uint32_t)__popc(m);
       }
       const int32_t dep[12] = {nd0.x, nd0.y, nd0.z, nd0.w, nd1.x, nd1.y, nd1.z, nd1.w, nd2.x, nd2.y, nd2.z, nd2.w};
-      const uint32_t ring_limit = e0 >= kBlk ? e0 - kBlk : 0u;  // entries below it have left the ring
-      // Every load of the block is issued before anything waits on one: the crease flags (their position needs the
-      // ballots only) and, per operand, one read of the scratch and one of the ring -- at a harmless address when the
-      // operand lives elsewhere -- so that a block costs one global-memory latency, not one per operand.
+      const uint32_t near_limit = e0 >= kBlk ? e0 - kBlk : 0u;        // block blk - 1 is being decoded right now
+      const uint32_t ring_limit = e0 >= 2u * kBlk ? e0 - 2u * kBlk : 0u;  // block blk - 2 is final and still in the ring
       const uint32_t ctx = np ? np - 1u : 0u;
       const bool short_of_flags = np && my_pos + np > have[ctx];  // :93
       const uint8_t *f = sc.flags[0] + (uint64_t)n * (ctx * (ctx + 1u) / 2u) + my_pos;
       uint32_t fl[4];
 #pragma unroll
       for (uint32_t i = 0; i < 4; ++i) fl[i] = f[(np && !short_of_flags) ? min(i, np - 1u) : 0u];
-      uint32_t kind[12];  // 0 unused | 1 entry p - 1 | 2 inside the block | 3 ring | 4 scratch
-      uint32_t far_v[12][NCP], ring_v[12][NCP];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const uint32_t e = (uint32_t)dep[i];
-        const bool valid = (uint32_t)(i / 3) < np;
-        kind[i] = !valid ? 0u : (e + 1u == p) ? 1u : (e >= e0) ? 2u : (e >= ring_limit) ? 3u : 4u;
-        const uint64_t g = kind[i] == 4u ? (uint64_t)e * NCP : 0ull;
-        const uint32_t r = kind[i] == 3u ? (e & (kRing - 1u)) * NCP : 0u;
-#pragma unroll
-        for (int c = 0; c < NCP; ++c) {
-          far_v[i][c] = (uint32_t)__ldcg(qints + g + c);
-          ring_v[i][c] = (uint32_t)s_ring[r + c];
-        }
-      }
-      if (__any_sync(0xffffffffu, short_of_flags)) status = DCB_ERR_PRED;
-      uint32_t keep = 0;  // bit i: parallelogram i is not a crease edge
-#pragma unroll
-      for (uint32_t i = 0; i < 4; ++i)
-        if (i < np && !short_of_flags && fl[i] == 0) keep |= 1u << i;
+      if (__any_sync(0xffffffffu, short_of_flags) && lane == 0) s_status[iter & 1u] = DCB_ERR_PRED;
       int32_t k = 0;
-      uint32_t used = (uint32_t)__popc(keep), n_in = 0;
+      uint32_t n_near = 0;
       uint32_t base[NCP];
 #pragma unroll
       for (int c = 0; c < NCP; ++c) base[c] = 0;
       uint32_t w[3] = {0, 0, 0};
+      uint32_t keep = 0;  // bit i: parallelogram i is not a crease edge
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const bool on = (keep >> (i / 3)) & 1u;
-        const bool neg = (i % 3) == 0;  // next + prev - opp (...ParallelogramDecoder.cs:84)
-        const uint32_t kd = on ? kind[i] : 0u;
-        if (kd == 1u) k += neg ? -1 : 1;  // entry p - 1 rides in the chain lane's register
-        if (kd == 2u) {
-          const uint32_t byte = ((uint32_t)dep[i] - e0) | (neg ? 0x80u : 0u);
+      for (uint32_t i = 0; i < 4; ++i)
+        if (i < np && !short_of_flags && fl[i] == 0) keep |= 1u << i;
+      const uint32_t used = (uint32_t)__popc(keep);
+      // two parallelograms at a time; the second pair only when some entry of the block has more than two
+      auto pair = [&](int first) {
+        uint32_t kind[6];  // 0 unused | 1 entry p - 1 | 2 near | 3 ring | 4 scratch
+        uint32_t far_v[6][NCP], ring_v[6][NCP];
 #pragma unroll
-          for (uint32_t sl = 0; sl < 3; ++sl)
-            if ((n_in >> 2) == sl) w[sl] |= byte << (8u * (n_in & 3u));
-          ++n_in;
+        for (int i = 0; i < 6; ++i) {
+          const int slot = first + i / 3;
+          const uint32_t e = (uint32_t)dep[3 * first + i];
+          const bool on = (keep >> slot) & 1u;
+          kind[i] = !on ? 0u : (e + 1u == p) ? 1u : (e >= near_limit) ? 2u : (e >= ring_limit) ? 3u : 4u;
+          const uint64_t g = kind[i] == 4u ? (uint64_t)e * NCP : 0ull;
+          const uint32_t r = kind[i] == 3u ? (e & (kRing - 1u)) * NCP : 0u;
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) {
+            far_v[i][c] = (uint32_t)__ldcg(qints + g + c);
+            ring_v[i][c] = (uint32_t)s_ring[r + c];
+          }
         }
 #pragma unroll
-        for (int c = 0; c < NCP; ++c) {
-          const uint32_t v = kd == 4u ? far_v[i][c] : kd == 3u ? ring_v[i][c] : 0u;
-          base[c] += neg ? 0u - v : v;
+        for (int i = 0; i < 6; ++i) {
+          const bool neg = (i % 3) == 0;  // next + prev - opp (...ParallelogramDecoder.cs:84)
+          const uint32_t kd = kind[i];
+          if (kd == 1u) k += neg ? -1 : 1;
+          if (kd == 2u) {
+            const uint32_t byte = ((uint32_t)dep[3 * first + i] & (kRing - 1u)) | (neg ? 0x80u : 0u);
+#pragma unroll
+            for (uint32_t sl = 0; sl < 3; ++sl)
+              if ((n_near >> 2) == sl) w[sl] |= byte << (8u * (n_near & 3u));
+            ++n_near;
+          }
+#pragma unroll
+          for (int c = 0; c < NCP; ++c) {
+            const uint32_t v = kd == 4u ? far_v[i][c] : kd == 3u ? ring_v[i][c] : 0u;
+            base[c] += neg ? 0u - v : v;
+          }
         }
-      }
+      };
+      pair(0);
+      if (__any_sync(0xffffffffu, np > 2u)) pair(2);
+      uint32_t dv = used;
       if (used == 0) {  // no parallelogram left: entry p - 1 (:105-108); entry 0 is predicted from zero (:43)
-        used = 1;
+        dv = 1;
         k = p > 0 ? 1 : 0;
       }
-      s_meta[lane] = make_uint2(((uint32_t)k & 0xFFu) | (used << 8) | (n_in << 16), w[0]);
-      s_more[lane] = make_uint2(w[1], w[2]);
+      const uint32_t mask = dv == 2u ? 1u : dv == 4u ? 3u : 0u, shift = dv == 2u ? 1u : dv == 4u ? 2u : 0u;
+      s_meta[buf][lane] = make_uint2(((uint32_t)k & 0xFFu) | (mask << 8) | (shift << 12) | ((dv == 3u ? 1u : 0u) << 14) | (n_near << 16), w[0]);
+      s_more[buf][lane] = make_uint2(w[1], w[2]);
 #pragma unroll
       for (int c = 0; c < NCP; ++c) {
-        s_base[lane * NCP + c] = (int32_t)base[c];
-        s_cor[lane * NCP + c] = ncor[c];
+        s_base[buf][lane * NCP + c] = (int32_t)base[c];
+        s_cor[buf][lane * NCP + c] = ncor[c];
       }
     };
-
-    __syncwarp();
-    fetch(0);
-    build(0);
-    __syncwarp();
-    int32_t prev = 0;  // chain lanes: value of entry p - 1, component `lane`
-    for (uint32_t blk = 0; blk < n_blocks && status == DCB_OK; ++blk) {
-      const uint32_t e0 = blk * kBlk, cnt = min(kBlk, n - e0);
-      fetch(blk + 1);  // in flight while the chain runs
-      if (lane < NCP) {
-        const uint32_t a_blk = a_ring + ((e0 & (kRing - 1u)) * NCP + lane) * 4u;  // this block in the ring (a block never wraps it)
-        uint2 meta = lds64(a_meta);
-        int32_t bs = lds32(a_base + lane * 4u), co = lds32(a_cor + lane * 4u);
-        for (uint32_t j = 0; j < cnt; ++j) {
-          const uint32_t j1 = j + 1 < cnt ? j + 1 : j;  // record of the next entry: independent of the chain
-          const uint2 nmeta = lds64(a_meta + 8u * j1);
-          const int32_t nbs = lds32(a_base + (j1 * NCP + lane) * 4u), nco = lds32(a_cor + (j1 * NCP + lane) * 4u);
-          uint32_t sum = (uint32_t)bs + (uint32_t)(int32_t)(int8_t)(meta.x & 0xFFu) * (uint32_t)prev;
-          uint32_t n_in = (meta.x >> 16) & 15u;
-          if (n_in) {  // operands decoded earlier in this block (never entry j - 1: that one is in k)
-            uint32_t wv = meta.y;
-            const uint2 more = n_in > 4u ? lds64(a_more + 8u * j) : make_uint2(0u, 0u);
-            for (uint32_t i = 0; i < n_in; ++i) {
-              if (i == 4u) wv = more.x;
-              if (i == 8u) wv = more.y;
-              const uint32_t b = wv & 0xFFu;
-              wv >>= 8;
-              const uint32_t v = (uint32_t)lds32(a_blk + (b & 31u) * (4u * NCP));
-              sum += (b & 0x80u) ? 0u - v : v;
-            }
-          }
-          const int32_t pred = div_small((int32_t)sum, (meta.x >> 8) & 7u);
-          prev = wrap_original(pred, co, pp.mn, pp.mx, pp.max_diff);
-          sts32(a_blk + j * (4u * NCP), prev);
-          meta = nmeta;
-          bs = nbs;
-          co = nco;
-        }
-      }
-      __syncwarp();
-      // finished block -> quantized-int scratch (later blocks and the tex-coord / normal predictors read it), dump, output
+    auto output = [&](uint32_t blk) {  // finished block -> quantized-int scratch (later blocks and the tex-coord / normal
+      const uint32_t e0 = blk * kBlk, cnt = min(kBlk, n - e0);  // predictors read it), dump, typed output
       if (lane < cnt) {
         const uint32_t p = e0 + lane;
         int32_t v[NCP];
@@ -361,12 +328,72 @@ __global__ void __launch_bounds__(32) cmp_chain_kernel(StreamDesc *streams, cons
         }
         store_entry<NCP>(pp, pp.store, pp.dsize, optr, p, v);
       }
-      __syncwarp();
-      if (blk + 1 < n_blocks) build(blk + 1);
-      __syncwarp();
+    };
+
+    __syncthreads();  // the previous stream's last block has left shared memory
+    if (threadIdx.x < 2) s_status[threadIdx.x] = DCB_OK;
+    __syncthreads();
+    if (warp == 1) {
+      fetch(0);
+      build(0, 1u);  // "iteration -1"
+      fetch(1);
     }
-    if (status != DCB_OK && lane == 0) d.status = status;
-    __syncwarp();
+    __syncthreads();
+    int32_t prev = 0;  // chain lanes: value of entry p - 1, component `lane`
+    uint32_t done_blocks = 0;
+    for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+      if (s_status[(blk + 1u) & 1u] != DCB_OK) break;  // uniform: written before the last barrier, not rewritten before the next
+      const uint32_t e0 = blk * kBlk, cnt = min(kBlk, n - e0), buf = blk & 1u;
+      if (warp == 0) {
+        if (lane < NCP) {
+          const uint32_t a_lane = a_ring + lane * 4u;
+          const uint32_t a_st = a_lane + (e0 & (kRing - 1u)) * (4u * NCP);  // a block never wraps the ring
+          const uint32_t a_meta = (uint32_t)__cvta_generic_to_shared(s_meta[buf]);
+          const uint32_t a_more = (uint32_t)__cvta_generic_to_shared(s_more[buf]);
+          const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(s_base[buf]) + lane * 4u;
+          const uint32_t a_cor = (uint32_t)__cvta_generic_to_shared(s_cor[buf]) + lane * 4u;
+          // records are independent of the chain: two entries ahead
+          uint2 m0 = lds64(a_meta), m1 = lds64(a_meta + 8u * (cnt > 1u ? 1u : 0u));
+          int32_t b0 = lds32(a_base), b1 = lds32(a_base + (cnt > 1u ? 1u : 0u) * (4u * NCP));
+          int32_t c0 = lds32(a_cor), c1 = lds32(a_cor + (cnt > 1u ? 1u : 0u) * (4u * NCP));
+          for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t j2 = j + 2 < cnt ? j + 2 : j;  // harmless re-read at the end of the block
+            const uint2 m2 = lds64(a_meta + 8u * j2);
+            const int32_t b2 = lds32(a_base + j2 * (4u * NCP)), c2 = lds32(a_cor + j2 * (4u * NCP));
+            uint32_t sum = (uint32_t)b0 + (uint32_t)(int32_t)(int8_t)(m0.x & 0xFFu) * (uint32_t)prev;
+            const uint32_t n_near = (m0.x >> 16) & 15u;
+            if (n_near) {  // operands decoded in this block or the one before (never entry j - 1: that one is in k)
+              uint32_t wv = m0.y;
+              const uint2 more = n_near > 4u ? lds64(a_more + 8u * j) : make_uint2(0u, 0u);
+              for (uint32_t i = 0; i < n_near; ++i) {
+                if (i == 4u) wv = more.x;
+                if (i == 8u) wv = more.y;
+                const uint32_t b = wv & 0xFFu;
+                wv >>= 8;
+                const uint32_t v = (uint32_t)lds32(a_lane + (b & (kRing - 1u)) * (4u * NCP));
+                sum += (b & 0x80u) ? 0u - v : v;
+              }
+            }
+            const int32_t pred = div_small((int32_t)sum, (m0.x >> 8) & 15u, (m0.x >> 12) & 3u, (m0.x >> 14) & 1u);
+            prev = wrap_original(pred, c0, pp.mn, pp.mx, pp.max_diff);
+            sts32(a_st + j * (4u * NCP), prev);
+            m0 = m1; m1 = m2;
+            b0 = b1; b1 = b2;
+            c0 = c1; c1 = c2;
+          }
+        }
+      } else {
+        if (blk > 0) output(blk - 1);
+        __syncwarp();
+        if (blk + 1 < n_blocks) build(blk + 1, blk);
+        fetch(blk + 2);
+      }
+      done_blocks = blk + 1;
+      __syncthreads();
+    }
+    const int status = s_status[0] != DCB_OK ? s_status[0] : s_status[1];
+    if (status == DCB_OK && warp == 1 && done_blocks == n_blocks) output(n_blocks - 1);
+    if (status != DCB_OK && threadIdx.x == 0) d.status = status;
   }
 }
 
@@ -388,9 +415,9 @@ cudaError_t dcb_launch_cmp(StreamDesc *d_streams, const uint32_t *d_order, uint3
 #define DCB_CMP_LAUNCH(N)                                                                                  \
   case N:                                                                                                  \
     if (dump)                                                                                              \
-      cmp_chain_kernel<N, true><<<n, 32, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump);       \
+      cmp_chain_kernel<N, true><<<n, 64, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump);       \
     else                                                                                                   \
-      cmp_chain_kernel<N, false><<<n, 32, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump);      \
+      cmp_chain_kernel<N, false><<<n, 64, 0, st>>>(d_streams, d_order, n, a.out, a.dbg, a.aux, dump);      \
     break;
   switch (ncp) {
     DCB_CMP_LAUNCH(1)
