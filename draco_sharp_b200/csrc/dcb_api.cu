@@ -1693,26 +1693,39 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
     }
     stats.n_streams += (int32_t)n;
   }
-  auto launch_flag_kernels = [&](cudaStream_t fs) -> int {
+  auto launch_flag_kernels = [&](cudaStream_t fs, cudaStream_t gs) -> int {
     for (int n = 1; n <= 4; ++n)
       if (!cmp[n].order.empty()) {
         CUDA_TRY(dcb_launch_cmp_flags(sh.d_streams, sh.d_order + cmp[n].order_off, (uint32_t)cmp[n].order.size(), A, fs));
         stats.n_launches++;
       }
     if (!geo.order.empty()) {
-      CUDA_TRY(dcb_launch_geo_flips(sh.d_streams, sh.d_order + geo.order_off, (uint32_t)geo.order.size(), A, fs));
+      CUDA_TRY(dcb_launch_geo_flips(sh.d_streams, sh.d_order + geo.order_off, (uint32_t)geo.order.size(), A, gs));
       stats.n_launches++;
     }
     return DCB_OK;
   };
-  if (flags_early) {  // issued behind the rANS launches so that those get their SMs first
-    int rcf = launch_flag_kernels(ctx->side[dev_index][2]);
+  if (flags_early) {  // issued behind the rANS launches so that those get their SMs first; crease flags and flip bits on a
+    int rcf = launch_flag_kernels(ctx->side[dev_index][2], ctx->side[dev_index][1]);  // stream each (serial chains both)
     if (rcf) return rcf;
-    side_used[2] = true;
+    side_used[2] = side_used[1] = true;
   }
   {  // mesh maps: behind the rANS launches (their chains hide the copy), in front of the parallelogram kernels
     int rcm = issue_maps_copy(ctx, b, sh, dev_index);
     if (rcm) return rcm;
+  }
+  auto launch_cmp_deps = [&](cudaStream_t ds) -> int {
+    for (int n = 1; n <= 4; ++n)
+      if (!cmp[n].order.empty()) {
+        CUDA_TRY(dcb_launch_cmp_deps(sh.d_streams, sh.d_order + cmp[n].order_off, (uint32_t)cmp[n].order.size(), cmp[n].max_entries, A, ds));
+        stats.n_launches++;
+      }
+    return DCB_OK;
+  };
+  if (flags_early) {  // the dependency lists need the maps only: next to the rANS kernels as well, behind the maps' copy
+    CUDA_TRY(cudaStreamWaitEvent(ctx->side[dev_index][2], ctx->maps_ev[dev_index], 0));
+    int rcd = launch_cmp_deps(ctx->side[dev_index][2]);
+    if (rcd) return rcd;
   }
   for (int k = 0; k < 3; ++k)
     if (side_used[k]) {
@@ -1781,14 +1794,15 @@ int decode_shard(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index, uint8_t *
       stats.n_launches += 2;
     }
   if (flag_kernels && !flags_early) {
-    int rcf = launch_flag_kernels(st);
+    int rcf = launch_flag_kernels(st, st);
+    if (rcf) return rcf;
+    rcf = launch_cmp_deps(st);
     if (rcf) return rcf;
   }
   for (int n = 1; n <= 4; ++n)
-    if (!cmp[n].order.empty()) {  // constrained multi-parallelogram: dependencies, chain
-      CUDA_TRY(dcb_launch_cmp(sh.d_streams, sh.d_order + cmp[n].order_off, (uint32_t)cmp[n].order.size(), n, cmp[n].max_entries,
-                              dump, A, st));
-      stats.n_launches += 2;
+    if (!cmp[n].order.empty()) {  // constrained multi-parallelogram: the chain
+      CUDA_TRY(dcb_launch_cmp(sh.d_streams, sh.d_order + cmp[n].order_off, (uint32_t)cmp[n].order.size(), n, dump, A, st));
+      stats.n_launches++;
     }
   if (!tex.order.empty()) {  // behind the parallelogram kernels: the predictor reads the decoded positions of its parent
     CUDA_TRY(dcb_launch_tex(sh.d_streams, sh.d_order + tex.order_off, (uint32_t)tex.order.size(), tex.max_entries, dump, A, st));

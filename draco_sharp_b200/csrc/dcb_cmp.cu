@@ -405,13 +405,17 @@ cudaError_t dcb_launch_cmp_flags(StreamDesc *d_streams, const uint32_t *d_order,
   return cudaGetLastError();
 }
 
-cudaError_t dcb_launch_cmp(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
-                           uint32_t dump, const DevArenas &a, cudaStream_t st) {
+cudaError_t dcb_launch_cmp_deps(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries, const DevArenas &a,
+                                cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)max_entries + 127) / 128, 1u << 20));
   cmp_deps_kernel<<<dim3(gx, n > 65535u ? 65535u : n), 128, 0, st>>>(d_streams, d_order, n, a.maps, a.aux);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_cmp(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t dump, const DevArenas &a,
+                           cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
 #define DCB_CMP_LAUNCH(N)                                                                                  \
   case N:                                                                                                  \
     if (dump)                                                                                              \

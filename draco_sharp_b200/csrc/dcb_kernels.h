@@ -70,8 +70,10 @@ cudaError_t dcb_launch_para(StreamDesc *d_streams, const uint32_t *d_order, uint
 // MeshPredictionSchemeConstrainedMultiParallelogramDecoder (dcb_cmp.cu): cmp_flags_kernel (rABS crease flags, one warp per
 // context; needs the bitstream only) | cmp_deps_kernel (point-parallel) + cmp_chain_kernel (one warp per stream)
 cudaError_t dcb_launch_cmp_flags(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, const DevArenas &a, cudaStream_t st);
-cudaError_t dcb_launch_cmp(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t max_entries,
-                           uint32_t dump, const DevArenas &a, cudaStream_t st);
+cudaError_t dcb_launch_cmp_deps(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, uint32_t max_entries, const DevArenas &a,
+                                cudaStream_t st);
+cudaError_t dcb_launch_cmp(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, int ncp, uint32_t dump, const DevArenas &a,
+                           cudaStream_t st);
 // MeshPredictionSchemeGeometricNormalDecoder (dcb_geonormal.cu): geo_flips_kernel (rABS flip bits, one warp per stream; needs
 // the bitstream only) | geo_normal_kernel (point-parallel: prediction from the parent's decoded positions, octahedron transform, unit vectors)
 cudaError_t dcb_launch_geo_flips(StreamDesc *d_streams, const uint32_t *d_order, uint32_t n, const DevArenas &a, cudaStream_t st);
