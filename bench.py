@@ -490,8 +490,10 @@ def run_mesh(args, rank, local_rank, world):
                          "algorithmic_bytes_per_step": algo_bytes,
                          "stage_ms": {"raw_fused": stats.ms_raw, "tag_rans": stats.ms_tag, "par_post": stats.ms_par,
                                       "parallelogram": stats.ms_para, "all_kernels": stats.ms_total},
-                         "note": "one serial rANS chain of %d symbols and one serial parallelogram chain per mesh "
-                                 "(dependency depth of a depth-first traversal ~ 0.86 n): %d chains in flight" % (3 * nv, n_bufs)},
+                         "stage_ms_what": "parallelogram = the whole mesh-prediction stage behind the rANS kernels (parallelogram / "
+                                          "constrained multi-parallelogram / tex-coord / geometric-normal kernels), one timed span",
+                         "note": "one serial rANS chain of %d symbols and one serial prediction chain per mesh attribute "
+                                 "(dependency depth of a depth-first traversal ~ 0.86 n): %d meshes in flight" % (3 * nv, n_bufs)},
             "e2e": {"value": total_points / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + maps_bytes,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_t, "steps": args.e2e_steps,
                     "what": "dcb_index + dcb_set_mesh_maps + dcb_index_finish + dcb_decode: host indexing, H2D of buffers and maps, kernels, D2H"},
