@@ -328,6 +328,45 @@ def test_geometric_normal_behind_cmp_positions_on_a_grid(gpu_decoder):
     batch.free()
 
 
+@pytest.mark.parametrize("kind", ["cmp", "geo"])
+def test_mesh_predictor_status_parity_on_malformed_buffers(gpu_decoder, kind):
+    """Truncated and bit-flipped constrained-multi-parallelogram / geometric-normal buffers in ONE batch: every buffer
+    ends with the oracle's status (parse errors from the walker, run-out-of-flags and map errors from the kernels), the
+    intact ones decode bit-exactly next to them."""
+    from test_cmp_cpu import cmp_section
+    from test_geometric_normal_cpu import normals_section
+    from test_mesh_predictors_walker_cpu import variants
+    b = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    o = O.decode(b)
+    rng = np.random.default_rng(99)
+    n0, n1 = o.maps[0]["data_to_corner"].size, o.maps[1]["data_to_corner"].size
+    maps = [o.maps[0], o.maps[1]]
+    if kind == "cmp":
+        sec, _ = cmp_section(rng.integers(0, 4096, size=n0 * 3), 3, o.maps[0], 12, rng)
+    else:
+        sec = normals_section(rng.integers(-40, 41, size=n0 * 3), rng.integers(0, 1024, size=n1 * 2), rng.integers(0, 2, size=n1), 10)
+    buf, aoff = _mesh_buffer(sec)
+    bufs = variants(np.frombuffer(buf, dtype=np.uint8).copy(), aoff, rng)
+    refs = [O.decode(v, maps, aoff, o.n_points) for v in bufs]
+    batch = gpu_decoder.index(bufs)
+    for k in range(len(bufs)):
+        batch.set_attr_section(k, aoff, o.n_points)
+        for dd, m in enumerate(maps):
+            batch.set_mesh_maps(k, dd, m["opposite"], m["corner_to_vertex"], m["data_to_corner"], m["vertex_to_data"])
+    batch.finish()
+    out, _ = gpu_decoder.decode(batch)
+    n_ok = 0
+    for k, ref in enumerate(refs):
+        assert batch.status(k) == ref.status, (k, len(bufs[k]), batch.status(k), ref.status)
+        if ref.status == 0:
+            n_ok += 1
+            for a, ra in enumerate(ref.attrs):
+                ai = batch.attr_info(k, a)
+                assert np.array_equal(out[ai.out_off: ai.out_off + ai.out_bytes], ra.out), (k, a)
+    assert 1 <= n_ok < len(bufs)
+    batch.free()
+
+
 def test_mesh_without_maps_fails_cleanly(gpu_decoder):
     sec = bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
     sec += W.portable_int(np.zeros(30, dtype=np.int64), 3, 1, 1, "raw", W.wrap_data(0, 7)) + W.quant_params([0, 0, 0], 1.0, 3)
