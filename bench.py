@@ -609,11 +609,13 @@ def run_sweep(args, rank, local_rank):
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / steps
             st = dec.stats()
-            print(json.dumps({"sweep": axis, "scheme": sname, "rank": rank, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            # one write per line: under torchrun the ranks share a stdout
+            sys.stdout.write(json.dumps({"sweep": axis, "scheme": sname, "rank": rank, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
                               "points_per_buffer": n, "buffers": b, "ms_per_step": ms,
                               "points_per_s": batch.points / (ms * 1e-3), "algorithmic_GBps": batch.algo_bytes / (ms * 1e-3) / 1e9,
                               "frac_of_hbm_peak": batch.algo_bytes / (ms * 1e-3) / 1e9 / peak, "parity_ok": bool(ok),
-                              "launches": st.n_launches, "stage_ms": {"raw": st.ms_raw, "tag": st.ms_tag, "par": st.ms_par}}), flush=True)
+                              "launches": st.n_launches, "stage_ms": {"raw": st.ms_raw, "tag": st.ms_tag, "par": st.ms_par}}) + "\n")
+            sys.stdout.flush()
             batch.free()
             del d_out
     dec.close()

@@ -173,6 +173,8 @@ struct Shard {
   uint32_t *d_order = nullptr;
   uint64_t order_cap = 0;
   uint8_t *h_stage = nullptr;  // pinned staging for the packed input
+  uint8_t *h_maps = nullptr;   // pinned staging for large sets of (borrowed, pageable) mesh maps
+  uint64_t cap_hmaps = 0;
   uint8_t *h_desc = nullptr;   // pinned staging: device-updated stream descriptors + walks travel back without blocking
   uint64_t cap_hdesc = 0;
   bool desc_pending = false;   // h_desc holds a copy-back that absorb_descs folds into streams / walks after the sync
@@ -548,7 +550,7 @@ void free_shard_device(Shard &sh) {
     sh.h_desc = nullptr;
     sh.desc_pending = false;
   }
-  if (!sh.d_in && !sh.d_streams && !sh.h_stage && !sh.d_out) return;
+  if (!sh.d_in && !sh.d_streams && !sh.h_stage && !sh.d_out && !sh.h_maps) return;
   cudaSetDevice(sh.device);
   pool_free(sh.pool, sh.device, sh.d_in, sh.cap_in);
   if (sh.own_out) pool_free(sh.pool, sh.device, sh.d_out, sh.cap_out);
@@ -560,6 +562,8 @@ void free_shard_device(Shard &sh) {
   pool_free(sh.pool, sh.device, sh.d_walks, sh.cap_walks);
   pool_free(sh.pool, sh.device, sh.d_order, sh.cap_order);
   if (sh.h_stage) pinned_free(sh.pool, sh.h_stage, sh.cap_stage);
+  if (sh.h_maps) pinned_free(sh.pool, sh.h_maps, sh.cap_hmaps);
+  sh.h_maps = nullptr;
   sh.d_in = sh.d_out = sh.d_dbg = sh.d_aux = sh.d_tab = sh.d_maps = nullptr;
   sh.d_streams = nullptr;
   sh.d_walks = nullptr;
@@ -1064,6 +1068,63 @@ int issue_maps_copy(dcb_ctx *ctx, dcb_batch *b, Shard &sh, int dev_index) {
   cudaStream_t st = ctx->streams[dev_index], cs = ctx->copy_in[dev_index];
   CUDA_TRY(cudaSetDevice(sh.device));
   tl_mark(ctx, "h2d maps s" + std::to_string(dev_index), cs, true);
+  // Large map sets (configs[3]: 56 MB per million-vertex mesh): the caller's arrays are pageable memory, from which
+  // cudaMemcpyAsync runs at a fraction of the link rate and blocks this thread.  A few host threads copy them piece by
+  // piece into pinned staging (same layout as the device arena) while the DMA of the finished pieces is already running.
+  constexpr uint64_t kMapsStageMin = 32ull << 20, kPiece = 8ull << 20;
+  bool staged = false;
+  if (sh.maps_bytes >= kMapsStageMin && !env_flags().no_fanout) {
+    if (!sh.h_maps && pinned_alloc(sh.pool, sh.maps_bytes, &sh.h_maps, &sh.cap_hmaps) != cudaSuccess) {
+      cudaGetLastError();
+      sh.h_maps = nullptr;
+    }
+    if (sh.h_maps) {
+      struct Piece { const uint8_t *src; uint64_t off, bytes; };
+      std::vector<Piece> pieces;
+      try {
+        for (int k : sh.bufs)
+          for (const MeshMapsHost &m : b->bufs[k].maps)
+            if (m.set) {
+              const void *src[4] = {m.opposite, m.corner_to_vertex, m.data_to_corner, m.vertex_to_data};
+              const uint64_t sz[4] = {m.n_corners * 4, m.n_corners * 4, m.n_entries * 4, m.n_vertices * 4};
+              for (int j = 0; j < 4; ++j)
+                for (uint64_t o = 0; o < sz[j]; o += kPiece)
+                  pieces.push_back({(const uint8_t *)src[j] + o, m.dev_off[j] + o, std::min(kPiece, sz[j] - o)});
+            }
+        std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[pieces.size()]);
+        for (size_t i = 0; i < pieces.size(); ++i) done[i].store(0, std::memory_order_relaxed);
+        std::atomic<size_t> next{0};
+        uint8_t *stage = sh.h_maps;
+        auto work = [&]() {
+          for (size_t i = next.fetch_add(1); i < pieces.size(); i = next.fetch_add(1)) {
+            memcpy(stage + pieces[i].off, pieces[i].src, pieces[i].bytes);
+            done[i].store(1, std::memory_order_release);
+          }
+        };
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        const size_t n_threads = std::min<size_t>(std::min<size_t>(8, hw / 2), pieces.size());
+        std::vector<std::thread> th;
+        th.reserve(n_threads);
+        try {
+          for (size_t t = 0; t < n_threads; ++t) th.emplace_back(work);
+        } catch (...) {  // no more threads to be had: the ones that started (or this one) do the copying
+        }
+        if (th.empty()) work();
+        cudaError_t ce = cudaSuccess;
+        for (size_t i = 0; i < pieces.size(); ++i) {
+          while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+          if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(sh.d_maps + pieces[i].off, stage + pieces[i].off, pieces[i].bytes, cudaMemcpyHostToDevice, cs);
+        }
+        for (std::thread &t : th) t.join();
+        CUDA_TRY(ce);
+        staged = true;
+      } catch (const std::bad_alloc &) {
+        return DCB_ERR_OOM;
+      }
+    }
+  }
+  if (!staged)
   for (int k : sh.bufs)
     for (const MeshMapsHost &m : b->bufs[k].maps)
       if (m.set) {

@@ -7,7 +7,7 @@ Not a pytest module (the sanitized build takes minutes): run it by hand,
 It (1) builds libdracob200 a second time into a scratch directory with `-Xcompiler -fsanitize=address,undefined
 -fno-sanitize-recover=undefined`, (2) re-executes itself in a child with libasan preloaded and DCB_LIB pointing at that
 build, and (3) in the child pushes mutated buffers -- the reference's sample mesh, synthetic point clouds of every
-symbol scheme, crafted tex-coord / parallelogram attribute sections -- through dcb_index -> dcb_host_connectivity ->
+symbol scheme, crafted tex-coord / parallelogram / constrained-multi-parallelogram / geometric-normal attribute sections -- through dcb_index -> dcb_host_connectivity ->
 dcb_index_finish -> every getter, with no device (index-only batches).  Any sanitizer report aborts the child; the
 parent prints its tail and exits non-zero.  The last run's summary is committed as profiles/r2_fuzz_host_asan.txt.
 """
@@ -64,9 +64,17 @@ def child(iterations, seed):
     sec += W.portable_int(rng.integers(-5, 6, size=24), 2, 5, 1, "tagged", W.tex_coords_data(flags, 0, 255)) + W.quant_params([0, 0], 1.0, 8)
     head = b"DRACO" + bytes([2, 2, 1, 1, 0, 0, 2]) + b"\xAA" * 37
     crafted = np.frombuffer(head + bytes(sec), dtype=np.uint8)
+    # ... and one with the other 8f-3 predictors: constrained multi-parallelogram positions (four crease-flag blocks) and
+    # geometric normals (flip bits behind the transform data)
+    sec2 = bytearray([1, 0xFF, 0, 0]) + W.varint(2) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([1, 9, 3, 0]) + W.varint(1) + bytes([2, 3])
+    crease = [list(rng.integers(0, 2, size=k)) for k in (5, 8, 0, 4)]
+    sec2 += W.portable_int(rng.integers(-5, 6, size=36), 3, 4, 1, "raw", W.cmp_data(crease, 0, 255))
+    sec2 += W.portable_int(rng.integers(0, 60, size=24), 2, 6, 3, "tagged", W.geometric_normal_data(rng.integers(0, 2, size=12), 8), zig=False)
+    sec2 += W.quant_params([0, 0, 0], 1.0, 8) + bytes([8])
+    crafted2 = np.frombuffer(head + bytes(sec2), dtype=np.uint8)
     stats = {"decodes": 0, "ok": 0, "failed": 0}
     for it in range(iterations):
-        base = seeds[it % len(seeds)] if it % 7 else crafted
+        base = seeds[it % len(seeds)] if it % 7 else (crafted if it % 14 else crafted2)
         b = base.copy()
         kind = int(rng.integers(0, 4))
         if kind == 0:      # byte flips
@@ -86,11 +94,11 @@ def child(iterations, seed):
             bi = bt.buffer_info(k)
             if bi.status == 0 and bi.needs_connectivity:
                 try:  # argument errors (an attribute section beyond a truncated buffer ...) come back as exceptions
-                    if base is crafted and k == 0:
+                    if (base is crafted or base is crafted2) and k == 0:
                         bt.set_attr_section(0, len(head), 12)
                         n = 12
                         idm = np.arange(3 * n, dtype=np.uint32)
-                        for d in range(2):
+                        for d in range(2 if base is crafted else 1):
                             bt.set_mesh_maps(0, d, idm, idm % n, np.arange(n, dtype=np.uint32) * 3, np.arange(n, dtype=np.int32))
                     else:
                         bt.host_connectivity(k)
