@@ -352,18 +352,16 @@ __global__ void __launch_bounds__(64) cmp_chain_kernel(StreamDesc *streams, cons
           const uint32_t a_more = (uint32_t)__cvta_generic_to_shared(s_more[buf]);
           const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(s_base[buf]) + lane * 4u;
           const uint32_t a_cor = (uint32_t)__cvta_generic_to_shared(s_cor[buf]) + lane * 4u;
-          // records are independent of the chain: two entries ahead
-          uint2 m0 = lds64(a_meta), m1 = lds64(a_meta + 8u * (cnt > 1u ? 1u : 0u));
-          int32_t b0 = lds32(a_base), b1 = lds32(a_base + (cnt > 1u ? 1u : 0u) * (4u * NCP));
-          int32_t c0 = lds32(a_cor), c1 = lds32(a_cor + (cnt > 1u ? 1u : 0u) * (4u * NCP));
-          for (uint32_t j = 0; j < cnt; ++j) {
-            const uint32_t j2 = j + 2 < cnt ? j + 2 : j;  // harmless re-read at the end of the block
-            const uint2 m2 = lds64(a_meta + 8u * j2);
-            const int32_t b2 = lds32(a_base + j2 * (4u * NCP)), c2 = lds32(a_cor + j2 * (4u * NCP));
-            uint32_t sum = (uint32_t)b0 + (uint32_t)(int32_t)(int8_t)(m0.x & 0xFFu) * (uint32_t)prev;
-            const uint32_t n_near = (m0.x >> 16) & 15u;
+          // Records are independent of the chain: they are read two entries ahead, into three register sets that take
+          // turns (the loop is unrolled by three so that no loaded value has to be moved -- a move waits for its load).
+          auto rec_meta = [&](uint32_t j) { return lds64(a_meta + 8u * min(j, cnt - 1u)); };  // harmless re-read past the end
+          auto rec_base = [&](uint32_t j) { return lds32(a_base + min(j, cnt - 1u) * (4u * NCP)); };
+          auto rec_cor = [&](uint32_t j) { return lds32(a_cor + min(j, cnt - 1u) * (4u * NCP)); };
+          auto entry = [&](uint32_t j, const uint2 &m, int32_t bs, int32_t co) {
+            uint32_t sum = (uint32_t)bs + (uint32_t)(int32_t)(int8_t)(m.x & 0xFFu) * (uint32_t)prev;
+            const uint32_t n_near = (m.x >> 16) & 15u;
             if (n_near) {  // operands decoded in this block or the one before (never entry j - 1: that one is in k)
-              uint32_t wv = m0.y;
+              uint32_t wv = m.y;
               const uint2 more = n_near > 4u ? lds64(a_more + 8u * j) : make_uint2(0u, 0u);
               for (uint32_t i = 0; i < n_near; ++i) {
                 if (i == 4u) wv = more.x;
@@ -374,12 +372,22 @@ __global__ void __launch_bounds__(64) cmp_chain_kernel(StreamDesc *streams, cons
                 sum += (b & 0x80u) ? 0u - v : v;
               }
             }
-            const int32_t pred = div_small((int32_t)sum, (m0.x >> 8) & 15u, (m0.x >> 12) & 3u, (m0.x >> 14) & 1u);
-            prev = wrap_original(pred, c0, pp.mn, pp.mx, pp.max_diff);
+            const int32_t pred = div_small((int32_t)sum, (m.x >> 8) & 15u, (m.x >> 12) & 3u, (m.x >> 14) & 1u);
+            prev = wrap_original(pred, co, pp.mn, pp.mx, pp.max_diff);
             sts32(a_st + j * (4u * NCP), prev);
-            m0 = m1; m1 = m2;
-            b0 = b1; b1 = b2;
-            c0 = c1; c1 = c2;
+          };
+          uint2 m0 = rec_meta(0), m1 = rec_meta(1), m2;
+          int32_t b0 = rec_base(0), b1 = rec_base(1), b2;
+          int32_t c0 = rec_cor(0), c1 = rec_cor(1), c2;
+          for (uint32_t j = 0; j < cnt; j += 3) {
+            m2 = rec_meta(j + 2); b2 = rec_base(j + 2); c2 = rec_cor(j + 2);
+            entry(j, m0, b0, c0);
+            if (j + 1 >= cnt) break;
+            m0 = rec_meta(j + 3); b0 = rec_base(j + 3); c0 = rec_cor(j + 3);
+            entry(j + 1, m1, b1, c1);
+            if (j + 2 >= cnt) break;
+            m1 = rec_meta(j + 4); b1 = rec_base(j + 4); c1 = rec_cor(j + 4);
+            entry(j + 2, m2, b2, c2);
           }
         }
       } else {
