@@ -367,6 +367,39 @@ def test_mesh_predictor_status_parity_on_malformed_buffers(gpu_decoder, kind):
     batch.free()
 
 
+def test_predictor_goldens_on_gpu_without_the_oracle(gpu_decoder):
+    """tests/golden/mesh_predictors.npz through the CUDA path with NOTHING of oracle/ involved: the connectivity maps come
+    from the product's own host helper run on the reference's sample (dcb_host_connectivity + dcb_mesh_map), the expected
+    values from the fixture (what the bitstream-specification encoder encoded / predicted, SHA-256 of the output bytes)."""
+    z = np.load(os.path.join(GOLD, "mesh_predictors.npz"))
+    house = np.fromfile(os.path.join(GOLD, "house_04.obj.drc"), dtype=np.uint8)
+    hb = gpu_decoder.index([house])
+    hb.host_connectivity(0)
+    maps = [[hb.mesh_map(0, d, w).copy() for w in range(4)] for d in range(2)]
+    hb.finish()
+    hb.free()
+    aoff, n = int(z["attr_off"]), int(z["n_points"])
+    bufs = [z["cmp_buf"], z["geo_buf"]]
+    batch = gpu_decoder.index(bufs)
+    for k in range(2):
+        batch.set_attr_section(k, aoff, n)
+        for d in range(2):
+            batch.set_mesh_maps(k, d, *maps[d])
+    batch.finish()
+    out, dbg = gpu_decoder.decode(batch, flags=N.DCB_DUMP_QINTS)
+    assert batch.status(0) == 0 and batch.status(1) == 0
+    want_q = {(0, 0): z["cmp_pos"], (0, 1): z["cmp_gen"], (1, 1): z["geo_pred"]}
+    want_sha = {0: list(z["cmp_sha"]), 1: list(z["geo_sha"])}
+    for k in range(2):
+        for a in range(2):
+            ai = batch.attr_info(k, a)
+            assert sha(out[ai.out_off: ai.out_off + ai.out_bytes]) == want_sha[k][a], (k, a)
+            if (k, a) in want_q:
+                w = want_q[(k, a)]
+                assert np.array_equal(dbg[ai.dbg_off: ai.dbg_off + 4 * w.size].view(np.int32), w), (k, a)
+    batch.free()
+
+
 def test_mesh_without_maps_fails_cleanly(gpu_decoder):
     sec = bytes([1, 0xFF, 0, 0]) + W.varint(1) + bytes([0, 9, 3, 0]) + W.varint(0) + bytes([2])
     sec += W.portable_int(np.zeros(30, dtype=np.int64), 3, 1, 1, "raw", W.wrap_data(0, 7)) + W.quant_params([0, 0, 0], 1.0, 3)
