@@ -97,7 +97,8 @@ typedef struct dcb_attr_info {
   uint32_t unique_id;
   int32_t seq_decoder_type; /* 0 generic 1 integer 2 quantization 3 normals */
   int32_t decoder_id;
-  int32_t pred_method;    /* PredictionSchemeMethod, -2 none */
+  int32_t pred_method;    /* PredictionSchemeMethod, -2 none; decoded on the GPU: 0 difference, 1 parallelogram, 4 constrained
+                             multi-parallelogram, 5 tex-coords-portable, 6 geometric normal (2, 3: pre-2.2 streams, UNSUPPORTED) */
   int32_t transform;      /* PredictionSchemeTransformType, -1 none */
   int32_t scheme;         /* 0 tagged 1 raw -1 n/a */
   int32_t precision_bits;
