@@ -617,8 +617,8 @@ void layout_shard(Shard &sh) {
         aux = align_up(aux + 2ull * nv * 4 + tail, 16);
       } else if (s.seq_type == SEQ_NORMALS) {
         s.aux_off = aux;  // quantized octahedral (s, t) pairs between the serial kernels and oct_unit_kernel
-        // (+ geometric normal: flip bits u8[n] behind the pairs)
-        aux = align_up(aux + 9ull * s.n_entries + 16ull, 16);
+        // (+ geometric normal, a mesh predictor: flip bits u8[n] behind the pairs)
+        aux = align_up(aux + (s.has_maps ? 9ull : 8ull) * s.n_entries + 16ull, 16);
       } else if (s.seq_type == SEQ_INTEGER && s.ncp > 4) {
         s.aux_off = aux;  // wide attributes: zig-zag decoded symbols of a Raw source, int32[n * nc]
         aux = align_up(aux + 4ull * nv, 16);
